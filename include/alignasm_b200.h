@@ -1,0 +1,165 @@
+/* alignasm_b200.h — C ABI of the B200-native alignasm hot path.
+ *
+ * This is the drop-in boundary for the one data-parallel path of ACCtools/alignasm:
+ *
+ *     void solve_ctg_read(std::vector<PafReadData>&, std::vector<PafOutputData>& out,
+ *                         std::vector<PafOutputData>& alt_out,
+ *                         std::vector<std::vector<PafOutputData>>& max_out);
+ *                                  (reference: src/paf_data.hpp:193, called at src/alignasm.cpp:357,373,391)
+ *
+ * The C++ seam is not ABI-stable (std::vector / std::string), so the C layer is batch-oriented and
+ * carries exactly the fields that cross it, as plain pointers and sizes:
+ *   in : all blocks of every contig in FILE order (ctg_index = position inside the contig,
+ *        alignasm.cpp:138-139), closed int64 intervals (alignasm.cpp:141-151), ref_str > ref_end for
+ *        '-' rows (alignasm.cpp:155-159), dense chromosome ids (alignasm.cpp:153), mapq, query length,
+ *        and the exact-match runs that get_overlap_range() derives from cs:Z: (paf_data.cpp:90-123).
+ *   out: the three per-contig lists of PafOutputData (paf_data.hpp:90-105) — primary chain
+ *        (.aln.paf), alternative chain (.aln.alt.paf) and the equal-coverage list (.aln.all.paf) —
+ *        plus ctg_sorted_index, the one side effect the reference writes into its input
+ *        (paf_data.cpp:236,244).
+ *
+ * Error behaviour: the reference throws / asserts (never caught); this ABI returns a
+ * non-zero aa_status and a message from aa_last_error().  There is NO CPU fallback: every aa_solve*
+ * entry point fails with AA_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * All functions are re-entrant per aa_ctx; there is no global mutable state.
+ */
+#ifndef ALIGNASM_B200_H
+#define ALIGNASM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum aa_status {
+    AA_OK = 0,
+    AA_ERR_INVALID = 1,    /* malformed batch (offsets not monotone, empty contig, ...)            */
+    AA_ERR_NO_DEVICE = 2,  /* no usable CUDA device: the product has no CPU path                    */
+    AA_ERR_CUDA = 3,       /* CUDA runtime error, message in aa_last_error                          */
+    AA_ERR_NOMEM = 4,      /* device or host allocation failed / contig too large for one GPU       */
+    AA_ERR_IO = 5,         /* PAF file could not be read / written                                  */
+    AA_ERR_FORMAT = 6,     /* PAF / cs:Z: syntax error (reference: std::invalid_argument)           */
+    AA_ERR_UNSOLVABLE = 7  /* a contig has no src->dest walk (reference: assert, paf_data.cpp:732)  */
+} aa_status;
+
+/* ---- input: one batch of contigs, structure-of-arrays, host memory ------------------------- */
+typedef struct aa_batch {
+    int64_t n_ctg;            /* number of contigs                                                  */
+    int64_t n_blk;            /* total alignment blocks (PAF rows)                                  */
+    int64_t n_run;            /* total exact-match runs over all blocks                             */
+    const int64_t *ctg_off;   /* [n_ctg+1] block offsets; blocks of a contig are in file order     */
+    const int64_t *qry_str;   /* [n_blk] closed interval on the query                               */
+    const int64_t *qry_end;
+    const int64_t *ref_str;   /* [n_blk] closed interval on the target; ref_str > ref_end on '-'    */
+    const int64_t *ref_end;
+    const int64_t *qry_total; /* [n_blk] query (contig) length, PAF column 2                        */
+    const int32_t *ref_chr;   /* [n_blk] dense target id                                            */
+    const uint8_t *aln_fwd;   /* [n_blk] 1 = '+', 0 = '-'                                           */
+    const uint8_t *map_qul;   /* [n_blk] mapq                                                       */
+    const int64_t *run_off;   /* [n_blk+1] offsets into the run arrays                              */
+    const int64_t *run_ql;    /* [n_run] query-closed [l,r] of each exact-match run (':' op)        */
+    const int64_t *run_qr;
+    const int64_t *run_rl;    /* [n_run] target coordinate of the run's first query base           */
+} aa_batch;
+
+typedef struct aa_opts {
+    int32_t non_skip_linkable; /* --non_skip_linkable (alignasm.cpp:54-57,74)                        */
+    int32_t want_all;          /* materialise the .aln.all.paf list (can be very large)              */
+    int32_t max_walks;         /* MAX_PATH_COUNT, paf_data.cpp:729; 0 = reference value 10000         */
+    int32_t keep_debug;        /* fill aa_result.dbg (graph / d / best / walk distances)             */
+} aa_opts;
+
+/* rows of PafOutputData (paf_data.hpp:90-105), structure-of-arrays */
+typedef struct aa_rows {
+    int64_t n;
+    int32_t *ctg_index;
+    int64_t *qry_str, *qry_end, *ref_str, *ref_end;
+    uint8_t *is_alt;
+} aa_rows;
+
+/* intermediate state for parity tests (only when aa_opts.keep_debug) — vertex ids are
+ * contig-local: singles 0..n-1, pair vertices n.., src = V-2, dest = V-1 (paf_data.cpp:286-291,
+ * 371-372, 699-700) */
+typedef struct aa_debug {
+    int64_t *vtx_off;   /* [n_ctg+1] */
+    int64_t *edge_off;  /* [n_ctg+1] */
+    int64_t *walk_off;  /* [n_ctg+1] */
+    int32_t *e_src, *e_dst;          /* [E] adjacency order (OC3)                                 */
+    int64_t *e_qry, *e_ref;          /* [E]                                                       */
+    int32_t *e_anom, *e_qnz, *e_qtot;
+    uint8_t *d_reach;                /* [V] */
+    int64_t *d_sum;                  /* [V] qry_score + ref_score of d[v] (CALC_SUM view)          */
+    int32_t *d_anom, *d_qnz, *d_qtot;
+    int32_t *best;                   /* [V] */
+    int32_t *order;                  /* [V] forward Kahn position of each vertex                   */
+    int64_t *w_sum;                  /* [W] walk distances, pop order                              */
+    int32_t *w_anom, *w_qnz, *w_qtot;
+    int64_t *anom_dis;               /* [n_ctg] anom_dis[dest], paf_data.cpp:713                   */
+} aa_debug;
+
+typedef struct aa_stats {
+    int64_t n_ctg, n_blk, n_run;
+    int64_t n_pair;      /* pair vertices P                                                          */
+    int64_t n_vtx;       /* V summed over solved contigs (n + P + 2 each)                            */
+    int64_t n_edge;      /* E                                                                        */
+    int64_t n_heap;      /* persistent leftist-heap nodes H                                          */
+    int64_t n_walk;      /* walks enumerated K                                                       */
+    int64_t n_task;      /* walks recovered + upgraded (edge_path_to_paf_path calls)                 */
+    int64_t n_launch;    /* kernels launched by the last solve                                       */
+    double ms_total;     /* device time of the last solve (CUDA events)                              */
+    double ms_phase[16]; /* per phase, see aa_phase_name()                                           */
+    double algo_bytes;   /* algorithmic bytes of the last solve (DESIGN.md formula)                  */
+    double algo_bytes_phase[16];
+} aa_stats;
+
+typedef struct aa_result {
+    int64_t n_ctg;
+    int64_t *out_off;      /* [n_ctg+1] rows of the primary chain per contig                        */
+    aa_rows out;
+    int64_t *alt_off;      /* [n_ctg+1]                                                             */
+    aa_rows alt;
+    int64_t *all_path_off; /* [n_ctg+1] -> paths (only with want_all, else all zero)                */
+    int64_t *all_row_off;  /* [n_paths+1] -> rows                                                   */
+    aa_rows all;
+    int32_t *sorted_index; /* [n_blk] ctg_sorted_index of every input block                         */
+    aa_debug *dbg;         /* NULL unless keep_debug                                                */
+    aa_stats stats;
+} aa_result;
+
+typedef struct aa_ctx aa_ctx;             /* one per (host thread, device)                          */
+typedef struct aa_dev_batch aa_dev_batch; /* a batch staged in HBM                                  */
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+aa_status aa_create(aa_ctx **ctx, int device);
+void aa_destroy(aa_ctx *ctx);
+const char *aa_last_error(const aa_ctx *ctx);
+
+/* solve_ctg_read over a whole batch, host buffers in, host buffers out (replaces the loop at
+ * alignasm.cpp:346-379).  `res` is filled with library-owned memory: release with aa_result_free. */
+aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_result *res);
+
+/* the same in three steps, so that a caller can keep a batch resident in HBM */
+aa_status aa_upload(aa_ctx *ctx, const aa_batch *batch, aa_dev_batch **dev);
+aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, aa_result *res /* may be NULL: results stay on the device */);
+void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev);
+
+void aa_result_free(aa_result *res);
+const char *aa_phase_name(int phase); /* NULL past the last phase */
+const char *aa_version(void);
+
+/* ---- host side of the drop-in: PAF reader / cs:Z: codec / writers ------------------------- */
+typedef struct aa_paf aa_paf;
+/* reader + contig bucketing + get_overlap_range (alignasm.cpp:110-181, paf_data.cpp:90-123) */
+aa_status aa_paf_read(const char *path, aa_paf **paf, char *err, int64_t err_cap);
+const aa_batch *aa_paf_batch(const aa_paf *paf);
+/* writers incl. get_edited_paf_data (alignasm.cpp:398-490, paf_data.cpp:125-220); writes
+ * <prefix>.aln.paf, <prefix>.aln.alt.paf, <prefix>.aln.all.paf */
+aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const char *out_prefix, char *err, int64_t err_cap);
+void aa_paf_free(aa_paf *paf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNASM_B200_H */

@@ -1,0 +1,1313 @@
+// aa_core.cuh — data layout in HBM and the per-item device functions of the alignasm hot path.
+//
+// Everything here is a __host__ __device__ function over plain pointers (struct Ws), so that the
+// kernels in aa_solve.cu are thin grids over items (blocks, candidate pairs, vertices, contigs, walk
+// tasks), and so that tests/emul can run the very same functions on the CPU to check the logic
+// against the reference without a GPU.  The product never runs them on the host.
+//
+// Reference map (all under reference src/):
+//   parts                      paf_data.cpp:249-261
+//   pair vertices + cut points paf_data.cpp:294-378
+//   linkable / get_score       paf_data.cpp:422-521
+//   make_Graph                 paf_data.cpp:531-696     (restated per source vertex, order OC3)
+//   anom distance              paf_data.cpp:705-713, k_weighted_bfs.hpp:15-37
+//   reverse relax (d, best)    k_shortest_walks.hpp:132-175, 180-184
+//   sidetrack heaps            k_shortest_walks.hpp:191-215, leftist_heap.hpp:29-40
+//   walk enumeration           k_shortest_walks.hpp:217-251
+//   walk recovery              k_shortest_walks.hpp:254-290
+//   gap filling DP / upgrade   paf_data.cpp:750-921
+//   rows, flags, selection     paf_data.cpp:1489-1649
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AA_HD __host__ __device__ __forceinline__
+#define AA_HDN __host__ __device__
+#else
+#define AA_HD inline
+#define AA_HDN inline
+#endif
+
+namespace aa {
+
+// ---- constants (paf_data.hpp:21-29, paf_data.cpp:729) ------------------------------------------
+constexpr int64_t SV_BASELINE = 1000000;
+constexpr int64_t SV_TRANS_PENALTY = 2000;
+constexpr int64_t SV_INV_PENALTY = 500;
+constexpr int64_t SV_FRONT_END = 2;
+constexpr int64_t REF_NEG_PENALTY = 2;
+constexpr int32_t HEAP_CHUNK = 1024;  // leftist-heap nodes handed to a contig per arena grab
+constexpr int64_t I64_MAX = 0x7fffffffffffffffLL;
+
+// ---- distance types -----------------------------------------------------------------------------
+// PafDistance (paf_data.hpp:121-189) in CALC_SUM mode only ever looks at qry+ref, so the k-walk
+// pipeline carries the sum.  aux: reach flag in d[], unused elsewhere.
+struct D4 {
+    int64_t sum;
+    int32_t anom, nz, tot, aux;
+};
+// QRY_SCORE mode (the gap-filling DP) needs qry and ref apart.
+struct D5 {
+    int64_t qry, ref;
+    int32_t anom, nz, tot, pad;
+};
+AA_HD int64_t den(int32_t t) { return t ? (int64_t)t : 1; }
+// operator< in CALC_SUM_MODE (paf_data.hpp:142-159); MAX never reaches here (callers test reach)
+AA_HD bool less4(const D4 &a, const D4 &b) {
+    if (a.sum != b.sum) return a.sum < b.sum;
+    if (a.anom != b.anom) return a.anom < b.anom;
+    return (int64_t)a.nz * den(b.tot) > (int64_t)b.nz * den(a.tot);
+}
+AA_HD bool less5(const D5 &a, const D5 &b) {  // QRY_SCORE_MODE
+    if (a.qry != b.qry) return a.qry < b.qry;
+    if (a.ref != b.ref) return a.ref < b.ref;
+    if (a.anom != b.anom) return a.anom < b.anom;
+    return (int64_t)a.nz * den(b.tot) > (int64_t)b.nz * den(a.tot);
+}
+
+// ---- edge record: 16 B ----------------------------------------------------------------------------
+// dst_fl: bits 0..26 contig-local destination vertex, 27..28 anom, 29 qul_nonzero, 30 qul_total
+struct Edge {
+    int64_t qry;
+    int32_t ref;
+    uint32_t dst_fl;
+};
+constexpr uint32_t DST_MASK = (1u << 27) - 1;
+AA_HD int32_t e_dst(const Edge &e) { return (int32_t)(e.dst_fl & DST_MASK); }
+AA_HD int32_t e_anom(const Edge &e) { return (int32_t)((e.dst_fl >> 27) & 3u); }
+AA_HD int32_t e_nz(const Edge &e) { return (int32_t)((e.dst_fl >> 29) & 1u); }
+AA_HD int32_t e_tot(const Edge &e) { return (int32_t)((e.dst_fl >> 30) & 1u); }
+
+// persistent leftist-heap node: 32 B, the (u,v) payload lives in hn_eid[]
+struct HNode {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t left, right;
+    int32_t rank;
+};
+// priority-queue entry of the enumeration: 32 B
+struct PQEnt {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t node;  // heap node id (allocation order == the reference's pointer order)
+    int32_t idx;   // entry index
+    int32_t pad;
+};
+
+struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
+    int32_t i, j;        // contig-local sorted block indices
+    int64_t pe_q, pe_r;  // edited_loc_pre_end[i][j]
+    int64_t st_q, st_r;  // edited_loc_str[i][j]
+};
+
+struct Task {  // one edge_path_to_paf_path call
+    int32_t ctg, walk;
+    int32_t call;   // call order inside the contig (OC11)
+    int32_t group;  // 0 = ties of walk 0; g>=1 = g-th alt answer group
+};
+
+// ---- workspace: every array of the pipeline (device pointers) ----------------------------------------
+struct Ws {
+    // batch
+    int64_t C, B, R;
+    int32_t nsl, K;
+    const int64_t *ctg_off;  // [C+1]
+    // original-order input
+    const int64_t *in_qs, *in_qe, *in_rs, *in_re, *in_qtot;
+    const int32_t *in_chr;
+    const uint8_t *in_fwd, *in_mapq;
+    const int64_t *run_off, *run_ql, *run_qr, *run_rl;
+    const int32_t *perm;  // [B] sorted position -> original position inside its contig
+    // sorted blocks
+    int32_t *blk_ctg;  // [B]
+    int64_t *qs, *qe, *rs, *re, *qtot;
+    int32_t *chr, *orig;
+    uint8_t *fwd, *mapq;
+    int64_t *run_beg;
+    int32_t *run_cnt;
+    int32_t *part_l, *part_r;  // [B] contig-local [l, r) of the block's part
+    // candidate pairs / pair vertices
+    int32_t *cand_cnt;   // [B]
+    int64_t *cand_off;   // [B+1]
+    CandRec *cand;       // [Ncand]
+    int32_t *cand_ok;    // [Ncand]
+    int64_t *cand_rank;  // [Ncand+1]
+    CandRec *pair;       // [P] compacted (global pair index)
+    int64_t *pair_beg;   // [B+1] first global pair index whose pre-block is b
+    // vertices / edges
+    int64_t *vtx_off;    // [C+1]
+    int32_t *deg;        // [Vtot]
+    int64_t *eoff;       // [Vtot+1]
+    Edge *edge;          // [E]
+    int32_t *e_src;      // [E] contig-local source
+    uint32_t *rkey_in, *rkey;   // [E] global destination vertex (sort key) before / after
+    uint32_t *rval_in, *rev_eid;  // [E] global edge id, sorted by destination, stable in source order
+    int64_t *rev_off;    // [Vtot+1]
+    // relax / topo
+    D4 *d;               // [Vtot]  aux = reachable
+    int32_t *best;       // [Vtot]
+    int32_t *cnt;        // [Vtot] scratch in/out-degree counters
+    int32_t *queue;      // [Vtot] scratch FIFO
+    int32_t *order;      // [Vtot] forward Kahn position
+    int32_t *topo;       // [Vtot] forward Kahn order (vertex at position)
+    int32_t *amin;       // [Vtot] min anom sum to dest
+    int64_t *anom_dis;   // [C]
+    int32_t *status;     // [C] 0 ok, 1 singleton, 2 unsolvable, 3 heap arena overflow
+    // sidetrack heaps
+    HNode *hn;           // [Hcap]
+    int32_t *hn_eid;     // [Hcap] contig-local edge id (u,v) of the sidetrack
+    int64_t Hcap;
+    unsigned long long *heap_top;  // arena bump pointer
+    int32_t *hroot;      // [Vtot]
+    int64_t *heap_used;  // [C]
+    // enumeration
+    int64_t *walk_off;   // [C+1] = c*K
+    int32_t *n_walk;     // [C]
+    D4 *wdist;           // [C*K]
+    int32_t *wlast;      // [C*K] path_last_node
+    int32_t *ent_node, *ent_prev;  // [C*3K]
+    PQEnt *pq;           // [C*3K]
+    // tasks
+    Task *task;          // [C*2K]
+    int32_t *n_task;     // [C]
+    int32_t *n_tie;      // [C] tasks of group 0
+    int32_t *last_group; // [C]
+    int64_t *task_off;   // [C+1] compacted offsets (after scan of n_task)
+    Task *tasks;         // [Ntask] compacted
+    int64_t *task_cov;   // [Ntask]
+    int32_t *task_rows;  // [Ntask]
+    int32_t *first_call; // [B] min call index that marked the block (not_alt_vertex_map)
+    // per-slot scratch for walk tasks
+    int64_t slot_stride;  // elements per slot (max V over contigs)
+    int32_t *sc_walk, *sc_up, *sc_side;  // [S*stride]
+    D5 *sc_dp;            // [S*stride]
+    int32_t *sc_pre;      // [S*stride]
+    uint8_t *sc_seen;     // [S*stride]
+    unsigned long long *task_next;  // dynamic task counter
+    int64_t n_tasks_total;
+    // selection + output
+    int32_t *win_out, *win_alt;  // [C] compacted task index (or -1)
+    int32_t *out_cnt, *alt_cnt, *all_cnt;  // [C] rows / rows / paths
+    int64_t *out_off, *alt_off, *all_path_off;  // [C+1]
+    int32_t *all_task;    // [Npaths] task index of each .all path
+    int32_t *all_rows;    // [Npaths]
+    int64_t *all_row_off; // [Npaths+1]
+    // rows: destination arrays (out / alt / all)
+    int32_t *r_idx[3];
+    int64_t *r_qs[3], *r_qe[3], *r_rs[3], *r_re[3];
+    uint8_t *r_alt[3];
+};
+
+struct Ctg {
+    int64_t b0;   // first (sorted) block
+    int32_t n;    // blocks
+    int64_t p0;   // first global pair index
+    int32_t P;    // pair vertices
+    int32_t V, src, dest;
+    int64_t v0;   // first global vertex
+};
+AA_HD Ctg ctg_view(const Ws &w, int64_t c) {
+    Ctg g;
+    g.b0 = w.ctg_off[c];
+    g.n = (int32_t)(w.ctg_off[c + 1] - g.b0);
+    g.p0 = w.pair_beg[g.b0];
+    g.P = (int32_t)(w.pair_beg[g.b0 + g.n] - g.p0);
+    g.V = g.n + g.P + 2;
+    g.src = g.n + g.P;
+    g.dest = g.src + 1;
+    g.v0 = w.vtx_off[c];
+    return g;
+}
+template <class T>
+AA_HD int64_t upper_idx(const T *off, int64_t n, T x) {  // largest c in [0,n) with off[c] <= x
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ================================================================================================
+// phase: gather blocks into sorted order
+AA_HDN void f_gather(const Ws &w, int64_t b) {
+    int64_t c = upper_idx(w.ctg_off, w.C, b);
+    int64_t b0 = w.ctg_off[c];
+    int64_t s = b0 + w.perm[b];
+    w.blk_ctg[b] = (int32_t)c;
+    w.qs[b] = w.in_qs[s];
+    w.qe[b] = w.in_qe[s];
+    w.rs[b] = w.in_rs[s];
+    w.re[b] = w.in_re[s];
+    w.qtot[b] = w.in_qtot[s];
+    w.chr[b] = w.in_chr[s];
+    w.fwd[b] = w.in_fwd[s];
+    w.mapq[b] = w.in_mapq[s];
+    w.orig[b] = w.perm[b];
+    w.run_beg[b] = w.run_off[s];
+    w.run_cnt[b] = (int32_t)(w.run_off[s + 1] - w.run_off[s]);
+    w.first_call[b] = 0x7fffffff;
+}
+
+// phase: parts (paf_data.cpp:249-261), one contig per call
+AA_HDN void f_parts(const Ws &w, int64_t c) {
+    int64_t b0 = w.ctg_off[c];
+    int32_t n = (int32_t)(w.ctg_off[c + 1] - b0);
+    w.status[c] = (n == 1) ? 1 : 0;
+    int64_t part_end = -1;
+    int32_t start = 0;
+    for (int32_t i = 0; i < n; i++) {
+        int64_t s = w.qs[b0 + i];
+        if (part_end < s) {
+            for (int32_t k = start; k < i; k++) w.part_r[b0 + k] = i;
+            start = i;
+        }
+        w.part_l[b0 + i] = start;
+        int64_t e = w.qe[b0 + i];
+        if (e > part_end) part_end = e;
+    }
+    for (int32_t k = start; k < n; k++) w.part_r[b0 + k] = n;
+}
+
+// qry_partial_overlap for sorted i < j (paf_data.hpp:78-86)
+AA_HD bool partial_ij(const Ws &w, int64_t gi, int64_t gj) {
+    int64_t is = w.qs[gi], ie = w.qe[gi], js = w.qs[gj], je = w.qe[gj];
+    if (is < js) return js <= ie && ie < je;
+    if (js < is) return is <= je && je < ie;
+    return false;
+}
+AA_HD bool contains_ij(const Ws &w, int64_t gi, int64_t gj) {  // i contains j (paf_data.hpp:74-77)
+    return w.qs[gi] <= w.qs[gj] && w.qe[gj] <= w.qe[gi];
+}
+
+// phase: count candidate pairs of block b (paf_data.cpp:297-302)
+AA_HDN void f_cand_count(const Ws &w, int64_t b) {
+    int64_t c = w.blk_ctg[b];
+    int64_t bend = w.ctg_off[c + 1];
+    int32_t cnt = 0;
+    int64_t ie = w.qe[b];
+    for (int64_t j = b + 1; j < bend; j++) {
+        if (ie < w.qs[j]) break;
+        if (partial_ij(w, b, j)) cnt++;
+    }
+    w.cand_cnt[b] = cnt;
+}
+
+// cut point of a partially overlapping pair: the two-pointer scan of paf_data.cpp:303-376
+AA_HDN bool find_cut(const Ws &w, int64_t gi, int64_t gj, CandRec &r) {
+    int64_t ai = w.run_beg[gi], bi = w.run_beg[gj];
+    int64_t na = w.run_cnt[gi], nb = w.run_cnt[gj];
+    int64_t step_a = w.fwd[gi] ? 1 : -1, step_b = w.fwd[gj] ? 1 : -1;
+    int64_t min_gap = -1, g_i = -1, g_j = -1;
+    int64_t pi = 0, pj = 0;
+    while (pi < na && pj < nb) {
+        int64_t li = w.run_ql[ai + pi], ri = w.run_qr[ai + pi];
+        int64_t lj = w.run_ql[bi + pj], rj = w.run_qr[bi + pj];
+        if (li == lj) {
+            if (lj == rj) {
+                pj++;
+                continue;
+            }
+            r.pe_q = li;
+            r.pe_r = w.run_rl[ai + pi];
+            r.st_q = lj + 1;
+            r.st_r = w.run_rl[bi + pj] + step_b;
+            return true;
+        }
+        if (li < lj) {
+            if (lj <= ri + 1) {
+                r.pe_q = lj - 1;
+                r.pe_r = w.run_rl[ai + pi] + ((lj - 1) - li) * step_a;
+                r.st_q = lj;
+                r.st_r = w.run_rl[bi + pj];
+                return true;
+            }
+            int64_t gap = lj - (ri + 1);
+            if (min_gap == -1 || gap < min_gap) {
+                min_gap = gap;
+                g_i = pi;
+                g_j = pj;
+            }
+            pi++;
+        } else {
+            if (li <= rj - 1) {
+                r.pe_q = li;
+                r.pe_r = w.run_rl[ai + pi];
+                r.st_q = li + 1;
+                r.st_r = w.run_rl[bi + pj] + (li + 1 - lj) * step_b;
+                return true;
+            }
+            pj++;
+        }
+    }
+    if (min_gap == -1) return false;  // the release build drops such a pair (paf_data.cpp:373-375)
+    int64_t li = w.run_ql[ai + g_i], ri = w.run_qr[ai + g_i];
+    r.pe_q = ri;
+    r.pe_r = w.run_rl[ai + g_i] + (ri - li) * step_a;
+    r.st_q = w.run_ql[bi + g_j];
+    r.st_r = w.run_rl[bi + g_j];
+    return true;
+}
+
+// phase: cut points of block b's candidates
+AA_HDN void f_cuts(const Ws &w, int64_t b) {
+    int64_t c = w.blk_ctg[b];
+    int64_t b0 = w.ctg_off[c], bend = w.ctg_off[c + 1];
+    int64_t slot = w.cand_off[b];
+    int64_t ie = w.qe[b];
+    for (int64_t j = b + 1; j < bend; j++) {
+        if (ie < w.qs[j]) break;
+        if (!partial_ij(w, b, j)) continue;
+        CandRec r;
+        r.i = (int32_t)(b - b0);
+        r.j = (int32_t)(j - b0);
+        r.pe_q = r.pe_r = r.st_q = r.st_r = -1;
+        bool ok = find_cut(w, b, j, r);
+        w.cand[slot] = r;
+        w.cand_ok[slot] = ok ? 1 : 0;
+        slot++;
+    }
+}
+
+// phase: compact valid candidates into pair vertices (discovery order i^, j^ : OC2); item = slot or block
+AA_HDN void f_compact(const Ws &w, int64_t k, int64_t ncand) {
+    if (k < ncand && w.cand_ok[k]) w.pair[w.cand_rank[k]] = w.cand[k];
+    if (k <= w.B) w.pair_beg[k] = w.cand_rank[w.cand_off[k]];
+}
+AA_HDN void f_vtx_off(const Ws &w, int64_t c) {  // c in [0, C]
+    int64_t b = w.ctg_off[c];
+    w.vtx_off[c] = b + w.pair_beg[b] + 2 * c;
+    if (c < w.C) w.walk_off[c] = c * (int64_t)w.K;
+}
+
+// ---- vertex view (Internal_Vertex, paf_data.cpp:392-411) ---------------------------------------------
+struct VV {
+    int64_t cur;  // global sorted block index of cur_idx
+    int64_t qs, qe, rs, re;
+};
+AA_HD VV vv_single(const Ws &w, int64_t gb) { return VV{gb, w.qs[gb], w.qe[gb], w.rs[gb], w.re[gb]}; }
+AA_HD VV vv_pair(const Ws &w, const Ctg &g, const CandRec &p) {
+    int64_t gj = g.b0 + p.j;
+    return VV{gj, p.st_q, w.qe[gj], p.st_r, w.re[gj]};
+}
+AA_HD int64_t ref_abs(int64_t x) { return x < 0 ? -x * REF_NEG_PENALTY : x; }
+
+// get_score (paf_data.cpp:449-521). rp != nullptr when the right vertex is a pair vertex.
+AA_HD Edge score(const Ws &w, VV l, const VV &r, const CandRec *rp, int32_t dst) {
+    if (rp) {
+        l.qe = rp->pe_q;
+        l.re = rp->pe_r;
+    }
+    int64_t ref_diff = 0;
+    uint32_t anom = 0;
+    bool lf = w.fwd[l.cur] != 0, rf = w.fwd[r.cur] != 0;
+    if (w.chr[l.cur] == w.chr[r.cur]) {
+        if (lf == rf) {
+            int64_t gap = lf ? r.rs - (l.re + 1) : l.re - (r.rs + 1);
+            ref_diff = ref_abs(gap);
+        } else {
+            anom = 1;
+            ref_diff = SV_INV_PENALTY + (lf ? ref_abs(r.re - (l.re + 1)) : ref_abs(r.rs - (l.rs + 1)));
+        }
+        if (ref_diff > SV_BASELINE) {
+            anom += 1;
+            ref_diff = SV_BASELINE;
+        }
+    } else {
+        anom = 1;
+        ref_diff = SV_TRANS_PENALTY;
+    }
+    Edge e;
+    e.qry = r.qs - l.qe - 1;
+    e.ref = (int32_t)ref_diff;
+    e.dst_fl = (uint32_t)dst | (anom << 27) | ((w.mapq[r.cur] ? 1u : 0u) << 29) | (1u << 30);
+    return e;
+}
+
+// index_of_vtx[i][j] for a pair vertex, -1 when (i,j) is no vertex.  Pairs of i are contiguous, j ascending.
+AA_HD int32_t pair_lookup(const Ws &w, const Ctg &g, int32_t i, int32_t j, int64_t &cursor) {
+    int64_t end = w.pair_beg[g.b0 + i + 1];
+    while (cursor < end && w.pair[cursor].j < j) cursor++;
+    if (cursor < end && w.pair[cursor].j == j) return g.n + (int32_t)(cursor - g.p0);
+    return -1;
+}
+
+// Enumerate the out-edges of contig-local vertex v in the reference's adjacency order (OC3).
+// make_Graph (paf_data.cpp:531-696) restated per source vertex; Emit is called once per edge.
+template <class Emit>
+AA_HDN void enum_edges(const Ws &w, const Ctg &g, int32_t v, Emit &emit) {
+    const bool nsl = w.nsl != 0;
+    const int64_t b0 = g.b0;
+    const int32_t n = g.n;
+    if (v == g.dest) return;
+    if (v == g.src) {  // paf_data.cpp:540-563
+        int32_t r = w.part_r[b0];
+        int64_t min_qe = I64_MAX;
+        for (int32_t i = 0; i < r; i++) {
+            int64_t s = w.qs[b0 + i];
+            if (nsl) {
+                if (min_qe < s) break;
+                int64_t e = w.qe[b0 + i];
+                if (e < min_qe) min_qe = e;
+            }
+            Edge ed;
+            ed.qry = s * SV_FRONT_END;
+            ed.ref = 0;
+            ed.dst_fl = (uint32_t)i | ((w.mapq[b0 + i] ? 1u : 0u) << 29) | (1u << 30);
+            emit(ed);
+        }
+        return;
+    }
+    const int32_t last_l = w.part_l[b0 + n - 1];
+    const int64_t max_qs = w.qs[b0 + n - 1];
+    int32_t j;        // cur_idx of the source vertex
+    VV lv;
+    const CandRec *sp = nullptr;
+    if (v < n) {
+        j = v;
+        lv = vv_single(w, b0 + v);
+    } else {
+        sp = &w.pair[g.p0 + (v - n)];
+        j = sp->j;
+        lv = vv_pair(w, g, *sp);
+    }
+    const int64_t gj = b0 + j;
+    const int32_t r = w.part_r[gj];
+    const int64_t j_qe = w.qe[gj];
+    // -> dest (paf_data.cpp:565-595)
+    if (w.part_l[gj] == last_l && !(nsl && j_qe < max_qs)) {
+        Edge ed;
+        ed.qry = (w.qtot[gj] - j_qe - 1) * SV_FRONT_END;
+        ed.ref = 0;
+        ed.dst_fl = (uint32_t)g.dest;
+        emit(ed);
+    }
+    // inside the part (paf_data.cpp:598-651)
+    {
+        int64_t min_after = I64_MAX;
+        int64_t cursor = w.pair_beg[gj];  // pairs (j, k)
+        for (int32_t k = j + 1; k < r; k++) {
+            const int64_t gk = b0 + k;
+            if (!sp && contains_ij(w, gj, gk)) continue;  // only the (i,i) row skips contained blocks (paf_data.cpp:605)
+            const int64_t k_qs = w.qs[gk];
+            if (nsl) {
+                if (min_after < k_qs) break;
+                if (j_qe < k_qs) {
+                    int64_t e = w.qe[gk];
+                    if (e < min_after) min_after = e;
+                }
+            }
+            if (j_qe < k_qs) {
+                emit(score(w, lv, vv_single(w, gk), nullptr, k));  // -> (k,k)
+            } else {
+                // -> (j,k): needs the pair vertex and lft.qry_str < rht.qry_str (paf_data.cpp:433-436)
+                int32_t pid = pair_lookup(w, g, j, k, cursor);
+                if (pid >= 0) {
+                    const CandRec &rp = w.pair[g.p0 + (pid - n)];
+                    if (lv.qs < rp.st_q) emit(score(w, lv, vv_pair(w, g, rp), &rp, pid));
+                }
+            }
+        }
+    }
+    // to the next part (paf_data.cpp:653-695)
+    if (r < n) {
+        int32_t r2 = w.part_r[b0 + r];
+        int64_t mn = I64_MAX;
+        for (int32_t k = r; k < r2; k++) {
+            const int64_t gk = b0 + k;
+            if (nsl) {
+                int64_t k_qs = w.qs[gk];
+                if (mn < k_qs) break;
+                if (j_qe < k_qs) {
+                    int64_t e = w.qe[gk];
+                    if (e < mn) mn = e;
+                }
+            }
+            emit(score(w, lv, vv_single(w, gk), nullptr, k));
+        }
+    }
+}
+
+struct EmitCount {
+    int32_t n = 0;
+    AA_HD void operator()(const Edge &) { n++; }
+};
+struct EmitFill {
+    Edge *edge;
+    int32_t *src;
+    uint32_t *key;
+    uint32_t *val;
+    int64_t at;
+    int32_t u;
+    uint32_t v0;
+    AA_HD void operator()(const Edge &e) {
+        edge[at] = e;
+        src[at] = u;
+        key[at] = v0 + (e.dst_fl & DST_MASK);
+        val[at] = (uint32_t)at;
+        at++;
+    }
+};
+
+// phase: out-degree of global vertex gv
+AA_HDN void f_degree(const Ws &w, int64_t gv) {
+    int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0) {
+        w.deg[gv] = 0;
+        return;
+    }
+    Ctg g = ctg_view(w, c);
+    EmitCount ec;
+    enum_edges(w, g, (int32_t)(gv - g.v0), ec);
+    w.deg[gv] = ec.n;
+}
+// phase: fill the out-edges of global vertex gv
+AA_HDN void f_fill(const Ws &w, int64_t gv) {
+    int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    EmitFill ef{w.edge, w.e_src, w.rkey_in, w.rval_in, w.eoff[gv], (int32_t)(gv - g.v0), (uint32_t)g.v0};
+    enum_edges(w, g, (int32_t)(gv - g.v0), ef);
+}
+// phase: reverse CSR offsets from the sorted destination keys
+AA_HDN void f_rev_off(const Ws &w, int64_t gv, int64_t E) {  // gv in [0, Vtot]
+    int64_t lo = 0, hi = E;  // first position with key >= gv
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)w.rkey[mid] < gv) lo = mid + 1;
+        else hi = mid;
+    }
+    w.rev_off[gv] = lo;
+}
+
+// ================================================================================================
+// phase: reverse relax.  Kahn FIFO order on the reverse graph, seeds = vertices without out-edges in
+// ascending id, first strict improvement wins (k_shortest_walks.hpp:132-175); plus the min-anom DP
+// that replaces Dial's BFS (only anom_dis[dest] is consumed, paf_data.cpp:713,1615).
+AA_HDN void f_relax(const Ws &w, int64_t c) {
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int64_t e0 = w.eoff[v0];
+    int32_t *q = w.queue + v0;
+    int32_t tail = 0;
+    for (int32_t v = 0; v < g.V; v++) {
+        int32_t od = (int32_t)(w.eoff[v0 + v + 1] - w.eoff[v0 + v]);
+        w.cnt[v0 + v] = od;
+        D4 z;
+        z.sum = 0;
+        z.anom = z.nz = z.tot = 0;
+        z.aux = 0;
+        w.d[v0 + v] = z;
+        w.best[v0 + v] = -1;
+        w.amin[v0 + v] = 0x3fffffff;
+        if (od == 0) q[tail++] = v;
+    }
+    w.d[v0 + g.dest].aux = 1;
+    w.amin[v0 + g.dest] = 0;
+    for (int32_t head = 0; head < tail; head++) {
+        int32_t v = q[head];
+        D4 dv = w.d[v0 + v];
+        int32_t av = w.amin[v0 + v];
+        int64_t ra = w.rev_off[v0 + v], rb = w.rev_off[v0 + v + 1];
+        for (int64_t k = ra; k < rb; k++) {
+            int64_t eid = w.rev_eid[k];
+            int32_t x = w.e_src[eid];
+            if (dv.aux) {
+                Edge e = w.edge[eid];
+                D4 cand;
+                cand.sum = dv.sum + e.qry + e.ref;
+                cand.anom = dv.anom + e_anom(e);
+                cand.nz = dv.nz + e_nz(e);
+                cand.tot = dv.tot + e_tot(e);
+                cand.aux = 1;
+                D4 cur = w.d[v0 + x];
+                if (!cur.aux || less4(cand, cur)) {
+                    w.d[v0 + x] = cand;
+                    w.best[v0 + x] = v;
+                }
+                int32_t na = av + e_anom(e);
+                if (na < w.amin[v0 + x]) w.amin[v0 + x] = na;
+            }
+            if (--w.cnt[v0 + x] == 0) q[tail++] = x;
+        }
+    }
+    (void)e0;
+    w.anom_dis[c] = w.amin[v0 + g.src];
+    if (!w.d[v0 + g.src].aux) w.status[c] = 2;
+}
+
+// phase: forward Kahn order (paf_data.cpp:742-746)
+AA_HDN void f_topo(const Ws &w, int64_t c) {
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    int32_t *q = w.topo + v0;
+    int32_t tail = 0;
+    for (int32_t v = 0; v < g.V; v++) {
+        int32_t id = (int32_t)(w.rev_off[v0 + v + 1] - w.rev_off[v0 + v]);
+        w.cnt[v0 + v] = id;
+        if (id == 0) q[tail++] = v;
+    }
+    for (int32_t head = 0; head < tail; head++) {
+        int32_t u = q[head];
+        w.order[v0 + u] = head;
+        int64_t ea = w.eoff[v0 + u], eb = w.eoff[v0 + u + 1];
+        for (int64_t k = ea; k < eb; k++) {
+            int32_t x = e_dst(w.edge[k]);
+            if (--w.cnt[v0 + x] == 0) q[tail++] = x;
+        }
+    }
+}
+
+// ---- persistent leftist heap (leftist_heap.hpp:29-40) -------------------------------------------------
+struct HeapAlloc {
+    int64_t cur, end;
+    int64_t used;
+    bool overflow;
+};
+AA_HD int32_t heap_new(const Ws &w, HeapAlloc &ha) {
+    if (ha.cur == ha.end) {
+#if defined(__CUDA_ARCH__)
+        unsigned long long at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+#else
+        unsigned long long at = *w.heap_top;
+        *w.heap_top = at + HEAP_CHUNK;
+#endif
+        if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
+            ha.overflow = true;
+            return -1;
+        }
+        ha.cur = (int64_t)at;
+        ha.end = ha.cur + HEAP_CHUNK;
+    }
+    ha.used++;
+    return (int32_t)(ha.cur++);
+}
+AA_HD D4 hkey(const HNode &h) {
+    D4 k;
+    k.sum = h.sum;
+    k.anom = h.anom;
+    k.nz = h.nz;
+    k.tot = h.tot;
+    k.aux = 0;
+    return k;
+}
+// insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on overflow).
+// spine[] is scratch for the right-spine walk; its depth is bounded by log2(size)+1.
+AA_HDN int32_t heap_insert(const Ws &w, HeapAlloc &ha, int32_t a, const D4 &k, int32_t eid) {
+    int32_t spine[64];
+    int32_t depth = 0;
+    while (a >= 0 && less4(hkey(w.hn[a]), k)) {  // not (a->key < k) stops the descent; ties go on top
+        spine[depth++] = a;
+        a = w.hn[a].right;
+    }
+    int32_t r = heap_new(w, ha);
+    if (r < 0) return -1;
+    HNode nn;
+    nn.sum = k.sum;
+    nn.anom = k.anom;
+    nn.nz = k.nz;
+    nn.tot = k.tot;
+    nn.left = a;
+    nn.right = -1;
+    nn.rank = 1;
+    w.hn[r] = nn;
+    w.hn_eid[r] = eid;
+    while (depth > 0) {
+        int32_t oid = spine[--depth];
+        HNode o = w.hn[oid];
+        int32_t l = o.left, rr = r;
+        if (l < 0 || w.hn[l].rank < w.hn[rr].rank) {
+            int32_t t = l;
+            l = rr;
+            rr = t;
+        }
+        int32_t id = heap_new(w, ha);
+        if (id < 0) return -1;
+        o.left = l;
+        o.right = rr;
+        o.rank = rr >= 0 ? w.hn[rr].rank + 1 : 0;
+        w.hn[id] = o;
+        w.hn_eid[id] = w.hn_eid[oid];
+        r = id;
+    }
+    return r;
+}
+
+// phase: sidetrack heaps, BFS over the shortest-path tree from dest (k_shortest_walks.hpp:191-215).
+// tree children of u = sources x of u's in-edges with best[x] == u, ascending x (the reverse list order).
+AA_HDN void f_heaps(const Ws &w, int64_t c) {
+    if (w.status[c] != 0 && w.status[c] != 3) return;
+    w.status[c] = 0;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int64_t e0 = w.eoff[v0];
+    HeapAlloc ha;
+    ha.cur = ha.end = 0;
+    ha.used = 0;
+    ha.overflow = false;
+    int32_t *q = w.queue + v0;
+    for (int32_t v = 0; v < g.V; v++) w.hroot[v0 + v] = -1;
+    int32_t tail = 0;
+    q[tail++] = g.dest;
+    for (int32_t head = 0; head < tail && !ha.overflow; head++) {
+        int32_t u = q[head];
+        int32_t hu = w.hroot[v0 + u];
+        D4 du = w.d[v0 + u];
+        int32_t bu = w.best[v0 + u];
+        int64_t ea = w.eoff[v0 + u], eb = w.eoff[v0 + u + 1];
+        for (int64_t k = ea; k < eb; k++) {
+            Edge e = w.edge[k];
+            int32_t v = e_dst(e);
+            D4 dv = w.d[v0 + v];
+            if (!dv.aux) continue;
+            if (v == bu) continue;  // the tree edge: c == IDENTITY, skipped once; (u,v) is unique in the graph
+            D4 key;
+            key.sum = e.qry + e.ref + dv.sum - du.sum;
+            key.anom = e_anom(e) + dv.anom - du.anom;
+            key.nz = e_nz(e) + dv.nz - du.nz;
+            key.tot = e_tot(e) + dv.tot - du.tot;
+            key.aux = 0;
+            hu = heap_insert(w, ha, hu, key, (int32_t)(k - e0));
+            if (hu < 0) break;
+        }
+        if (ha.overflow) break;
+        w.hroot[v0 + u] = hu;
+        int64_t ra = w.rev_off[v0 + u], rb = w.rev_off[v0 + u + 1];
+        for (int64_t k = ra; k < rb; k++) {
+            int32_t x = w.e_src[w.rev_eid[k]];
+            if (w.best[v0 + x] == u) {
+                w.hroot[v0 + x] = hu;
+                q[tail++] = x;
+            }
+        }
+    }
+    w.heap_used[c] = ha.used;
+    if (ha.overflow) w.status[c] = 3;
+}
+
+// ---- enumeration priority queue: binary min-heap under the total order (distance, node id, entry index)
+AA_HD bool pq_less(const PQEnt &a, const PQEnt &b) {
+    if (a.sum != b.sum) return a.sum < b.sum;
+    if (a.anom != b.anom) return a.anom < b.anom;
+    int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+    if (x != y) return x > y;
+    if (a.node != b.node) return a.node < b.node;
+    return a.idx < b.idx;
+}
+AA_HD void pq_push(PQEnt *h, int32_t &n, const PQEnt &e) {
+    int32_t i = n++;
+    while (i > 0) {
+        int32_t p = (i - 1) >> 1;
+        PQEnt pe = h[p];
+        if (!pq_less(e, pe)) break;
+        h[i] = pe;
+        i = p;
+    }
+    h[i] = e;
+}
+AA_HD PQEnt pq_pop(PQEnt *h, int32_t &n) {
+    PQEnt top = h[0];
+    PQEnt last = h[--n];
+    int32_t i = 0;
+    for (;;) {
+        int32_t l = 2 * i + 1;
+        if (l >= n) break;
+        int32_t m = l;
+        PQEnt me = h[l];
+        if (l + 1 < n) {
+            PQEnt re = h[l + 1];
+            if (pq_less(re, me)) {
+                m = l + 1;
+                me = re;
+            }
+        }
+        if (!pq_less(me, last)) break;
+        h[i] = me;
+        i = m;
+    }
+    if (n > 0) h[i] = last;
+    return top;
+}
+
+// phase: enumerate the K shortest walks (k_shortest_walks.hpp:217-251)
+AA_HDN void f_enum(const Ws &w, int64_t c) {
+    if (w.status[c] != 0) {
+        w.n_walk[c] = 0;
+        return;
+    }
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int64_t e0 = w.eoff[v0];
+    const int64_t wo = w.walk_off[c];
+    D4 *dist = w.wdist + wo;
+    int32_t *last = w.wlast + wo;
+    int32_t *en = w.ent_node + 3 * wo;
+    int32_t *ep = w.ent_prev + 3 * wo;
+    PQEnt *pq = w.pq + 3 * wo;
+    const int32_t K = w.K;
+    int32_t nd = 0, ne = 0, np = 0;
+    D4 ds = w.d[v0 + g.src];
+    dist[nd] = ds;
+    last[nd] = -1;
+    nd++;
+    int32_t hs = w.hroot[v0 + g.src];
+    if (hs >= 0) {
+        HNode hr = w.hn[hs];
+        PQEnt e;
+        e.sum = ds.sum + hr.sum;
+        e.anom = ds.anom + hr.anom;
+        e.nz = ds.nz + hr.nz;
+        e.tot = ds.tot + hr.tot;
+        e.node = hs;
+        e.idx = ne;
+        e.pad = 0;
+        en[ne] = hs;
+        ep[ne] = -1;
+        ne++;
+        pq_push(pq, np, e);
+        while (np > 0 && nd < K) {
+            PQEnt t = pq_pop(pq, np);
+            D4 cd;
+            cd.sum = t.sum;
+            cd.anom = t.anom;
+            cd.nz = t.nz;
+            cd.tot = t.tot;
+            cd.aux = 0;
+            dist[nd] = cd;
+            last[nd] = t.idx;
+            nd++;
+            HNode ch = w.hn[t.node];
+            int32_t hv = w.hroot[v0 + e_dst(w.edge[e0 + w.hn_eid[t.node]])];
+            int32_t pre = ep[t.idx];
+            if (hv >= 0) {
+                HNode x = w.hn[hv];
+                PQEnt a;
+                a.sum = t.sum + x.sum;
+                a.anom = t.anom + x.anom;
+                a.nz = t.nz + x.nz;
+                a.tot = t.tot + x.tot;
+                a.node = hv;
+                a.idx = ne;
+                a.pad = 0;
+                en[ne] = hv;
+                ep[ne] = t.idx;
+                ne++;
+                pq_push(pq, np, a);
+            }
+            if (ch.left >= 0) {
+                HNode x = w.hn[ch.left];
+                PQEnt a;
+                a.sum = t.sum + x.sum - ch.sum;
+                a.anom = t.anom + x.anom - ch.anom;
+                a.nz = t.nz + x.nz - ch.nz;
+                a.tot = t.tot + x.tot - ch.tot;
+                a.node = ch.left;
+                a.idx = ne;
+                a.pad = 0;
+                en[ne] = ch.left;
+                ep[ne] = pre;
+                ne++;
+                pq_push(pq, np, a);
+            }
+            if (ch.right >= 0) {
+                HNode x = w.hn[ch.right];
+                PQEnt a;
+                a.sum = t.sum + x.sum - ch.sum;
+                a.anom = t.anom + x.anom - ch.anom;
+                a.nz = t.nz + x.nz - ch.nz;
+                a.tot = t.tot + x.tot - ch.tot;
+                a.node = ch.right;
+                a.idx = ne;
+                a.pad = 0;
+                en[ne] = ch.right;
+                ep[ne] = pre;
+                ne++;
+                pq_push(pq, np, a);
+            }
+        }
+    }
+    w.n_walk[c] = nd;
+}
+
+// phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
+// walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.
+AA_HD bool same_sa(const D4 &a, const D4 &b) { return a.sum == b.sum && a.anom == b.anom; }
+AA_HDN void f_plan(const Ws &w, int64_t c) {
+    w.n_task[c] = 0;
+    w.n_tie[c] = 0;
+    w.last_group[c] = 0;
+    if (w.status[c] != 0) return;
+    const int64_t wo = w.walk_off[c];
+    const D4 *dist = w.wdist + wo;
+    Task *t = w.task + 2 * wo;
+    const int32_t nw = w.n_walk[c];
+    int32_t nt = 0;
+    const D4 mind = dist[0];
+    t[nt] = Task{(int32_t)c, 0, nt, 0};
+    nt++;
+    for (int32_t i = 1; i < nw && same_sa(mind, dist[i]); i++) {
+        t[nt] = Task{(int32_t)c, i, nt, 0};
+        nt++;
+    }
+    w.n_tie[c] = nt;
+    int32_t group = 0;
+    if (nw >= 2 && (int64_t)mind.anom != w.anom_dis[c]) {
+        int64_t ans_up = 0, ans_down = 0;
+        int32_t ans = -1;
+        for (int32_t i = 1; i < nw; i++) {
+            D4 x = dist[i];
+            if (x.anom >= mind.anom) continue;
+            int64_t up = x.sum - mind.sum;
+            int64_t down = (int64_t)mind.anom - x.anom;
+            if (ans == -1 || up * ans_down < down * ans_up) {
+                ans_up = up;
+                ans_down = down;
+                ans = i;
+                group++;
+                t[nt] = Task{(int32_t)c, i, nt, group};
+                nt++;
+            } else if (same_sa(x, dist[ans])) {
+                t[nt] = Task{(int32_t)c, i, nt, group};
+                nt++;
+            }
+        }
+    }
+    w.n_task[c] = nt;
+    w.last_group[c] = group;
+}
+AA_HDN void f_task_compact(const Ws &w, int64_t c) {
+    int64_t o = w.task_off[c];
+    const Task *t = w.task + 2 * w.walk_off[c];
+    for (int32_t k = 0; k < w.n_task[c]; k++) w.tasks[o + k] = t[k];
+}
+
+// ---- walk task: recover + mark + upgrade + rows ---------------------------------------------------
+struct Slot {
+    int32_t *walk, *up, *side;
+    D5 *dp;
+    int32_t *pre;
+    uint8_t *seen;
+};
+AA_HD Slot slot_view(const Ws &w, int64_t s) {
+    Slot x;
+    int64_t o = s * w.slot_stride;
+    x.walk = w.sc_walk + o;
+    x.up = w.sc_up + o;
+    x.side = w.sc_side + o;
+    x.dp = w.sc_dp + o;
+    x.pre = w.sc_pre + o;
+    x.seen = w.sc_seen + o;
+    return x;
+}
+AA_HD void vtx_xy(const Ws &w, const Ctg &g, int32_t v, int32_t &x, int32_t &y) {  // index_to_vtx
+    if (v < g.n) {
+        x = y = v;
+    } else {
+        const CandRec &p = w.pair[g.p0 + (v - g.n)];
+        x = p.i;
+        y = p.j;
+    }
+}
+
+// kth_shortest_walk_recover (k_shortest_walks.hpp:254-290) as a vertex sequence src..dest; returns length
+AA_HDN int32_t recover_walk(const Ws &w, const Ctg &g, int64_t c, int32_t k, const Slot &s) {
+    const int64_t v0 = g.v0, e0 = w.eoff[v0], wo = w.walk_off[c];
+    const int32_t *en = w.ent_node + 3 * wo;
+    const int32_t *ep = w.ent_prev + 3 * wo;
+    int32_t ns = 0;
+    for (int32_t cur = w.wlast[wo + k]; cur != -1; cur = ep[cur]) s.side[ns++] = w.hn_eid[en[cur]];
+    // side[] holds the sidetrack edges last-to-first
+    int32_t len = 0;
+    int32_t cur = g.src;
+    s.walk[len++] = cur;
+    int32_t idx = ns - 1;
+    while (cur != g.dest || idx >= 0) {
+        if (idx >= 0 && cur == w.e_src[e0 + s.side[idx]]) {
+            cur = e_dst(w.edge[e0 + s.side[idx]]);
+            idx--;
+        } else {
+            cur = w.best[v0 + cur];
+        }
+        s.walk[len++] = cur;
+    }
+    return len;
+}
+
+// internal_shortest_path_recover (paf_data.cpp:750-792): QRY_SCORE-mode DP over the forward topological
+// range [order[s], order[t]).  Appends the vertices after s (optionally without t itself) to up[];
+// returns false when s == t (the reference's empty path).
+AA_HDN bool sub_path(const Ws &w, const Ctg &g, const Slot &s, int32_t vs, int32_t vt, bool wl_flag, int32_t wl,
+                     bool drop_last, int32_t &up_len) {
+    if (vs == vt) return false;
+    const int64_t v0 = g.v0;
+    const int32_t os = w.order[v0 + vs], ot = w.order[v0 + vt];
+    const int32_t span = ot - os + 1;
+    for (int32_t k = 0; k < span; k++) s.seen[k] = 0;
+    D5 z;
+    z.qry = z.ref = 0;
+    z.anom = z.nz = z.tot = z.pad = 0;
+    s.dp[0] = z;
+    s.pre[0] = -1;
+    s.seen[0] = 1;
+    for (int32_t i = os; i < ot; i++) {
+        if (!s.seen[i - os]) continue;
+        const int32_t u = w.topo[v0 + i];
+        const D5 cur = s.dp[i - os];
+        int32_t ux = -1, uy = -1;
+        if (wl_flag && u != g.src && u != g.dest) vtx_xy(w, g, u, ux, uy);
+        const int64_t ea = w.eoff[v0 + u], eb = w.eoff[v0 + u + 1];
+        for (int64_t k = ea; k < eb; k++) {
+            const Edge e = w.edge[k];
+            const int32_t v = e_dst(e);
+            if (wl_flag && v == vt) {
+                if (u == g.src || u == g.dest) continue;
+                if (uy != wl) continue;
+            }
+            const int32_t ov = w.order[v0 + v];
+            if (ov > ot) continue;  // outside the range: never read again by the reference's loop
+            D5 nx;
+            nx.qry = cur.qry + e.qry;
+            nx.ref = cur.ref + e.ref;
+            nx.anom = cur.anom + e_anom(e);
+            nx.nz = cur.nz + e_nz(e);
+            nx.tot = cur.tot + e_tot(e);
+            nx.pad = 0;
+            const int32_t at = ov - os;
+            if (!s.seen[at] || less5(nx, s.dp[at])) {
+                s.dp[at] = nx;
+                s.pre[at] = u;
+                s.seen[at] = 1;
+            }
+        }
+    }
+    // walk back t -> s, then append in forward order
+    int32_t cnt = 0;
+    for (int32_t last = vt; last != vs; last = s.pre[w.order[v0 + last] - os]) cnt++;
+    int32_t keep = drop_last ? cnt - 1 : cnt;  // vertices after s that are appended
+    int32_t pos = up_len + cnt - 1;
+    for (int32_t last = vt; last != vs; last = s.pre[w.order[v0 + last] - os]) {
+        if (pos < up_len + keep) s.up[pos] = last;
+        pos--;
+    }
+    up_len += keep;
+    return true;
+}
+
+// upgrade_edge_path_with_alt_path (paf_data.cpp:795-921) on vertex sequences; returns the new length
+AA_HDN int32_t upgrade_walk(const Ws &w, const Ctg &g, const Slot &s, int32_t len) {
+    int32_t ul = 0;
+    s.up[ul++] = g.src;
+    for (int32_t e = 0; e + 1 < len; e++) {
+        const int32_t u = s.walk[e], v = s.walk[e + 1];
+        if (v == g.dest) {  // paf_data.cpp:845-858
+            sub_path(w, g, s, s.up[ul - 1], v, false, -1, false, ul);
+            continue;
+        }
+        int32_t x, y;
+        vtx_xy(w, g, v, x, y);
+        if (u != g.src && x != y) {  // paf_data.cpp:866-873
+            s.up[ul++] = v;
+            continue;
+        }
+        const int32_t cs = s.up[ul - 1];
+        const int32_t nv = s.walk[e + 2];
+        int32_t nx = -1, ny = -1;
+        if (nv != g.dest) vtx_xy(w, g, nv, nx, ny);
+        if (nv == g.dest || nx == ny) {  // paf_data.cpp:812-833, 879-899
+            if (!sub_path(w, g, s, cs, nv, true, y, true, ul)) s.up[ul++] = v;
+        } else {  // nv = (y, ny): paf_data.cpp:834-843, 900-909
+            if (!sub_path(w, g, s, cs, nv, false, -1, false, ul)) {
+                s.up[ul++] = v;
+                s.up[ul++] = nv;
+            }
+            e++;
+        }
+    }
+    return ul;
+}
+
+AA_HD void mark_block(const Ws &w, int64_t gb, int32_t call) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(&w.first_call[gb], call);
+#else
+    if (call < w.first_call[gb]) w.first_call[gb] = call;
+#endif
+}
+
+// One edge_path_to_paf_path call (paf_data.cpp:1489-1568).  Pass A (dst < 0): mark blocks, coverage and
+// row count.  Pass B (dst = 0 out, 1 alt, 2 all): write the rows at row offset `at`.
+AA_HDN void walk_task(const Ws &w, const Task &t, const Slot &s, int dst, int64_t at, int64_t *cov_out, int32_t *rows_out) {
+    const int64_t c = t.ctg;
+    Ctg g = ctg_view(w, c);
+    int32_t len = recover_walk(w, g, c, t.walk, s);
+    if (dst < 0) {
+        for (int32_t k = 1; k + 1 < len; k++) {
+            int32_t x, y;
+            vtx_xy(w, g, s.walk[k], x, y);
+            mark_block(w, g.b0 + x, t.call);
+            mark_block(w, g.b0 + y, t.call);
+        }
+    }
+    int32_t ul = upgrade_walk(w, g, s, len);
+    // rows: one per inner vertex; arriving at a pair vertex trims both neighbours (paf_data.cpp:1502-1557)
+    int64_t cov = 0;
+    int32_t nrows = 0;
+    int64_t pqs = 0, pqe = 0, prs = 0, pre = 0;
+    int64_t pb = -1;
+    for (int32_t k = 1; k + 1 <= ul; k++) {
+        int64_t nqs = 0, nqe = 0, nrs = 0, nre = 0, nb = -1;
+        if (k + 1 < ul) {
+            const int32_t v = s.up[k];
+            int32_t x, y;
+            vtx_xy(w, g, v, x, y);
+            nb = g.b0 + y;
+            nqs = w.qs[nb];
+            nqe = w.qe[nb];
+            nrs = w.rs[nb];
+            nre = w.re[nb];
+            if (x != y) {
+                const CandRec &p = w.pair[g.p0 + (v - g.n)];
+                pqe = p.pe_q;
+                pre = p.pe_r;
+                nqs = p.st_q;
+                nrs = p.st_r;
+            }
+        }
+        if (pb >= 0) {  // the previous row is final now
+            int64_t dr = pre - prs;
+            cov += (pqe - pqs) + (dr < 0 ? -dr : dr);
+            if (dst >= 0) {
+                int64_t o = at + nrows;
+                w.r_idx[dst][o] = w.orig[pb];
+                w.r_qs[dst][o] = pqs;
+                w.r_qe[dst][o] = pqe;
+                w.r_rs[dst][o] = prs;
+                w.r_re[dst][o] = pre;
+                w.r_alt[dst][o] = w.first_call[pb] > t.call ? 1 : 0;  // paf_data.cpp:1560-1566
+            }
+            nrows++;
+        }
+        pb = nb;
+        pqs = nqs;
+        pqe = nqe;
+        prs = nrs;
+        pre = nre;
+    }
+    if (cov_out) *cov_out = cov;
+    if (rows_out) *rows_out = nrows;
+}
+
+// worker loops (dynamic scheduling over tasks); slot = worker index
+AA_HDN void f_tasks_a(const Ws &w, int64_t slot) {
+    Slot s = slot_view(w, slot);
+    for (;;) {
+#if defined(__CUDA_ARCH__)
+        unsigned long long t = atomicAdd(w.task_next, 1ull);
+#else
+        unsigned long long t = (*w.task_next)++;
+#endif
+        if ((int64_t)t >= w.n_tasks_total) break;
+        walk_task(w, w.tasks[t], s, -1, 0, &w.task_cov[t], &w.task_rows[t]);
+    }
+}
+
+// phase: selection (paf_data.cpp:1585-1649) from the per-task coverages
+AA_HDN void f_select(const Ws &w, int64_t c, int32_t want_all) {
+    w.win_out[c] = -1;
+    w.win_alt[c] = -1;
+    w.out_cnt[c] = 0;
+    w.alt_cnt[c] = 0;
+    w.all_cnt[c] = 0;
+    if (w.status[c] == 1) {
+        w.out_cnt[c] = 1;
+        return;
+    }
+    if (w.status[c] != 0) return;
+    const int64_t o = w.task_off[c];
+    const int32_t nt = w.n_task[c], ntie = w.n_tie[c];
+    int64_t best = -1;
+    int32_t first = -1, equal_after = 0;
+    for (int32_t k = 0; k < ntie; k++) {
+        int64_t cv = w.task_cov[o + k];
+        if (cv > best) {
+            best = cv;
+            first = k;
+            equal_after = 0;
+        } else if (cv == best) {
+            equal_after++;
+        }
+    }
+    w.win_out[c] = (int32_t)(o + first);
+    w.out_cnt[c] = w.task_rows[o + first];
+    if (want_all) w.all_cnt[c] = equal_after;
+    const int32_t lg = w.last_group[c];
+    if (lg > 0) {
+        int64_t bc = -1;
+        int32_t bk = -1;
+        for (int32_t k = ntie; k < nt; k++) {
+            if (w.tasks[o + k].group != lg) continue;
+            int64_t cv = w.task_cov[o + k];
+            if (bk < 0 || cv > bc) {
+                bc = cv;
+                bk = k;
+            }
+        }
+        w.win_alt[c] = (int32_t)(o + bk);
+        w.alt_cnt[c] = w.task_rows[o + bk];
+    }
+}
+// list the .all paths of contig c (ties after the first maximum, in call order)
+AA_HDN void f_all_list(const Ws &w, int64_t c) {
+    if (w.all_cnt[c] == 0) return;
+    const int64_t o = w.task_off[c];
+    const int32_t ntie = w.n_tie[c];
+    const int32_t first = w.win_out[c] - (int32_t)o;
+    const int64_t best = w.task_cov[o + first];
+    int64_t at = w.all_path_off[c];
+    for (int32_t k = first + 1; k < ntie; k++)
+        if (w.task_cov[o + k] == best) {
+            w.all_task[at] = (int32_t)(o + k);
+            w.all_rows[at] = w.task_rows[o + k];
+            at++;
+        }
+}
+
+// pass B work items: [0,C) primary chains, [C,2C) alt chains, [2C, 2C+Npaths) .all paths
+AA_HDN void f_tasks_b(const Ws &w, int64_t slot, int64_t n_items, int64_t n_paths) {
+    Slot s = slot_view(w, slot);
+    (void)n_paths;
+    for (;;) {
+#if defined(__CUDA_ARCH__)
+        unsigned long long it = atomicAdd(w.task_next, 1ull);
+#else
+        unsigned long long it = (*w.task_next)++;
+#endif
+        if ((int64_t)it >= n_items) break;
+        int64_t i = (int64_t)it;
+        if (i < w.C) {
+            int64_t c = i;
+            if (w.status[c] == 1) {  // singleton contig (paf_data.cpp:235-239)
+                int64_t b = w.ctg_off[c], o = w.out_off[c];
+                w.r_idx[0][o] = 0;
+                w.r_qs[0][o] = w.qs[b];
+                w.r_qe[0][o] = w.qe[b];
+                w.r_rs[0][o] = w.rs[b];
+                w.r_re[0][o] = w.re[b];
+                w.r_alt[0][o] = 0;
+            } else if (w.win_out[c] >= 0) {
+                walk_task(w, w.tasks[w.win_out[c]], s, 0, w.out_off[c], nullptr, nullptr);
+            }
+        } else if (i < 2 * w.C) {
+            int64_t c = i - w.C;
+            if (w.win_alt[c] >= 0) walk_task(w, w.tasks[w.win_alt[c]], s, 1, w.alt_off[c], nullptr, nullptr);
+        } else {
+            int64_t p = i - 2 * w.C;
+            walk_task(w, w.tasks[w.all_task[p]], s, 2, w.all_row_off[p], nullptr, nullptr);
+        }
+    }
+}
+
+}  // namespace aa

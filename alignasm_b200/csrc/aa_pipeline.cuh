@@ -1,0 +1,741 @@
+// aa_pipeline.cuh — phase orchestration of the hot path, written once against a Backend policy.
+//
+// Backend = where the items of a phase run.  The product instantiates it with CudaBackend
+// (aa_backend_cuda.cuh: kernels on sm_100a, CUB scans/sorts, a pooled HBM allocator).  tests/emul
+// instantiates it with a host-loop backend to check the same phase functions on the CPU against the
+// reference; that instantiation is never part of libalignasm_b200.so.
+//
+// Phases (names from aa_phase_name, one CUDA-event pair each):
+//   0 sort      host std::sort of (qry_str, qry_end) per contig — OC1: the reference's unstable
+//               std::sort must see the same comparison outcomes (paf_data.cpp:241), then gather on device
+//   1 parts     paf_data.cpp:249-261
+//   2 pairs     candidate pairs, cut points, compaction into pair vertices (paf_data.cpp:294-378)
+//   3 edges     out-degree count, scan, fill in adjacency order (paf_data.cpp:531-696)
+//   4 reverse   stable radix sort of edges by destination -> reverse CSR (k_shortest_walks.hpp:180-183)
+//   5 relax     reverse Kahn + first-wins relaxation + min-anom DP
+//   6 topo      forward Kahn order (paf_data.cpp:742-746)
+//   7 heaps     persistent leftist sidetrack heaps (k_shortest_walks.hpp:191-215)
+//   8 enum      K-walk enumeration (k_shortest_walks.hpp:217-251)
+//   9 plan      which walks the selection recovers, in call order (paf_data.cpp:1585-1649)
+//  10 walksA    recover + upgrade every planned walk: coverage, row count, block marks
+//  11 select    primary / alt / .all winners
+//  12 walksB    rows of the winners
+//  13 d2h       result download
+#pragma once
+#include "../../include/alignasm_b200.h"
+#include "aa_core.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace aa {
+
+enum Phase { PH_SORT = 0, PH_PARTS, PH_PAIRS, PH_EDGES, PH_REVERSE, PH_RELAX, PH_TOPO, PH_HEAPS, PH_ENUM, PH_PLAN,
+             PH_WALKS_A, PH_SELECT, PH_WALKS_B, PH_D2H, PH_COUNT };
+inline const char *phase_name(int p) {
+    static const char *names[PH_COUNT] = {"sort", "parts", "pairs", "edges", "reverse", "relax", "topo", "heaps",
+                                          "enum", "plan", "walksA", "select", "walksB", "d2h"};
+    return (p >= 0 && p < PH_COUNT) ? names[p] : nullptr;
+}
+
+// ---- phase functors: one call per item ----------------------------------------------------------------
+#define AA_FUNCTOR(Name, body)                                  \
+    struct Name {                                               \
+        Ws w;                                                   \
+        AA_HD void operator()(int64_t i) const { body; }        \
+    };
+AA_FUNCTOR(FnGather, f_gather(w, i))
+AA_FUNCTOR(FnCandCount, f_cand_count(w, i))
+AA_FUNCTOR(FnCuts, f_cuts(w, i))
+AA_FUNCTOR(FnVtxOff, f_vtx_off(w, i))
+AA_FUNCTOR(FnDegree, f_degree(w, i))
+AA_FUNCTOR(FnFill, f_fill(w, i))
+AA_FUNCTOR(FnTasksA, f_tasks_a(w, i))
+struct FnCompact {
+    Ws w;
+    int64_t ncand;
+    AA_HD void operator()(int64_t i) const { f_compact(w, i, ncand); }
+};
+struct FnRevOff {
+    Ws w;
+    int64_t E;
+    AA_HD void operator()(int64_t i) const { f_rev_off(w, i, E); }
+};
+struct FnTasksB {
+    Ws w;
+    int64_t n_items, n_paths;
+    AA_HD void operator()(int64_t i) const { f_tasks_b(w, i, n_items, n_paths); }
+};
+// per-contig phases go through an order array (largest contigs first)
+#define AA_CTG_FUNCTOR(Name, body)                                  \
+    struct Name {                                                   \
+        Ws w;                                                       \
+        const int32_t *ord;                                         \
+        AA_HD void operator()(int64_t i) const {                    \
+            int64_t c = ord[i];                                     \
+            body;                                                   \
+        }                                                           \
+    };
+AA_CTG_FUNCTOR(FnParts, f_parts(w, c))
+AA_CTG_FUNCTOR(FnRelax, f_relax(w, c))
+AA_CTG_FUNCTOR(FnTopo, f_topo(w, c))
+AA_CTG_FUNCTOR(FnHeaps, f_heaps(w, c))
+AA_CTG_FUNCTOR(FnEnum, f_enum(w, c))
+AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
+AA_CTG_FUNCTOR(FnTaskCompact, f_task_compact(w, c))
+AA_CTG_FUNCTOR(FnAllList, f_all_list(w, c))
+struct FnSelect {
+    Ws w;
+    const int32_t *ord;
+    int32_t want_all;
+    AA_HD void operator()(int64_t i) const { f_select(w, ord[i], want_all); }
+};
+
+// ---- a batch staged on the device ------------------------------------------------------------------------
+struct DevBatch {
+    int64_t C = 0, B = 0, R = 0;
+    // device copies of the aa_batch arrays
+    int64_t *ctg_off = nullptr, *qs = nullptr, *qe = nullptr, *rs = nullptr, *re = nullptr, *qtot = nullptr;
+    int32_t *chr = nullptr;
+    uint8_t *fwd = nullptr, *mapq = nullptr;
+    int64_t *run_off = nullptr, *run_ql = nullptr, *run_qr = nullptr, *run_rl = nullptr;
+    // host mirror of what the host-side sort needs (OC1)
+    std::vector<int64_t> h_ctg_off, h_qs, h_qe;
+    std::vector<void *> owned;
+};
+
+inline void rows_alloc_host(aa_rows &r, int64_t n) {
+    r.n = n;
+    size_t m = (size_t)(n > 0 ? n : 1);
+    r.ctg_index = (int32_t *)std::malloc(m * 4);
+    r.qry_str = (int64_t *)std::malloc(m * 8);
+    r.qry_end = (int64_t *)std::malloc(m * 8);
+    r.ref_str = (int64_t *)std::malloc(m * 8);
+    r.ref_end = (int64_t *)std::malloc(m * 8);
+    r.is_alt = (uint8_t *)std::malloc(m);
+}
+inline void rows_free_host(aa_rows &r) {
+    std::free(r.ctg_index);
+    std::free(r.qry_str);
+    std::free(r.qry_end);
+    std::free(r.ref_str);
+    std::free(r.ref_end);
+    std::free(r.is_alt);
+    std::memset(&r, 0, sizeof r);
+}
+template <class T>
+inline T *host_n(int64_t n) {
+    return (T *)std::calloc((size_t)(n > 0 ? n : 1), sizeof(T));
+}
+inline void result_free_host(aa_result *res) {
+    if (!res) return;
+    std::free(res->out_off);
+    std::free(res->alt_off);
+    std::free(res->all_path_off);
+    std::free(res->all_row_off);
+    std::free(res->sorted_index);
+    rows_free_host(res->out);
+    rows_free_host(res->alt);
+    rows_free_host(res->all);
+    if (aa_debug *g = res->dbg) {
+        void *ptrs[] = {g->vtx_off, g->edge_off, g->walk_off, g->e_src, g->e_dst, g->e_qry, g->e_ref, g->e_anom, g->e_qnz,
+                        g->e_qtot, g->d_reach, g->d_sum, g->d_anom, g->d_qnz, g->d_qtot, g->best, g->order, g->w_sum,
+                        g->w_anom, g->w_qnz, g->w_qtot, g->anom_dis};
+        for (void *p : ptrs) std::free(p);
+        std::free(g);
+    }
+    std::memset(res, 0, sizeof *res);
+}
+
+// Validate offsets; returns an error text or empty
+inline std::string validate_batch(const aa_batch *b) {
+    if (!b) return "null batch";
+    if (b->n_ctg <= 0 || b->n_blk <= 0) return "empty batch";
+    if (!b->ctg_off || !b->qry_str || !b->qry_end || !b->ref_str || !b->ref_end || !b->qry_total || !b->ref_chr ||
+        !b->aln_fwd || !b->map_qul || !b->run_off)
+        return "null array in batch";
+    if (b->ctg_off[0] != 0 || b->ctg_off[b->n_ctg] != b->n_blk) return "ctg_off does not span the blocks";
+    for (int64_t c = 0; c < b->n_ctg; c++)
+        if (b->ctg_off[c + 1] <= b->ctg_off[c]) return "empty contig (the reference asserts at least one block)";
+    if (b->run_off[0] != 0 || b->run_off[b->n_blk] != b->n_run) return "run_off does not span the runs";
+    for (int64_t i = 0; i < b->n_blk; i++)
+        if (b->run_off[i + 1] < b->run_off[i]) return "run_off not monotone";
+    if (b->n_run > 0 && (!b->run_ql || !b->run_qr || !b->run_rl)) return "null run array";
+    return "";
+}
+
+// Host std::sort per contig with the reference comparator (paf_data.hpp:69-73).  perm[b0+i] = original
+// in-contig position of the block that lands at sorted position i.
+inline void host_sort_perm(const DevBatch &d, std::vector<int32_t> &perm, std::vector<int32_t> &sorted_index,
+                           std::vector<int32_t> &ctg_order, int threads) {
+    const int64_t C = d.C;
+    perm.resize((size_t)d.B);
+    sorted_index.resize((size_t)d.B);
+    struct Key {
+        int64_t qs, qe;
+        int32_t idx;
+        bool operator<(const Key &r) const { return qs != r.qs ? qs < r.qs : qe < r.qe; }
+    };
+    std::atomic<int64_t> next{0};
+    auto worker = [&]() {
+        std::vector<Key> keys;
+        for (;;) {
+            int64_t c0 = next.fetch_add(16);
+            if (c0 >= C) break;
+            int64_t c1 = std::min<int64_t>(C, c0 + 16);
+            for (int64_t c = c0; c < c1; c++) {
+                int64_t b0 = d.h_ctg_off[(size_t)c], n = d.h_ctg_off[(size_t)c + 1] - b0;
+                keys.resize((size_t)n);
+                for (int64_t i = 0; i < n; i++) keys[(size_t)i] = {d.h_qs[(size_t)(b0 + i)], d.h_qe[(size_t)(b0 + i)], (int32_t)i};
+                if (n > 1) std::sort(keys.begin(), keys.end());
+                for (int64_t i = 0; i < n; i++) {
+                    perm[(size_t)(b0 + i)] = keys[(size_t)i].idx;
+                    sorted_index[(size_t)(b0 + keys[(size_t)i].idx)] = (int32_t)i;
+                }
+            }
+        }
+    };
+    if (threads <= 1 || C < 64) {
+        worker();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
+    }
+    // contig processing order for the per-contig phases: largest first
+    ctg_order.resize((size_t)C);
+    for (int64_t c = 0; c < C; c++) ctg_order[(size_t)c] = (int32_t)c;
+    std::stable_sort(ctg_order.begin(), ctg_order.end(), [&](int32_t a, int32_t b) {
+        return d.h_ctg_off[(size_t)a + 1] - d.h_ctg_off[(size_t)a] > d.h_ctg_off[(size_t)b + 1] - d.h_ctg_off[(size_t)b];
+    });
+}
+
+template <class BK>
+struct Pipeline {
+    BK &bk;
+    std::string err;
+    explicit Pipeline(BK &b) : bk(b) {}
+
+    template <class T>
+    T *A(int64_t n) {
+        return (T *)bk.alloc_bytes((size_t)(n > 0 ? n : 1) * sizeof(T));
+    }
+
+    aa_status upload(const aa_batch *b, DevBatch *&out) {
+        std::string v = validate_batch(b);
+        if (!v.empty()) {
+            err = v;
+            return AA_ERR_INVALID;
+        }
+        DevBatch *d = new DevBatch();
+        d->C = b->n_ctg;
+        d->B = b->n_blk;
+        d->R = b->n_run;
+        auto up = [&](auto *&dst, const auto *src, int64_t n) {
+            using T = std::remove_const_t<std::remove_pointer_t<decltype(src)>>;
+            dst = (T *)bk.alloc_persistent((size_t)(n > 0 ? n : 1) * sizeof(T));
+            if (!dst) return false;
+            d->owned.push_back(dst);
+            if (n > 0) bk.h2d(dst, src, (size_t)n * sizeof(T));
+            return true;
+        };
+        bool ok = up(d->ctg_off, b->ctg_off, d->C + 1) && up(d->qs, b->qry_str, d->B) && up(d->qe, b->qry_end, d->B) &&
+                  up(d->rs, b->ref_str, d->B) && up(d->re, b->ref_end, d->B) && up(d->qtot, b->qry_total, d->B) &&
+                  up(d->chr, b->ref_chr, d->B) && up(d->fwd, b->aln_fwd, d->B) && up(d->mapq, b->map_qul, d->B) &&
+                  up(d->run_off, b->run_off, d->B + 1) && up(d->run_ql, b->run_ql, d->R) &&
+                  up(d->run_qr, b->run_qr, d->R) && up(d->run_rl, b->run_rl, d->R);
+        if (!ok) {
+            free_batch(d);
+            err = "device allocation failed while staging the batch";
+            return AA_ERR_NOMEM;
+        }
+        d->h_ctg_off.assign(b->ctg_off, b->ctg_off + d->C + 1);
+        d->h_qs.assign(b->qry_str, b->qry_str + d->B);
+        d->h_qe.assign(b->qry_end, b->qry_end + d->B);
+        bk.sync();
+        out = d;
+        return AA_OK;
+    }
+    void free_batch(DevBatch *d) {
+        if (!d) return;
+        for (void *p : d->owned) bk.free_persistent(p);
+        delete d;
+    }
+
+    // ---- the whole hot path over a staged batch ------------------------------------------------------
+    aa_status solve(DevBatch &d, const aa_opts &opt, aa_result *res) {
+        bk.begin_solve();
+        aa_stats st;
+        std::memset(&st, 0, sizeof st);
+        const int64_t C = d.C, B = d.B;
+        const int32_t K = opt.max_walks > 0 ? opt.max_walks : 10000;
+        if (B >= (int64_t)1 << 31 || C >= (int64_t)1 << 30) {
+            err = "batch too large for 32-bit block ids";
+            return AA_ERR_NOMEM;
+        }
+        Ws w;
+        std::memset(&w, 0, sizeof w);
+        w.C = C;
+        w.B = B;
+        w.R = d.R;
+        w.nsl = opt.non_skip_linkable ? 1 : 0;
+        w.K = K;
+        w.ctg_off = d.ctg_off;
+        w.in_qs = d.qs;
+        w.in_qe = d.qe;
+        w.in_rs = d.rs;
+        w.in_re = d.re;
+        w.in_qtot = d.qtot;
+        w.in_chr = d.chr;
+        w.in_fwd = d.fwd;
+        w.in_mapq = d.mapq;
+        w.run_off = d.run_off;
+        w.run_ql = d.run_ql;
+        w.run_qr = d.run_qr;
+        w.run_rl = d.run_rl;
+
+        // ---- phase 0: host sort (OC1) + device gather ----
+        bk.phase_begin(PH_SORT);
+        std::vector<int32_t> perm, sorted_index, ctg_order;
+        host_sort_perm(d, perm, sorted_index, ctg_order, bk.host_threads());
+        int32_t *d_perm = A<int32_t>(B);
+        int32_t *d_ord = A<int32_t>(C);
+        bk.h2d(d_perm, perm.data(), (size_t)B * 4);
+        bk.h2d(d_ord, ctg_order.data(), (size_t)C * 4);
+        w.perm = d_perm;
+        w.blk_ctg = A<int32_t>(B);
+        w.qs = A<int64_t>(B);
+        w.qe = A<int64_t>(B);
+        w.rs = A<int64_t>(B);
+        w.re = A<int64_t>(B);
+        w.qtot = A<int64_t>(B);
+        w.chr = A<int32_t>(B);
+        w.orig = A<int32_t>(B);
+        w.fwd = A<uint8_t>(B);
+        w.mapq = A<uint8_t>(B);
+        w.run_beg = A<int64_t>(B);
+        w.run_cnt = A<int32_t>(B);
+        w.first_call = A<int32_t>(B);
+        w.part_l = A<int32_t>(B);
+        w.part_r = A<int32_t>(B);
+        w.status = A<int32_t>(C);
+        bk.for_each("gather", B, FnGather{w});
+        bk.phase_end(PH_SORT);
+
+        // ---- phase 1: parts ----
+        bk.phase_begin(PH_PARTS);
+        bk.for_each_contig("parts", C, FnParts{w, d_ord});
+        bk.phase_end(PH_PARTS);
+
+        // ---- phase 2: pair vertices ----
+        bk.phase_begin(PH_PAIRS);
+        w.cand_cnt = A<int32_t>(B + 1);
+        w.cand_off = A<int64_t>(B + 2);
+        bk.zero(w.cand_cnt + B, 4);
+        bk.for_each("cand_count", B, FnCandCount{w});
+        bk.scan_i32(w.cand_cnt, w.cand_off, B + 1);  // cand_off[B] = total; [B+1] unused
+        const int64_t ncand = bk.read_i64(w.cand_off + B);
+        w.cand = A<CandRec>(ncand);
+        w.cand_ok = A<int32_t>(ncand + 1);
+        w.cand_rank = A<int64_t>(ncand + 2);
+        bk.zero(w.cand_ok + ncand, 4);
+        bk.for_each("cuts", B, FnCuts{w});
+        bk.scan_i32(w.cand_ok, w.cand_rank, ncand + 1);
+        const int64_t P = bk.read_i64(w.cand_rank + ncand);
+        w.pair = A<CandRec>(P);
+        w.pair_beg = A<int64_t>(B + 1);
+        bk.for_each("compact", std::max<int64_t>(ncand, B + 1), FnCompact{w, ncand});
+        w.vtx_off = A<int64_t>(C + 1);
+        w.walk_off = A<int64_t>(C + 1);
+        bk.for_each("vtx_off", C + 1, FnVtxOff{w});
+        const int64_t Vtot = B + P + 2 * C;
+        bk.phase_end(PH_PAIRS);
+        if (Vtot >= ((int64_t)1 << 32) - 1) {
+            err = "too many vertices for one device batch";
+            return AA_ERR_NOMEM;
+        }
+
+        // ---- phase 3: edges ----
+        bk.phase_begin(PH_EDGES);
+        w.deg = A<int32_t>(Vtot + 1);
+        w.eoff = A<int64_t>(Vtot + 2);
+        bk.zero(w.deg + Vtot, 4);
+        bk.for_each("degree", Vtot, FnDegree{w});
+        bk.scan_i32(w.deg, w.eoff, Vtot + 1);
+        const int64_t E = bk.read_i64(w.eoff + Vtot);
+        if (E >= ((int64_t)1 << 32) - 1) {
+            err = "too many edges for one device batch (dense contig: see DESIGN.md, lazy edge mode is future work)";
+            return AA_ERR_NOMEM;
+        }
+        w.edge = A<Edge>(E);
+        w.e_src = A<int32_t>(E);
+        w.rkey_in = A<uint32_t>(E);
+        w.rval_in = A<uint32_t>(E);
+        w.rkey = A<uint32_t>(E);
+        w.rev_eid = A<uint32_t>(E);
+        if (!w.edge || !w.e_src || !w.rkey_in || !w.rval_in || !w.rkey || !w.rev_eid) {
+            err = "device allocation failed (edges)";
+            return AA_ERR_NOMEM;
+        }
+        bk.for_each("fill", Vtot, FnFill{w});
+        bk.phase_end(PH_EDGES);
+
+        // ---- phase 4: reverse CSR (stable sort by destination keeps ascending source order: OC4) ----
+        bk.phase_begin(PH_REVERSE);
+        int vbits = 1;
+        while (((int64_t)1 << vbits) < Vtot) vbits++;
+        bk.sort_pairs_u32(w.rkey_in, w.rkey, w.rval_in, w.rev_eid, E, vbits);
+        w.rev_off = A<int64_t>(Vtot + 1);
+        bk.for_each("rev_off", Vtot + 1, FnRevOff{w, E});
+        bk.phase_end(PH_REVERSE);
+
+        // ---- phase 5/6: relax + forward order ----
+        w.d = A<D4>(Vtot);
+        w.best = A<int32_t>(Vtot);
+        w.cnt = A<int32_t>(Vtot);
+        w.queue = A<int32_t>(Vtot);
+        w.order = A<int32_t>(Vtot);
+        w.topo = A<int32_t>(Vtot);
+        w.amin = A<int32_t>(Vtot);
+        w.hroot = A<int32_t>(Vtot);
+        w.anom_dis = A<int64_t>(C);
+        w.heap_used = A<int64_t>(C);
+        if (!w.d || !w.best || !w.cnt || !w.queue || !w.order || !w.topo || !w.amin || !w.hroot) {
+            err = "device allocation failed (vertex state)";
+            return AA_ERR_NOMEM;
+        }
+        bk.phase_begin(PH_RELAX);
+        bk.for_each_contig("relax", C, FnRelax{w, d_ord});
+        bk.phase_end(PH_RELAX);
+        bk.phase_begin(PH_TOPO);
+        bk.for_each_contig("topo", C, FnTopo{w, d_ord});
+        bk.phase_end(PH_TOPO);
+
+        // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
+        bk.phase_begin(PH_HEAPS);
+        w.heap_top = (unsigned long long *)A<int64_t>(1);
+        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
+        std::vector<int32_t> h_status((size_t)C);
+        for (int attempt = 0;; attempt++) {
+            if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
+            w.Hcap = hcap;
+            w.hn = A<HNode>(hcap);
+            w.hn_eid = A<int32_t>(hcap);
+            if (!w.hn || !w.hn_eid) {
+                err = "device allocation failed (sidetrack heap arena)";
+                return AA_ERR_NOMEM;
+            }
+            bk.zero(w.heap_top, 8);
+            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord});
+            bk.d2h(h_status.data(), w.status, (size_t)C * 4);
+            bool overflow = false;
+            for (int32_t s : h_status) overflow = overflow || s == 3;
+            if (!overflow) break;
+            if (hcap >= 0x7ffffff0LL || attempt > 8) {
+                err = "sidetrack heap arena exhausted (contig too dense for one device)";
+                return AA_ERR_NOMEM;
+            }
+            bk.release_last(2);  // give the two arena arrays back before growing
+            hcap *= 4;
+        }
+        bk.phase_end(PH_HEAPS);
+
+        // ---- phase 8: enumeration ----
+        bk.phase_begin(PH_ENUM);
+        const int64_t WK = C * (int64_t)K;
+        w.n_walk = A<int32_t>(C + 1);
+        w.wdist = A<D4>(WK);
+        w.wlast = A<int32_t>(WK);
+        w.ent_node = A<int32_t>(3 * WK);
+        w.ent_prev = A<int32_t>(3 * WK);
+        w.pq = A<PQEnt>(3 * WK);
+        if (!w.wdist || !w.wlast || !w.ent_node || !w.ent_prev || !w.pq) {
+            err = "device allocation failed (walk enumeration)";
+            return AA_ERR_NOMEM;
+        }
+        bk.for_each_contig("enum", C, FnEnum{w, d_ord});
+        bk.phase_end(PH_ENUM);
+
+        // ---- phase 9: plan ----
+        bk.phase_begin(PH_PLAN);
+        w.task = A<Task>(2 * WK);
+        w.n_task = A<int32_t>(C + 1);
+        w.n_tie = A<int32_t>(C);
+        w.last_group = A<int32_t>(C);
+        w.task_off = A<int64_t>(C + 2);
+        if (!w.task) {
+            err = "device allocation failed (task plan)";
+            return AA_ERR_NOMEM;
+        }
+        bk.zero(w.n_task + C, 4);
+        bk.for_each_contig("plan", C, FnPlan{w, d_ord});
+        bk.scan_i32(w.n_task, w.task_off, C + 1);
+        const int64_t NT = bk.read_i64(w.task_off + C);
+        w.n_tasks_total = NT;
+        w.tasks = A<Task>(NT);
+        w.task_cov = A<int64_t>(NT);
+        w.task_rows = A<int32_t>(NT);
+        bk.for_each_contig("task_compact", C, FnTaskCompact{w, d_ord});
+        bk.phase_end(PH_PLAN);
+
+        // ---- phase 10: walks, pass A ----
+        bk.phase_begin(PH_WALKS_A);
+        int64_t maxV = 3;
+        {
+            std::vector<int64_t> h_voff((size_t)C + 1);
+            bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
+            for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
+        }
+        w.slot_stride = maxV + 1;
+        const int64_t slot_bytes = w.slot_stride * (int64_t)(4 + 4 + 4 + sizeof(D5) + 4 + 1);
+        int64_t S = std::min<int64_t>(std::max<int64_t>(NT, 2 * C), bk.max_workers());
+        S = std::max<int64_t>(1, std::min<int64_t>(S, bk.scratch_budget() / std::max<int64_t>(1, slot_bytes)));
+        w.sc_walk = A<int32_t>(S * w.slot_stride);
+        w.sc_up = A<int32_t>(S * w.slot_stride);
+        w.sc_side = A<int32_t>(S * w.slot_stride);
+        w.sc_dp = A<D5>(S * w.slot_stride);
+        w.sc_pre = A<int32_t>(S * w.slot_stride);
+        w.sc_seen = A<uint8_t>(S * w.slot_stride);
+        w.task_next = (unsigned long long *)A<int64_t>(1);
+        if (!w.sc_walk || !w.sc_up || !w.sc_side || !w.sc_dp || !w.sc_pre || !w.sc_seen) {
+            err = "device allocation failed (walk scratch)";
+            return AA_ERR_NOMEM;
+        }
+        bk.zero(w.task_next, 8);
+        bk.workers("walksA", std::min<int64_t>(S, std::max<int64_t>(NT, 1)), FnTasksA{w});
+        bk.phase_end(PH_WALKS_A);
+
+        // ---- phase 11: select ----
+        bk.phase_begin(PH_SELECT);
+        w.win_out = A<int32_t>(C);
+        w.win_alt = A<int32_t>(C);
+        w.out_cnt = A<int32_t>(C + 1);
+        w.alt_cnt = A<int32_t>(C + 1);
+        w.all_cnt = A<int32_t>(C + 1);
+        w.out_off = A<int64_t>(C + 2);
+        w.alt_off = A<int64_t>(C + 2);
+        w.all_path_off = A<int64_t>(C + 2);
+        bk.zero(w.out_cnt + C, 4);
+        bk.zero(w.alt_cnt + C, 4);
+        bk.zero(w.all_cnt + C, 4);
+        bk.for_each_contig("select", C, FnSelect{w, d_ord, opt.want_all ? 1 : 0});
+        bk.scan_i32(w.out_cnt, w.out_off, C + 1);
+        bk.scan_i32(w.alt_cnt, w.alt_off, C + 1);
+        bk.scan_i32(w.all_cnt, w.all_path_off, C + 1);
+        const int64_t n_out = bk.read_i64(w.out_off + C), n_alt = bk.read_i64(w.alt_off + C);
+        const int64_t n_paths = bk.read_i64(w.all_path_off + C);
+        w.all_task = A<int32_t>(n_paths);
+        w.all_rows = A<int32_t>(n_paths + 1);
+        w.all_row_off = A<int64_t>(n_paths + 2);
+        bk.zero(w.all_rows + n_paths, 4);
+        if (n_paths > 0) bk.for_each_contig("all_list", C, FnAllList{w, d_ord});
+        bk.scan_i32(w.all_rows, w.all_row_off, n_paths + 1);
+        const int64_t n_all = bk.read_i64(w.all_row_off + n_paths);
+        bk.phase_end(PH_SELECT);
+
+        // ---- phase 12: walks, pass B (rows of the winners) ----
+        bk.phase_begin(PH_WALKS_B);
+        const int64_t nrow[3] = {n_out, n_alt, n_all};
+        for (int k = 0; k < 3; k++) {
+            w.r_idx[k] = A<int32_t>(nrow[k]);
+            w.r_qs[k] = A<int64_t>(nrow[k]);
+            w.r_qe[k] = A<int64_t>(nrow[k]);
+            w.r_rs[k] = A<int64_t>(nrow[k]);
+            w.r_re[k] = A<int64_t>(nrow[k]);
+            w.r_alt[k] = A<uint8_t>(nrow[k]);
+            if (!w.r_idx[k] || !w.r_qs[k] || !w.r_qe[k] || !w.r_rs[k] || !w.r_re[k] || !w.r_alt[k]) {
+                err = "device allocation failed (result rows; .aln.all.paf too large?)";
+                return AA_ERR_NOMEM;
+            }
+        }
+        bk.zero(w.task_next, 8);
+        const int64_t n_items = 2 * C + n_paths;
+        bk.workers("walksB", std::min<int64_t>(S, n_items), FnTasksB{w, n_items, n_paths});
+        bk.phase_end(PH_WALKS_B);
+
+        // ---- phase 13: download ----
+        bk.phase_begin(PH_D2H);
+        bk.d2h(h_status.data(), w.status, (size_t)C * 4);
+        std::vector<int32_t> h_nwalk((size_t)C);
+        std::vector<int64_t> h_heap((size_t)C);
+        bk.d2h(h_nwalk.data(), w.n_walk, (size_t)C * 4);
+        bk.d2h(h_heap.data(), w.heap_used, (size_t)C * 8);
+        bool unsolvable = false;
+        st.n_ctg = C;
+        st.n_blk = B;
+        st.n_run = d.R;
+        st.n_pair = P;
+        st.n_edge = E;
+        st.n_task = NT;
+        for (int64_t c = 0; c < C; c++) {
+            if (h_status[(size_t)c] == 2) unsolvable = true;
+            if (h_status[(size_t)c] == 0) {
+                st.n_walk += h_nwalk[(size_t)c];
+                st.n_heap += h_heap[(size_t)c];
+            }
+        }
+        std::vector<int64_t> h_voff((size_t)C + 1);
+        bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
+        for (int64_t c = 0; c < C; c++)
+            if (h_status[(size_t)c] != 1) st.n_vtx += h_voff[(size_t)c + 1] - h_voff[(size_t)c];
+        if (res) {
+            std::memset(res, 0, sizeof *res);
+            res->n_ctg = C;
+            res->out_off = host_n<int64_t>(C + 1);
+            res->alt_off = host_n<int64_t>(C + 1);
+            res->all_path_off = host_n<int64_t>(C + 1);
+            res->all_row_off = host_n<int64_t>(n_paths + 1);
+            res->sorted_index = host_n<int32_t>(B);
+            std::memcpy(res->sorted_index, sorted_index.data(), (size_t)B * 4);
+            bk.d2h(res->out_off, w.out_off, (size_t)(C + 1) * 8);
+            bk.d2h(res->alt_off, w.alt_off, (size_t)(C + 1) * 8);
+            bk.d2h(res->all_path_off, w.all_path_off, (size_t)(C + 1) * 8);
+            bk.d2h(res->all_row_off, w.all_row_off, (size_t)(n_paths + 1) * 8);
+            aa_rows *dst[3] = {&res->out, &res->alt, &res->all};
+            for (int k = 0; k < 3; k++) {
+                rows_alloc_host(*dst[k], nrow[k]);
+                if (nrow[k] > 0) {
+                    bk.d2h(dst[k]->ctg_index, w.r_idx[k], (size_t)nrow[k] * 4);
+                    bk.d2h(dst[k]->qry_str, w.r_qs[k], (size_t)nrow[k] * 8);
+                    bk.d2h(dst[k]->qry_end, w.r_qe[k], (size_t)nrow[k] * 8);
+                    bk.d2h(dst[k]->ref_str, w.r_rs[k], (size_t)nrow[k] * 8);
+                    bk.d2h(dst[k]->ref_end, w.r_re[k], (size_t)nrow[k] * 8);
+                    bk.d2h(dst[k]->is_alt, w.r_alt[k], (size_t)nrow[k]);
+                }
+            }
+            if (opt.keep_debug) download_debug(w, res, h_status, h_voff, h_nwalk, E, Vtot);
+        }
+        bk.phase_end(PH_D2H);
+        bk.end_solve(st);
+        // algorithmic bytes (DESIGN.md §"roofline"; SURVEY.md §8(d) with this repo's record sizes)
+        {
+            double *a = st.algo_bytes_phase;
+            const double Bd = (double)B, Rd = (double)d.R, Pd = (double)P, Vd = (double)Vtot, Ed = (double)E;
+            const double Hd = (double)st.n_heap, Kd = (double)st.n_walk;
+            a[PH_SORT] = 2.0 * 50.0 * Bd;                 // gather: read + write one 50-B block record
+            a[PH_PARTS] = 16.0 * Bd + 8.0 * Bd;           // qs,qe read; part_l,part_r write
+            a[PH_PAIRS] = 24.0 * Rd + 16.0 * Bd + 2.0 * 48.0 * Pd;  // runs once, keys, pair record write+compact
+            a[PH_EDGES] = 50.0 * Bd + 48.0 * Pd + (16.0 + 4.0 + 8.0) * Ed;  // vertex data read, edge+src+key write
+            a[PH_REVERSE] = 2.0 * 8.0 * Ed * 4.0 + 8.0 * Vd;   // 4 radix passes over (key,val), offsets
+            a[PH_RELAX] = (16.0 + 4.0 + 4.0) * Ed + (24.0 + 4.0) * Vd;      // edge, rev id, src read; d + best write
+            a[PH_TOPO] = 16.0 * Ed + 8.0 * Vd;
+            a[PH_HEAPS] = 16.0 * Ed + 24.0 * Vd + 36.0 * Hd;
+            a[PH_ENUM] = Kd * (32.0 + 36.0 + 3.0 * (32.0 + 32.0 + 8.0) + 28.0);  // pop, node, <=3 (node read, push, entry), out
+            a[PH_PLAN] = 24.0 * Kd;
+            a[PH_WALKS_A] = 0;  // data dependent; reported as time only
+            st.algo_bytes = 0;
+            for (int p = 0; p < PH_COUNT; p++) st.algo_bytes += a[p];
+        }
+        last_stats = st;
+        if (res) res->stats = st;
+        if (unsolvable) {
+            err = "a contig has no src->dest walk (reference: assert, paf_data.cpp:732)";
+            return AA_ERR_UNSOLVABLE;
+        }
+        return AA_OK;
+    }
+
+    aa_stats last_stats{};
+
+    void download_debug(const Ws &w, aa_result *res, const std::vector<int32_t> &h_status, const std::vector<int64_t> &h_voff,
+                        const std::vector<int32_t> &h_nwalk, int64_t E, int64_t Vtot) {
+        const int64_t C = w.C;
+        aa_debug *g = (aa_debug *)std::calloc(1, sizeof(aa_debug));
+        res->dbg = g;
+        std::vector<int64_t> h_eoff((size_t)Vtot + 1);
+        bk.d2h(h_eoff.data(), w.eoff, (size_t)(Vtot + 1) * 8);
+        std::vector<Edge> h_edge((size_t)E);
+        std::vector<int32_t> h_src((size_t)E);
+        if (E > 0) {
+            bk.d2h(h_edge.data(), w.edge, (size_t)E * sizeof(Edge));
+            bk.d2h(h_src.data(), w.e_src, (size_t)E * 4);
+        }
+        std::vector<D4> h_d((size_t)Vtot);
+        std::vector<int32_t> h_best((size_t)Vtot), h_order((size_t)Vtot);
+        bk.d2h(h_d.data(), w.d, (size_t)Vtot * sizeof(D4));
+        bk.d2h(h_best.data(), w.best, (size_t)Vtot * 4);
+        bk.d2h(h_order.data(), w.order, (size_t)Vtot * 4);
+        std::vector<int64_t> h_anom((size_t)C);
+        bk.d2h(h_anom.data(), w.anom_dis, (size_t)C * 8);
+        g->vtx_off = host_n<int64_t>(C + 1);
+        g->edge_off = host_n<int64_t>(C + 1);
+        g->walk_off = host_n<int64_t>(C + 1);
+        g->anom_dis = host_n<int64_t>(C);
+        int64_t tv = 0, te = 0, tw = 0;
+        for (int64_t c = 0; c < C; c++) {
+            if (h_status[(size_t)c] == 0) {
+                tv += h_voff[(size_t)c + 1] - h_voff[(size_t)c];
+                te += h_eoff[(size_t)h_voff[(size_t)c + 1]] - h_eoff[(size_t)h_voff[(size_t)c]];
+                tw += h_nwalk[(size_t)c];
+            }
+            g->vtx_off[c + 1] = tv;
+            g->edge_off[c + 1] = te;
+            g->walk_off[c + 1] = tw;
+        }
+        g->e_src = host_n<int32_t>(te);
+        g->e_dst = host_n<int32_t>(te);
+        g->e_qry = host_n<int64_t>(te);
+        g->e_ref = host_n<int64_t>(te);
+        g->e_anom = host_n<int32_t>(te);
+        g->e_qnz = host_n<int32_t>(te);
+        g->e_qtot = host_n<int32_t>(te);
+        g->d_reach = host_n<uint8_t>(tv);
+        g->d_sum = host_n<int64_t>(tv);
+        g->d_anom = host_n<int32_t>(tv);
+        g->d_qnz = host_n<int32_t>(tv);
+        g->d_qtot = host_n<int32_t>(tv);
+        g->best = host_n<int32_t>(tv);
+        g->order = host_n<int32_t>(tv);
+        g->w_sum = host_n<int64_t>(tw);
+        g->w_anom = host_n<int32_t>(tw);
+        g->w_qnz = host_n<int32_t>(tw);
+        g->w_qtot = host_n<int32_t>(tw);
+        std::vector<D4> h_w;
+        for (int64_t c = 0; c < C; c++) {
+            if (h_status[(size_t)c] != 0) {
+                g->anom_dis[c] = -1;
+                continue;
+            }
+            g->anom_dis[c] = h_anom[(size_t)c];
+            int64_t v0 = h_voff[(size_t)c], nv = h_voff[(size_t)c + 1] - v0;
+            int64_t e0 = h_eoff[(size_t)v0], ne = h_eoff[(size_t)(v0 + nv)] - e0;
+            int64_t go = g->edge_off[c], gvv = g->vtx_off[c], gw = g->walk_off[c];
+            for (int64_t k = 0; k < ne; k++) {
+                const Edge &e = h_edge[(size_t)(e0 + k)];
+                g->e_src[go + k] = h_src[(size_t)(e0 + k)];
+                g->e_dst[go + k] = e_dst(e);
+                g->e_qry[go + k] = e.qry;
+                g->e_ref[go + k] = e.ref;
+                g->e_anom[go + k] = e_anom(e);
+                g->e_qnz[go + k] = e_nz(e);
+                g->e_qtot[go + k] = e_tot(e);
+            }
+            for (int64_t v = 0; v < nv; v++) {
+                const D4 &x = h_d[(size_t)(v0 + v)];
+                g->d_reach[gvv + v] = x.aux ? 1 : 0;
+                g->d_sum[gvv + v] = x.aux ? x.sum : 0;
+                g->d_anom[gvv + v] = x.aux ? x.anom : 0;
+                g->d_qnz[gvv + v] = x.aux ? x.nz : 0;
+                g->d_qtot[gvv + v] = x.aux ? x.tot : 0;
+                g->best[gvv + v] = h_best[(size_t)(v0 + v)];
+                g->order[gvv + v] = h_order[(size_t)(v0 + v)];
+            }
+            int64_t nw = h_nwalk[(size_t)c];
+            h_w.resize((size_t)nw);
+            if (nw > 0) bk.d2h(h_w.data(), w.wdist + c * (int64_t)w.K, (size_t)nw * sizeof(D4));
+            for (int64_t k = 0; k < nw; k++) {
+                g->w_sum[gw + k] = h_w[(size_t)k].sum;
+                g->w_anom[gw + k] = h_w[(size_t)k].anom;
+                g->w_qnz[gw + k] = h_w[(size_t)k].nz;
+                g->w_qtot[gw + k] = h_w[(size_t)k].tot;
+            }
+        }
+    }
+};
+
+}  // namespace aa

@@ -253,7 +253,7 @@ class Solver:
         h = C.c_void_p()
         st = self._lib.aa_create(C.byref(h), int(device))
         if st != 0:
-            msg = self._lib.aa_last_error(h).decode() if h else "aa_create failed"
+            msg = self._lib.aa_last_error(h if h else None).decode()
             raise AlignasmError(st, msg)
         self._h = h
         self.device = device

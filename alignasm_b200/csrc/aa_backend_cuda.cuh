@@ -1,0 +1,277 @@
+// aa_backend_cuda.cuh — the product Backend: sm_100a kernels, CUB scan / radix sort, pooled HBM workspace.
+//
+// Launch shapes:
+//   for_each         one thread per item (blocks, candidate slots, vertices), 256-thread CTAs
+//   for_each_contig  one warp per contig, one CTA per warp so that the block scheduler spreads the
+//                    (largest-first ordered) contigs over all 148 SMs
+//   workers          persistent one-warp CTAs pulling walk tasks from a global counter
+// The workspace is a bump allocator over a few large cudaMalloc blocks that live in the aa_ctx, so a
+// steady-state solve performs no cudaMalloc at all.
+#pragma once
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "aa_pipeline.cuh"
+
+namespace aa {
+
+template <class F>
+__global__ void __launch_bounds__(256) k_items(int64_t n, F f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+// one warp per item (contig / worker slot)
+template <class F>
+__global__ void __launch_bounds__(32) k_warp_items(int64_t n, F f) {
+    int64_t i = blockIdx.x;
+    if (threadIdx.x == 0 && i < n) f(i);
+}
+
+struct CastI32 {
+    __host__ __device__ __forceinline__ int64_t operator()(const int32_t &x) const { return (int64_t)x; }
+};
+
+struct CudaBackend {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool failed = false;
+    std::string errmsg;
+    int64_t n_launch = 0;
+    int sm_count = 148;
+
+    struct Block {
+        char *base;
+        size_t cap, top;
+    };
+    std::vector<Block> pool;
+    struct Mark {
+        int block;
+        size_t top;
+    };
+    std::vector<Mark> log;  // one entry per allocation (for release_last)
+    cudaEvent_t ev[PH_COUNT][2];
+    bool ev_on[PH_COUNT];
+    cudaEvent_t ev_total[2];
+
+    bool ok() const { return !failed; }
+    const std::string &error() const { return errmsg; }
+    void fail(const char *what, cudaError_t e) {
+        if (!failed) {
+            failed = true;
+            errmsg = std::string(what) + ": " + cudaGetErrorString(e);
+        }
+    }
+#define AA_CUDA(call)                          \
+    do {                                       \
+        cudaError_t e__ = (call);              \
+        if (e__ != cudaSuccess) fail(#call, e__); \
+    } while (0)
+
+    bool init(int dev) {
+        device = dev;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0 || dev < 0 || dev >= n) {
+            errmsg = e != cudaSuccess ? std::string("no usable CUDA device: ") + cudaGetErrorString(e)
+                                      : "no usable CUDA device (count " + std::to_string(n) + ", asked for " + std::to_string(dev) + ")";
+            failed = true;
+            return false;
+        }
+        AA_CUDA(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        AA_CUDA(cudaGetDeviceProperties(&prop, dev));
+        sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+        AA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int p = 0; p < PH_COUNT; p++) {
+            AA_CUDA(cudaEventCreate(&ev[p][0]));
+            AA_CUDA(cudaEventCreate(&ev[p][1]));
+            ev_on[p] = false;
+        }
+        AA_CUDA(cudaEventCreate(&ev_total[0]));
+        AA_CUDA(cudaEventCreate(&ev_total[1]));
+        return !failed;
+    }
+    void shutdown() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto &b : pool) cudaFree(b.base);
+        pool.clear();
+        if (stream) {
+            for (int p = 0; p < PH_COUNT; p++) {
+                cudaEventDestroy(ev[p][0]);
+                cudaEventDestroy(ev[p][1]);
+            }
+            cudaEventDestroy(ev_total[0]);
+            cudaEventDestroy(ev_total[1]);
+            cudaStreamDestroy(stream);
+            stream = nullptr;
+        }
+    }
+
+    // ---- pooled workspace ----
+    void *alloc_bytes(size_t n) {
+        if (failed) return nullptr;
+        n = (n + 255) & ~(size_t)255;
+        if (n == 0) n = 256;
+        if (pool.empty() || pool.back().top + n > pool.back().cap) {
+            size_t last = pool.empty() ? 0 : pool.back().cap;
+            size_t want = std::max<size_t>(n, std::max<size_t>(2 * last, (size_t)256 << 20));
+            char *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess && want > n) {
+                cudaGetLastError();
+                want = n;
+                e = cudaMalloc(&p, want);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                fail("cudaMalloc(workspace)", e);
+                return nullptr;
+            }
+            pool.push_back({p, want, 0});
+        }
+        Block &b = pool.back();
+        log.push_back({(int)pool.size() - 1, b.top});
+        void *r = b.base + b.top;
+        b.top += n;
+        return r;
+    }
+    void release_last(int k) {
+        while (k-- > 0 && !log.empty()) {
+            Mark m = log.back();
+            log.pop_back();
+            // only the newest block can shrink; older blocks keep their tail unused for this solve
+            if (m.block == (int)pool.size() - 1) pool[(size_t)m.block].top = m.top;
+        }
+    }
+    void *alloc_persistent(size_t n) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, n ? n : 256);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            fail("cudaMalloc(batch)", e);
+            return nullptr;
+        }
+        return p;
+    }
+    void free_persistent(void *p) { cudaFree(p); }
+
+    void begin_solve() {
+        AA_CUDA(cudaSetDevice(device));
+        // coalesce a fragmented pool into one block so the next solve bumps through contiguous memory
+        if (pool.size() > 1) {
+            AA_CUDA(cudaStreamSynchronize(stream));
+            size_t total = 0;
+            for (auto &b : pool) {
+                total += b.cap;
+                cudaFree(b.base);
+            }
+            pool.clear();
+            char *p = nullptr;
+            if (cudaMalloc(&p, total) == cudaSuccess) pool.push_back({p, total, 0});
+            else cudaGetLastError();
+        }
+        for (auto &b : pool) b.top = 0;
+        log.clear();
+        n_launch = 0;
+        for (int p = 0; p < PH_COUNT; p++) ev_on[p] = false;
+        AA_CUDA(cudaEventRecord(ev_total[0], stream));
+    }
+    void end_solve(aa_stats &st) {
+        AA_CUDA(cudaEventRecord(ev_total[1], stream));
+        AA_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        if (!failed) {
+            cudaEventElapsedTime(&ms, ev_total[0], ev_total[1]);
+            st.ms_total = ms;
+            for (int p = 0; p < PH_COUNT; p++)
+                if (ev_on[p]) {
+                    cudaEventElapsedTime(&ms, ev[p][0], ev[p][1]);
+                    st.ms_phase[p] = ms;
+                }
+        }
+        st.n_launch = n_launch;
+    }
+    void phase_begin(int p) { AA_CUDA(cudaEventRecord(ev[p][0], stream)); }
+    void phase_end(int p) {
+        AA_CUDA(cudaEventRecord(ev[p][1], stream));
+        ev_on[p] = true;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) fail(phase_name(p), e);
+    }
+
+    void h2d(void *d, const void *h, size_t n) {
+        if (n && !failed) AA_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream));
+    }
+    void d2h(void *h, const void *d, size_t n) {
+        if (n && !failed) {
+            AA_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream));
+            AA_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
+    void zero(void *p, size_t n) {
+        if (n && !failed) AA_CUDA(cudaMemsetAsync(p, 0, n, stream));
+    }
+    void sync() { AA_CUDA(cudaStreamSynchronize(stream)); }
+    int64_t read_i64(const int64_t *p) {
+        int64_t v = 0;
+        d2h(&v, p, 8);
+        return v;
+    }
+
+    template <class F>
+    void for_each(const char *, int64_t n, F f) {
+        if (n <= 0 || failed) return;
+        int64_t grid = (n + 255) / 256;
+        k_items<F><<<(unsigned)grid, 256, 0, stream>>>(n, f);
+        n_launch++;
+    }
+    template <class F>
+    void for_each_contig(const char *, int64_t n, F f) {
+        if (n <= 0 || failed) return;
+        k_warp_items<F><<<(unsigned)n, 32, 0, stream>>>(n, f);
+        n_launch++;
+    }
+    template <class F>
+    void workers(const char *, int64_t n, F f) {
+        if (n <= 0 || failed) return;
+        k_warp_items<F><<<(unsigned)n, 32, 0, stream>>>(n, f);
+        n_launch++;
+    }
+    void scan_i32(const int32_t *in, int64_t *out, int64_t n) {
+        if (n <= 0 || failed) return;
+        cub::TransformInputIterator<int64_t, CastI32, const int32_t *> it(in, CastI32());
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, out, n, stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceScan::ExclusiveSum(t, tmp, it, out, n, stream));
+        n_launch++;
+    }
+    void sort_pairs_u32(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit) {
+        if (n <= 0 || failed) return;
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceRadixSort::SortPairs(t, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
+        n_launch++;
+    }
+    int host_threads() {
+        unsigned h = std::thread::hardware_concurrency();
+        return (int)std::min<unsigned>(h ? h : 1, 32);
+    }
+    int64_t max_workers() { return (int64_t)sm_count * 32; }
+    int64_t scratch_budget() {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (int64_t)4 << 30;
+        return (int64_t)std::min<size_t>(fr / 4, (size_t)24 << 30);
+    }
+};
+
+}  // namespace aa

@@ -267,6 +267,13 @@ struct Pipeline {
         delete d;
     }
 
+#define AA_BK_CHECK()            \
+    do {                         \
+        if (!bk.ok()) {          \
+            err = bk.error();    \
+            return AA_ERR_CUDA;  \
+        }                        \
+    } while (0)
     // ---- the whole hot path over a staged batch ------------------------------------------------------
     aa_status solve(DevBatch &d, const aa_opts &opt, aa_result *res) {
         bk.begin_solve();
@@ -326,11 +333,13 @@ struct Pipeline {
         w.status = A<int32_t>(C);
         bk.for_each("gather", B, FnGather{w});
         bk.phase_end(PH_SORT);
+        AA_BK_CHECK();
 
         // ---- phase 1: parts ----
         bk.phase_begin(PH_PARTS);
         bk.for_each_contig("parts", C, FnParts{w, d_ord});
         bk.phase_end(PH_PARTS);
+        AA_BK_CHECK();
 
         // ---- phase 2: pair vertices ----
         bk.phase_begin(PH_PAIRS);
@@ -355,6 +364,7 @@ struct Pipeline {
         bk.for_each("vtx_off", C + 1, FnVtxOff{w});
         const int64_t Vtot = B + P + 2 * C;
         bk.phase_end(PH_PAIRS);
+        AA_BK_CHECK();
         if (Vtot >= ((int64_t)1 << 32) - 1) {
             err = "too many vertices for one device batch";
             return AA_ERR_NOMEM;
@@ -384,6 +394,7 @@ struct Pipeline {
         }
         bk.for_each("fill", Vtot, FnFill{w});
         bk.phase_end(PH_EDGES);
+        AA_BK_CHECK();
 
         // ---- phase 4: reverse CSR (stable sort by destination keeps ascending source order: OC4) ----
         bk.phase_begin(PH_REVERSE);
@@ -393,6 +404,7 @@ struct Pipeline {
         w.rev_off = A<int64_t>(Vtot + 1);
         bk.for_each("rev_off", Vtot + 1, FnRevOff{w, E});
         bk.phase_end(PH_REVERSE);
+        AA_BK_CHECK();
 
         // ---- phase 5/6: relax + forward order ----
         w.d = A<D4>(Vtot);
@@ -412,9 +424,11 @@ struct Pipeline {
         bk.phase_begin(PH_RELAX);
         bk.for_each_contig("relax", C, FnRelax{w, d_ord});
         bk.phase_end(PH_RELAX);
+        AA_BK_CHECK();
         bk.phase_begin(PH_TOPO);
         bk.for_each_contig("topo", C, FnTopo{w, d_ord});
         bk.phase_end(PH_TOPO);
+        AA_BK_CHECK();
 
         // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
         bk.phase_begin(PH_HEAPS);
@@ -433,6 +447,7 @@ struct Pipeline {
             bk.zero(w.heap_top, 8);
             bk.for_each_contig("heaps", C, FnHeaps{w, d_ord});
             bk.d2h(h_status.data(), w.status, (size_t)C * 4);
+            AA_BK_CHECK();
             bool overflow = false;
             for (int32_t s : h_status) overflow = overflow || s == 3;
             if (!overflow) break;
@@ -444,6 +459,7 @@ struct Pipeline {
             hcap *= 4;
         }
         bk.phase_end(PH_HEAPS);
+        AA_BK_CHECK();
 
         // ---- phase 8: enumeration ----
         bk.phase_begin(PH_ENUM);
@@ -460,6 +476,7 @@ struct Pipeline {
         }
         bk.for_each_contig("enum", C, FnEnum{w, d_ord});
         bk.phase_end(PH_ENUM);
+        AA_BK_CHECK();
 
         // ---- phase 9: plan ----
         bk.phase_begin(PH_PLAN);
@@ -482,6 +499,7 @@ struct Pipeline {
         w.task_rows = A<int32_t>(NT);
         bk.for_each_contig("task_compact", C, FnTaskCompact{w, d_ord});
         bk.phase_end(PH_PLAN);
+        AA_BK_CHECK();
 
         // ---- phase 10: walks, pass A ----
         bk.phase_begin(PH_WALKS_A);
@@ -509,6 +527,7 @@ struct Pipeline {
         bk.zero(w.task_next, 8);
         bk.workers("walksA", std::min<int64_t>(S, std::max<int64_t>(NT, 1)), FnTasksA{w});
         bk.phase_end(PH_WALKS_A);
+        AA_BK_CHECK();
 
         // ---- phase 11: select ----
         bk.phase_begin(PH_SELECT);
@@ -537,6 +556,7 @@ struct Pipeline {
         bk.scan_i32(w.all_rows, w.all_row_off, n_paths + 1);
         const int64_t n_all = bk.read_i64(w.all_row_off + n_paths);
         bk.phase_end(PH_SELECT);
+        AA_BK_CHECK();
 
         // ---- phase 12: walks, pass B (rows of the winners) ----
         bk.phase_begin(PH_WALKS_B);
@@ -557,6 +577,7 @@ struct Pipeline {
         const int64_t n_items = 2 * C + n_paths;
         bk.workers("walksB", std::min<int64_t>(S, n_items), FnTasksB{w, n_items, n_paths});
         bk.phase_end(PH_WALKS_B);
+        AA_BK_CHECK();
 
         // ---- phase 13: download ----
         bk.phase_begin(PH_D2H);
@@ -611,6 +632,7 @@ struct Pipeline {
             if (opt.keep_debug) download_debug(w, res, h_status, h_voff, h_nwalk, E, Vtot);
         }
         bk.phase_end(PH_D2H);
+        AA_BK_CHECK();
         bk.end_solve(st);
         // algorithmic bytes (DESIGN.md §"roofline"; SURVEY.md §8(d) with this repo's record sizes)
         {

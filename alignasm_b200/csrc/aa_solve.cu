@@ -1,16 +1,102 @@
-// placeholder (replaced by the real pipeline)
-#include "../../include/alignasm_b200.h"
-#include <cstring>
-struct aa_ctx { char err[256]; };
-extern "C" {
-aa_status aa_create(aa_ctx **ctx, int) { *ctx = nullptr; return AA_ERR_NO_DEVICE; }
-void aa_destroy(aa_ctx *) {}
-const char *aa_last_error(const aa_ctx *) { return "stub"; }
-aa_status aa_solve(aa_ctx *, const aa_batch *, const aa_opts *, aa_result *) { return AA_ERR_NO_DEVICE; }
-aa_status aa_upload(aa_ctx *, const aa_batch *, aa_dev_batch **) { return AA_ERR_NO_DEVICE; }
-aa_status aa_solve_device(aa_ctx *, aa_dev_batch *, const aa_opts *, aa_result *) { return AA_ERR_NO_DEVICE; }
-void aa_dev_batch_free(aa_ctx *, aa_dev_batch *) {}
-void aa_result_free(aa_result *) {}
-const char *aa_phase_name(int) { return nullptr; }
-const char *aa_version(void) { return "stub"; }
+// aa_solve.cu — C ABI of the hot path (include/alignasm_b200.h) on top of the CUDA backend.
+// There is no CPU path in this library: without a usable CUDA device every entry point fails.
+#include "aa_backend_cuda.cuh"
+
+#include <new>
+
+struct aa_ctx {
+    aa::CudaBackend bk;
+    aa::Pipeline<aa::CudaBackend> pipe;
+    std::string err;
+    aa_ctx() : pipe(bk) {}
+};
+struct aa_dev_batch {
+    aa::DevBatch *d;
+};
+
+namespace {
+thread_local std::string g_create_err = "";
 }
+
+extern "C" {
+
+const char *aa_version(void) { return "alignasm_b200 0.1.0 (sm_100a)"; }
+const char *aa_phase_name(int phase) { return aa::phase_name(phase); }
+
+aa_status aa_create(aa_ctx **ctx, int device) {
+    if (!ctx) return AA_ERR_INVALID;
+    *ctx = nullptr;
+    aa_ctx *c = new (std::nothrow) aa_ctx();
+    if (!c) return AA_ERR_NOMEM;
+    if (!c->bk.init(device)) {
+        g_create_err = c->bk.error();
+        delete c;
+        return AA_ERR_NO_DEVICE;
+    }
+    *ctx = c;
+    return AA_OK;
+}
+void aa_destroy(aa_ctx *ctx) {
+    if (!ctx) return;
+    ctx->bk.shutdown();
+    delete ctx;
+}
+const char *aa_last_error(const aa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+aa_status aa_upload(aa_ctx *ctx, const aa_batch *batch, aa_dev_batch **dev) {
+    if (!ctx || !dev) return AA_ERR_INVALID;
+    *dev = nullptr;
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        return AA_ERR_CUDA;
+    }
+    cudaSetDevice(ctx->bk.device);
+    aa::DevBatch *d = nullptr;
+    aa_status st = ctx->pipe.upload(batch, d);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        return st;
+    }
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        ctx->pipe.free_batch(d);
+        return AA_ERR_CUDA;
+    }
+    *dev = new aa_dev_batch{d};
+    return AA_OK;
+}
+void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev) {
+    if (!ctx || !dev) return;
+    ctx->pipe.free_batch(dev->d);
+    delete dev;
+}
+aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, aa_result *res) {
+    if (!ctx || !dev || !dev->d) return AA_ERR_INVALID;
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        return AA_ERR_CUDA;
+    }
+    aa_opts o{};
+    if (opts) o = *opts;
+    aa_status st = ctx->pipe.solve(*dev->d, o, res);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        if (st != AA_ERR_UNSOLVABLE) {
+            if (res) aa::result_free_host(res);
+            cudaStreamSynchronize(ctx->bk.stream);
+        }
+    }
+    return st;
+}
+aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_result *res) {
+    if (!ctx || !res) return AA_ERR_INVALID;
+    aa_dev_batch *dev = nullptr;
+    aa_status st = aa_upload(ctx, batch, &dev);
+    if (st != AA_OK) return st;
+    st = aa_solve_device(ctx, dev, opts, res);
+    aa_dev_batch_free(ctx, dev);
+    return st;
+}
+void aa_result_free(aa_result *res) { aa::result_free_host(res); }
+
+}  // extern "C"

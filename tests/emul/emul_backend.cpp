@@ -5,11 +5,15 @@
 // emul_solve(), which nothing in alignasm_b200/ links or loads.
 #include "../../alignasm_b200/csrc/aa_pipeline.cuh"
 
+#include <cstdio>
 #include <numeric>
 
 namespace {
 struct HostBackend {
     std::vector<void *> blocks;
+    std::string none;
+    bool ok() const { return true; }
+    const std::string &error() const { return none; }
     void *alloc_bytes(size_t n) {
         void *p = std::malloc(n ? n : 1);
         blocks.push_back(p);

@@ -62,6 +62,8 @@ def load_library():
     lib.aa_dev_batch_free.restype = None
     lib.aa_result_free.argtypes = [C.POINTER(aa_result)]
     lib.aa_result_free.restype = None
+    lib.aa_get_stats.argtypes = [vp, C.POINTER(_abi.aa_stats)]
+    lib.aa_get_stats.restype = C.c_int
     lib.aa_phase_name.argtypes = [C.c_int]
     lib.aa_phase_name.restype = C.c_char_p
     lib.aa_version.argtypes = []
@@ -135,6 +137,14 @@ def _rows(r):
             "ref_str": np_from(r.ref_str, n), "ref_end": np_from(r.ref_end, n), "is_alt": np_from(r.is_alt, n)}
 
 
+def _stats_dict(st):
+    d = {k: getattr(st, k) for k in ("n_ctg", "n_blk", "n_run", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task",
+                                     "n_launch", "ms_total", "algo_bytes")}
+    d["ms_phase"] = list(st.ms_phase)
+    d["algo_bytes_phase"] = list(st.algo_bytes_phase)
+    return d
+
+
 class Result:
     """Host copy of an aa_result: three per-contig CSR lists of PafOutputData rows + statistics."""
 
@@ -148,11 +158,7 @@ class Result:
         self.all_row_off = np_from(cres.all_row_off, npaths + 1)
         self.out, self.alt, self.all = _rows(cres.out), _rows(cres.alt), _rows(cres.all)
         self.sorted_index = np_from(cres.sorted_index, n_blk)
-        st = cres.stats
-        self.stats = {k: getattr(st, k) for k in ("n_ctg", "n_blk", "n_run", "n_pair", "n_vtx", "n_edge", "n_heap",
-                                                  "n_walk", "n_task", "n_launch", "ms_total", "algo_bytes")}
-        self.stats["ms_phase"] = list(st.ms_phase)
-        self.stats["algo_bytes_phase"] = list(st.algo_bytes_phase)
+        self.stats = _stats_dict(cres.stats)
         self.dbg = None
         if cres.dbg:
             g = cres.dbg.contents
@@ -284,8 +290,11 @@ class Solver:
         self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), C.byref(res)))
         return Result(res, dev.n_blk, self._lib.aa_result_free)
 
-    def last_stats(self, dev, **kw):
-        return self.solve_device(dev, fetch=True, **kw).stats
+    def stats(self):
+        """Sizes, per-phase device times and algorithmic bytes of the last solve on this context."""
+        st = _abi.aa_stats()
+        self._check(self._lib.aa_get_stats(self._h, C.byref(st)))
+        return _stats_dict(st)
 
     def phase_names(self):
         names, i = [], 0

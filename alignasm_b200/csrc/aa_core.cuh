@@ -184,6 +184,15 @@ struct Ws {
     int32_t *sc_pre;      // [S*stride]
     uint8_t *sc_seen;     // [S*stride]
     unsigned long long *task_next;  // dynamic task counter
+    // main chain of every contig = upgrade-automaton states along walk 0 (the shortest-path-tree walk from
+    // src), with prefix sums; the other walks only simulate where they leave it (see walk_task_inc)
+    int32_t *main_pos;   // [Vtot] position of the vertex on walk 0, -1 when not on it
+    int32_t *main_walk;  // [Vtot] vertex at position i of walk 0
+    int32_t *m_cs;       // [Vtot] upgraded end point when the automaton stands at position i (-1: no state)
+    int64_t *m_cov;      // [Vtot] coverage of the rows closed before position i
+    int32_t *m_rows;     // [Vtot] rows closed before position i
+    int64_t *m_tot_cov;  // [C]
+    int32_t *m_tot_rows; // [C]
     int64_t n_tasks_total;
     // selection + output
     int32_t *win_out, *win_alt;  // [C] compacted task index (or -1)
@@ -1200,8 +1209,213 @@ AA_HDN void walk_task(const Ws &w, const Task &t, const Slot &s, int dst, int64_
     if (rows_out) *rows_out = nrows;
 }
 
+
+// ---- the upgrade automaton, one step at a time -----------------------------------------------------------
+// State = (position on the walk, cs = last vertex appended to the upgraded path).  A step looks at the next
+// two walk vertices (v, nv), appends vertices and consumes one or two walk edges (paf_data.cpp:801-911).
+// Coverage is accounted when a row is closed, i.e. when the vertex after it is appended, because a pair
+// vertex trims the end of the row before it (paf_data.cpp:1523-1531, 1546-1553).
+struct Auto {
+    int32_t cs;
+    int64_t cov;
+    int32_t rows;
+};
+AA_HD void auto_append(const Ws &w, const Ctg &g, Auto &A, int32_t b) {
+    if (A.cs != g.src) {
+        int64_t qs_, rs_, qe_, re_;
+        if (A.cs < g.n) {
+            const int64_t gb = g.b0 + A.cs;
+            qs_ = w.qs[gb];
+            rs_ = w.rs[gb];
+            qe_ = w.qe[gb];
+            re_ = w.re[gb];
+        } else {
+            const CandRec &p = w.pair[g.p0 + (A.cs - g.n)];
+            const int64_t gb = g.b0 + p.j;
+            qs_ = p.st_q;
+            rs_ = p.st_r;
+            qe_ = w.qe[gb];
+            re_ = w.re[gb];
+        }
+        if (b >= g.n && b < g.src) {
+            const CandRec &pb = w.pair[g.p0 + (b - g.n)];
+            qe_ = pb.pe_q;
+            re_ = pb.pe_r;
+        }
+        int64_t dr = re_ - rs_;
+        A.cov += (qe_ - qs_) + (dr < 0 ? -dr : dr);
+        A.rows++;
+    }
+    A.cs = b;
+}
+// one automaton step; returns the number of walk edges consumed (1 or 2)
+AA_HDN int32_t auto_step(const Ws &w, const Ctg &g, const Slot &s, Auto &A, int32_t v, int32_t nv) {
+    int32_t ul = 0;
+    if (v == g.dest) {  // paf_data.cpp:845-858
+        sub_path(w, g, s, A.cs, v, false, -1, false, ul);
+        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+        return 1;
+    }
+    int32_t x, y;
+    vtx_xy(w, g, v, x, y);
+    if (x != y) {  // paf_data.cpp:866-873 (after src the first vertex is always a single)
+        auto_append(w, g, A, v);
+        return 1;
+    }
+    int32_t nx = -1, ny = -1;
+    if (nv != g.dest) vtx_xy(w, g, nv, nx, ny);
+    if (nv == g.dest || nx == ny) {  // paf_data.cpp:812-833, 879-899
+        if (!sub_path(w, g, s, A.cs, nv, true, y, true, ul)) {
+            auto_append(w, g, A, v);
+        } else {
+            for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+        }
+        return 1;
+    }
+    // nv = (y, ny): paf_data.cpp:834-843, 900-909
+    if (!sub_path(w, g, s, A.cs, nv, false, -1, false, ul)) {
+        auto_append(w, g, A, v);
+        auto_append(w, g, A, nv);
+    } else {
+        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+    }
+    return 2;
+}
+
+// walk 0 of a contig (no sidetracks: the tree walk from src): mark its blocks with call 0, run the automaton
+// over it and record the main chain.
+AA_HDN void main_chain(const Ws &w, int64_t c, const Slot &s, int64_t task_index) {
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    for (int32_t v = 0; v < g.V; v++) w.main_pos[v0 + v] = -1;
+    int32_t m = 0;
+    for (int32_t cur = g.src;; cur = w.best[v0 + cur]) {
+        w.main_walk[v0 + m] = cur;
+        w.main_pos[v0 + cur] = m;
+        if (cur == g.dest) break;
+        if (cur != g.src) {
+            int32_t x, y;
+            vtx_xy(w, g, cur, x, y);
+            mark_block(w, g.b0 + x, 0);
+            mark_block(w, g.b0 + y, 0);
+        }
+        m++;
+    }
+    Auto A;
+    A.cs = g.src;
+    A.cov = 0;
+    A.rows = 0;
+    int32_t i = 0;
+    while (i < m) {
+        w.m_cs[v0 + i] = A.cs;
+        w.m_cov[v0 + i] = A.cov;
+        w.m_rows[v0 + i] = A.rows;
+        const int32_t v = w.main_walk[v0 + i + 1];
+        const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
+        const int32_t used = auto_step(w, g, s, A, v, nv);
+        if (used == 2) w.m_cs[v0 + i + 1] = -1;
+        i += used;
+    }
+    w.m_cs[v0 + m] = -1;
+    w.m_tot_cov[c] = A.cov;
+    w.m_tot_rows[c] = A.rows;
+    w.task_cov[task_index] = A.cov;
+    w.task_rows[task_index] = A.rows;
+}
+
+// any other walk: follow the main chain by prefix-sum differences, simulate only around its sidetracks
+AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, int64_t *cov_out, int32_t *rows_out) {
+    const int64_t c = t.ctg;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0, e0 = w.eoff[v0], wo = w.walk_off[c];
+    const int32_t *en = w.ent_node + 3 * wo;
+    const int32_t *ep = w.ent_prev + 3 * wo;
+    int32_t ns = 0;
+    for (int32_t cur = w.wlast[wo + t.walk]; cur != -1; cur = ep[cur]) s.side[ns++] = w.hn_eid[en[cur]];
+    int32_t si = ns - 1;  // side[] is last-to-first
+    Auto A;
+    A.cs = g.src;
+    A.cov = 0;
+    A.rows = 0;
+    int32_t a = g.src, i = 0;
+    bool onmain = true;
+    for (;;) {
+        if (onmain) {
+            if (si < 0) {  // the rest is the main chain's suffix
+                A.cov += w.m_tot_cov[c] - w.m_cov[v0 + i];
+                A.rows += w.m_tot_rows[c] - w.m_rows[v0 + i];
+                break;
+            }
+            const int32_t p = w.main_pos[v0 + w.e_src[e0 + s.side[si]]];
+            // main states at positions <= p-2 never look past the tail of the next sidetrack: take them as a block
+            int32_t j = p - 1 > i ? p - 1 : i;
+            if (w.m_cs[v0 + j] == -1) j++;
+            A.cov += w.m_cov[v0 + j] - w.m_cov[v0 + i];
+            A.rows += w.m_rows[v0 + j] - w.m_rows[v0 + i];
+            A.cs = w.m_cs[v0 + j];
+            a = w.main_walk[v0 + j];
+            i = j;
+            onmain = false;
+        }
+        // one simulated step from walk vertex a
+        int32_t si1 = si, si2;
+        int32_t v, nv = -1;
+        if (si1 >= 0 && a == w.e_src[e0 + s.side[si1]]) v = e_dst(w.edge[e0 + s.side[si1--]]);
+        else v = w.best[v0 + a];
+        si2 = si1;
+        if (v != g.dest) {
+            if (si2 >= 0 && v == w.e_src[e0 + s.side[si2]]) nv = e_dst(w.edge[e0 + s.side[si2--]]);
+            else nv = w.best[v0 + v];
+        }
+        const int32_t used = auto_step(w, g, s, A, v, nv);
+        if (v != g.dest && w.main_pos[v0 + v] < 0) {
+            int32_t x, y;
+            vtx_xy(w, g, v, x, y);
+            mark_block(w, g.b0 + x, t.call);
+            mark_block(w, g.b0 + y, t.call);
+        }
+        if (v == g.dest) break;
+        if (used == 2) {
+            if (w.main_pos[v0 + nv] < 0) {
+                int32_t x, y;
+                vtx_xy(w, g, nv, x, y);
+                mark_block(w, g.b0 + x, t.call);
+                mark_block(w, g.b0 + y, t.call);
+            }
+            a = nv;
+            si = si2;
+        } else {
+            a = v;
+            si = si1;
+        }
+        const int32_t mp = w.main_pos[v0 + a];
+        if (mp >= 0 && w.m_cs[v0 + mp] == A.cs) {
+            onmain = true;
+            i = mp;
+        }
+    }
+    *cov_out = A.cov;
+    *rows_out = A.rows;
+}
+
 // worker loops (dynamic scheduling over tasks); slot = worker index
-AA_HDN void f_tasks_a(const Ws &w, int64_t slot) {
+// pass A0: walk 0 of every contig (largest contigs first through ord[])
+AA_HDN void f_tasks_a0(const Ws &w, int64_t slot, const int32_t *ord) {
+    Slot s = slot_view(w, slot);
+    for (;;) {
+#if defined(__CUDA_ARCH__)
+        unsigned long long k = atomicAdd(w.task_next, 1ull);
+#else
+        unsigned long long k = (*w.task_next)++;
+#endif
+        if ((int64_t)k >= w.C) break;
+        const int64_t c = ord[k];
+        if (w.status[c] != 0) continue;
+        main_chain(w, c, s, w.task_off[c]);
+    }
+}
+// pass A1: every other planned walk
+AA_HDN void f_tasks_a1(const Ws &w, int64_t slot) {
     Slot s = slot_view(w, slot);
     for (;;) {
 #if defined(__CUDA_ARCH__)
@@ -1210,7 +1424,9 @@ AA_HDN void f_tasks_a(const Ws &w, int64_t slot) {
         unsigned long long t = (*w.task_next)++;
 #endif
         if ((int64_t)t >= w.n_tasks_total) break;
-        walk_task(w, w.tasks[t], s, -1, 0, &w.task_cov[t], &w.task_rows[t]);
+        const Task tk = w.tasks[t];
+        if (tk.call == 0) continue;
+        walk_task_inc(w, tk, s, &w.task_cov[t], &w.task_rows[t]);
     }
 }
 

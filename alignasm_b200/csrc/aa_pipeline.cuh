@@ -55,7 +55,12 @@ AA_FUNCTOR(FnCuts, f_cuts(w, i))
 AA_FUNCTOR(FnVtxOff, f_vtx_off(w, i))
 AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
-AA_FUNCTOR(FnTasksA, f_tasks_a(w, i))
+AA_FUNCTOR(FnTasksA1, f_tasks_a1(w, i))
+struct FnTasksA0 {
+    Ws w;
+    const int32_t *ord;
+    AA_HD void operator()(int64_t i) const { f_tasks_a0(w, i, ord); }
+};
 struct FnCompact {
     Ws w;
     int64_t ncand;
@@ -524,8 +529,21 @@ struct Pipeline {
             err = "device allocation failed (walk scratch)";
             return AA_ERR_NOMEM;
         }
+        w.main_pos = A<int32_t>(Vtot);
+        w.main_walk = A<int32_t>(Vtot);
+        w.m_cs = A<int32_t>(Vtot);
+        w.m_cov = A<int64_t>(Vtot);
+        w.m_rows = A<int32_t>(Vtot);
+        w.m_tot_cov = A<int64_t>(C);
+        w.m_tot_rows = A<int32_t>(C);
+        if (!w.main_pos || !w.main_walk || !w.m_cs || !w.m_cov || !w.m_rows) {
+            err = "device allocation failed (main chain)";
+            return AA_ERR_NOMEM;
+        }
         bk.zero(w.task_next, 8);
-        bk.workers("walksA", std::min<int64_t>(S, std::max<int64_t>(NT, 1)), FnTasksA{w});
+        bk.workers("walksA0", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});
+        bk.zero(w.task_next, 8);
+        if (NT > C) bk.workers("walksA1", std::min<int64_t>(S, NT), FnTasksA1{w});
         bk.phase_end(PH_WALKS_A);
         AA_BK_CHECK();
 

@@ -98,5 +98,10 @@ aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_r
     return st;
 }
 void aa_result_free(aa_result *res) { aa::result_free_host(res); }
+aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats) {
+    if (!ctx || !stats) return AA_ERR_INVALID;
+    *stats = ctx->pipe.last_stats;
+    return AA_OK;
+}
 
 }  // extern "C"

@@ -146,6 +146,8 @@ aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, a
 void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev);
 
 void aa_result_free(aa_result *res);
+/* statistics (sizes, per-phase CUDA-event times, algorithmic bytes) of the last solve on this context */
+aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats);
 const char *aa_phase_name(int phase); /* NULL past the last phase */
 const char *aa_version(void);
 

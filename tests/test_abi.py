@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library loads, exports every symbol include/alignasm_b200.h declares, matches the ctypes
+layouts, and fails loudly (no CPU fallback) when there is no CUDA device.  Host PAF codec error behaviour."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import parity_util as pu
+
+
+def test_exports_every_declared_symbol(product_lib):
+    from alignasm_b200 import _abi
+    hdr = open(os.path.join(pu.ROOT, "include", "alignasm_b200.h")).read()
+    declared = set(re.findall(r"\b(aa_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
+    for sym in _abi.EXPORTS:
+        assert hasattr(product_lib, sym), sym
+
+
+def test_struct_layouts_match_header(workdir):
+    from alignasm_b200 import _abi
+    src = os.path.join(workdir, "sizes.c")
+    exe = os.path.join(workdir, "sizes")
+    with open(src, "w") as f:
+        f.write('#include <stdio.h>\n#include "alignasm_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                "sizeof(aa_batch),sizeof(aa_opts),sizeof(aa_rows),sizeof(aa_debug),sizeof(aa_stats),sizeof(aa_result));return 0;}\n")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-I", os.path.join(pu.ROOT, "include"), "-o", exe, src], check=True)
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(t) for t in (_abi.aa_batch, _abi.aa_opts, _abi.aa_rows, _abi.aa_debug, _abi.aa_stats, _abi.aa_result)]
+    assert got == want
+
+
+def test_no_device_fails_loudly(product_lib):
+    """Without a GPU the solver must refuse to run; with one this test is vacuous (the gpu tests cover it)."""
+    import torch
+    import alignasm_b200 as aa
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(aa.AlignasmError) as e:
+        aa.Solver(0)
+    assert e.value.status == 2  # AA_ERR_NO_DEVICE
+    assert "CUDA" in str(e.value)
+
+
+def test_product_does_not_link_the_oracle(product_lib):
+    import alignasm_b200 as aa
+    out = subprocess.run(["ldd", aa.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "emul" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", aa.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle_solve" not in syms and "emul_solve" not in syms
+
+
+def _read_err(paf_text, workdir, name):
+    import alignasm_b200 as aa
+    p = os.path.join(workdir, name + ".paf")
+    with open(p, "w") as f:
+        f.write(paf_text)
+    with pytest.raises(aa.AlignasmError) as e:
+        aa.read_paf(p)
+    return e.value
+
+
+ROW = "q\t5000\t100\t1100\t+\tchr1\t248956422\t1000\t2000\t1000\t1000\t60\ttp:A:P\t{cs}\n"
+
+
+def test_reader_errors(product_lib, workdir):
+    """The reference throws std::invalid_argument / returns 1 at these sites (paf_data.cpp:31,46,52,63,66,121;
+    alignasm.cpp:165-168); the C ABI reports AA_ERR_FORMAT with the same message text."""
+    assert "Missing cs:Z tag" in str(_read_err(ROW.replace("\t{cs}", ""), workdir, "nocs"))
+    assert "does not match PAF coordinates" in str(_read_err(ROW.format(cs="cs:Z::999"), workdir, "short"))
+    assert "Invalid :length" in str(_read_err(ROW.format(cs="cs:Z::0:1000"), workdir, "zero"))
+    assert "Invalid substitution" in str(_read_err(ROW.format(cs="cs:Z::999*a"), workdir, "sub"))
+    assert "Empty indel" in str(_read_err(ROW.format(cs="cs:Z::500+:500"), workdir, "indel"))
+    assert "Unsupported operation" in str(_read_err(ROW.format(cs="cs:Z::500~gt12ag:500"), workdir, "intron"))
+    assert _read_err("", workdir, "empty").status == 6
+
+
+def test_reader_buckets_on_name_change(product_lib, workdir):
+    """A query name that re-appears opens a new contig (alignasm.cpp:125-133)."""
+    import alignasm_b200 as aa
+    p = os.path.join(workdir, "names.paf")
+    with open(p, "w") as f:
+        f.write(ROW.format(cs="cs:Z::1000") + ROW.format(cs="cs:Z::1000").replace("q\t", "r\t") + ROW.format(cs="cs:Z::1000"))
+    b = aa.read_paf(p).batch
+    assert b.n_ctg == 3 and b.ctg_off.tolist() == [0, 1, 2, 3]
+    assert b.qry_end.tolist() == [1099] * 3 and b.run_ql.tolist() == [100] * 3 and b.run_qr.tolist() == [1099] * 3
+
+
+def test_minus_strand_runs(product_lib, workdir):
+    """'-' rows swap ref_str/ref_end (alignasm.cpp:155-159) and walk the cs ops backwards (paf_data.cpp:74-86)."""
+    import alignasm_b200 as aa
+    p = os.path.join(workdir, "minus.paf")
+    with open(p, "w") as f:
+        f.write("q\t5000\t100\t402\t-\tchr1\t248956422\t1000\t1303\t300\t304\t60\tcs:Z::100-tt*ag:50+a:150\n")
+    b = aa.read_paf(p).batch
+    assert (int(b.ref_str[0]), int(b.ref_end[0])) == (1302, 1000)
+    # query order: :150 +a :50 *ag -tt :100
+    assert b.run_ql.tolist() == [100, 251, 302] and b.run_qr.tolist() == [249, 300, 401]
+    assert b.run_rl.tolist() == [1302, 1152, 1099]

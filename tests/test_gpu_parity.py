@@ -32,3 +32,90 @@ def test_matches_oracle(name, solver, workdir):
         for k in ("n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task"):
             assert got.stats[k] == want.stats[k], k
         assert got.stats["n_launch"] > 0
+
+
+@pytest.mark.parametrize("nsl", [False, True])
+@pytest.mark.parametrize("case", ["micro", "tiny", "ties", "dense"])
+def test_matches_reference_golden(case, nsl, solver, workdir):
+    """The CUDA path against the golden vectors the reference itself produced (tests/golden/make_golden.py)."""
+    import alignasm_b200 as aa
+    from golden_util import check_against_golden
+    pf = aa.read_paf(os.path.join(pu.GOLDEN, case + ".paf"))
+    res = check_against_golden(case, nsl, solver.solve, pf, workdir)
+    assert res.stats["n_launch"] > 0
+
+
+def test_resident_batch_and_repeatability(solver, workdir):
+    """aa_upload + aa_solve_device (batch resident in HBM) gives the same rows as aa_solve, run after run
+    (the pooled workspace is reused between solves)."""
+    import alignasm_b200 as aa
+    args, _ = SMALL["c1_small"]
+    pf = aa.read_paf(pu.synth(os.path.join(workdir, "resident.paf"), *args))
+    first = solver.solve(pf.batch, want_all=True)
+    dev = solver.upload(pf.batch)
+    for _ in range(3):
+        again = solver.solve_device(dev, want_all=True)
+        assert pu.result_rows_equal(first, again) is None
+    assert solver.solve_device(dev, fetch=False) is None
+    assert solver.stats()["n_blk"] == pf.batch.n_blk
+    dev.free()
+
+
+def test_full_size_properties(solver, workdir):
+    """BASELINE config 2 at full size (~500k blocks; the oracle needs minutes there): size-independent
+    properties of the result, plus exact agreement with the oracle on a sample of its contigs."""
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    pf = aa.read_paf(pu.synth(os.path.join(workdir, "c2_full.paf"), "--preset", "c2"))
+    b = pf.batch
+    res = solver.solve(b)
+    n = np.diff(b.ctg_off)
+    # every contig has a primary chain; rows reference blocks of their own contig
+    assert np.all(np.diff(res.out_off) >= 1)
+    for which, off in (("out", res.out_off), ("alt", res.alt_off)):
+        r = getattr(res, which)
+        ctg = np.repeat(np.arange(b.n_ctg), np.diff(off))
+        assert np.all(r["ctg_index"] >= 0) and np.all(r["ctg_index"] < n[ctg])
+        g = b.ctg_off[ctg] + r["ctg_index"]
+        # trimmed intervals stay inside the block they came from and are non-empty
+        assert np.all(r["qry_str"] >= b.qry_str[g]) and np.all(r["qry_end"] <= b.qry_end[g])
+        assert np.all(r["qry_str"] <= r["qry_end"])
+        lo, hi = np.minimum(b.ref_str[g], b.ref_end[g]), np.maximum(b.ref_str[g], b.ref_end[g])
+        assert np.all(np.minimum(r["ref_str"], r["ref_end"]) >= lo) and np.all(np.maximum(r["ref_str"], r["ref_end"]) <= hi)
+        # a chain is strictly increasing and non-overlapping on the query
+        same = ctg[1:] == ctg[:-1]
+        assert np.all(r["qry_str"][1:][same] > r["qry_end"][:-1][same])
+    # the primary chain never carries the secondary flag (its blocks are marked by its own walk or an earlier one)
+    # ctg_sorted_index is a permutation per contig that sorts (qry_str, qry_end)
+    for c in np.random.default_rng(0).choice(b.n_ctg, 40, replace=False):
+        a, e = int(b.ctg_off[c]), int(b.ctg_off[c + 1])
+        si = res.sorted_index[a:e]
+        assert np.array_equal(np.sort(si), np.arange(e - a))
+        inv = np.empty(e - a, dtype=np.int64)
+        inv[si] = np.arange(e - a)
+        keys = list(zip(b.qry_str[a:e][inv].tolist(), b.qry_end[a:e][inv].tolist()))
+        assert keys == sorted(keys)
+    # idempotence: a second solve of the same batch gives identical rows
+    assert pu.result_rows_equal(res, solver.solve(b), check_all=False) is None
+    # exact agreement with the oracle on contigs it can do in seconds
+    pick = np.nonzero(n <= 600)[0][:60]
+    sub = b.select(pick)
+    got, want = solver.solve(sub, want_all=True), oracle_py.oracle_solve(sub, threads=8, want_all=True)
+    assert pu.result_rows_equal(got, want) is None
+    full_rows = [res.rows_of("out", int(c)) for c in pick]
+    assert full_rows == [got.rows_of("out", k) for k in range(len(pick))]
+
+
+def test_cli_writes_reference_bytes(product_lib, workdir):
+    """`alignasm <input.paf>` (the drop-in surface) reproduces the reference's three files byte for byte."""
+    import shutil
+    import subprocess
+    paf = os.path.join(workdir, "cli_ties.paf")
+    shutil.copy(os.path.join(pu.GOLDEN, "ties.paf"), paf)
+    exe = os.path.join(pu.ROOT, "alignasm_b200", "alignasm")
+    out = subprocess.run([exe, paf], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "File read complete" in out.stdout and "Write output PAF file" in out.stdout
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(paf[:-4] + "." + ext, os.path.join(pu.GOLDEN, "ties." + ext)), ext
+    assert subprocess.run([exe, os.path.join(workdir, "nope.txt")], capture_output=True).returncode == 1

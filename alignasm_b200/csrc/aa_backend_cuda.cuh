@@ -24,13 +24,14 @@ namespace aa {
 template <class F>
 __global__ void __launch_bounds__(256) k_items(int64_t n, F f) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) f(i);
+    if (i < n) f(i, nullptr);
 }
 // one warp per item (contig / worker slot)
 template <class F>
 __global__ void __launch_bounds__(32) k_warp_items(int64_t n, F f) {
+    extern __shared__ __align__(16) unsigned char aa_smem[];
     int64_t i = blockIdx.x;
-    if (threadIdx.x == 0 && i < n) f(i);
+    if (i < n) f(i, (void *)aa_smem);  // all 32 lanes enter; sequential phases continue on lane 0 only
 }
 
 struct CastI32 {
@@ -232,15 +233,15 @@ struct CudaBackend {
         n_launch++;
     }
     template <class F>
-    void for_each_contig(const char *, int64_t n, F f) {
+    void for_each_contig(const char *, int64_t n, F f, size_t smem = 0) {
         if (n <= 0 || failed) return;
-        k_warp_items<F><<<(unsigned)n, 32, 0, stream>>>(n, f);
+        k_warp_items<F><<<(unsigned)n, 32, smem, stream>>>(n, f);
         n_launch++;
     }
     template <class F>
-    void workers(const char *, int64_t n, F f) {
+    void workers(const char *, int64_t n, F f, size_t smem = 0) {
         if (n <= 0 || failed) return;
-        k_warp_items<F><<<(unsigned)n, 32, 0, stream>>>(n, f);
+        k_warp_items<F><<<(unsigned)n, 32, smem, stream>>>(n, f);
         n_launch++;
     }
     void scan_i32(const int32_t *in, int64_t *out, int64_t n) {

@@ -30,6 +30,17 @@
 
 namespace aa {
 
+// ---- warp helpers: per-contig phases run one warp per contig.  On the host (tests/emul) a "warp" is one lane.
+#if defined(__CUDA_ARCH__)
+#define AA_LANES 32
+AA_HD int aa_lane() { return (int)(threadIdx.x & 31); }
+AA_HD void aa_syncwarp() { __syncwarp(); }
+#else
+#define AA_LANES 1
+inline int aa_lane() { return 0; }
+inline void aa_syncwarp() {}
+#endif
+
 // ---- constants (paf_data.hpp:21-29, paf_data.cpp:729) ------------------------------------------
 constexpr int64_t SV_BASELINE = 1000000;
 constexpr int64_t SV_TRANS_PENALTY = 2000;
@@ -79,11 +90,41 @@ AA_HD int32_t e_nz(const Edge &e) { return (int32_t)((e.dst_fl >> 29) & 1u); }
 AA_HD int32_t e_tot(const Edge &e) { return (int32_t)((e.dst_fl >> 30) & 1u); }
 
 // persistent leftist-heap node: 32 B, the (u,v) payload lives in hn_eid[]
-struct HNode {
+struct __attribute__((aligned(16))) HNode {
     int64_t sum;
     int32_t anom, nz, tot;
     int32_t left, right;
-    int32_t rank;
+    int16_t rank;   // node_rank of leftist_heap.hpp
+    int16_t lrank;  // rank of the left child (saves a dependent load when the node is copied)
+};
+struct __attribute__((aligned(16))) V16 {
+    int64_t a, b;
+};
+AA_HD HNode hn_load(const HNode *p) {  // two 128-bit loads
+    union {
+        HNode n;
+        V16 v[2];
+    } u;
+    const V16 *q = reinterpret_cast<const V16 *>(p);
+    u.v[0] = q[0];
+    u.v[1] = q[1];
+    return u.n;
+}
+AA_HD void hn_store(HNode *p, const HNode &n) {  // two 128-bit stores
+    union {
+        HNode n;
+        V16 v[2];
+    } u;
+    u.n = n;
+    V16 *q = reinterpret_cast<V16 *>(p);
+    q[0] = u.v[0];
+    q[1] = u.v[1];
+}
+// sidetrack key of an edge, precomputed by a parallel pass: c = w + d[v] - d[u] (k_shortest_walks.hpp:206)
+struct __attribute__((aligned(8))) SKey {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t use;  // 0: not inserted (head unreachable, or the tree edge u -> best[u])
 };
 // priority-queue entry of the enumeration: 32 B
 struct PQEnt {
@@ -159,6 +200,9 @@ struct Ws {
     int64_t Hcap;
     unsigned long long *heap_top;  // arena bump pointer
     int32_t *hroot;      // [Vtot]
+    SKey *skey;          // [E] sidetrack keys (parallel pre-pass)
+    int32_t *child;      // [E] tree children of v, compacted at rev_off[v] (ascending source)
+    int32_t *nchild;     // [Vtot]
     int64_t *heap_used;  // [C]
     // enumeration
     int64_t *walk_off;   // [C+1] = c*K
@@ -193,6 +237,16 @@ struct Ws {
     int32_t *m_rows;     // [Vtot] rows closed before position i
     int64_t *m_tot_cov;  // [C]
     int32_t *m_tot_rows; // [C]
+    int32_t *m_len;      // [C] number of edges of walk 0 (dest sits at position m_len)
+    uint8_t *m_done;     // [Vtot] 1: the resolve pass computed (and emitted) this state's step itself
+    // speculative step results, assuming cs == walk vertex (true for >99% of the states)
+    int32_t *sp_cs;      // [Vtot] cs after the step
+    int32_t *sp_rows;    // [Vtot] rows closed by the step
+    int64_t *sp_cov;     // [Vtot] coverage closed by the step
+    uint8_t *sp_used;    // [Vtot] walk edges consumed (1/2), 0 = not speculated (DP range too large)
+    // rows of the upgraded walk 0, index = row number (emitted in parallel by f_main_rows)
+    int32_t *mr_blk;     // [Vtot] contig-local sorted block
+    int64_t *mr_qs, *mr_qe, *mr_rs, *mr_re;
     int64_t n_tasks_total;
     // selection + output
     int32_t *win_out, *win_alt;  // [C] compacted task index (or -1)
@@ -261,6 +315,7 @@ AA_HDN void f_gather(const Ws &w, int64_t b) {
 
 // phase: parts (paf_data.cpp:249-261), one contig per call
 AA_HDN void f_parts(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     int64_t b0 = w.ctg_off[c];
     int32_t n = (int32_t)(w.ctg_off[c + 1] - b0);
     w.status[c] = (n == 1) ? 1 : 0;
@@ -595,6 +650,7 @@ AA_HDN void f_rev_off(const Ws &w, int64_t gv, int64_t E) {  // gv in [0, Vtot]
 // ascending id, first strict improvement wins (k_shortest_walks.hpp:132-175); plus the min-anom DP
 // that replaces Dial's BFS (only anom_dis[dest] is consumed, paf_data.cpp:713,1615).
 AA_HDN void f_relax(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     if (w.status[c] != 0) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
@@ -649,6 +705,7 @@ AA_HDN void f_relax(const Ws &w, int64_t c) {
 
 // phase: forward Kahn order (paf_data.cpp:742-746)
 AA_HDN void f_topo(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     if (w.status[c] != 0) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
@@ -703,14 +760,59 @@ AA_HD D4 hkey(const HNode &h) {
     k.aux = 0;
     return k;
 }
-// insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on overflow).
-// spine[] is scratch for the right-spine walk; its depth is bounded by log2(size)+1.
-AA_HDN int32_t heap_insert(const Ws &w, HeapAlloc &ha, int32_t a, const D4 &k, int32_t eid) {
-    int32_t spine[64];
-    int32_t depth = 0;
-    while (a >= 0 && less4(hkey(w.hn[a]), k)) {  // not (a->key < k) stops the descent; ties go on top
-        spine[depth++] = a;
-        a = w.hn[a].right;
+// parallel pre-pass over vertices: sidetrack keys of u's out-edges and u's tree children
+// (children of u = sources x of u's in-edges with best[x] == u, ascending x = reverse-list order)
+AA_HDN void f_heap_prep(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0 && w.status[c] != 3) return;
+    const int64_t v0 = w.vtx_off[c];
+    const D4 du = w.d[gv];
+    const int32_t bu = w.best[gv];
+    const int64_t ea = w.eoff[gv], eb = w.eoff[gv + 1];
+    for (int64_t k = ea; k < eb; k++) {
+        const Edge e = w.edge[k];
+        const int32_t v = e_dst(e);
+        const D4 dv = w.d[v0 + v];
+        SKey sk;
+        sk.sum = e.qry + e.ref + dv.sum - du.sum;
+        sk.anom = e_anom(e) + dv.anom - du.anom;
+        sk.nz = e_nz(e) + dv.nz - du.nz;
+        sk.tot = e_tot(e) + dv.tot - du.tot;
+        // unreachable heads are skipped; the tree edge has c == IDENTITY and is skipped once (it is unique)
+        sk.use = (du.aux && dv.aux && v != bu) ? 1 : 0;
+        w.skey[k] = sk;
+    }
+    const int32_t u = (int32_t)(gv - v0);
+    const int64_t ra = w.rev_off[gv], rb = w.rev_off[gv + 1];
+    int32_t n = 0;
+    for (int64_t k = ra; k < rb; k++) {
+        const int32_t x = w.e_src[w.rev_eid[k]];
+        if (w.best[v0 + x] == u) w.child[ra + n++] = x;
+    }
+    w.nchild[gv] = n;
+}
+
+// insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on arena overflow).
+// leftist_heap.hpp:29-40 made iterative: walk down the right spine while a->key < k (ties stop: the new key
+// goes on top), then copy the spine bottom-up.  Nodes are immutable, 32 B, moved with 128-bit accesses.
+AA_HDN int32_t heap_insert(HNode *__restrict__ hn, int32_t *__restrict__ hn_eid, const Ws &w, HeapAlloc &ha, int32_t a,
+                           const SKey &k, int32_t eid) {
+    HNode spine[48];
+    int32_t spine_id[48];
+    int32_t depth = 0, arank = 0;
+    while (a >= 0) {
+        const HNode an = hn_load(hn + a);
+        arank = an.rank;
+        // a->key < k ? (paf_data.hpp:142-159, CALC_SUM_MODE)
+        bool lt;
+        if (an.sum != k.sum) lt = an.sum < k.sum;
+        else if (an.anom != k.anom) lt = an.anom < k.anom;
+        else lt = (int64_t)an.nz * den(k.tot) > (int64_t)k.nz * den(an.tot);
+        if (!lt) break;
+        spine[depth] = an;
+        spine_id[depth] = a;
+        depth++;
+        a = an.right;
     }
     int32_t r = heap_new(w, ha);
     if (r < 0) return -1;
@@ -722,75 +824,77 @@ AA_HDN int32_t heap_insert(const Ws &w, HeapAlloc &ha, int32_t a, const D4 &k, i
     nn.left = a;
     nn.right = -1;
     nn.rank = 1;
-    w.hn[r] = nn;
-    w.hn_eid[r] = eid;
+    nn.lrank = (int16_t)(a >= 0 ? arank : 0);
+    hn_store(hn + r, nn);
+    hn_eid[r] = eid;
+    int32_t rrank = 1;
     while (depth > 0) {
-        int32_t oid = spine[--depth];
-        HNode o = w.hn[oid];
-        int32_t l = o.left, rr = r;
-        if (l < 0 || w.hn[l].rank < w.hn[rr].rank) {
+        --depth;
+        HNode o = spine[depth];
+        int32_t l = o.left, lr = o.lrank, rr = r, rk = rrank;
+        if (l < 0 || lr < rk) {  // swap so that the left rank is not smaller
             int32_t t = l;
             l = rr;
             rr = t;
+            t = lr;
+            lr = rk;
+            rk = t;
         }
-        int32_t id = heap_new(w, ha);
+        const int32_t id = heap_new(w, ha);
         if (id < 0) return -1;
         o.left = l;
         o.right = rr;
-        o.rank = rr >= 0 ? w.hn[rr].rank + 1 : 0;
-        w.hn[id] = o;
-        w.hn_eid[id] = w.hn_eid[oid];
+        o.lrank = (int16_t)lr;
+        o.rank = (int16_t)(rr >= 0 ? rk + 1 : 0);
+        hn_store(hn + id, o);
+        hn_eid[id] = hn_eid[spine_id[depth]];
         r = id;
+        rrank = o.rank;
     }
     return r;
 }
 
-// phase: sidetrack heaps, BFS over the shortest-path tree from dest (k_shortest_walks.hpp:191-215).
-// tree children of u = sources x of u's in-edges with best[x] == u, ascending x (the reverse list order).
+// phase: sidetrack heaps, BFS over the shortest-path tree from dest (k_shortest_walks.hpp:191-215)
 AA_HDN void f_heaps(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     if (w.status[c] != 0 && w.status[c] != 3) return;
     w.status[c] = 0;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     const int64_t e0 = w.eoff[v0];
+    HNode *__restrict__ hn = w.hn;
+    int32_t *__restrict__ hn_eid = w.hn_eid;
+    const SKey *__restrict__ skey = w.skey;
+    const int64_t *__restrict__ eoff = w.eoff + v0;
+    const int64_t *__restrict__ rev_off = w.rev_off + v0;
+    const int32_t *__restrict__ nchild = w.nchild + v0;
+    int32_t *__restrict__ hroot = w.hroot + v0;
     HeapAlloc ha;
     ha.cur = ha.end = 0;
     ha.used = 0;
     ha.overflow = false;
     int32_t *q = w.queue + v0;
-    for (int32_t v = 0; v < g.V; v++) w.hroot[v0 + v] = -1;
+    for (int32_t v = 0; v < g.V; v++) hroot[v] = -1;
     int32_t tail = 0;
     q[tail++] = g.dest;
     for (int32_t head = 0; head < tail && !ha.overflow; head++) {
-        int32_t u = q[head];
-        int32_t hu = w.hroot[v0 + u];
-        D4 du = w.d[v0 + u];
-        int32_t bu = w.best[v0 + u];
-        int64_t ea = w.eoff[v0 + u], eb = w.eoff[v0 + u + 1];
+        const int32_t u = q[head];
+        int32_t hu = hroot[u];
+        const int64_t ea = eoff[u], eb = eoff[u + 1];
         for (int64_t k = ea; k < eb; k++) {
-            Edge e = w.edge[k];
-            int32_t v = e_dst(e);
-            D4 dv = w.d[v0 + v];
-            if (!dv.aux) continue;
-            if (v == bu) continue;  // the tree edge: c == IDENTITY, skipped once; (u,v) is unique in the graph
-            D4 key;
-            key.sum = e.qry + e.ref + dv.sum - du.sum;
-            key.anom = e_anom(e) + dv.anom - du.anom;
-            key.nz = e_nz(e) + dv.nz - du.nz;
-            key.tot = e_tot(e) + dv.tot - du.tot;
-            key.aux = 0;
-            hu = heap_insert(w, ha, hu, key, (int32_t)(k - e0));
+            const SKey sk = skey[k];
+            if (!sk.use) continue;
+            hu = heap_insert(hn, hn_eid, w, ha, hu, sk, (int32_t)(k - e0));
             if (hu < 0) break;
         }
         if (ha.overflow) break;
-        w.hroot[v0 + u] = hu;
-        int64_t ra = w.rev_off[v0 + u], rb = w.rev_off[v0 + u + 1];
-        for (int64_t k = ra; k < rb; k++) {
-            int32_t x = w.e_src[w.rev_eid[k]];
-            if (w.best[v0 + x] == u) {
-                w.hroot[v0 + x] = hu;
-                q[tail++] = x;
-            }
+        hroot[u] = hu;
+        const int32_t *ch = w.child + rev_off[u];
+        const int32_t nc = nchild[u];
+        for (int32_t k = 0; k < nc; k++) {
+            const int32_t x = ch[k];
+            hroot[x] = hu;
+            q[tail++] = x;
         }
     }
     w.heap_used[c] = ha.used;
@@ -843,6 +947,7 @@ AA_HD PQEnt pq_pop(PQEnt *h, int32_t &n) {
 
 // phase: enumerate the K shortest walks (k_shortest_walks.hpp:217-251)
 AA_HDN void f_enum(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     if (w.status[c] != 0) {
         w.n_walk[c] = 0;
         return;
@@ -945,6 +1050,7 @@ AA_HDN void f_enum(const Ws &w, int64_t c) {
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.
 AA_HD bool same_sa(const D4 &a, const D4 &b) { return a.sum == b.sum && a.anom == b.anom; }
 AA_HDN void f_plan(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     w.n_task[c] = 0;
     w.n_tie[c] = 0;
     w.last_group[c] = 0;
@@ -988,29 +1094,52 @@ AA_HDN void f_plan(const Ws &w, int64_t c) {
     w.last_group[c] = group;
 }
 AA_HDN void f_task_compact(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     int64_t o = w.task_off[c];
     const Task *t = w.task + 2 * w.walk_off[c];
     for (int32_t k = 0; k < w.n_task[c]; k++) w.tasks[o + k] = t[k];
 }
 
 // ---- walk task: recover + mark + upgrade + rows ---------------------------------------------------
-struct Slot {
-    int32_t *walk, *up, *side;
+struct DPBuf {  // scratch of one gap-filling DP
     D5 *dp;
     int32_t *pre;
     uint8_t *seen;
+    int32_t *up;   // vertices appended by the last sub_path call
+    int32_t cap;   // largest topological span the buffers hold
+};
+struct Slot {
+    int32_t *walk, *side;
+    DPBuf buf;
 };
 AA_HD Slot slot_view(const Ws &w, int64_t s) {
     Slot x;
     int64_t o = s * w.slot_stride;
     x.walk = w.sc_walk + o;
-    x.up = w.sc_up + o;
     x.side = w.sc_side + o;
-    x.dp = w.sc_dp + o;
-    x.pre = w.sc_pre + o;
-    x.seen = w.sc_seen + o;
+    x.buf.up = w.sc_up + o;
+    x.buf.dp = w.sc_dp + o;
+    x.buf.pre = w.sc_pre + o;
+    x.buf.seen = w.sc_seen + o;
+    x.buf.cap = (int32_t)(w.slot_stride < 0x7fffffff ? w.slot_stride : 0x7fffffff);
     return x;
 }
+constexpr int32_t LOCAL_SPAN = 32;
+struct LocalDP {  // per-thread scratch of the parallel (speculative / row emitting) passes
+    D5 dp[LOCAL_SPAN];
+    int32_t pre[LOCAL_SPAN];
+    int32_t up[LOCAL_SPAN];
+    uint8_t seen[LOCAL_SPAN];
+    AA_HD DPBuf buf() {
+        DPBuf b;
+        b.dp = dp;
+        b.pre = pre;
+        b.seen = seen;
+        b.up = up;
+        b.cap = LOCAL_SPAN;
+        return b;
+    }
+};
 AA_HD void vtx_xy(const Ws &w, const Ctg &g, int32_t v, int32_t &x, int32_t &y) {  // index_to_vtx
     if (v < g.n) {
         x = y = v;
@@ -1046,14 +1175,16 @@ AA_HDN int32_t recover_walk(const Ws &w, const Ctg &g, int64_t c, int32_t k, con
 }
 
 // internal_shortest_path_recover (paf_data.cpp:750-792): QRY_SCORE-mode DP over the forward topological
-// range [order[s], order[t]).  Appends the vertices after s (optionally without t itself) to up[];
-// returns false when s == t (the reference's empty path).
-AA_HDN bool sub_path(const Ws &w, const Ctg &g, const Slot &s, int32_t vs, int32_t vt, bool wl_flag, int32_t wl,
-                     bool drop_last, int32_t &up_len) {
-    if (vs == vt) return false;
+// range [order[s], order[t]).  Appends the vertices after s (optionally without t itself) to buf.up[] from
+// up_len on.  Returns 0 when s == t (the reference's empty path), 1 on success, -1 when the range does not
+// fit the scratch (only possible with the small per-thread buffers).
+AA_HDN int sub_path(const Ws &w, const Ctg &g, const DPBuf &s, int32_t vs, int32_t vt, bool wl_flag, int32_t wl,
+                    bool drop_last, int32_t &up_len) {
+    if (vs == vt) return 0;
     const int64_t v0 = g.v0;
     const int32_t os = w.order[v0 + vs], ot = w.order[v0 + vt];
     const int32_t span = ot - os + 1;
+    if (span > s.cap) return -1;
     for (int32_t k = 0; k < span; k++) s.seen[k] = 0;
     D5 z;
     z.qry = z.ref = 0;
@@ -1102,40 +1233,7 @@ AA_HDN bool sub_path(const Ws &w, const Ctg &g, const Slot &s, int32_t vs, int32
         pos--;
     }
     up_len += keep;
-    return true;
-}
-
-// upgrade_edge_path_with_alt_path (paf_data.cpp:795-921) on vertex sequences; returns the new length
-AA_HDN int32_t upgrade_walk(const Ws &w, const Ctg &g, const Slot &s, int32_t len) {
-    int32_t ul = 0;
-    s.up[ul++] = g.src;
-    for (int32_t e = 0; e + 1 < len; e++) {
-        const int32_t u = s.walk[e], v = s.walk[e + 1];
-        if (v == g.dest) {  // paf_data.cpp:845-858
-            sub_path(w, g, s, s.up[ul - 1], v, false, -1, false, ul);
-            continue;
-        }
-        int32_t x, y;
-        vtx_xy(w, g, v, x, y);
-        if (u != g.src && x != y) {  // paf_data.cpp:866-873
-            s.up[ul++] = v;
-            continue;
-        }
-        const int32_t cs = s.up[ul - 1];
-        const int32_t nv = s.walk[e + 2];
-        int32_t nx = -1, ny = -1;
-        if (nv != g.dest) vtx_xy(w, g, nv, nx, ny);
-        if (nv == g.dest || nx == ny) {  // paf_data.cpp:812-833, 879-899
-            if (!sub_path(w, g, s, cs, nv, true, y, true, ul)) s.up[ul++] = v;
-        } else {  // nv = (y, ny): paf_data.cpp:834-843, 900-909
-            if (!sub_path(w, g, s, cs, nv, false, -1, false, ul)) {
-                s.up[ul++] = v;
-                s.up[ul++] = nv;
-            }
-            e++;
-        }
-    }
-    return ul;
+    return 1;
 }
 
 AA_HD void mark_block(const Ws &w, int64_t gb, int32_t call) {
@@ -1146,148 +1244,120 @@ AA_HD void mark_block(const Ws &w, int64_t gb, int32_t call) {
 #endif
 }
 
-// One edge_path_to_paf_path call (paf_data.cpp:1489-1568).  Pass A (dst < 0): mark blocks, coverage and
-// row count.  Pass B (dst = 0 out, 1 alt, 2 all): write the rows at row offset `at`.
-AA_HDN void walk_task(const Ws &w, const Task &t, const Slot &s, int dst, int64_t at, int64_t *cov_out, int32_t *rows_out) {
-    const int64_t c = t.ctg;
-    Ctg g = ctg_view(w, c);
-    int32_t len = recover_walk(w, g, c, t.walk, s);
-    if (dst < 0) {
-        for (int32_t k = 1; k + 1 < len; k++) {
-            int32_t x, y;
-            vtx_xy(w, g, s.walk[k], x, y);
-            mark_block(w, g.b0 + x, t.call);
-            mark_block(w, g.b0 + y, t.call);
-        }
-    }
-    int32_t ul = upgrade_walk(w, g, s, len);
-    // rows: one per inner vertex; arriving at a pair vertex trims both neighbours (paf_data.cpp:1502-1557)
-    int64_t cov = 0;
-    int32_t nrows = 0;
-    int64_t pqs = 0, pqe = 0, prs = 0, pre = 0;
-    int64_t pb = -1;
-    for (int32_t k = 1; k + 1 <= ul; k++) {
-        int64_t nqs = 0, nqe = 0, nrs = 0, nre = 0, nb = -1;
-        if (k + 1 < ul) {
-            const int32_t v = s.up[k];
-            int32_t x, y;
-            vtx_xy(w, g, v, x, y);
-            nb = g.b0 + y;
-            nqs = w.qs[nb];
-            nqe = w.qe[nb];
-            nrs = w.rs[nb];
-            nre = w.re[nb];
-            if (x != y) {
-                const CandRec &p = w.pair[g.p0 + (v - g.n)];
-                pqe = p.pe_q;
-                pre = p.pe_r;
-                nqs = p.st_q;
-                nrs = p.st_r;
-            }
-        }
-        if (pb >= 0) {  // the previous row is final now
-            int64_t dr = pre - prs;
-            cov += (pqe - pqs) + (dr < 0 ? -dr : dr);
-            if (dst >= 0) {
-                int64_t o = at + nrows;
-                w.r_idx[dst][o] = w.orig[pb];
-                w.r_qs[dst][o] = pqs;
-                w.r_qe[dst][o] = pqe;
-                w.r_rs[dst][o] = prs;
-                w.r_re[dst][o] = pre;
-                w.r_alt[dst][o] = w.first_call[pb] > t.call ? 1 : 0;  // paf_data.cpp:1560-1566
-            }
-            nrows++;
-        }
-        pb = nb;
-        pqs = nqs;
-        pqe = nqe;
-        prs = nrs;
-        pre = nre;
-    }
-    if (cov_out) *cov_out = cov;
-    if (rows_out) *rows_out = nrows;
-}
-
-
 // ---- the upgrade automaton, one step at a time -----------------------------------------------------------
+// upgrade_edge_path_with_alt_path (paf_data.cpp:795-921) + the row construction of edge_path_to_paf_path
+// (paf_data.cpp:1502-1557) as an automaton over the walk's vertex sequence.
 // State = (position on the walk, cs = last vertex appended to the upgraded path).  A step looks at the next
-// two walk vertices (v, nv), appends vertices and consumes one or two walk edges (paf_data.cpp:801-911).
-// Coverage is accounted when a row is closed, i.e. when the vertex after it is appended, because a pair
-// vertex trims the end of the row before it (paf_data.cpp:1523-1531, 1546-1553).
+// two walk vertices (v, nv), appends vertices and consumes one or two walk edges.  A row is closed, i.e.
+// final, when the vertex after it is appended, because arriving at a pair vertex trims the end of the row
+// before it (paf_data.cpp:1523-1531, 1546-1553).
 struct Auto {
     int32_t cs;
     int64_t cov;
     int32_t rows;
 };
-AA_HD void auto_append(const Ws &w, const Ctg &g, Auto &A, int32_t b) {
+struct Emit {      // where closed rows go
+    int32_t mode;  // 0 nowhere, 1 main-chain rows (mr_*), 2 result rows (r_*[dst])
+    int32_t dst;
+    int64_t base;  // row index = base + number of rows closed before
+    int32_t call;  // for the tp flag (paf_data.cpp:1560-1566)
+};
+AA_HD void auto_append(const Ws &w, const Ctg &g, Auto &A, int32_t b, const Emit &em) {
     if (A.cs != g.src) {
-        int64_t qs_, rs_, qe_, re_;
+        int64_t qs_, rs_, qe_, re_, gb;
         if (A.cs < g.n) {
-            const int64_t gb = g.b0 + A.cs;
+            gb = g.b0 + A.cs;
             qs_ = w.qs[gb];
             rs_ = w.rs[gb];
-            qe_ = w.qe[gb];
-            re_ = w.re[gb];
         } else {
             const CandRec &p = w.pair[g.p0 + (A.cs - g.n)];
-            const int64_t gb = g.b0 + p.j;
+            gb = g.b0 + p.j;
             qs_ = p.st_q;
             rs_ = p.st_r;
-            qe_ = w.qe[gb];
-            re_ = w.re[gb];
         }
         if (b >= g.n && b < g.src) {
             const CandRec &pb = w.pair[g.p0 + (b - g.n)];
             qe_ = pb.pe_q;
             re_ = pb.pe_r;
+        } else {
+            qe_ = w.qe[gb];
+            re_ = w.re[gb];
         }
         int64_t dr = re_ - rs_;
         A.cov += (qe_ - qs_) + (dr < 0 ? -dr : dr);
+        if (em.mode == 1) {
+            const int64_t o = em.base + A.rows;
+            w.mr_blk[o] = (int32_t)(gb - g.b0);
+            w.mr_qs[o] = qs_;
+            w.mr_qe[o] = qe_;
+            w.mr_rs[o] = rs_;
+            w.mr_re[o] = re_;
+        } else if (em.mode == 2) {
+            const int64_t o = em.base + A.rows;
+            w.r_idx[em.dst][o] = w.orig[gb];
+            w.r_qs[em.dst][o] = qs_;
+            w.r_qe[em.dst][o] = qe_;
+            w.r_rs[em.dst][o] = rs_;
+            w.r_re[em.dst][o] = re_;
+            w.r_alt[em.dst][o] = w.first_call[gb] > em.call ? 1 : 0;
+        }
         A.rows++;
     }
     A.cs = b;
 }
-// one automaton step; returns the number of walk edges consumed (1 or 2)
-AA_HDN int32_t auto_step(const Ws &w, const Ctg &g, const Slot &s, Auto &A, int32_t v, int32_t nv) {
+// one automaton step; returns the number of walk edges consumed (1 or 2), or -1 when the DP range does not
+// fit the scratch (nothing has been appended then)
+AA_HDN int32_t auto_step(const Ws &w, const Ctg &g, const DPBuf &s, Auto &A, int32_t v, int32_t nv, const Emit &em) {
     int32_t ul = 0;
     if (v == g.dest) {  // paf_data.cpp:845-858
-        sub_path(w, g, s, A.cs, v, false, -1, false, ul);
-        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+        if (sub_path(w, g, s, A.cs, v, false, -1, false, ul) < 0) return -1;
+        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k], em);
         return 1;
     }
     int32_t x, y;
     vtx_xy(w, g, v, x, y);
     if (x != y) {  // paf_data.cpp:866-873 (after src the first vertex is always a single)
-        auto_append(w, g, A, v);
+        auto_append(w, g, A, v, em);
         return 1;
     }
     int32_t nx = -1, ny = -1;
     if (nv != g.dest) vtx_xy(w, g, nv, nx, ny);
     if (nv == g.dest || nx == ny) {  // paf_data.cpp:812-833, 879-899
-        if (!sub_path(w, g, s, A.cs, nv, true, y, true, ul)) {
-            auto_append(w, g, A, v);
+        const int r = sub_path(w, g, s, A.cs, nv, true, y, true, ul);
+        if (r < 0) return -1;
+        if (r == 0) {
+            auto_append(w, g, A, v, em);
         } else {
-            for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+            for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k], em);
         }
         return 1;
     }
     // nv = (y, ny): paf_data.cpp:834-843, 900-909
-    if (!sub_path(w, g, s, A.cs, nv, false, -1, false, ul)) {
-        auto_append(w, g, A, v);
-        auto_append(w, g, A, nv);
+    const int r = sub_path(w, g, s, A.cs, nv, false, -1, false, ul);
+    if (r < 0) return -1;
+    if (r == 0) {
+        auto_append(w, g, A, v, em);
+        auto_append(w, g, A, nv, em);
     } else {
-        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k]);
+        for (int32_t k = 0; k < ul; k++) auto_append(w, g, A, s.up[k], em);
     }
     return 2;
 }
 
-// walk 0 of a contig (no sidetracks: the tree walk from src): mark its blocks with call 0, run the automaton
-// over it and record the main chain.
-AA_HDN void main_chain(const Ws &w, int64_t c, const Slot &s, int64_t task_index) {
+// ---- main chain = the automaton's states along walk 0 (no sidetracks: the tree walk from src) -----------------
+// S0 (per contig): trace walk 0, mark its blocks with call 0
+AA_HDN void f_main_trace(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
+    w.m_len[c] = 0;
+    if (w.status[c] != 0) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
-    for (int32_t v = 0; v < g.V; v++) w.main_pos[v0 + v] = -1;
+    for (int32_t v = 0; v < g.V; v++) {
+        w.main_pos[v0 + v] = -1;
+        w.m_cs[v0 + v] = -1;
+        w.m_done[v0 + v] = 0;
+        w.sp_used[v0 + v] = 0;
+    }
     int32_t m = 0;
     for (int32_t cur = g.src;; cur = w.best[v0 + cur]) {
         w.main_walk[v0 + m] = cur;
@@ -1301,37 +1371,127 @@ AA_HDN void main_chain(const Ws &w, int64_t c, const Slot &s, int64_t task_index
         }
         m++;
     }
+    w.m_len[c] = m;
+}
+// S1 (per walk-0 position, parallel): the step at position i under the assumption cs == walk vertex
+AA_HDN void f_main_spec(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0) return;
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t i = (int32_t)(gv - v0), m = w.m_len[c];
+    if (i >= m) return;
+    Ctg g = ctg_view(w, c);
+    LocalDP loc;
+    Auto A;
+    A.cs = w.main_walk[v0 + i];
+    A.cov = 0;
+    A.rows = 0;
+    Emit em;
+    em.mode = 0;
+    em.dst = 0;
+    em.base = 0;
+    em.call = 0;
+    const int32_t v = w.main_walk[v0 + i + 1];
+    const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
+    const int32_t used = auto_step(w, g, loc.buf(), A, v, nv, em);
+    if (used < 0) return;  // sp_used stays 0
+    w.sp_cs[gv] = A.cs;
+    w.sp_cov[gv] = A.cov;
+    w.sp_rows[gv] = A.rows;
+    w.sp_used[gv] = (uint8_t)used;
+}
+// S2 (per contig, sequential but cheap): resolve the true cs chain; take the speculated step whenever its
+// assumption holds, otherwise run the step with the real cs (and emit its rows right away)
+AA_HDN void f_main_resolve(const Ws &w, int64_t c, const Slot &s) {
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int32_t m = w.m_len[c];
     Auto A;
     A.cs = g.src;
     A.cov = 0;
     A.rows = 0;
+    Emit em;
+    em.mode = 1;
+    em.dst = 0;
+    em.base = v0;
+    em.call = 0;
     int32_t i = 0;
     while (i < m) {
         w.m_cs[v0 + i] = A.cs;
         w.m_cov[v0 + i] = A.cov;
         w.m_rows[v0 + i] = A.rows;
-        const int32_t v = w.main_walk[v0 + i + 1];
-        const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
-        const int32_t used = auto_step(w, g, s, A, v, nv);
-        if (used == 2) w.m_cs[v0 + i + 1] = -1;
+        int32_t used = w.sp_used[v0 + i];
+        if (used != 0 && A.cs == w.main_walk[v0 + i]) {
+            A.cov += w.sp_cov[v0 + i];
+            A.rows += w.sp_rows[v0 + i];
+            A.cs = w.sp_cs[v0 + i];
+        } else {
+            const int32_t v = w.main_walk[v0 + i + 1];
+            const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
+            used = auto_step(w, g, s.buf, A, v, nv, em);
+            w.m_done[v0 + i] = 1;
+        }
         i += used;
     }
-    w.m_cs[v0 + m] = -1;
     w.m_tot_cov[c] = A.cov;
     w.m_tot_rows[c] = A.rows;
-    w.task_cov[task_index] = A.cov;
-    w.task_rows[task_index] = A.rows;
+    const int64_t t0 = w.task_off[c];
+    w.task_cov[t0] = A.cov;
+    w.task_rows[t0] = A.rows;
+}
+// S3 (per walk-0 position, parallel): emit the rows of every state the resolve pass took from speculation
+AA_HDN void f_main_rows(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0) return;
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t i = (int32_t)(gv - v0), m = w.m_len[c];
+    if (i >= m || w.m_cs[gv] < 0 || w.m_done[gv]) return;
+    Ctg g = ctg_view(w, c);
+    LocalDP loc;
+    Auto A;
+    A.cs = w.m_cs[gv];
+    A.cov = 0;
+    A.rows = w.m_rows[gv];
+    Emit em;
+    em.mode = 1;
+    em.dst = 0;
+    em.base = v0;
+    em.call = 0;
+    const int32_t v = w.main_walk[v0 + i + 1];
+    const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
+    auto_step(w, g, loc.buf(), A, v, nv, em);
 }
 
-// any other walk: follow the main chain by prefix-sum differences, simulate only around its sidetracks
-AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, int64_t *cov_out, int32_t *rows_out) {
+// copy rows [r0, r1) of the main chain into the task's output (lanes stride the range)
+AA_HD void copy_main_rows(const Ws &w, const Ctg &g, int32_t r0, int32_t r1, const Emit &em, int32_t rows_before) {
+    if (em.mode != 2) return;
+    for (int32_t r = r0 + aa_lane(); r < r1; r += AA_LANES) {
+        const int64_t src = g.v0 + r, o = em.base + rows_before + (r - r0);
+        const int64_t gb = g.b0 + w.mr_blk[src];
+        w.r_idx[em.dst][o] = w.orig[gb];
+        w.r_qs[em.dst][o] = w.mr_qs[src];
+        w.r_qe[em.dst][o] = w.mr_qe[src];
+        w.r_rs[em.dst][o] = w.mr_rs[src];
+        w.r_re[em.dst][o] = w.mr_re[src];
+        w.r_alt[em.dst][o] = w.first_call[gb] > em.call ? 1 : 0;
+    }
+}
+
+// One edge_path_to_paf_path call (paf_data.cpp:1489-1568) for an arbitrary planned walk: follow the main
+// chain by prefix-sum differences (and block copies of its rows), simulate only around the walk's sidetracks.
+// mark: record the blocks of the un-upgraded walk (pass A).  All lanes of the warp call this; lane 0 drives.
+AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit &em, bool mark, int64_t *cov_out,
+                          int32_t *rows_out) {
     const int64_t c = t.ctg;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0, e0 = w.eoff[v0], wo = w.walk_off[c];
     const int32_t *en = w.ent_node + 3 * wo;
     const int32_t *ep = w.ent_prev + 3 * wo;
+    const bool lead = aa_lane() == 0;
     int32_t ns = 0;
-    for (int32_t cur = w.wlast[wo + t.walk]; cur != -1; cur = ep[cur]) s.side[ns++] = w.hn_eid[en[cur]];
+    if (lead)
+        for (int32_t cur = w.wlast[wo + t.walk]; cur != -1; cur = ep[cur]) s.side[ns++] = w.hn_eid[en[cur]];
     int32_t si = ns - 1;  // side[] is last-to-first
     Auto A;
     A.cs = g.src;
@@ -1340,98 +1500,134 @@ AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, int64_t *co
     int32_t a = g.src, i = 0;
     bool onmain = true;
     for (;;) {
-        if (onmain) {
-            if (si < 0) {  // the rest is the main chain's suffix
-                A.cov += w.m_tot_cov[c] - w.m_cov[v0 + i];
-                A.rows += w.m_tot_rows[c] - w.m_rows[v0 + i];
-                break;
+        // ---- lane 0 decides the next block copy [r0, r1) (or none) and whether the walk is finished ----
+        int32_t r0 = 0, r1 = 0, rows_before = A.rows, finished = 0;
+        if (lead) {
+            if (onmain) {
+                if (si < 0) {  // the rest is the main chain's suffix
+                    r0 = w.m_rows[v0 + i];
+                    r1 = w.m_tot_rows[c];
+                    A.cov += w.m_tot_cov[c] - w.m_cov[v0 + i];
+                    A.rows += r1 - r0;
+                    finished = 1;
+                } else {
+                    const int32_t p = w.main_pos[v0 + w.e_src[e0 + s.side[si]]];
+                    // main states at positions <= p-2 never look past the tail of the next sidetrack
+                    int32_t j = p - 1 > i ? p - 1 : i;
+                    if (w.m_cs[v0 + j] == -1) j++;
+                    r0 = w.m_rows[v0 + i];
+                    r1 = w.m_rows[v0 + j];
+                    A.cov += w.m_cov[v0 + j] - w.m_cov[v0 + i];
+                    A.rows += r1 - r0;
+                    A.cs = w.m_cs[v0 + j];
+                    a = w.main_walk[v0 + j];
+                    i = j;
+                    onmain = false;
+                }
             }
-            const int32_t p = w.main_pos[v0 + w.e_src[e0 + s.side[si]]];
-            // main states at positions <= p-2 never look past the tail of the next sidetrack: take them as a block
-            int32_t j = p - 1 > i ? p - 1 : i;
-            if (w.m_cs[v0 + j] == -1) j++;
-            A.cov += w.m_cov[v0 + j] - w.m_cov[v0 + i];
-            A.rows += w.m_rows[v0 + j] - w.m_rows[v0 + i];
-            A.cs = w.m_cs[v0 + j];
-            a = w.main_walk[v0 + j];
-            i = j;
-            onmain = false;
         }
-        // one simulated step from walk vertex a
-        int32_t si1 = si, si2;
-        int32_t v, nv = -1;
-        if (si1 >= 0 && a == w.e_src[e0 + s.side[si1]]) v = e_dst(w.edge[e0 + s.side[si1--]]);
-        else v = w.best[v0 + a];
-        si2 = si1;
-        if (v != g.dest) {
-            if (si2 >= 0 && v == w.e_src[e0 + s.side[si2]]) nv = e_dst(w.edge[e0 + s.side[si2--]]);
-            else nv = w.best[v0 + v];
+#if defined(__CUDA_ARCH__)
+        if (em.mode == 2) {
+            r0 = __shfl_sync(0xffffffffu, r0, 0);
+            r1 = __shfl_sync(0xffffffffu, r1, 0);
+            rows_before = __shfl_sync(0xffffffffu, rows_before, 0);
         }
-        const int32_t used = auto_step(w, g, s, A, v, nv);
-        if (v != g.dest && w.main_pos[v0 + v] < 0) {
-            int32_t x, y;
-            vtx_xy(w, g, v, x, y);
-            mark_block(w, g.b0 + x, t.call);
-            mark_block(w, g.b0 + y, t.call);
-        }
-        if (v == g.dest) break;
-        if (used == 2) {
-            if (w.main_pos[v0 + nv] < 0) {
+        finished = __shfl_sync(0xffffffffu, finished, 0);
+#endif
+        if (r1 > r0) copy_main_rows(w, g, r0, r1, em, rows_before);
+        if (finished) break;
+        // ---- one simulated step from walk vertex a (lane 0) ----
+        if (lead) {
+            int32_t si1 = si, si2;
+            int32_t v, nv = -1;
+            if (si1 >= 0 && a == w.e_src[e0 + s.side[si1]]) v = e_dst(w.edge[e0 + s.side[si1--]]);
+            else v = w.best[v0 + a];
+            si2 = si1;
+            if (v != g.dest) {
+                if (si2 >= 0 && v == w.e_src[e0 + s.side[si2]]) nv = e_dst(w.edge[e0 + s.side[si2--]]);
+                else nv = w.best[v0 + v];
+            }
+            const int32_t used = auto_step(w, g, s.buf, A, v, nv, em);
+            if (mark && v != g.dest && w.main_pos[v0 + v] < 0) {
                 int32_t x, y;
-                vtx_xy(w, g, nv, x, y);
+                vtx_xy(w, g, v, x, y);
                 mark_block(w, g.b0 + x, t.call);
                 mark_block(w, g.b0 + y, t.call);
             }
-            a = nv;
-            si = si2;
-        } else {
-            a = v;
-            si = si1;
+            if (v == g.dest) {
+                finished = 1;
+            } else {
+                if (used == 2) {
+                    if (mark && w.main_pos[v0 + nv] < 0) {
+                        int32_t x, y;
+                        vtx_xy(w, g, nv, x, y);
+                        mark_block(w, g.b0 + x, t.call);
+                        mark_block(w, g.b0 + y, t.call);
+                    }
+                    a = nv;
+                    si = si2;
+                } else {
+                    a = v;
+                    si = si1;
+                }
+                const int32_t mp = w.main_pos[v0 + a];
+                if (mp >= 0 && w.m_cs[v0 + mp] == A.cs) {
+                    onmain = true;
+                    i = mp;
+                }
+            }
         }
-        const int32_t mp = w.main_pos[v0 + a];
-        if (mp >= 0 && w.m_cs[v0 + mp] == A.cs) {
-            onmain = true;
-            i = mp;
-        }
+#if defined(__CUDA_ARCH__)
+        finished = __shfl_sync(0xffffffffu, finished, 0);
+#endif
+        if (finished) break;
     }
-    *cov_out = A.cov;
-    *rows_out = A.rows;
+    if (lead) {
+        if (cov_out) *cov_out = A.cov;
+        if (rows_out) *rows_out = A.rows;
+    }
 }
 
-// worker loops (dynamic scheduling over tasks); slot = worker index
-// pass A0: walk 0 of every contig (largest contigs first through ord[])
+// worker loops (dynamic scheduling); slot = worker index.  All lanes run the loop, lane 0 pulls the work.
+AA_HD int64_t next_item(const Ws &w) {
+    unsigned long long k = 0;
+#if defined(__CUDA_ARCH__)
+    if (aa_lane() == 0) k = atomicAdd(w.task_next, 1ull);
+    k = __shfl_sync(0xffffffffu, k, 0);
+#else
+    k = (*w.task_next)++;
+#endif
+    return (int64_t)k;
+}
+// pass A0/S2: resolve the main chain of every contig (largest contigs first through ord[])
 AA_HDN void f_tasks_a0(const Ws &w, int64_t slot, const int32_t *ord) {
     Slot s = slot_view(w, slot);
     for (;;) {
-#if defined(__CUDA_ARCH__)
-        unsigned long long k = atomicAdd(w.task_next, 1ull);
-#else
-        unsigned long long k = (*w.task_next)++;
-#endif
-        if ((int64_t)k >= w.C) break;
-        const int64_t c = ord[k];
-        if (w.status[c] != 0) continue;
-        main_chain(w, c, s, w.task_off[c]);
+        const int64_t k = next_item(w);
+        if (k >= w.C) break;
+        if (aa_lane() == 0) f_main_resolve(w, ord[k], s);
     }
 }
-// pass A1: every other planned walk
+// pass A1: every other planned walk (coverage, row count, block marks)
 AA_HDN void f_tasks_a1(const Ws &w, int64_t slot) {
     Slot s = slot_view(w, slot);
+    Emit em;
+    em.mode = 0;
+    em.dst = 0;
+    em.base = 0;
+    em.call = 0;
     for (;;) {
-#if defined(__CUDA_ARCH__)
-        unsigned long long t = atomicAdd(w.task_next, 1ull);
-#else
-        unsigned long long t = (*w.task_next)++;
-#endif
-        if ((int64_t)t >= w.n_tasks_total) break;
+        const int64_t t = next_item(w);
+        if (t >= w.n_tasks_total) break;
         const Task tk = w.tasks[t];
         if (tk.call == 0) continue;
-        walk_task_inc(w, tk, s, &w.task_cov[t], &w.task_rows[t]);
+        walk_task_inc(w, tk, s, em, true, &w.task_cov[t], &w.task_rows[t]);
     }
 }
 
 // phase: selection (paf_data.cpp:1585-1649) from the per-task coverages
 AA_HDN void f_select(const Ws &w, int64_t c, int32_t want_all) {
+    if (aa_lane() != 0) return;
     w.win_out[c] = -1;
     w.win_alt[c] = -1;
     w.out_cnt[c] = 0;
@@ -1477,6 +1673,7 @@ AA_HDN void f_select(const Ws &w, int64_t c, int32_t want_all) {
 }
 // list the .all paths of contig c (ties after the first maximum, in call order)
 AA_HDN void f_all_list(const Ws &w, int64_t c) {
+    if (aa_lane() != 0) return;
     if (w.all_cnt[c] == 0) return;
     const int64_t o = w.task_off[c];
     const int32_t ntie = w.n_tie[c];
@@ -1496,33 +1693,43 @@ AA_HDN void f_tasks_b(const Ws &w, int64_t slot, int64_t n_items, int64_t n_path
     Slot s = slot_view(w, slot);
     (void)n_paths;
     for (;;) {
-#if defined(__CUDA_ARCH__)
-        unsigned long long it = atomicAdd(w.task_next, 1ull);
-#else
-        unsigned long long it = (*w.task_next)++;
-#endif
-        if ((int64_t)it >= n_items) break;
-        int64_t i = (int64_t)it;
+        const int64_t i = next_item(w);
+        if (i >= n_items) break;
+        Emit em;
+        em.mode = 2;
+        int64_t task = -1;
         if (i < w.C) {
-            int64_t c = i;
+            const int64_t c = i;
             if (w.status[c] == 1) {  // singleton contig (paf_data.cpp:235-239)
-                int64_t b = w.ctg_off[c], o = w.out_off[c];
-                w.r_idx[0][o] = 0;
-                w.r_qs[0][o] = w.qs[b];
-                w.r_qe[0][o] = w.qe[b];
-                w.r_rs[0][o] = w.rs[b];
-                w.r_re[0][o] = w.re[b];
-                w.r_alt[0][o] = 0;
-            } else if (w.win_out[c] >= 0) {
-                walk_task(w, w.tasks[w.win_out[c]], s, 0, w.out_off[c], nullptr, nullptr);
+                if (aa_lane() == 0) {
+                    int64_t b = w.ctg_off[c], o = w.out_off[c];
+                    w.r_idx[0][o] = 0;
+                    w.r_qs[0][o] = w.qs[b];
+                    w.r_qe[0][o] = w.qe[b];
+                    w.r_rs[0][o] = w.rs[b];
+                    w.r_re[0][o] = w.re[b];
+                    w.r_alt[0][o] = 0;
+                }
+                continue;
             }
+            task = w.win_out[c];
+            em.dst = 0;
+            em.base = w.out_off[c];
         } else if (i < 2 * w.C) {
-            int64_t c = i - w.C;
-            if (w.win_alt[c] >= 0) walk_task(w, w.tasks[w.win_alt[c]], s, 1, w.alt_off[c], nullptr, nullptr);
+            const int64_t c = i - w.C;
+            task = w.win_alt[c];
+            em.dst = 1;
+            em.base = w.alt_off[c];
         } else {
-            int64_t p = i - 2 * w.C;
-            walk_task(w, w.tasks[w.all_task[p]], s, 2, w.all_row_off[p], nullptr, nullptr);
+            const int64_t p = i - 2 * w.C;
+            task = w.all_task[p];
+            em.dst = 2;
+            em.base = w.all_row_off[p];
         }
+        if (task < 0) continue;
+        const Task tk = w.tasks[task];
+        em.call = tk.call;
+        walk_task_inc(w, tk, s, em, false, nullptr, nullptr);
     }
 }
 

@@ -47,7 +47,10 @@ inline const char *phase_name(int p) {
 #define AA_FUNCTOR(Name, body)                                  \
     struct Name {                                               \
         Ws w;                                                   \
-        AA_HD void operator()(int64_t i) const { body; }        \
+        AA_HD void operator()(int64_t i, void *scratch) const {  \
+            (void)scratch;                                      \
+            body;                                               \
+        }        \
     };
 AA_FUNCTOR(FnGather, f_gather(w, i))
 AA_FUNCTOR(FnCandCount, f_cand_count(w, i))
@@ -55,33 +58,37 @@ AA_FUNCTOR(FnCuts, f_cuts(w, i))
 AA_FUNCTOR(FnVtxOff, f_vtx_off(w, i))
 AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
+AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
+AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
+AA_FUNCTOR(FnMainRows, f_main_rows(w, i))
 AA_FUNCTOR(FnTasksA1, f_tasks_a1(w, i))
 struct FnTasksA0 {
     Ws w;
     const int32_t *ord;
-    AA_HD void operator()(int64_t i) const { f_tasks_a0(w, i, ord); }
+    AA_HD void operator()(int64_t i, void *) const { f_tasks_a0(w, i, ord); }
 };
 struct FnCompact {
     Ws w;
     int64_t ncand;
-    AA_HD void operator()(int64_t i) const { f_compact(w, i, ncand); }
+    AA_HD void operator()(int64_t i, void *) const { f_compact(w, i, ncand); }
 };
 struct FnRevOff {
     Ws w;
     int64_t E;
-    AA_HD void operator()(int64_t i) const { f_rev_off(w, i, E); }
+    AA_HD void operator()(int64_t i, void *) const { f_rev_off(w, i, E); }
 };
 struct FnTasksB {
     Ws w;
     int64_t n_items, n_paths;
-    AA_HD void operator()(int64_t i) const { f_tasks_b(w, i, n_items, n_paths); }
+    AA_HD void operator()(int64_t i, void *) const { f_tasks_b(w, i, n_items, n_paths); }
 };
 // per-contig phases go through an order array (largest contigs first)
 #define AA_CTG_FUNCTOR(Name, body)                                  \
     struct Name {                                                   \
         Ws w;                                                       \
         const int32_t *ord;                                         \
-        AA_HD void operator()(int64_t i) const {                    \
+        AA_HD void operator()(int64_t i, void *scratch) const {     \
+            (void)scratch;                                          \
             int64_t c = ord[i];                                     \
             body;                                                   \
         }                                                           \
@@ -94,11 +101,12 @@ AA_CTG_FUNCTOR(FnEnum, f_enum(w, c))
 AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
 AA_CTG_FUNCTOR(FnTaskCompact, f_task_compact(w, c))
 AA_CTG_FUNCTOR(FnAllList, f_all_list(w, c))
+AA_CTG_FUNCTOR(FnMainTrace, f_main_trace(w, c))
 struct FnSelect {
     Ws w;
     const int32_t *ord;
     int32_t want_all;
-    AA_HD void operator()(int64_t i) const { f_select(w, ord[i], want_all); }
+    AA_HD void operator()(int64_t i, void *) const { f_select(w, ord[i], want_all); }
 };
 
 // ---- a batch staged on the device ------------------------------------------------------------------------
@@ -438,6 +446,14 @@ struct Pipeline {
         // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
         bk.phase_begin(PH_HEAPS);
         w.heap_top = (unsigned long long *)A<int64_t>(1);
+        w.skey = A<SKey>(E);
+        w.child = A<int32_t>(E);
+        w.nchild = A<int32_t>(Vtot);
+        if (!w.skey || !w.child || !w.nchild) {
+            err = "device allocation failed (sidetrack keys)";
+            return AA_ERR_NOMEM;
+        }
+        bk.for_each("heap_prep", Vtot, FnHeapPrep{w});
         int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {
@@ -534,14 +550,31 @@ struct Pipeline {
         w.m_cs = A<int32_t>(Vtot);
         w.m_cov = A<int64_t>(Vtot);
         w.m_rows = A<int32_t>(Vtot);
+        w.m_done = A<uint8_t>(Vtot);
+        w.sp_cs = A<int32_t>(Vtot);
+        w.sp_rows = A<int32_t>(Vtot);
+        w.sp_cov = A<int64_t>(Vtot);
+        w.sp_used = A<uint8_t>(Vtot);
+        w.mr_blk = A<int32_t>(Vtot);
+        w.mr_qs = A<int64_t>(Vtot);
+        w.mr_qe = A<int64_t>(Vtot);
+        w.mr_rs = A<int64_t>(Vtot);
+        w.mr_re = A<int64_t>(Vtot);
         w.m_tot_cov = A<int64_t>(C);
         w.m_tot_rows = A<int32_t>(C);
-        if (!w.main_pos || !w.main_walk || !w.m_cs || !w.m_cov || !w.m_rows) {
+        w.m_len = A<int32_t>(C);
+        if (!w.main_pos || !w.main_walk || !w.m_cs || !w.m_cov || !w.m_rows || !w.m_done || !w.sp_cs || !w.sp_rows ||
+            !w.sp_cov || !w.sp_used || !w.mr_blk || !w.mr_qs || !w.mr_qe || !w.mr_rs || !w.mr_re) {
             err = "device allocation failed (main chain)";
             return AA_ERR_NOMEM;
         }
+        // walk 0 of every contig: trace, speculate every step in parallel, resolve sequentially, emit rows in parallel
+        bk.for_each_contig("main_trace", C, FnMainTrace{w, d_ord});
+        bk.for_each("main_spec", Vtot, FnMainSpec{w});
         bk.zero(w.task_next, 8);
-        bk.workers("walksA0", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});
+        bk.workers("main_resolve", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});
+        bk.for_each("main_rows", Vtot, FnMainRows{w});
+        // every other planned walk
         bk.zero(w.task_next, 8);
         if (NT > C) bk.workers("walksA1", std::min<int64_t>(S, NT), FnTasksA1{w});
         bk.phase_end(PH_WALKS_A);

@@ -33,15 +33,17 @@ struct HostBackend {
     void sync() {}
     template <class F>
     void for_each(const char *, int64_t n, F f) {
-        for (int64_t i = 0; i < n; i++) f(i);
+        for (int64_t i = 0; i < n; i++) f(i, nullptr);
     }
     template <class F>
-    void for_each_contig(const char *, int64_t n, F f) {
-        for (int64_t i = 0; i < n; i++) f(i);
+    void for_each_contig(const char *, int64_t n, F f, size_t smem = 0) {
+        std::vector<unsigned char> scratch(smem + 16);
+        for (int64_t i = 0; i < n; i++) f(i, scratch.data());
     }
     template <class F>
-    void workers(const char *, int64_t n, F f) {
-        for (int64_t i = 0; i < n; i++) f(i);
+    void workers(const char *, int64_t n, F f, size_t smem = 0) {
+        std::vector<unsigned char> scratch(smem + 16);
+        for (int64_t i = 0; i < n; i++) f(i, scratch.data());
     }
     void scan_i32(const int32_t *in, int64_t *out, int64_t n) {
         int64_t s = 0;

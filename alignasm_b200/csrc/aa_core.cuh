@@ -18,6 +18,7 @@
 //   gap filling DP / upgrade   paf_data.cpp:750-921
 //   rows, flags, selection     paf_data.cpp:1489-1649
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -900,6 +901,264 @@ AA_HDN void f_heaps(const Ws &w, int64_t c) {
     w.heap_used[c] = ha.used;
     if (ha.overflow) w.status[c] = 3;
 }
+
+#if defined(__CUDA_ARCH__)
+// ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------
+// The sequential insert is bound by the issue rate of one warp (~100 dependent instructions per copied
+// node).  Here the known prefix of the current heap's right spine lives in shared memory, one entry per lane:
+//   descent      = one parallel key compare + ballot (unknown tail nodes are fetched on demand)
+//   rank update  = a short warp-uniform recurrence over shared memory
+//   path copying = every lane writes its own new node (ids are consecutive: N first, then bottom-up, the
+//                  allocation order of leftist_heap.hpp:29-40, which is what the PQ tie-break sees)
+// Spines of recently finished vertices are kept (keyed by root id) because BFS visits siblings and then
+// their children, all of which start from a heap built a few vertices earlier.
+constexpr int32_t SPMAX = 32;
+constexpr int32_t NSAVE = 8;
+constexpr int32_t QRING = 512;
+struct HeapSmem {
+    HNode node[SPMAX];
+    int32_t id[SPMAX];
+    int32_t eid[SPMAX];
+    HNode snode[NSAVE][SPMAX];
+    int32_t sid[NSAVE][SPMAX];
+    int32_t seid[NSAVE][SPMAX];
+    int32_t sroot[NSAVE], sL[NSAVE], snext[NSAVE];
+    int32_t ring[QRING];
+};
+static_assert(sizeof(HeapSmem) <= 16 * 1024, "HeapSmem does not fit its shared-memory allotment");
+__device__ __forceinline__ bool key_lt(const HNode &an, const SKey &k) {  // a->key < k (paf_data.hpp:142-159)
+    if (an.sum != k.sum) return an.sum < k.sum;
+    if (an.anom != k.anom) return an.anom < k.anom;
+    return (int64_t)an.nz * den(k.tot) > (int64_t)k.nz * den(an.tot);
+}
+__device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
+    HeapSmem &sm = *reinterpret_cast<HeapSmem *>(scratch);
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0 && w.status[c] != 3) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int64_t e0 = w.eoff[v0];
+    HNode *__restrict__ hn = w.hn;
+    int32_t *__restrict__ hn_eid = w.hn_eid;
+    const SKey *__restrict__ skey = w.skey;
+    const int64_t *__restrict__ eoff = w.eoff + v0;
+    const int64_t *__restrict__ rev_off = w.rev_off + v0;
+    const int32_t *__restrict__ nchild = w.nchild + v0;
+    int32_t *__restrict__ hroot = w.hroot + v0;
+    int32_t *__restrict__ q = w.queue + v0;
+    for (int32_t v = lane; v < g.V; v += 32) hroot[v] = -1;
+    if (lane < NSAVE) sm.sroot[lane] = -2;
+    __syncwarp();
+    int64_t cur = 0, end = 0, used = 0;  // arena chunk of this contig (warp-uniform)
+    bool overflow = false;
+    int32_t head = 0, tail = 0, save_at = 0;
+    if (lane == 0) {
+        q[0] = g.dest;
+        sm.ring[0] = g.dest;
+    }
+    tail = 1;
+    __syncwarp();
+    while (head < tail && !overflow) {
+        // ---- next BFS vertex (uniform) ----
+        const int32_t u = (tail - head <= QRING) ? sm.ring[head & (QRING - 1)] : q[head];
+        head++;
+        int32_t root = hroot[u];
+        const int64_t ea = eoff[u], eb = eoff[u + 1];
+        const int32_t nc = nchild[u];
+        const int64_t cbase = rev_off[u];
+        // ---- working spine := spine of `root` ----
+        int32_t L = 0, next = root;
+        {
+            const int32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
+            if (root >= 0 && hit) {
+                const int32_t sl = __ffs(hit) - 1;
+                L = sm.sL[sl];
+                next = sm.snext[sl];
+                if (lane < L) {
+                    sm.node[lane] = sm.snode[sl][lane];
+                    sm.id[lane] = sm.sid[sl][lane];
+                    sm.eid[lane] = sm.seid[sl][lane];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- inserts, 32 sidetrack keys prefetched at a time ----
+        for (int64_t kb = ea; kb < eb && !overflow; kb += 32) {
+            SKey mine;
+            mine.use = 0;
+            mine.sum = 0;
+            mine.anom = mine.nz = mine.tot = 0;
+            if (kb + lane < eb) mine = skey[kb + lane];
+            uint32_t todo = __ballot_sync(FULL, mine.use != 0);
+            while (todo && !overflow) {
+                const int32_t src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                SKey k;
+                k.sum = __shfl_sync(FULL, mine.sum, src);
+                k.anom = __shfl_sync(FULL, mine.anom, src);
+                k.nz = __shfl_sync(FULL, mine.nz, src);
+                k.tot = __shfl_sync(FULL, mine.tot, src);
+                k.use = 1;
+                const int32_t eid = (int32_t)(kb + src - e0);
+                // descent: first spine position whose key is not < k
+                int32_t p;
+                for (;;) {
+                    const bool stop = lane < L && !key_lt(sm.node[lane], k);
+                    const uint32_t sm_stop = __ballot_sync(FULL, stop);
+                    if (sm_stop) {
+                        p = __ffs(sm_stop) - 1;
+                        break;
+                    }
+                    if (next < 0) {
+                        p = L;
+                        break;
+                    }
+                    if (L >= SPMAX) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
+                        overflow = true;
+                        p = 0;
+                        break;
+                    }
+                    const HNode nd = hn_load(hn + next);  // same address on every lane: one transaction
+                    const int32_t ne = hn_eid[next];
+                    if (lane == 0) {
+                        sm.node[L] = nd;
+                        sm.id[L] = next;
+                        sm.eid[L] = ne;
+                    }
+                    __syncwarp();
+                    L++;
+                    next = nd.right;
+                }
+                if (overflow) break;
+                // ids: N = base, level q's copy = base + (p - q)
+                const int32_t need = p + 1;
+                if (cur + need > end) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+                    at = __shfl_sync(FULL, at, 0);
+                    if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
+                        overflow = true;
+                        break;
+                    }
+                    cur = (int64_t)at;
+                    end = cur + HEAP_CHUNK;
+                }
+                const int32_t base = (int32_t)cur;
+                cur += need;
+                used += need;
+                // rank recurrence bottom-up (uniform): r = rank of the child just built
+                int32_t r = 1, my_child_rank = 1, my_rank = 1, sstar = -1;
+                bool my_swap = false;
+                for (int32_t qq = p - 1; qq >= 0; --qq) {
+                    const int32_t l = sm.node[qq].left;
+                    const int32_t lr = sm.node[qq].lrank;
+                    const bool sw = l < 0 || lr < r;
+                    const int32_t nr = sw ? (l >= 0 ? lr + 1 : 0) : r + 1;
+                    if (lane == qq) {
+                        my_child_rank = r;
+                        my_swap = sw;
+                        my_rank = nr;
+                    }
+                    if (sw) sstar = qq;
+                    r = nr;
+                }
+                // build this lane's node
+                HNode nn;
+                int32_t my_id = -1, my_eid = 0;
+                if (lane < p) {
+                    nn = sm.node[lane];
+                    my_eid = sm.eid[lane];
+                    const int32_t child = base + (p - 1 - lane);
+                    const int32_t l = nn.left, lr = nn.lrank;
+                    if (my_swap) {
+                        nn.left = child;
+                        nn.lrank = (int16_t)my_child_rank;
+                        nn.right = l;
+                    } else {
+                        nn.left = l;
+                        nn.lrank = (int16_t)lr;
+                        nn.right = child;
+                    }
+                    nn.rank = (int16_t)my_rank;
+                    my_id = base + (p - lane);
+                } else if (lane == p) {
+                    nn.sum = k.sum;
+                    nn.anom = k.anom;
+                    nn.nz = k.nz;
+                    nn.tot = k.tot;
+                    nn.left = p < L ? sm.id[p] : -1;
+                    nn.right = -1;
+                    nn.rank = 1;
+                    nn.lrank = (int16_t)(p < L ? sm.node[p].rank : 0);
+                    my_id = base;
+                    my_eid = eid;
+                }
+                __syncwarp();
+                // new known spine: copies 0..sstar (then the old left of sstar, unknown), or copies 0..p-1 and N
+                const int32_t newL = sstar >= 0 ? sstar + 1 : p + 1;
+                if (lane <= p) {
+                    hn_store(hn + my_id, nn);
+                    hn_eid[my_id] = my_eid;
+                    if (lane < newL) {
+                        sm.node[lane] = nn;
+                        sm.id[lane] = my_id;
+                        sm.eid[lane] = my_eid;
+                    }
+                }
+                const int32_t nright = __shfl_sync(FULL, nn.right, sstar >= 0 ? sstar : 0);
+                next = sstar >= 0 ? nright : -1;
+                L = newL;
+                root = p > 0 ? base + p : base;
+                __syncwarp();
+            }
+        }
+        if (overflow) break;
+        // ---- publish: root of u, its children inherit it; remember the spine for them ----
+        if (lane == 0) hroot[u] = root;
+        if (nc > 0) {
+            for (int32_t k = lane; k < nc; k += 32) {
+                const int32_t x = w.child[cbase + k];
+                hroot[x] = root;
+                q[tail + k] = x;
+                sm.ring[(tail + k) & (QRING - 1)] = x;
+            }
+            tail += nc;
+            if (root >= 0) {
+                const int32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
+                if (!have) {
+                    const int32_t sl = save_at;
+                    save_at = (save_at + 1) % NSAVE;
+                    if (lane < L) {
+                        sm.snode[sl][lane] = sm.node[lane];
+                        sm.sid[sl][lane] = sm.id[lane];
+                        sm.seid[sl][lane] = sm.eid[lane];
+                    }
+                    if (lane == 0) {
+                        sm.sroot[sl] = root;
+                        sm.sL[sl] = L;
+                        sm.snext[sl] = next;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        w.heap_used[c] = used;
+        w.status[c] = overflow ? 3 : 0;
+    }
+}
+#endif
+AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_heaps_warp(w, c, scratch);
+#else
+    (void)scratch;
+    f_heaps(w, c);
+#endif
+}
+constexpr size_t HEAP_SMEM_BYTES = 16 * 1024;  // >= sizeof(HeapSmem) (device only)
 
 // ---- enumeration priority queue: binary min-heap under the total order (distance, node id, entry index)
 AA_HD bool pq_less(const PQEnt &a, const PQEnt &b) {

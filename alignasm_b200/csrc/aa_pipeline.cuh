@@ -96,7 +96,7 @@ struct FnTasksB {
 AA_CTG_FUNCTOR(FnParts, f_parts(w, c))
 AA_CTG_FUNCTOR(FnRelax, f_relax(w, c))
 AA_CTG_FUNCTOR(FnTopo, f_topo(w, c))
-AA_CTG_FUNCTOR(FnHeaps, f_heaps(w, c))
+AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnEnum, f_enum(w, c))
 AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
 AA_CTG_FUNCTOR(FnTaskCompact, f_task_compact(w, c))
@@ -466,7 +466,7 @@ struct Pipeline {
                 return AA_ERR_NOMEM;
             }
             bk.zero(w.heap_top, 8);
-            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord});
+            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, HEAP_SMEM_BYTES);
             bk.d2h(h_status.data(), w.status, (size_t)C * 4);
             AA_BK_CHECK();
             bool overflow = false;

@@ -40,7 +40,10 @@ struct CastI32 {
 
 struct CudaBackend {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // the stream launches currently go to
+    cudaStream_t main_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+    bool side_pending = false;
     bool failed = false;
     std::string errmsg;
     int64_t n_launch = 0;
@@ -88,7 +91,11 @@ struct CudaBackend {
         cudaDeviceProp prop;
         AA_CUDA(cudaGetDeviceProperties(&prop, dev));
         sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
-        AA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        AA_CUDA(cudaStreamCreateWithFlags(&main_stream, cudaStreamNonBlocking));
+        AA_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+        AA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        AA_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        stream = main_stream;
         for (int p = 0; p < PH_COUNT; p++) {
             AA_CUDA(cudaEventCreate(&ev[p][0]));
             AA_CUDA(cudaEventCreate(&ev[p][1]));
@@ -109,8 +116,12 @@ struct CudaBackend {
             }
             cudaEventDestroy(ev_total[0]);
             cudaEventDestroy(ev_total[1]);
-            cudaStreamDestroy(stream);
-            stream = nullptr;
+            cudaStreamSynchronize(side_stream);
+            cudaEventDestroy(ev_fork);
+            cudaEventDestroy(ev_side);
+            cudaStreamDestroy(side_stream);
+            cudaStreamDestroy(main_stream);
+            stream = main_stream = side_stream = nullptr;
         }
     }
 
@@ -177,6 +188,9 @@ struct CudaBackend {
             if (cudaMalloc(&p, total) == cudaSuccess) pool.push_back({p, total, 0});
             else cudaGetLastError();
         }
+        stream = main_stream;
+        if (side_pending) AA_CUDA(cudaStreamSynchronize(side_stream));
+        side_pending = false;
         for (auto &b : pool) b.top = 0;
         log.clear();
         n_launch = 0;
@@ -262,6 +276,22 @@ struct CudaBackend {
         if (!t) return;
         AA_CUDA(cub::DeviceRadixSort::SortPairs(t, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
         n_launch++;
+    }
+    // ---- side stream: work that is off the critical path runs concurrently with the main stream ----
+    bool device_kahn() const { return true; }
+    void side_begin() {
+        AA_CUDA(cudaEventRecord(ev_fork, main_stream));
+        AA_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+        stream = side_stream;
+    }
+    void side_end() {
+        AA_CUDA(cudaEventRecord(ev_side, side_stream));
+        stream = main_stream;
+        side_pending = true;
+    }
+    void side_join() {
+        if (side_pending) AA_CUDA(cudaStreamWaitEvent(main_stream, ev_side, 0));
+        side_pending = false;
     }
     int host_threads() {
         unsigned h = std::thread::hardware_concurrency();

@@ -136,6 +136,20 @@ struct PQEnt {
     int32_t pad;
 };
 
+// packed reverse-graph record: everything the relax step needs about one in-edge, 16 B
+struct __attribute__((aligned(16))) RevRec {
+    int64_t sum;   // qry + ref
+    int32_t src;   // contig-local source vertex
+    uint32_t fl;   // bits 0..1 anom, 2 qul_nonzero, 3 qul_total
+};
+// relax state of one vertex, 32 B: d[v] (CALC_SUM view), best[v], remaining out-degree, min anom to dest
+struct __attribute__((aligned(16))) VState {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t best;
+    int32_t cnt;
+    int32_t amin_reach;  // bit 0: reaches dest; bits 1..: min anom sum to dest
+};
 struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
     int32_t i, j;        // contig-local sorted block indices
     int64_t pe_q, pe_r;  // edited_loc_pre_end[i][j]
@@ -185,6 +199,9 @@ struct Ws {
     uint32_t *rkey_in, *rkey;   // [E] global destination vertex (sort key) before / after
     uint32_t *rval_in, *rev_eid;  // [E] global edge id, sorted by destination, stable in source order
     int64_t *rev_off;    // [Vtot+1]
+    struct RevRec *rrec; // [E] packed reverse records (source, weight), same order as rev_eid
+    struct VState *vs;   // [Vtot] relax state record (device relax only)
+    int32_t *cnt2;       // [Vtot] in-degree counters of the forward Kahn pass (runs concurrently with relax)
     // relax / topo
     D4 *d;               // [Vtot]  aux = reachable
     int32_t *best;       // [Vtot]
@@ -704,6 +721,40 @@ AA_HDN void f_relax(const Ws &w, int64_t c) {
     if (!w.d[v0 + g.src].aux) w.status[c] = 2;
 }
 
+// ---- parallel helpers around the warp-cooperative relax / topo (device path) ----------------------------------
+AA_HDN void f_rev_pack(const Ws &w, int64_t k) {  // one reverse slot
+    const int64_t eid = w.rev_eid[k];
+    const Edge e = w.edge[eid];
+    RevRec r;
+    r.sum = e.qry + e.ref;
+    r.src = w.e_src[eid];
+    r.fl = (uint32_t)e_anom(e) | ((uint32_t)e_nz(e) << 2) | ((uint32_t)e_tot(e) << 3);
+    w.rrec[k] = r;
+}
+AA_HDN void f_relax_init(const Ws &w, int64_t gv) {  // one vertex
+    VState s;
+    s.sum = 0;
+    s.anom = s.nz = s.tot = 0;
+    s.best = -1;
+    s.cnt = (int32_t)(w.eoff[gv + 1] - w.eoff[gv]);
+    s.amin_reach = 0x3fffffff << 1;
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (gv == w.vtx_off[c + 1] - 1) s.amin_reach = 1;  // dest: reaches itself, anom 0
+    w.vs[gv] = s;
+    w.cnt2[gv] = (int32_t)(w.rev_off[gv + 1] - w.rev_off[gv]);
+}
+AA_HDN void f_relax_unpack(const Ws &w, int64_t gv) {  // one vertex: VState -> d / best
+    const VState s = w.vs[gv];
+    D4 d;
+    d.sum = s.sum;
+    d.anom = s.anom;
+    d.nz = s.nz;
+    d.tot = s.tot;
+    d.aux = s.amin_reach & 1;
+    w.d[gv] = d;
+    w.best[gv] = s.best;
+}
+
 // phase: forward Kahn order (paf_data.cpp:742-746)
 AA_HDN void f_topo(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
@@ -901,6 +952,153 @@ AA_HDN void f_heaps(const Ws &w, int64_t c) {
     w.heap_used[c] = ha.used;
     if (ha.overflow) w.status[c] = 3;
 }
+
+#if defined(__CUDA_ARCH__)
+// ---- warp-cooperative Kahn passes (device only; the host emulation runs f_relax / f_topo) ----------------------
+// One warp per contig.  The FIFO is kept in a shared-memory ring (plus global memory when it overflows);
+// the edges of the popped vertex are spread over the lanes; vertices that become ready are appended in
+// lane order, which is the list order the reference pushes them in (k_shortest_walks.hpp:149-153).
+constexpr int32_t KRING = 1024;
+struct KahnSmem {
+    int32_t ring[KRING];
+};
+__device__ __forceinline__ int32_t kahn_pop(const KahnSmem &sm, const int32_t *q, int32_t head, int32_t tail) {
+    return (tail - head <= KRING) ? sm.ring[head & (KRING - 1)] : q[head];
+}
+// ordered append of the lanes with `ready` (lane order); returns the new tail
+__device__ __forceinline__ int32_t kahn_push(KahnSmem &sm, int32_t *q, int32_t tail, bool ready, int32_t x) {
+    const uint32_t m = __ballot_sync(0xffffffffu, ready);
+    if (ready) {
+        const int32_t pos = tail + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        q[pos] = x;
+        sm.ring[pos & (KRING - 1)] = x;
+    }
+    __syncwarp();
+    return tail + __popc(m);
+}
+// reverse Kahn + relaxation + min-anom DP (k_shortest_walks.hpp:132-175; paf_data.cpp:705-713)
+__device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
+    KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    VState *__restrict__ vs = w.vs + v0;
+    const RevRec *__restrict__ rrec = w.rrec;
+    const int64_t *__restrict__ rev_off = w.rev_off + v0;
+    int32_t *__restrict__ q = w.queue + v0;
+    int32_t head = 0, tail = 0;
+    // seeds: vertices without out-edges, ascending id (k_shortest_walks.hpp:139-141)
+    for (int32_t vb = 0; vb < g.V; vb += 32) {
+        const int32_t v = vb + lane;
+        const bool seed = v < g.V && vs[v].cnt == 0;
+        tail = kahn_push(sm, q, tail, seed, v);
+    }
+    while (head < tail) {
+        const int32_t v = kahn_pop(sm, q, head, tail);
+        head++;
+        const VState sv = vs[v];
+        const bool vreach = (sv.amin_reach & 1) != 0;
+        const int32_t av = sv.amin_reach >> 1;
+        const int64_t ra = rev_off[v], rb = rev_off[v + 1];
+        for (int64_t kb = ra; kb < rb; kb += 32) {
+            const int64_t k = kb + lane;
+            bool ready = false;
+            int32_t x = 0;
+            if (k < rb) {
+                const RevRec r = rrec[k];
+                x = r.src;
+                VState sx = vs[x];
+                if (vreach) {
+                    D4 cand, cur;
+                    cand.sum = sv.sum + r.sum;
+                    cand.anom = sv.anom + (int32_t)(r.fl & 3u);
+                    cand.nz = sv.nz + (int32_t)((r.fl >> 2) & 1u);
+                    cand.tot = sv.tot + (int32_t)((r.fl >> 3) & 1u);
+                    cur.sum = sx.sum;
+                    cur.anom = sx.anom;
+                    cur.nz = sx.nz;
+                    cur.tot = sx.tot;
+                    int32_t am = sx.amin_reach >> 1;
+                    const int32_t na = av + (int32_t)(r.fl & 3u);
+                    if (!(sx.amin_reach & 1) || less4(cand, cur)) {  // strict: the first relaxer wins among equals
+                        sx.sum = cand.sum;
+                        sx.anom = cand.anom;
+                        sx.nz = cand.nz;
+                        sx.tot = cand.tot;
+                        sx.best = v;
+                    }
+                    if (na < am) am = na;
+                    sx.amin_reach = (am << 1) | 1;
+                }
+                sx.cnt -= 1;
+                vs[x] = sx;
+                ready = sx.cnt == 0;
+            }
+            tail = kahn_push(sm, q, tail, ready, x);
+        }
+    }
+    if (lane == 0) {
+        const VState ss = vs[g.src];
+        w.anom_dis[c] = ss.amin_reach >> 1;
+        if (!(ss.amin_reach & 1)) w.status[c] = 2;
+    }
+}
+// forward Kahn order (paf_data.cpp:742-746)
+__device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
+    KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] == 1) return;  // singleton; (unsolvable contigs are not known yet: relax runs concurrently)
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    int32_t *__restrict__ cnt = w.cnt2 + v0;
+    const int64_t *__restrict__ eoff = w.eoff + v0;
+    const Edge *__restrict__ edge = w.edge;
+    int32_t *__restrict__ q = w.topo + v0;
+    int32_t *__restrict__ order = w.order + v0;
+    int32_t head = 0, tail = 0;
+    for (int32_t vb = 0; vb < g.V; vb += 32) {
+        const int32_t v = vb + lane;
+        const bool seed = v < g.V && cnt[v] == 0;
+        tail = kahn_push(sm, q, tail, seed, v);
+    }
+    while (head < tail) {
+        const int32_t u = kahn_pop(sm, q, head, tail);
+        if (lane == 0) order[u] = head;
+        head++;
+        const int64_t ea = eoff[u], eb = eoff[u + 1];
+        for (int64_t kb = ea; kb < eb; kb += 32) {
+            const int64_t k = kb + lane;
+            bool ready = false;
+            int32_t x = 0;
+            if (k < eb) {
+                x = e_dst(edge[k]);
+                const int32_t left = cnt[x] - 1;  // out-edges of u have distinct heads: no conflict inside the warp
+                cnt[x] = left;
+                ready = left == 0;
+            }
+            tail = kahn_push(sm, q, tail, ready, x);
+        }
+    }
+}
+#endif
+AA_HDN void f_relax_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_relax_warp(w, c, scratch);
+#else
+    (void)scratch;
+    f_relax(w, c);
+#endif
+}
+AA_HDN void f_topo_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_topo_warp(w, c, scratch);
+#else
+    (void)scratch;
+    f_topo(w, c);
+#endif
+}
+constexpr size_t KAHN_SMEM_BYTES = 4 * 1024;
 
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------

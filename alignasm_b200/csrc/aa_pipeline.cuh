@@ -59,6 +59,9 @@ AA_FUNCTOR(FnVtxOff, f_vtx_off(w, i))
 AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
 AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
+AA_FUNCTOR(FnRevPack, f_rev_pack(w, i))
+AA_FUNCTOR(FnRelaxInit, f_relax_init(w, i))
+AA_FUNCTOR(FnRelaxUnpack, f_relax_unpack(w, i))
 AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
 AA_FUNCTOR(FnMainRows, f_main_rows(w, i))
 AA_FUNCTOR(FnTasksA1, f_tasks_a1(w, i))
@@ -94,8 +97,8 @@ struct FnTasksB {
         }                                                           \
     };
 AA_CTG_FUNCTOR(FnParts, f_parts(w, c))
-AA_CTG_FUNCTOR(FnRelax, f_relax(w, c))
-AA_CTG_FUNCTOR(FnTopo, f_topo(w, c))
+AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
+AA_CTG_FUNCTOR(FnTopo, f_topo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnEnum, f_enum(w, c))
 AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
@@ -434,13 +437,30 @@ struct Pipeline {
             err = "device allocation failed (vertex state)";
             return AA_ERR_NOMEM;
         }
+        // the forward Kahn order is only consumed by the walk phases: it runs on the side stream, concurrently
+        // with relax / heaps / enum
+        if (bk.device_kahn()) {
+            w.rrec = A<RevRec>(E);
+            w.vs = A<VState>(Vtot);
+            w.cnt2 = A<int32_t>(Vtot);
+            if (!w.rrec || !w.vs || !w.cnt2) {
+                err = "device allocation failed (relax records)";
+                return AA_ERR_NOMEM;
+            }
+        }
         bk.phase_begin(PH_RELAX);
-        bk.for_each_contig("relax", C, FnRelax{w, d_ord});
-        bk.phase_end(PH_RELAX);
-        AA_BK_CHECK();
+        if (bk.device_kahn()) {
+            bk.for_each("rev_pack", E, FnRevPack{w});
+            bk.for_each("relax_init", Vtot, FnRelaxInit{w});
+        }
+        bk.side_begin();
         bk.phase_begin(PH_TOPO);
-        bk.for_each_contig("topo", C, FnTopo{w, d_ord});
+        bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
         bk.phase_end(PH_TOPO);
+        bk.side_end();
+        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, KAHN_SMEM_BYTES);
+        if (bk.device_kahn()) bk.for_each("relax_unpack", Vtot, FnRelaxUnpack{w});
+        bk.phase_end(PH_RELAX);
         AA_BK_CHECK();
 
         // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
@@ -523,6 +543,7 @@ struct Pipeline {
         AA_BK_CHECK();
 
         // ---- phase 10: walks, pass A ----
+        bk.side_join();
         bk.phase_begin(PH_WALKS_A);
         int64_t maxV = 3;
         {

@@ -62,6 +62,10 @@ struct HostBackend {
         }
     }
     int64_t read_i64(const int64_t *p) { return *p; }
+    bool device_kahn() const { return false; }
+    void side_begin() {}
+    void side_end() {}
+    void side_join() {}
     int host_threads() { return 1; }
     int64_t max_workers() { return 3; }  // >1 so that slot indexing is exercised
     int64_t scratch_budget() { return (int64_t)1 << 30; }

@@ -128,7 +128,7 @@ struct __attribute__((aligned(8))) SKey {
     int32_t use;  // 0: not inserted (head unreachable, or the tree edge u -> best[u])
 };
 // priority-queue entry of the enumeration: 32 B
-struct PQEnt {
+struct __attribute__((aligned(16))) PQEnt {
     int64_t sum;
     int32_t anom, nz, tot;
     int32_t node;  // heap node id (allocation order == the reference's pointer order)
@@ -149,6 +149,12 @@ struct __attribute__((aligned(16))) VState {
     int32_t best;
     int32_t cnt;
     int32_t amin_reach;  // bit 0: reaches dest; bits 1..: min anom sum to dest
+};
+// per edge (u,v): root of v's sidetrack heap and its key, so that a pop needs one load instead of three
+struct __attribute__((aligned(8))) ENext {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t hv;  // hroot[v] or -1
 };
 struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
     int32_t i, j;        // contig-local sorted block indices
@@ -221,6 +227,7 @@ struct Ws {
     SKey *skey;          // [E] sidetrack keys (parallel pre-pass)
     int32_t *child;      // [E] tree children of v, compacted at rev_off[v] (ascending source)
     int32_t *nchild;     // [Vtot]
+    ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
     // enumeration
     int64_t *walk_off;   // [C+1] = c*K
@@ -1502,6 +1509,263 @@ AA_HDN void f_enum(const Ws &w, int64_t c) {
     }
     w.n_walk[c] = nd;
 }
+
+// parallel pre-pass over vertices for the warp enumeration: next-heap root + key of every out-edge
+AA_HDN void f_enext(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.status[c] != 0) return;
+    const int64_t v0 = w.vtx_off[c];
+    const int64_t ea = w.eoff[gv], eb = w.eoff[gv + 1];
+    for (int64_t k = ea; k < eb; k++) {
+        const int32_t v = e_dst(w.edge[k]);
+        const int32_t hv = w.hroot[v0 + v];
+        ENext n;
+        n.hv = hv;
+        n.sum = 0;
+        n.anom = n.nz = n.tot = 0;
+        if (hv >= 0) {
+            const HNode h = hn_load(w.hn + hv);
+            n.sum = h.sum;
+            n.anom = h.anom;
+            n.nz = h.nz;
+            n.tot = h.tot;
+        }
+        w.enext[k] = n;
+    }
+}
+#if defined(__CUDA_ARCH__)
+// ---- warp-cooperative K-walk enumeration (device only; the host emulation runs f_enum) ------------------------
+// The priority queue is a 32-ary min-heap under the same total order as the reference's
+// std::priority_queue<tuple<Distance, heap_t*, int64_t>> (distance, node allocation order, entry index).
+// Heap positions below ENUM_CACHE live in shared memory (root, level 1 and most of level 2), the rest in
+// global memory; one sift-down level = one coalesced 32-entry load + a warp argmin.
+constexpr int32_t ENUM_CACHE = 960;  // 30 KB of 32-B entries per warp: 7 warps per SM
+struct EnumSmem {
+    PQEnt top[ENUM_CACHE];
+};
+__device__ __forceinline__ PQEnt pq_ld(const PQEnt *p) {
+    union {
+        PQEnt e;
+        V16 v[2];
+    } u;
+    const V16 *q = reinterpret_cast<const V16 *>(p);
+    u.v[0] = q[0];
+    u.v[1] = q[1];
+    return u.e;
+}
+__device__ __forceinline__ void pq_st(PQEnt *p, const PQEnt &e) {
+    union {
+        PQEnt e;
+        V16 v[2];
+    } u;
+    u.e = e;
+    V16 *q = reinterpret_cast<V16 *>(p);
+    q[0] = u.v[0];
+    q[1] = u.v[1];
+}
+__device__ __forceinline__ PQEnt pq_get(const EnumSmem &sm, const PQEnt *g, int32_t pos) {
+    return pos < ENUM_CACHE ? pq_ld(&sm.top[pos]) : pq_ld(g + pos);
+}
+__device__ __forceinline__ void pq_put(EnumSmem &sm, PQEnt *g, int32_t pos, const PQEnt &e) {
+    if (pos < ENUM_CACHE) pq_st(&sm.top[pos], e);
+    else pq_st(g + pos, e);
+}
+__device__ __forceinline__ PQEnt pq_bcast(const PQEnt &e, int32_t src) {
+    const uint32_t FULL = 0xffffffffu;
+    PQEnt r;
+    r.sum = __shfl_sync(FULL, e.sum, src);
+    r.anom = __shfl_sync(FULL, e.anom, src);
+    r.nz = __shfl_sync(FULL, e.nz, src);
+    r.tot = __shfl_sync(FULL, e.tot, src);
+    r.node = __shfl_sync(FULL, e.node, src);
+    r.idx = __shfl_sync(FULL, e.idx, src);
+    r.pad = 0;
+    return r;
+}
+// lane holding the minimum of the valid entries under pq_less (at least one lane is valid)
+__device__ int32_t warp_argmin(const PQEnt &e, bool valid) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t me = 1u << (threadIdx.x & 31);
+    const int32_t hi = valid ? (int32_t)(e.sum >> 32) : 0x7fffffff;
+    const int32_t mh = __reduce_min_sync(FULL, hi);
+    const bool c1 = valid && hi == mh;
+    const uint32_t lo = c1 ? (uint32_t)e.sum : 0xffffffffu;
+    const uint32_t ml = __reduce_min_sync(FULL, lo);
+    uint32_t cand = __ballot_sync(FULL, c1 && lo == ml);
+    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
+    const int32_t an = (cand & me) ? e.anom : 0x7fffffff;
+    const int32_t ma = __reduce_min_sync(FULL, an);
+    cand = __ballot_sync(FULL, (cand & me) && e.anom == ma);
+    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
+    // mapq ratio, descending: follow strictly better leaders
+    int32_t leader = __ffs(cand) - 1;
+    int32_t nzl, totl;
+    for (;;) {
+        nzl = __shfl_sync(FULL, e.nz, leader);
+        totl = __shfl_sync(FULL, e.tot, leader);
+        const bool better = (cand & me) && (int64_t)e.nz * den(totl) > (int64_t)nzl * den(e.tot);
+        const uint32_t b = __ballot_sync(FULL, better);
+        if (!b) break;
+        leader = __ffs(b) - 1;
+    }
+    cand = __ballot_sync(FULL, (cand & me) && (int64_t)e.nz * den(totl) == (int64_t)nzl * den(e.tot));
+    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
+    const int32_t nd = (cand & me) ? e.node : 0x7fffffff;
+    const int32_t mn = __reduce_min_sync(FULL, nd);
+    cand = __ballot_sync(FULL, (cand & me) && e.node == mn);
+    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
+    const int32_t ix = (cand & me) ? e.idx : 0x7fffffff;
+    const int32_t mi = __reduce_min_sync(FULL, ix);
+    cand = __ballot_sync(FULL, (cand & me) && e.idx == mi);
+    return __ffs(cand) - 1;
+}
+__device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
+    EnumSmem &sm = *reinterpret_cast<EnumSmem *>(scratch);
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0) {
+        if (lane == 0) w.n_walk[c] = 0;
+        return;
+    }
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int64_t e0 = w.eoff[v0];
+    const int64_t wo = w.walk_off[c];
+    D4 *__restrict__ dist = w.wdist + wo;
+    int32_t *__restrict__ last = w.wlast + wo;
+    int32_t *__restrict__ en = w.ent_node + 3 * wo;
+    int32_t *__restrict__ ep = w.ent_prev + 3 * wo;
+    PQEnt *__restrict__ pq = w.pq + 3 * wo;
+    const HNode *__restrict__ hn = w.hn;
+    const int32_t K = w.K;
+    int32_t nd = 0, ne = 0, n = 0;
+    const D4 ds = w.d[v0 + g.src];
+    if (lane == 0) {
+        dist[0] = ds;
+        last[0] = -1;
+    }
+    nd = 1;
+    const int32_t hs = w.hroot[v0 + g.src];
+    if (hs >= 0) {
+        const HNode hr = hn_load(hn + hs);
+        PQEnt e;
+        e.sum = ds.sum + hr.sum;
+        e.anom = ds.anom + hr.anom;
+        e.nz = ds.nz + hr.nz;
+        e.tot = ds.tot + hr.tot;
+        e.node = hs;
+        e.idx = 0;
+        e.pad = 0;
+        if (lane == 0) {
+            en[0] = hs;
+            ep[0] = -1;
+            pq_st(&sm.top[0], e);
+        }
+        ne = 1;
+        n = 1;
+        __syncwarp();
+        while (n > 0 && nd < K) {
+            // ---- pop the minimum ----
+            const PQEnt t = pq_ld(&sm.top[0]);
+            if (lane == 0) {
+                D4 cd;
+                cd.sum = t.sum;
+                cd.anom = t.anom;
+                cd.nz = t.nz;
+                cd.tot = t.tot;
+                cd.aux = 0;
+                dist[nd] = cd;
+                last[nd] = t.idx;
+            }
+            nd++;
+            n--;
+            // start the loads of the popped sidetrack's heap node early (consumed after the sift-down)
+            const HNode ch = hn_load(hn + t.node);
+            const int32_t ceid = w.hn_eid[t.node];
+            const int32_t pre = ep[t.idx];
+            if (n > 0) {
+                const PQEnt mv = pq_get(sm, pq, n);  // the last entry moves down from the root
+                int32_t pos = 0;
+                for (;;) {
+                    const int32_t first = (pos << 5) + 1;
+                    if (first >= n) break;
+                    const bool valid = first + lane < n;
+                    PQEnt mine;
+                    if (valid) mine = pq_get(sm, pq, first + lane);
+                    const int32_t ml = warp_argmin(mine, valid);
+                    const PQEnt best = pq_bcast(mine, ml);
+                    if (!pq_less(best, mv)) break;
+                    if (lane == 0) pq_put(sm, pq, pos, best);
+                    pos = first + ml;
+                }
+                if (lane == 0) pq_put(sm, pq, pos, mv);
+                __syncwarp();
+            }
+            // ---- the (up to) three successors: lane 0 next-heap root, lane 1 left child, lane 2 right child ----
+            PQEnt a;
+            a.sum = 0;
+            a.anom = a.nz = a.tot = 0;
+            a.node = -1;
+            a.idx = 0;
+            a.pad = 0;
+            int32_t aprev = -1;
+            if (lane == 0) {
+                const ENext x = w.enext[e0 + ceid];
+                if (x.hv >= 0) {
+                    a.sum = t.sum + x.sum;
+                    a.anom = t.anom + x.anom;
+                    a.nz = t.nz + x.nz;
+                    a.tot = t.tot + x.tot;
+                    a.node = x.hv;
+                    aprev = t.idx;
+                }
+            } else if (lane <= 2) {
+                const int32_t cid = lane == 1 ? ch.left : ch.right;
+                if (cid >= 0) {
+                    const HNode x = hn_load(hn + cid);
+                    a.sum = t.sum + x.sum - ch.sum;
+                    a.anom = t.anom + x.anom - ch.anom;
+                    a.nz = t.nz + x.nz - ch.nz;
+                    a.tot = t.tot + x.tot - ch.tot;
+                    a.node = cid;
+                    aprev = pre;
+                }
+            }
+            const uint32_t vm = __ballot_sync(FULL, a.node >= 0);
+            if (a.node >= 0) {
+                a.idx = ne + __popc(vm & ((1u << lane) - 1u));
+                en[a.idx] = a.node;
+                ep[a.idx] = aprev;
+            }
+            ne += __popc(vm);
+            // ---- push them in entry order ----
+            for (uint32_t m = vm; m; m &= m - 1) {
+                const PQEnt e2 = pq_bcast(a, __ffs(m) - 1);
+                int32_t pos = n++;
+                while (pos > 0) {
+                    const int32_t par = (pos - 1) >> 5;
+                    const PQEnt pe = pq_get(sm, pq, par);
+                    if (!pq_less(e2, pe)) break;
+                    if (lane == 0) pq_put(sm, pq, pos, pe);
+                    pos = par;
+                }
+                if (lane == 0) pq_put(sm, pq, pos, e2);
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) w.n_walk[c] = nd;
+}
+#endif
+AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_enum_warp(w, c, scratch);
+#else
+    (void)scratch;
+    f_enum(w, c);
+#endif
+}
+constexpr size_t ENUM_SMEM_BYTES = 960 * 32;
 
 // phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.

@@ -60,6 +60,7 @@ AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
 AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
 AA_FUNCTOR(FnRevPack, f_rev_pack(w, i))
+AA_FUNCTOR(FnENext, f_enext(w, i))
 AA_FUNCTOR(FnRelaxInit, f_relax_init(w, i))
 AA_FUNCTOR(FnRelaxUnpack, f_relax_unpack(w, i))
 AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
@@ -100,7 +101,7 @@ AA_CTG_FUNCTOR(FnParts, f_parts(w, c))
 AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnTopo, f_topo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
-AA_CTG_FUNCTOR(FnEnum, f_enum(w, c))
+AA_CTG_FUNCTOR(FnEnum, f_enum_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
 AA_CTG_FUNCTOR(FnTaskCompact, f_task_compact(w, c))
 AA_CTG_FUNCTOR(FnAllList, f_all_list(w, c))
@@ -515,7 +516,15 @@ struct Pipeline {
             err = "device allocation failed (walk enumeration)";
             return AA_ERR_NOMEM;
         }
-        bk.for_each_contig("enum", C, FnEnum{w, d_ord});
+        if (bk.device_kahn()) {
+            w.enext = A<ENext>(E);
+            if (!w.enext) {
+                err = "device allocation failed (enumeration)";
+                return AA_ERR_NOMEM;
+            }
+            bk.for_each("enext", Vtot, FnENext{w});
+        }
+        bk.for_each_contig("enum", C, FnEnum{w, d_ord}, ENUM_SMEM_BYTES);
         bk.phase_end(PH_ENUM);
         AA_BK_CHECK();
 

@@ -13,6 +13,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,6 +64,27 @@ struct CudaBackend {
     cudaEvent_t ev[PH_COUNT][2];
     bool ev_on[PH_COUNT];
     cudaEvent_t ev_total[2];
+    // AA_TRACE=1: one event after every launch, printed as a timeline (ms since the start of the solve) by end_solve
+    bool trace = false;
+    struct TraceMark {
+        const char *name;
+        cudaEvent_t ev;
+        bool side;
+    };
+    std::vector<TraceMark> marks;
+    size_t n_marks = 0;
+    void mark(const char *name) {
+        if (!trace || failed) return;
+        if (n_marks == marks.size()) {
+            TraceMark m{name, nullptr, false};
+            cudaEventCreate(&m.ev);
+            marks.push_back(m);
+        }
+        marks[n_marks].name = name;
+        marks[n_marks].side = stream == side_stream;
+        cudaEventRecord(marks[n_marks].ev, stream);
+        n_marks++;
+    }
 
     bool ok() const { return !failed; }
     const std::string &error() const { return errmsg; }
@@ -103,6 +126,8 @@ struct CudaBackend {
         }
         AA_CUDA(cudaEventCreate(&ev_total[0]));
         AA_CUDA(cudaEventCreate(&ev_total[1]));
+        const char *tr = std::getenv("AA_TRACE");
+        trace = tr && tr[0] && tr[0] != '0';
         return !failed;
     }
     void shutdown() {
@@ -194,6 +219,7 @@ struct CudaBackend {
         for (auto &b : pool) b.top = 0;
         log.clear();
         n_launch = 0;
+        n_marks = 0;
         for (int p = 0; p < PH_COUNT; p++) ev_on[p] = false;
         AA_CUDA(cudaEventRecord(ev_total[0], stream));
     }
@@ -211,6 +237,17 @@ struct CudaBackend {
                 }
         }
         st.n_launch = n_launch;
+        if (trace && !failed) {
+            cudaStreamSynchronize(side_stream);
+            float prev[2] = {0, 0};
+            for (size_t i = 0; i < n_marks; i++) {
+                float t = 0;
+                cudaEventElapsedTime(&t, ev_total[0], marks[i].ev);
+                const int s = marks[i].side ? 1 : 0;
+                std::fprintf(stderr, "[aa_trace] %-6s %-14s end %9.3f ms  (+%.3f)\n", s ? "side" : "main", marks[i].name, t, t - prev[s]);
+                prev[s] = t;
+            }
+        }
     }
     void phase_begin(int p) { AA_CUDA(cudaEventRecord(ev[p][0], stream)); }
     void phase_end(int p) {
@@ -240,23 +277,26 @@ struct CudaBackend {
     }
 
     template <class F>
-    void for_each(const char *, int64_t n, F f) {
+    void for_each(const char *name, int64_t n, F f) {
         if (n <= 0 || failed) return;
         int64_t grid = (n + 255) / 256;
         k_items<F><<<(unsigned)grid, 256, 0, stream>>>(n, f);
         n_launch++;
+        mark(name);
     }
     template <class F>
-    void for_each_contig(const char *, int64_t n, F f, size_t smem = 0) {
+    void for_each_contig(const char *name, int64_t n, F f, size_t smem = 0) {
         if (n <= 0 || failed) return;
         k_warp_items<F><<<(unsigned)n, 32, smem, stream>>>(n, f);
         n_launch++;
+        mark(name);
     }
     template <class F>
-    void workers(const char *, int64_t n, F f, size_t smem = 0) {
+    void workers(const char *name, int64_t n, F f, size_t smem = 0) {
         if (n <= 0 || failed) return;
         k_warp_items<F><<<(unsigned)n, 32, smem, stream>>>(n, f);
         n_launch++;
+        mark(name);
     }
     void scan_i32(const int32_t *in, int64_t *out, int64_t n) {
         if (n <= 0 || failed) return;
@@ -267,6 +307,7 @@ struct CudaBackend {
         if (!t) return;
         AA_CUDA(cub::DeviceScan::ExclusiveSum(t, tmp, it, out, n, stream));
         n_launch++;
+        mark("scan");
     }
     void sort_pairs_u32(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit) {
         if (n <= 0 || failed) return;
@@ -276,6 +317,7 @@ struct CudaBackend {
         if (!t) return;
         AA_CUDA(cub::DeviceRadixSort::SortPairs(t, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
         n_launch++;
+        mark("radix_sort");
     }
     // ---- side stream: work that is off the critical path runs concurrently with the main stream ----
     bool device_kahn() const { return true; }

@@ -1814,6 +1814,165 @@ AA_HDN void f_plan(const Ws &w, int64_t c) {
     w.n_task[c] = nt;
     w.last_group[c] = group;
 }
+#if defined(__CUDA_ARCH__)
+// ---- warp-parallel parts (paf_data.cpp:249-261): a boundary is a block whose start lies beyond the running
+// maximum of the ends before it; part_l = last boundary at or before, part_r = next boundary after
+__device__ void f_parts_warp(const Ws &w, int64_t c) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int64_t b0 = w.ctg_off[c];
+    const int32_t n = (int32_t)(w.ctg_off[c + 1] - b0);
+    if (lane == 0) w.status[c] = (n == 1) ? 1 : 0;
+    int64_t carry_max = -1;   // max qry_end over the blocks before this chunk
+    int32_t carry_l = 0;      // last boundary so far
+    for (int32_t base = 0; base < n; base += 32) {
+        const int32_t i = base + lane;
+        const bool in = i < n;
+        const int64_t s = in ? w.qs[b0 + i] : 0;
+        int64_t e = in ? w.qe[b0 + i] : -1;
+        // exclusive prefix max of the ends
+        int64_t inc = e;
+        for (int32_t d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d && o > inc) inc = o;
+        }
+        int64_t exc = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) exc = -1;
+        if (carry_max > exc) exc = carry_max;
+        const bool bnd = in && exc < s;
+        // last boundary at or before i
+        int32_t pl = bnd ? i : -1;
+        for (int32_t d = 1; d < 32; d <<= 1) {
+            const int32_t o = __shfl_up_sync(FULL, pl, d);
+            if (lane >= d && o > pl) pl = o;
+        }
+        if (pl < 0) pl = carry_l;
+        if (in) w.part_l[b0 + i] = pl;
+        carry_l = __shfl_sync(FULL, pl, 31 < n - base - 1 ? 31 : n - base - 1);
+        const int64_t last_inc = __shfl_sync(FULL, inc, 31);
+        if (last_inc > carry_max) carry_max = last_inc;
+    }
+    __syncwarp();
+    // part_r: next boundary after i = part_l of the first later block whose part_l differs; scan from the right
+    int32_t carry_r = n;  // boundary following the current chunk
+    for (int32_t base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int32_t i = base + lane;
+        const bool in = i < n;
+        const int32_t pl = in ? w.part_l[b0 + i] : 0x7fffffff;
+        // a block is a boundary iff part_l == i; next boundary strictly after i
+        int32_t nb = (in && pl == i) ? i : 0x7fffffff;   // boundary index or +inf
+        // suffix min over lanes > me (exclusive)
+        int32_t suf = nb;
+        for (int32_t d = 1; d < 32; d <<= 1) {
+            const int32_t o = __shfl_down_sync(FULL, suf, d);
+            if (lane + d < 32 && o < suf) suf = o;
+        }
+        int32_t exc = __shfl_down_sync(FULL, suf, 1);
+        if (lane == 31) exc = 0x7fffffff;
+        if (exc > carry_r) exc = carry_r;   // nothing later in the chunk: the carried one
+        if (exc == 0x7fffffff) exc = carry_r;
+        if (in) w.part_r[b0 + i] = exc < carry_r ? exc : carry_r;
+        const int32_t first = __shfl_sync(FULL, suf, 0);
+        if (first < carry_r) carry_r = first;
+    }
+}
+// ---- warp-parallel plan (paf_data.cpp:1585-1649): lanes scan the distance list, the rare candidates
+// (anom below the minimum walk's) are handled in order
+__device__ void f_plan_warp(const Ws &w, int64_t c) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (lane == 0) {
+        w.n_task[c] = 0;
+        w.n_tie[c] = 0;
+        w.last_group[c] = 0;
+    }
+    if (w.status[c] != 0) return;
+    const int64_t wo = w.walk_off[c];
+    const D4 *__restrict__ dist = w.wdist + wo;
+    Task *__restrict__ t = w.task + 2 * wo;
+    const int32_t nw = w.n_walk[c];
+    const D4 mind = dist[0];
+    // walks tied with walk 0: the longest prefix with equal (score_sum, anom)
+    int32_t ntie = nw;
+    for (int32_t base = 0; base < nw; base += 32) {
+        const int32_t i = base + lane;
+        bool diff = false;
+        if (i < nw) {
+            const D4 x = dist[i];
+            diff = !same_sa(mind, x);
+            if (!diff) t[i] = Task{(int32_t)c, i, i, 0};  // harmless beyond the first difference: overwritten below
+        }
+        const uint32_t m = __ballot_sync(FULL, diff);
+        if (m) {
+            ntie = base + __ffs(m) - 1;
+            break;
+        }
+    }
+    __syncwarp();
+    int32_t nt = ntie, group = 0;
+    if (nw >= 2 && (int64_t)mind.anom != w.anom_dis[c]) {
+        int64_t ans_up = 0, ans_down = 0;
+        int32_t ans = -1;
+        D4 ansd = mind;
+        for (int32_t base = 0; base < nw; base += 32) {
+            const int32_t i = base + lane;
+            D4 x = mind;
+            bool cand = false;
+            if (i >= 1 && i < nw) {
+                x = dist[i];
+                cand = x.anom < mind.anom;
+            }
+            uint32_t m = __ballot_sync(FULL, cand);
+            while (m) {
+                const int32_t l = __ffs(m) - 1;
+                m &= m - 1;
+                D4 y;
+                y.sum = __shfl_sync(FULL, x.sum, l);
+                y.anom = __shfl_sync(FULL, x.anom, l);
+                y.nz = 0;
+                y.tot = 0;
+                y.aux = 0;
+                const int32_t idx = base + l;
+                const int64_t up = y.sum - mind.sum;
+                const int64_t down = (int64_t)mind.anom - y.anom;
+                if (ans == -1 || up * ans_down < down * ans_up) {
+                    ans_up = up;
+                    ans_down = down;
+                    ans = idx;
+                    ansd = y;
+                    group++;
+                    if (lane == 0) t[nt] = Task{(int32_t)c, idx, nt, group};
+                    nt++;
+                } else if (same_sa(y, ansd)) {
+                    if (lane == 0) t[nt] = Task{(int32_t)c, idx, nt, group};
+                    nt++;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        w.n_tie[c] = ntie;
+        w.n_task[c] = nt;
+        w.last_group[c] = group;
+    }
+}
+#endif
+AA_HDN void f_parts_any(const Ws &w, int64_t c) {
+#if defined(__CUDA_ARCH__)
+    f_parts_warp(w, c);
+#else
+    f_parts(w, c);
+#endif
+}
+AA_HDN void f_plan_any(const Ws &w, int64_t c) {
+#if defined(__CUDA_ARCH__)
+    f_plan_warp(w, c);
+#else
+    f_plan(w, c);
+#endif
+}
+
 AA_HDN void f_task_compact(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
     int64_t o = w.task_off[c];

@@ -97,12 +97,12 @@ struct FnTasksB {
             body;                                                   \
         }                                                           \
     };
-AA_CTG_FUNCTOR(FnParts, f_parts(w, c))
+AA_CTG_FUNCTOR(FnParts, f_parts_any(w, c))
 AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnTopo, f_topo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnEnum, f_enum_any(w, c, scratch))
-AA_CTG_FUNCTOR(FnPlan, f_plan(w, c))
+AA_CTG_FUNCTOR(FnPlan, f_plan_any(w, c))
 AA_CTG_FUNCTOR(FnTaskCompact, f_task_compact(w, c))
 AA_CTG_FUNCTOR(FnAllList, f_all_list(w, c))
 AA_CTG_FUNCTOR(FnMainTrace, f_main_trace(w, c))
@@ -464,6 +464,35 @@ struct Pipeline {
         bk.phase_end(PH_RELAX);
         AA_BK_CHECK();
 
+        // walk 0 of every contig is traced on the side stream (after topo), concurrently with heaps / enum
+        w.main_pos = A<int32_t>(Vtot);
+        w.main_walk = A<int32_t>(Vtot);
+        w.m_cs = A<int32_t>(Vtot);
+        w.m_cov = A<int64_t>(Vtot);
+        w.m_rows = A<int32_t>(Vtot);
+        w.m_done = A<uint8_t>(Vtot);
+        w.sp_cs = A<int32_t>(Vtot);
+        w.sp_rows = A<int32_t>(Vtot);
+        w.sp_cov = A<int64_t>(Vtot);
+        w.sp_used = A<uint8_t>(Vtot);
+        w.mr_blk = A<int32_t>(Vtot);
+        w.mr_qs = A<int64_t>(Vtot);
+        w.mr_qe = A<int64_t>(Vtot);
+        w.mr_rs = A<int64_t>(Vtot);
+        w.mr_re = A<int64_t>(Vtot);
+        w.m_tot_cov = A<int64_t>(C);
+        w.m_tot_rows = A<int32_t>(C);
+        w.m_len = A<int32_t>(C);
+        w.task_off = A<int64_t>(C + 2);
+        if (!w.main_pos || !w.main_walk || !w.m_cs || !w.m_cov || !w.m_rows || !w.m_done || !w.sp_cs || !w.sp_rows ||
+            !w.sp_cov || !w.sp_used || !w.mr_blk || !w.mr_qs || !w.mr_qe || !w.mr_rs || !w.mr_re) {
+            err = "device allocation failed (main chain)";
+            return AA_ERR_NOMEM;
+        }
+        bk.side_begin();
+        bk.for_each_contig("main_trace", C, FnMainTrace{w, d_ord});
+        bk.side_end();
+
         // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
         bk.phase_begin(PH_HEAPS);
         w.heap_top = (unsigned long long *)A<int64_t>(1);
@@ -534,7 +563,6 @@ struct Pipeline {
         w.n_task = A<int32_t>(C + 1);
         w.n_tie = A<int32_t>(C);
         w.last_group = A<int32_t>(C);
-        w.task_off = A<int64_t>(C + 2);
         if (!w.task) {
             err = "device allocation failed (task plan)";
             return AA_ERR_NOMEM;
@@ -575,31 +603,7 @@ struct Pipeline {
             err = "device allocation failed (walk scratch)";
             return AA_ERR_NOMEM;
         }
-        w.main_pos = A<int32_t>(Vtot);
-        w.main_walk = A<int32_t>(Vtot);
-        w.m_cs = A<int32_t>(Vtot);
-        w.m_cov = A<int64_t>(Vtot);
-        w.m_rows = A<int32_t>(Vtot);
-        w.m_done = A<uint8_t>(Vtot);
-        w.sp_cs = A<int32_t>(Vtot);
-        w.sp_rows = A<int32_t>(Vtot);
-        w.sp_cov = A<int64_t>(Vtot);
-        w.sp_used = A<uint8_t>(Vtot);
-        w.mr_blk = A<int32_t>(Vtot);
-        w.mr_qs = A<int64_t>(Vtot);
-        w.mr_qe = A<int64_t>(Vtot);
-        w.mr_rs = A<int64_t>(Vtot);
-        w.mr_re = A<int64_t>(Vtot);
-        w.m_tot_cov = A<int64_t>(C);
-        w.m_tot_rows = A<int32_t>(C);
-        w.m_len = A<int32_t>(C);
-        if (!w.main_pos || !w.main_walk || !w.m_cs || !w.m_cov || !w.m_rows || !w.m_done || !w.sp_cs || !w.sp_rows ||
-            !w.sp_cov || !w.sp_used || !w.mr_blk || !w.mr_qs || !w.mr_qe || !w.mr_rs || !w.mr_re) {
-            err = "device allocation failed (main chain)";
-            return AA_ERR_NOMEM;
-        }
         // walk 0 of every contig: trace, speculate every step in parallel, resolve sequentially, emit rows in parallel
-        bk.for_each_contig("main_trace", C, FnMainTrace{w, d_ord});
         bk.for_each("main_spec", Vtot, FnMainSpec{w});
         bk.zero(w.task_next, 8);
         bk.workers("main_resolve", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});

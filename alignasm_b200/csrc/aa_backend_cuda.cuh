@@ -13,6 +13,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -50,6 +51,7 @@ struct CudaBackend {
     std::string errmsg;
     int64_t n_launch = 0;
     int sm_count = 148;
+    size_t free_at_init = (size_t)16 << 30;
 
     struct Block {
         char *base;
@@ -70,18 +72,21 @@ struct CudaBackend {
         const char *name;
         cudaEvent_t ev;
         bool side;
+        double host_ms;  // host clock when the launch was issued
     };
+    std::chrono::steady_clock::time_point t_host0;
     std::vector<TraceMark> marks;
     size_t n_marks = 0;
     void mark(const char *name) {
         if (!trace || failed) return;
         if (n_marks == marks.size()) {
-            TraceMark m{name, nullptr, false};
+            TraceMark m{name, nullptr, false, 0.0};
             cudaEventCreate(&m.ev);
             marks.push_back(m);
         }
         marks[n_marks].name = name;
         marks[n_marks].side = stream == side_stream;
+        marks[n_marks].host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
         cudaEventRecord(marks[n_marks].ev, stream);
         n_marks++;
     }
@@ -114,6 +119,11 @@ struct CudaBackend {
         cudaDeviceProp prop;
         AA_CUDA(cudaGetDeviceProperties(&prop, dev));
         sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+        {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) free_at_init = fr;
+            else cudaGetLastError();
+        }
         AA_CUDA(cudaStreamCreateWithFlags(&main_stream, cudaStreamNonBlocking));
         AA_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
         AA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -220,6 +230,7 @@ struct CudaBackend {
         log.clear();
         n_launch = 0;
         n_marks = 0;
+        t_host0 = std::chrono::steady_clock::now();
         for (int p = 0; p < PH_COUNT; p++) ev_on[p] = false;
         AA_CUDA(cudaEventRecord(ev_total[0], stream));
     }
@@ -244,7 +255,7 @@ struct CudaBackend {
                 float t = 0;
                 cudaEventElapsedTime(&t, ev_total[0], marks[i].ev);
                 const int s = marks[i].side ? 1 : 0;
-                std::fprintf(stderr, "[aa_trace] %-6s %-14s end %9.3f ms  (+%.3f)\n", s ? "side" : "main", marks[i].name, t, t - prev[s]);
+                std::fprintf(stderr, "[aa_trace] %-6s %-14s end %9.3f ms  (+%.3f)  issued at host %9.3f ms\n", s ? "side" : "main", marks[i].name, t, t - prev[s], marks[i].host_ms);
                 prev[s] = t;
             }
         }
@@ -340,11 +351,9 @@ struct CudaBackend {
         return (int)std::min<unsigned>(h ? h : 1, 32);
     }
     int64_t max_workers() { return (int64_t)sm_count * 32; }
-    int64_t scratch_budget() {
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (int64_t)4 << 30;
-        return (int64_t)std::min<size_t>(fr / 4, (size_t)24 << 30);
-    }
+    // memory the walk scratch may take: a quarter of what was free when the context was created, minus nothing
+    // else -- no driver query on the solve path (cudaMemGetInfo stalls the host for milliseconds)
+    int64_t scratch_budget() { return (int64_t)std::min<size_t>(free_at_init / 4, (size_t)24 << 30); }
 };
 
 }  // namespace aa

@@ -380,6 +380,8 @@ struct Pipeline {
         w.walk_off = A<int64_t>(C + 1);
         bk.for_each("vtx_off", C + 1, FnVtxOff{w});
         const int64_t Vtot = B + P + 2 * C;
+        std::vector<int64_t> h_voff((size_t)C + 1);  // the one download of the vertex offsets (sizes the walk scratch, stats)
+        bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
         bk.phase_end(PH_PAIRS);
         AA_BK_CHECK();
         if (Vtot >= ((int64_t)1 << 32) - 1) {
@@ -583,11 +585,7 @@ struct Pipeline {
         bk.side_join();
         bk.phase_begin(PH_WALKS_A);
         int64_t maxV = 3;
-        {
-            std::vector<int64_t> h_voff((size_t)C + 1);
-            bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
-            for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
-        }
+        for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
         w.slot_stride = maxV + 1;
         const int64_t slot_bytes = w.slot_stride * (int64_t)(4 + 4 + 4 + sizeof(D5) + 4 + 1);
         int64_t S = std::min<int64_t>(std::max<int64_t>(NT, 2 * C), bk.max_workers());
@@ -685,8 +683,6 @@ struct Pipeline {
                 st.n_heap += h_heap[(size_t)c];
             }
         }
-        std::vector<int64_t> h_voff((size_t)C + 1);
-        bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
         for (int64_t c = 0; c < C; c++)
             if (h_status[(size_t)c] != 1) st.n_vtx += h_voff[(size_t)c + 1] - h_voff[(size_t)c];
         if (res) {

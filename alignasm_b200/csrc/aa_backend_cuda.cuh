@@ -330,6 +330,19 @@ struct CudaBackend {
         n_launch++;
         mark("radix_sort");
     }
+    void sort_pairs_u64(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit) {
+        if (n <= 0 || failed) return;
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceRadixSort::SortPairs(t, tmp, kin, kout, vin, vout, n, 0, end_bit, stream));
+        n_launch++;
+        mark("radix_sort64");
+    }
+    void fill_ff(void *p, size_t n) {
+        if (n && !failed) AA_CUDA(cudaMemsetAsync(p, 0xff, n, stream));
+    }
     // ---- side stream: work that is off the critical path runs concurrently with the main stream ----
     bool device_kahn() const { return true; }
     void side_begin() {

@@ -156,6 +156,27 @@ struct __attribute__((aligned(8))) ENext {
     int32_t anom, nz, tot;
     int32_t hv;  // hroot[v] or -1
 };
+// ---- BFS order of the shortest-path tree, computed in parallel (Euler tour + list ranking), and the
+// flat stream of sidetrack inserts in that order (k_shortest_walks.hpp:196-215) -------------------------------
+constexpr uint32_t TOUR_END = 0xffffffffu;
+struct __attribute__((aligned(16))) Tour {  // one tour element: D_x = 2x (entering x), U_x = 2x+1 (leaving x)
+    uint32_t nxt;  // successor element (global index) or TOUR_END
+    int32_t sp;    // suffix count of D elements: preorder rank from the end
+    int32_t sd;    // suffix sum of +1 (D) / -1 (U): depth
+    int32_t pad;
+};
+struct __attribute__((aligned(16))) VInfo {  // one tree vertex at its BFS position
+    int32_t x;         // contig-local vertex
+    uint32_t ins_beg;  // first record of its inserts in ins[] (global index)
+    int32_t nins;      // number of inserts; bit 30: has tree children
+    int32_t ppos;      // BFS position of its tree parent (-1 for dest)
+};
+constexpr int32_t VI_KIDS = 1 << 30;
+struct __attribute__((aligned(8))) InsKey {  // one sidetrack to insert: key c = w + d[v] - d[u] and its edge
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t eid;  // contig-local edge id
+};
 struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
     int32_t i, j;        // contig-local sorted block indices
     int64_t pe_q, pe_r;  // edited_loc_pre_end[i][j]
@@ -227,6 +248,19 @@ struct Ws {
     SKey *skey;          // [E] sidetrack keys (parallel pre-pass)
     int32_t *child;      // [E] tree children of v, compacted at rev_off[v] (ascending source)
     int32_t *nchild;     // [Vtot]
+    int32_t *nins;       // [Vtot] sidetracks of the vertex that are inserted
+    uint32_t *cslot;     // [Vtot] slot of the vertex in its parent's child list (index into child[])
+    Tour *tour_a, *tour_b;  // [2*Vtot] Euler tour of every contig's tree, double-buffered for pointer jumping
+    uint64_t *bkey_in, *bkey;  // [Vtot] (contig, depth, preorder) sort keys
+    uint32_t *bval_in, *bfs_vtx;  // [Vtot] global vertex ids; bfs_vtx[v0 + pos] = vertex at BFS position pos
+    int32_t *bfspos;     // [Vtot] BFS position of a tree vertex, -1 outside the tree
+    int32_t *ntree;      // [C] vertices in the tree
+    VInfo *vinfo;        // [Vtot] by BFS position
+    int32_t *ins_cnt;    // [Vtot+1] inserts per BFS position
+    int64_t *ins_off;    // [Vtot+2]
+    InsKey *ins;         // [Nins] inserts of every contig, BFS order then edge order
+    int32_t *root_at;    // [Vtot] heap root by BFS position
+    int32_t key_bits;    // bits of the depth / preorder fields of the sort key
     ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
     // enumeration
@@ -823,11 +857,14 @@ AA_HD D4 hkey(const HNode &h) {
 // (children of u = sources x of u's in-edges with best[x] == u, ascending x = reverse-list order)
 AA_HDN void f_heap_prep(const Ws &w, int64_t gv) {
     const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    w.nins[gv] = 0;
+    w.nchild[gv] = 0;
     if (w.status[c] != 0 && w.status[c] != 3) return;
     const int64_t v0 = w.vtx_off[c];
     const D4 du = w.d[gv];
     const int32_t bu = w.best[gv];
     const int64_t ea = w.eoff[gv], eb = w.eoff[gv + 1];
+    int32_t ni = 0;
     for (int64_t k = ea; k < eb; k++) {
         const Edge e = w.edge[k];
         const int32_t v = e_dst(e);
@@ -839,16 +876,133 @@ AA_HDN void f_heap_prep(const Ws &w, int64_t gv) {
         sk.tot = e_tot(e) + dv.tot - du.tot;
         // unreachable heads are skipped; the tree edge has c == IDENTITY and is skipped once (it is unique)
         sk.use = (du.aux && dv.aux && v != bu) ? 1 : 0;
+        ni += sk.use;
         w.skey[k] = sk;
     }
+    w.nins[gv] = ni;
     const int32_t u = (int32_t)(gv - v0);
     const int64_t ra = w.rev_off[gv], rb = w.rev_off[gv + 1];
     int32_t n = 0;
-    for (int64_t k = ra; k < rb; k++) {
-        const int32_t x = w.e_src[w.rev_eid[k]];
-        if (w.best[v0 + x] == u) w.child[ra + n++] = x;
-    }
+    if (du.aux)
+        for (int64_t k = ra; k < rb; k++) {
+            const int32_t x = w.e_src[w.rev_eid[k]];
+            if (w.best[v0 + x] == u) {
+                w.cslot[v0 + x] = (uint32_t)(ra + n);
+                w.child[ra + n++] = x;
+            }
+        }
     w.nchild[gv] = n;
+}
+// ---- BFS order of the tree without walking it: Euler tour, list ranking, sort by (depth, preorder) --------
+// BFS (FIFO from dest, children in ascending id: k_shortest_walks.hpp:191-200) visits the tree level by level
+// and, inside a level, in left-to-right order, which is the DFS preorder restricted to that level.
+AA_HD bool in_tree(const Ws &w, int64_t c, int64_t gv, int32_t x, int32_t dest) {
+    if (w.status[c] != 0 && w.status[c] != 3) return false;
+    return w.d[gv].aux != 0 && (x == dest || w.best[gv] >= 0);
+}
+AA_HDN void f_tour_build(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t x = (int32_t)(gv - v0), dest = (int32_t)(w.vtx_off[c + 1] - v0) - 1;
+    Tour dn, up;
+    dn.pad = up.pad = 0;
+    if (!in_tree(w, c, gv, x, dest)) {
+        dn.nxt = up.nxt = TOUR_END;
+        dn.sp = dn.sd = up.sp = up.sd = 0;
+    } else {
+        dn.sp = 1;
+        dn.sd = 1;
+        dn.nxt = w.nchild[gv] > 0 ? (uint32_t)(2 * (v0 + w.child[w.rev_off[gv]])) : (uint32_t)(2 * gv + 1);
+        up.sp = 0;
+        up.sd = -1;
+        if (x == dest) {
+            up.nxt = TOUR_END;
+        } else {
+            const int64_t gp = v0 + w.best[gv];
+            const int64_t slot = (int64_t)w.cslot[gv] + 1;
+            up.nxt = slot < w.rev_off[gp] + w.nchild[gp] ? (uint32_t)(2 * (v0 + w.child[slot])) : (uint32_t)(2 * gp + 1);
+        }
+    }
+    w.tour_a[2 * gv] = dn;
+    w.tour_a[2 * gv + 1] = up;
+}
+AA_HD void tour_jump(const Tour *__restrict__ src, Tour *__restrict__ dst, int64_t i) {  // one pointer-jumping round
+    Tour t = src[i];
+    if (t.nxt != TOUR_END) {
+        const Tour n = src[t.nxt];
+        t.sp += n.sp;
+        t.sd += n.sd;
+        t.nxt = n.nxt;
+    }
+    dst[i] = t;
+}
+// sort key of a vertex: (contig, depth, preorder); vertices outside the tree go behind their contig's tree
+AA_HDN void f_bfs_key(const Ws &w, int64_t gv, const Tour *__restrict__ tour) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t V = (int32_t)(w.vtx_off[c + 1] - v0);
+    const int32_t x = (int32_t)(gv - v0), dest = V - 1;
+    const int kb = w.key_bits;
+    uint64_t depth, pre;
+    if (in_tree(w, c, gv, x, dest)) {
+        const Tour me = tour[2 * gv], root = tour[2 * (v0 + dest)];
+        depth = (uint64_t)(1 - me.sd);
+        pre = (uint64_t)(root.sp - me.sp);
+        if (x == dest) w.ntree[c] = root.sp;
+    } else {
+        depth = ((uint64_t)1 << kb) - 1;
+        pre = (uint64_t)x;
+        if (x == dest) w.ntree[c] = 0;
+    }
+    w.bkey_in[gv] = ((uint64_t)c << (2 * kb)) | (depth << kb) | pre;
+    w.bval_in[gv] = (uint32_t)gv;
+}
+AA_HDN void f_bfs_pos(const Ws &w, int64_t i) {  // i = sorted slot; contigs keep their vertex ranges
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    const int64_t gv = w.bfs_vtx[i];
+    w.bfspos[gv] = (i - v0) < w.ntree[c] ? (int32_t)(i - v0) : -1;
+}
+AA_HDN void f_vinfo(const Ws &w, int64_t i) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t dest = (int32_t)(w.vtx_off[c + 1] - v0) - 1;
+    VInfo vi;
+    vi.x = -1;
+    vi.ins_beg = 0;
+    vi.nins = 0;
+    vi.ppos = -1;
+    int32_t cnt = 0;
+    if (i - v0 < w.ntree[c]) {
+        const int64_t gv = w.bfs_vtx[i];
+        vi.x = (int32_t)(gv - v0);
+        cnt = w.nins[gv];
+        vi.nins = cnt | (w.nchild[gv] > 0 ? VI_KIDS : 0);
+        vi.ppos = vi.x == dest ? -1 : w.bfspos[v0 + w.best[gv]];
+    }
+    w.vinfo[i] = vi;
+    w.ins_cnt[i] = cnt;
+}
+AA_HDN void f_ins_fill(const Ws &w, int64_t i) {  // the inserts of the vertex at sorted slot i, in edge order
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    int64_t o = w.ins_off[i];
+    w.vinfo[i].ins_beg = (uint32_t)o;
+    if (i - v0 >= w.ntree[c] || w.ins_cnt[i] == 0) return;
+    const int64_t gv = w.bfs_vtx[i];
+    const int64_t e0 = w.eoff[v0];
+    const int64_t ea = w.eoff[gv], eb = w.eoff[gv + 1];
+    for (int64_t k = ea; k < eb; k++) {
+        const SKey sk = w.skey[k];
+        if (!sk.use) continue;
+        InsKey ik;
+        ik.sum = sk.sum;
+        ik.anom = sk.anom;
+        ik.nz = sk.nz;
+        ik.tot = sk.tot;
+        ik.eid = (int32_t)(k - e0);
+        w.ins[o++] = ik;
+    }
 }
 
 // insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on arena overflow).
@@ -913,48 +1067,39 @@ AA_HDN int32_t heap_insert(HNode *__restrict__ hn, int32_t *__restrict__ hn_eid,
     return r;
 }
 
-// phase: sidetrack heaps, BFS over the shortest-path tree from dest (k_shortest_walks.hpp:191-215)
+// phase: sidetrack heaps (k_shortest_walks.hpp:191-215): the tree vertices in BFS order, each inserting its
+// sidetracks into the heap it inherits from its tree parent.  Sequential form (host emulation).
 AA_HDN void f_heaps(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
     if (w.status[c] != 0 && w.status[c] != 3) return;
     w.status[c] = 0;
-    Ctg g = ctg_view(w, c);
-    const int64_t v0 = g.v0;
-    const int64_t e0 = w.eoff[v0];
-    HNode *__restrict__ hn = w.hn;
-    int32_t *__restrict__ hn_eid = w.hn_eid;
-    const SKey *__restrict__ skey = w.skey;
-    const int64_t *__restrict__ eoff = w.eoff + v0;
-    const int64_t *__restrict__ rev_off = w.rev_off + v0;
-    const int32_t *__restrict__ nchild = w.nchild + v0;
-    int32_t *__restrict__ hroot = w.hroot + v0;
+    const int64_t v0 = w.vtx_off[c];
+    const VInfo *vinfo = w.vinfo + v0;
+    int32_t *root_at = w.root_at + v0;
+    int32_t *hroot = w.hroot + v0;
     HeapAlloc ha;
     ha.cur = ha.end = 0;
     ha.used = 0;
     ha.overflow = false;
-    int32_t *q = w.queue + v0;
-    for (int32_t v = 0; v < g.V; v++) hroot[v] = -1;
-    int32_t tail = 0;
-    q[tail++] = g.dest;
-    for (int32_t head = 0; head < tail && !ha.overflow; head++) {
-        const int32_t u = q[head];
-        int32_t hu = hroot[u];
-        const int64_t ea = eoff[u], eb = eoff[u + 1];
-        for (int64_t k = ea; k < eb; k++) {
-            const SKey sk = skey[k];
-            if (!sk.use) continue;
-            hu = heap_insert(hn, hn_eid, w, ha, hu, sk, (int32_t)(k - e0));
-            if (hu < 0) break;
+    const int32_t nt = w.ntree[c];
+    for (int32_t pos = 0; pos < nt && !ha.overflow; pos++) {
+        const VInfo vi = vinfo[pos];
+        int32_t root = vi.ppos < 0 ? -1 : root_at[vi.ppos];
+        const int32_t n = vi.nins & (VI_KIDS - 1);
+        for (int32_t k = 0; k < n; k++) {
+            const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
+            SKey sk;
+            sk.sum = ik.sum;
+            sk.anom = ik.anom;
+            sk.nz = ik.nz;
+            sk.tot = ik.tot;
+            sk.use = 1;
+            root = heap_insert(w.hn, w.hn_eid, w, ha, root, sk, ik.eid);
+            if (root < 0) break;
         }
         if (ha.overflow) break;
-        hroot[u] = hu;
-        const int32_t *ch = w.child + rev_off[u];
-        const int32_t nc = nchild[u];
-        for (int32_t k = 0; k < nc; k++) {
-            const int32_t x = ch[k];
-            hroot[x] = hu;
-            q[tail++] = x;
-        }
+        root_at[pos] = root;
+        hroot[vi.x] = root;
     }
     w.heap_used[c] = ha.used;
     if (ha.overflow) w.status[c] = 3;
@@ -1109,245 +1254,289 @@ constexpr size_t KAHN_SMEM_BYTES = 4 * 1024;
 
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------
-// The sequential insert is bound by the issue rate of one warp (~100 dependent instructions per copied
-// node).  Here the known prefix of the current heap's right spine lives in shared memory, one entry per lane:
-//   descent      = one parallel key compare + ballot (unknown tail nodes are fetched on demand)
-//   rank update  = a short warp-uniform recurrence over shared memory
+// One warp per contig streams two flat arrays prepared in parallel: the tree vertices in BFS order (vinfo) and
+// their inserts (ins).  Nothing on the serial chain chases the tree: both streams are read 32 records at a time,
+// one batch ahead.  The known prefix of the current heap's right spine lives in REGISTERS, spine level i on
+// lane i, so that one insert (leftist_heap.hpp:29-40) is a handful of warp-wide steps:
+//   descent      = one key compare per lane + ballot (the next unknown spine node is loaded ahead of need)
+//   rank update  = a suffix scan over the lanes: level q maps the rank r of its new right child to
+//                  f_q(r) = left ? min(left.rank, r) + 1 : 0, i.e. min(a, r + b); such maps compose as
+//                  (min(a2, a1 + b2), b1 + b2), so log2(p) shuffle rounds give every level its incoming rank
 //   path copying = every lane writes its own new node (ids are consecutive: N first, then bottom-up, the
 //                  allocation order of leftist_heap.hpp:29-40, which is what the PQ tie-break sees)
-// Spines of recently finished vertices are kept (keyed by root id) because BFS visits siblings and then
-// their children, all of which start from a heap built a few vertices earlier.
+// Spines of finished vertices with children are kept in shared memory (keyed by root id): BFS visits siblings
+// and then their children, all of which start from a heap built a few vertices earlier.
 constexpr int32_t SPMAX = 32;
 constexpr int32_t NSAVE = 8;
-constexpr int32_t QRING = 512;
-struct HeapSmem {
-    HNode node[SPMAX];
-    int32_t id[SPMAX];
-    int32_t eid[SPMAX];
-    HNode snode[NSAVE][SPMAX];
-    int32_t sid[NSAVE][SPMAX];
-    int32_t seid[NSAVE][SPMAX];
-    int32_t sroot[NSAVE], sL[NSAVE], snext[NSAVE];
-    int32_t ring[QRING];
+struct __attribute__((aligned(8))) IdEid {
+    int32_t id, eid;
 };
-static_assert(sizeof(HeapSmem) <= 16 * 1024, "HeapSmem does not fit its shared-memory allotment");
-__device__ __forceinline__ bool key_lt(const HNode &an, const SKey &k) {  // a->key < k (paf_data.hpp:142-159)
+struct HeapSmem {
+    HNode snode[NSAVE][SPMAX];
+    IdEid sid[NSAVE][SPMAX];
+    int32_t sroot[NSAVE], sL[NSAVE], snext[NSAVE];
+};
+static_assert(sizeof(HeapSmem) <= 12 * 1024, "HeapSmem does not fit its shared-memory allotment");
+__device__ __forceinline__ bool key_lt(const HNode &an, const InsKey &k) {  // a->key < k (paf_data.hpp:142-159)
     if (an.sum != k.sum) return an.sum < k.sum;
     if (an.anom != k.anom) return an.anom < k.anom;
     return (int64_t)an.nz * den(k.tot) > (int64_t)k.nz * den(an.tot);
+}
+__device__ __forceinline__ InsKey ins_ld(const InsKey *p) {  // 24 B, 8-byte aligned: three 64-bit loads
+    union {
+        InsKey k;
+        int64_t v[3];
+    } u;
+    const int64_t *q = reinterpret_cast<const int64_t *>(p);
+    u.v[0] = q[0];
+    u.v[1] = q[1];
+    u.v[2] = q[2];
+    return u.k;
+}
+__device__ __forceinline__ VInfo vinfo_ld(const VInfo *p) {
+    union {
+        VInfo v;
+        V16 q;
+    } u;
+    u.q = *reinterpret_cast<const V16 *>(p);
+    return u.v;
 }
 __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
     HeapSmem &sm = *reinterpret_cast<HeapSmem *>(scratch);
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int32_t BIG = 1 << 24;
     if (w.status[c] != 0 && w.status[c] != 3) return;
-    Ctg g = ctg_view(w, c);
-    const int64_t v0 = g.v0;
-    const int64_t e0 = w.eoff[v0];
+    const int64_t v0 = w.vtx_off[c];
     HNode *__restrict__ hn = w.hn;
     int32_t *__restrict__ hn_eid = w.hn_eid;
-    const SKey *__restrict__ skey = w.skey;
-    const int64_t *__restrict__ eoff = w.eoff + v0;
-    const int64_t *__restrict__ rev_off = w.rev_off + v0;
-    const int32_t *__restrict__ nchild = w.nchild + v0;
+    const VInfo *__restrict__ vinfo = w.vinfo + v0;
+    const InsKey *__restrict__ ins = w.ins;
     int32_t *__restrict__ hroot = w.hroot + v0;
-    int32_t *__restrict__ q = w.queue + v0;
-    for (int32_t v = lane; v < g.V; v += 32) hroot[v] = -1;
+    int32_t *__restrict__ root_at = w.root_at + v0;
+    const int32_t nt = w.ntree[c];
     if (lane < NSAVE) sm.sroot[lane] = -2;
     __syncwarp();
     int64_t cur = 0, end = 0, used = 0;  // arena chunk of this contig (warp-uniform)
     bool overflow = false;
-    int32_t head = 0, tail = 0, save_at = 0;
-    if (lane == 0) {
-        q[0] = g.dest;
-        sm.ring[0] = g.dest;
-    }
-    tail = 1;
-    __syncwarp();
-    while (head < tail && !overflow) {
-        // ---- next BFS vertex (uniform) ----
-        const int32_t u = (tail - head <= QRING) ? sm.ring[head & (QRING - 1)] : q[head];
-        head++;
-        int32_t root = hroot[u];
-        const int64_t ea = eoff[u], eb = eoff[u + 1];
-        const int32_t nc = nchild[u];
-        const int64_t cbase = rev_off[u];
-        // ---- working spine := spine of `root` ----
-        int32_t L = 0, next = root;
-        {
-            const int32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
-            if (root >= 0 && hit) {
-                const int32_t sl = __ffs(hit) - 1;
-                L = sm.sL[sl];
-                next = sm.snext[sl];
-                if (lane < L) {
-                    sm.node[lane] = sm.snode[sl][lane];
-                    sm.id[lane] = sm.sid[sl][lane];
-                    sm.eid[lane] = sm.seid[sl][lane];
+    int32_t save_at = 0;
+    // ---- insert stream: chunk [kbase, kbase+32) in kreg, the following chunk in knext ----
+    const int64_t kend = w.ins_off[v0 + nt];  // vertices behind the tree have no inserts, so this is the contig's end
+    int64_t kbase = w.ins_off[v0];
+    InsKey kreg, knext;
+    kreg.sum = knext.sum = 0;
+    kreg.anom = kreg.nz = kreg.tot = kreg.eid = 0;
+    knext.anom = knext.nz = knext.tot = knext.eid = 0;
+    if (kbase + lane < kend) kreg = ins_ld(ins + kbase + lane);
+    if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
+    // ---- working spine: level `lane` (valid below L); `next` = id of the first unknown spine node (or -1),
+    //      nx = that node, loaded ahead of need ----
+    HNode nd, nx;
+    nd.sum = nx.sum = 0;
+    nd.anom = nd.nz = nd.tot = nx.anom = nx.nz = nx.tot = 0;
+    nd.left = nd.right = nx.left = nx.right = -1;
+    nd.rank = nd.lrank = nx.rank = nx.lrank = 0;
+    int32_t nd_id = -1, nd_eid = 0, nx_eid = 0;
+    int32_t L = 0, next = -1, cur_root = -1;  // the working spine is the spine of heap cur_root (-1: empty heap)
+    // ---- vertex stream ----
+    VInfo vnext;
+    vnext.x = -1;
+    vnext.ins_beg = 0;
+    vnext.nins = 0;
+    vnext.ppos = -1;
+    if (lane < nt) vnext = vinfo_ld(vinfo + lane);
+    for (int32_t base = 0; base < nt && !overflow; base += 32) {
+        const VInfo vi = vnext;
+        if (base + 32 + lane < nt) vnext = vinfo_ld(vinfo + base + 32 + lane);
+        // roots of parents that were finished in earlier batches (parents inside this batch come by shuffle)
+        int32_t proot = -1;
+        if (base + lane < nt && vi.ppos >= 0 && vi.ppos < base) proot = root_at[vi.ppos];
+        int32_t myroot = -1;
+        const int32_t cnt = nt - base < 32 ? nt - base : 32;
+        for (int32_t j = 0; j < cnt && !overflow; j++) {
+            const int32_t nins_f = __shfl_sync(FULL, vi.nins, j);
+            const int32_t ppos = __shfl_sync(FULL, vi.ppos, j);
+            const int32_t pr = __shfl_sync(FULL, proot, j);
+            const int32_t inb = __shfl_sync(FULL, myroot, ppos >= base ? ppos - base : 0);
+            int32_t root = ppos >= base ? inb : pr;
+            const int32_t nins = nins_f & (VI_KIDS - 1);
+            if (nins > 0) {
+                int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
+                // ---- working spine := spine of `root` ----
+                if (root != cur_root) {
+                    L = 0;
+                    next = root;
+                    const uint32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
+                    if (root >= 0 && hit) {
+                        const int32_t sl = __ffs(hit) - 1;
+                        L = sm.sL[sl];
+                        next = sm.snext[sl];
+                        if (lane < L) {
+                            nd = hn_load(&sm.snode[sl][lane]);
+                            const IdEid ie = sm.sid[sl][lane];
+                            nd_id = ie.id;
+                            nd_eid = ie.eid;
+                        }
+                    }
+                    if (next >= 0) {
+                        nx = hn_load(hn + next);
+                        nx_eid = hn_eid[next];
+                    }
                 }
-            }
-            __syncwarp();
-        }
-        // ---- inserts, 32 sidetrack keys prefetched at a time ----
-        for (int64_t kb = ea; kb < eb && !overflow; kb += 32) {
-            SKey mine;
-            mine.use = 0;
-            mine.sum = 0;
-            mine.anom = mine.nz = mine.tot = 0;
-            if (kb + lane < eb) mine = skey[kb + lane];
-            uint32_t todo = __ballot_sync(FULL, mine.use != 0);
-            while (todo && !overflow) {
-                const int32_t src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                SKey k;
-                k.sum = __shfl_sync(FULL, mine.sum, src);
-                k.anom = __shfl_sync(FULL, mine.anom, src);
-                k.nz = __shfl_sync(FULL, mine.nz, src);
-                k.tot = __shfl_sync(FULL, mine.tot, src);
-                k.use = 1;
-                const int32_t eid = (int32_t)(kb + src - e0);
-                // descent: first spine position whose key is not < k
-                int32_t p;
-                for (;;) {
-                    const bool stop = lane < L && !key_lt(sm.node[lane], k);
-                    const uint32_t sm_stop = __ballot_sync(FULL, stop);
-                    if (sm_stop) {
-                        p = __ffs(sm_stop) - 1;
-                        break;
+                for (int32_t t = 0; t < nins && !overflow; t++, ki++) {
+                    // ---- the key (stream position ki) ----
+                    if (ki - kbase >= 32) {  // inserts are consumed in stream order: at most one chunk forward
+                        kreg = knext;
+                        kbase += 32;
+                        if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
                     }
-                    if (next < 0) {
-                        p = L;
-                        break;
+                    const int32_t src = (int32_t)(ki - kbase);
+                    InsKey k;
+                    k.sum = __shfl_sync(FULL, kreg.sum, src);
+                    k.anom = __shfl_sync(FULL, kreg.anom, src);
+                    k.nz = __shfl_sync(FULL, kreg.nz, src);
+                    k.tot = __shfl_sync(FULL, kreg.tot, src);
+                    k.eid = __shfl_sync(FULL, kreg.eid, src);
+                    // ---- descent: first spine level whose key is not < k ----
+                    int32_t p;
+                    for (;;) {
+                        const uint32_t stop = __ballot_sync(FULL, lane < L && !key_lt(nd, k));
+                        if (stop) {
+                            p = __ffs(stop) - 1;
+                            break;
+                        }
+                        if (next < 0) {
+                            p = L;
+                            break;
+                        }
+                        if (L >= SPMAX - 1) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
+                            overflow = true;
+                            p = 0;
+                            break;
+                        }
+                        if (lane == L) {
+                            nd = nx;
+                            nd_id = next;
+                            nd_eid = nx_eid;
+                        }
+                        L++;
+                        next = nx.right;
+                        if (next >= 0) {
+                            nx = hn_load(hn + next);  // same address on every lane: one transaction
+                            nx_eid = hn_eid[next];
+                        }
                     }
-                    if (L >= SPMAX) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
-                        overflow = true;
-                        p = 0;
-                        break;
+                    if (overflow) break;
+                    // ---- ids: N = base, level q's copy = base + (p - q) ----
+                    const int32_t need = p + 1;
+                    if (cur + need > end) {
+                        unsigned long long at = 0;
+                        if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+                        at = __shfl_sync(FULL, at, 0);
+                        if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
+                            overflow = true;
+                            break;
+                        }
+                        cur = (int64_t)at;
+                        end = cur + HEAP_CHUNK;
                     }
-                    const HNode nd = hn_load(hn + next);  // same address on every lane: one transaction
-                    const int32_t ne = hn_eid[next];
-                    if (lane == 0) {
-                        sm.node[L] = nd;
-                        sm.id[L] = next;
-                        sm.eid[L] = ne;
+                    const int32_t nbase = (int32_t)cur;
+                    cur += need;
+                    used += need;
+                    // ---- ranks: suffix scan of the per-level maps r -> min(a, r + b) over levels < p ----
+                    int32_t fa = BIG, fb = 0;
+                    if (lane < p) {
+                        fa = nd.left < 0 ? 0 : (int32_t)nd.lrank + 1;
+                        fb = nd.left < 0 ? BIG : 1;
                     }
-                    __syncwarp();
-                    L++;
-                    next = nd.right;
+                    for (int32_t d = 1; d < p; d <<= 1) {
+                        const int32_t oa = __shfl_down_sync(FULL, fa, d);
+                        const int32_t ob = __shfl_down_sync(FULL, fb, d);
+                        if (lane + d < 32) {
+                            fa = min(fa, oa + fb);
+                            fb = fb + ob;
+                        }
+                    }
+                    const int32_t my_rank = min(fa, 1 + fb);           // rank of this level's copy
+                    int32_t rin = __shfl_down_sync(FULL, my_rank, 1);  // rank of its new right child
+                    if (lane >= p - 1) rin = 1;                        // level p-1 gets N (rank 1)
+                    const bool my_swap = lane < p && (nd.left < 0 || (int32_t)nd.lrank < rin);
+                    const uint32_t swaps = __ballot_sync(FULL, my_swap);
+                    const int32_t sstar = swaps ? __ffs(swaps) - 1 : -1;
+                    // the stop node (level p, if any) becomes N's left child
+                    const int32_t stop_id = __shfl_sync(FULL, nd_id, p & 31);
+                    const int32_t stop_rank = __shfl_sync(FULL, (int32_t)nd.rank, p & 31);
+                    // ---- build and write this lane's node ----
+                    if (lane < p) {
+                        const int32_t ch = nbase + (p - 1 - lane);
+                        if (my_swap) {
+                            nd.right = nd.left;
+                            nd.left = ch;
+                            nd.lrank = (int16_t)rin;
+                        } else {
+                            nd.right = ch;
+                        }
+                        nd.rank = (int16_t)my_rank;
+                        nd_id = nbase + (p - lane);
+                    } else if (lane == p) {
+                        nd.sum = k.sum;
+                        nd.anom = k.anom;
+                        nd.nz = k.nz;
+                        nd.tot = k.tot;
+                        nd.left = p < L ? stop_id : -1;
+                        nd.right = -1;
+                        nd.rank = 1;
+                        nd.lrank = (int16_t)(p < L ? stop_rank : 0);
+                        nd_id = nbase;
+                        nd_eid = k.eid;
+                    }
+                    if (lane <= p) {
+                        hn_store(hn + nd_id, nd);
+                        hn_eid[nd_id] = nd_eid;
+                    }
+                    // ---- new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N ----
+                    const int32_t nright = __shfl_sync(FULL, nd.right, sstar >= 0 ? sstar : 0);
+                    const int32_t old_next = next;
+                    next = sstar >= 0 ? nright : -1;
+                    L = sstar >= 0 ? sstar + 1 : p + 1;
+                    root = p > 0 ? nbase + p : nbase;
+                    if (next >= 0 && next != old_next) {
+                        nx = hn_load(hn + next);
+                        nx_eid = hn_eid[next];
+                    }
                 }
                 if (overflow) break;
-                // ids: N = base, level q's copy = base + (p - q)
-                const int32_t need = p + 1;
-                if (cur + need > end) {
-                    unsigned long long at = 0;
-                    if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
-                    at = __shfl_sync(FULL, at, 0);
-                    if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
-                        overflow = true;
-                        break;
-                    }
-                    cur = (int64_t)at;
-                    end = cur + HEAP_CHUNK;
-                }
-                const int32_t base = (int32_t)cur;
-                cur += need;
-                used += need;
-                // rank recurrence bottom-up (uniform): r = rank of the child just built
-                int32_t r = 1, my_child_rank = 1, my_rank = 1, sstar = -1;
-                bool my_swap = false;
-                for (int32_t qq = p - 1; qq >= 0; --qq) {
-                    const int32_t l = sm.node[qq].left;
-                    const int32_t lr = sm.node[qq].lrank;
-                    const bool sw = l < 0 || lr < r;
-                    const int32_t nr = sw ? (l >= 0 ? lr + 1 : 0) : r + 1;
-                    if (lane == qq) {
-                        my_child_rank = r;
-                        my_swap = sw;
-                        my_rank = nr;
-                    }
-                    if (sw) sstar = qq;
-                    r = nr;
-                }
-                // build this lane's node
-                HNode nn;
-                int32_t my_id = -1, my_eid = 0;
-                if (lane < p) {
-                    nn = sm.node[lane];
-                    my_eid = sm.eid[lane];
-                    const int32_t child = base + (p - 1 - lane);
-                    const int32_t l = nn.left, lr = nn.lrank;
-                    if (my_swap) {
-                        nn.left = child;
-                        nn.lrank = (int16_t)my_child_rank;
-                        nn.right = l;
-                    } else {
-                        nn.left = l;
-                        nn.lrank = (int16_t)lr;
-                        nn.right = child;
-                    }
-                    nn.rank = (int16_t)my_rank;
-                    my_id = base + (p - lane);
-                } else if (lane == p) {
-                    nn.sum = k.sum;
-                    nn.anom = k.anom;
-                    nn.nz = k.nz;
-                    nn.tot = k.tot;
-                    nn.left = p < L ? sm.id[p] : -1;
-                    nn.right = -1;
-                    nn.rank = 1;
-                    nn.lrank = (int16_t)(p < L ? sm.node[p].rank : 0);
-                    my_id = base;
-                    my_eid = eid;
-                }
-                __syncwarp();
-                // new known spine: copies 0..sstar (then the old left of sstar, unknown), or copies 0..p-1 and N
-                const int32_t newL = sstar >= 0 ? sstar + 1 : p + 1;
-                if (lane <= p) {
-                    hn_store(hn + my_id, nn);
-                    hn_eid[my_id] = my_eid;
-                    if (lane < newL) {
-                        sm.node[lane] = nn;
-                        sm.id[lane] = my_id;
-                        sm.eid[lane] = my_eid;
+                cur_root = root;
+                // ---- remember the spine for the children ----
+                if ((nins_f & VI_KIDS) && root >= 0) {
+                    const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
+                    if (!have) {
+                        const int32_t sl = save_at;
+                        save_at = (save_at + 1) % NSAVE;
+                        if (lane < L) {
+                            hn_store(&sm.snode[sl][lane], nd);
+                            IdEid ie;
+                            ie.id = nd_id;
+                            ie.eid = nd_eid;
+                            sm.sid[sl][lane] = ie;
+                        }
+                        if (lane == 0) {
+                            sm.sroot[sl] = root;
+                            sm.sL[sl] = L;
+                            sm.snext[sl] = next;
+                        }
+                        __syncwarp();
                     }
                 }
-                const int32_t nright = __shfl_sync(FULL, nn.right, sstar >= 0 ? sstar : 0);
-                next = sstar >= 0 ? nright : -1;
-                L = newL;
-                root = p > 0 ? base + p : base;
-                __syncwarp();
             }
+            if (lane == j) myroot = root;
         }
         if (overflow) break;
-        // ---- publish: root of u, its children inherit it; remember the spine for them ----
-        if (lane == 0) hroot[u] = root;
-        if (nc > 0) {
-            for (int32_t k = lane; k < nc; k += 32) {
-                const int32_t x = w.child[cbase + k];
-                hroot[x] = root;
-                q[tail + k] = x;
-                sm.ring[(tail + k) & (QRING - 1)] = x;
-            }
-            tail += nc;
-            if (root >= 0) {
-                const int32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
-                if (!have) {
-                    const int32_t sl = save_at;
-                    save_at = (save_at + 1) % NSAVE;
-                    if (lane < L) {
-                        sm.snode[sl][lane] = sm.node[lane];
-                        sm.sid[sl][lane] = sm.id[lane];
-                        sm.seid[sl][lane] = sm.eid[lane];
-                    }
-                    if (lane == 0) {
-                        sm.sroot[sl] = root;
-                        sm.sL[sl] = L;
-                        sm.snext[sl] = next;
-                    }
-                }
-            }
-            __syncwarp();
+        if (base + lane < nt) {
+            root_at[base + lane] = myroot;
+            hroot[vi.x] = myroot;
         }
+        __syncwarp();
     }
     if (lane == 0) {
         w.heap_used[c] = used;
@@ -1363,7 +1552,7 @@ AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
     f_heaps(w, c);
 #endif
 }
-constexpr size_t HEAP_SMEM_BYTES = 16 * 1024;  // >= sizeof(HeapSmem) (device only)
+constexpr size_t HEAP_SMEM_BYTES = 12 * 1024;  // >= sizeof(HeapSmem) (device only)
 
 // ---- enumeration priority queue: binary min-heap under the total order (distance, node id, entry index)
 AA_HD bool pq_less(const PQEnt &a, const PQEnt &b) {

@@ -59,6 +59,20 @@ AA_FUNCTOR(FnVtxOff, f_vtx_off(w, i))
 AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
 AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
+AA_FUNCTOR(FnTourBuild, f_tour_build(w, i))
+AA_FUNCTOR(FnBfsPos, f_bfs_pos(w, i))
+AA_FUNCTOR(FnVInfo, f_vinfo(w, i))
+AA_FUNCTOR(FnInsFill, f_ins_fill(w, i))
+struct FnTourJump {
+    const Tour *src;
+    Tour *dst;
+    AA_HD void operator()(int64_t i, void *) const { tour_jump(src, dst, i); }
+};
+struct FnBfsKey {
+    Ws w;
+    const Tour *tour;
+    AA_HD void operator()(int64_t i, void *) const { f_bfs_key(w, i, tour); }
+};
 AA_FUNCTOR(FnRevPack, f_rev_pack(w, i))
 AA_FUNCTOR(FnENext, f_enext(w, i))
 AA_FUNCTOR(FnRelaxInit, f_relax_init(w, i))
@@ -501,11 +515,61 @@ struct Pipeline {
         w.skey = A<SKey>(E);
         w.child = A<int32_t>(E);
         w.nchild = A<int32_t>(Vtot);
-        if (!w.skey || !w.child || !w.nchild) {
-            err = "device allocation failed (sidetrack keys)";
+        w.nins = A<int32_t>(Vtot);
+        w.cslot = A<uint32_t>(Vtot);
+        w.tour_a = A<Tour>(2 * Vtot);
+        w.tour_b = A<Tour>(2 * Vtot);
+        w.bkey_in = A<uint64_t>(Vtot);
+        w.bkey = A<uint64_t>(Vtot);
+        w.bval_in = A<uint32_t>(Vtot);
+        w.bfs_vtx = A<uint32_t>(Vtot);
+        w.bfspos = A<int32_t>(Vtot);
+        w.ntree = A<int32_t>(C);
+        w.vinfo = A<VInfo>(Vtot);
+        w.ins_cnt = A<int32_t>(Vtot + 1);
+        w.ins_off = A<int64_t>(Vtot + 2);
+        w.root_at = A<int32_t>(Vtot);
+        if (!w.skey || !w.child || !w.nchild || !w.nins || !w.cslot || !w.tour_a || !w.tour_b || !w.bkey_in || !w.bkey ||
+            !w.bval_in || !w.bfs_vtx || !w.bfspos || !w.ntree || !w.vinfo || !w.ins_cnt || !w.ins_off || !w.root_at) {
+            err = "device allocation failed (sidetrack keys / tree order)";
             return AA_ERR_NOMEM;
         }
         bk.for_each("heap_prep", Vtot, FnHeapPrep{w});
+        // BFS order of every contig's shortest-path tree, in parallel: Euler tour -> list ranking by pointer
+        // jumping -> sort by (contig, depth, preorder); then the flat stream of inserts in that order
+        {
+            int64_t maxV = 3;
+            for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
+            int kb = 1, cb = 1, rounds = 1;
+            while (((int64_t)1 << kb) <= maxV + 1) kb++;
+            while (((int64_t)1 << cb) < C) cb++;
+            while (((int64_t)1 << rounds) < 2 * maxV) rounds++;
+            if (2 * kb + cb > 64) {
+                err = "batch shape not supported by the tree-order sort key (contig count x largest contig)";
+                return AA_ERR_NOMEM;
+            }
+            w.key_bits = kb;
+            bk.for_each("tour_build", Vtot, FnTourBuild{w});
+            Tour *src = w.tour_a, *dst = w.tour_b;
+            for (int r = 0; r < rounds; r++) {
+                bk.for_each("tour_jump", 2 * Vtot, FnTourJump{src, dst});
+                std::swap(src, dst);
+            }
+            bk.for_each("bfs_key", Vtot, FnBfsKey{w, src});
+            bk.sort_pairs_u64(w.bkey_in, w.bkey, w.bval_in, w.bfs_vtx, Vtot, 2 * kb + cb);
+            bk.for_each("bfs_pos", Vtot, FnBfsPos{w});
+            bk.zero(w.ins_cnt + Vtot, 4);
+            bk.for_each("vinfo", Vtot, FnVInfo{w});
+            bk.scan_i32(w.ins_cnt, w.ins_off, Vtot + 1);
+            const int64_t n_ins = bk.read_i64(w.ins_off + Vtot);
+            w.ins = A<InsKey>(n_ins);
+            if (!w.ins) {
+                err = "device allocation failed (insert stream)";
+                return AA_ERR_NOMEM;
+            }
+            bk.for_each("ins_fill", Vtot, FnInsFill{w});
+            bk.fill_ff(w.hroot, (size_t)Vtot * 4);  // vertices outside the tree have no heap
+        }
         int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {

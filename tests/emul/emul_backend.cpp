@@ -61,6 +61,16 @@ struct HostBackend {
             vout[i] = vin[idx[(size_t)i]];
         }
     }
+    void sort_pairs_u64(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int) {
+        std::vector<int64_t> idx((size_t)n);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return kin[a] < kin[b]; });
+        for (int64_t i = 0; i < n; i++) {
+            kout[i] = kin[idx[(size_t)i]];
+            vout[i] = vin[idx[(size_t)i]];
+        }
+    }
+    void fill_ff(void *p, size_t n) { std::memset(p, 0xff, n); }
     int64_t read_i64(const int64_t *p) { return *p; }
     bool device_kahn() const { return false; }
     void side_begin() {}

@@ -1129,8 +1129,19 @@ __device__ __forceinline__ int32_t kahn_push(KahnSmem &sm, int32_t *q, int32_t t
     return tail + __popc(m);
 }
 // reverse Kahn + relaxation + min-anom DP (k_shortest_walks.hpp:132-175; paf_data.cpp:705-713)
+// The FIFO ring carries everything a pop needs (final distance of the vertex, its in-edge range), so a pop reads
+// shared memory only; the in-edge records of every touched source are pulled into L1 ahead of its own pop.
+constexpr int32_t RRING = 256;
+struct RelaxSmem {
+    int64_t sum[RRING];
+    int32_t v[RRING], anom[RRING], nz[RRING], tot[RRING], amin_reach[RRING], deg[RRING];
+    uint32_t ra[RRING];
+};
+static_assert(sizeof(RelaxSmem) <= 10 * 1024, "RelaxSmem does not fit its shared-memory allotment");
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
-    KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
+    RelaxSmem &sm = *reinterpret_cast<RelaxSmem *>(scratch);
+    const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     if (w.status[c] != 0) return;
     Ctg g = ctg_view(w, c);
@@ -1140,27 +1151,79 @@ __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
     const int64_t *__restrict__ rev_off = w.rev_off + v0;
     int32_t *__restrict__ q = w.queue + v0;
     int32_t head = 0, tail = 0;
+    // ordered append of the lanes with `ready`; the entry carries the vertex's final state and in-edge range
+    auto push = [&](bool ready, int32_t x, const VState &sx, int64_t xa, int64_t xb) {
+        const uint32_t m = __ballot_sync(FULL, ready);
+        if (ready) {
+            const int32_t pos = tail + __popc(m & ((1u << lane) - 1u));
+            const int32_t s = pos & (RRING - 1);
+            q[pos] = x;
+            sm.v[s] = x;
+            sm.sum[s] = sx.sum;
+            sm.anom[s] = sx.anom;
+            sm.nz[s] = sx.nz;
+            sm.tot[s] = sx.tot;
+            sm.amin_reach[s] = sx.amin_reach;
+            sm.ra[s] = (uint32_t)xa;
+            sm.deg[s] = (int32_t)(xb - xa);
+        }
+        __syncwarp();
+        tail += __popc(m);
+    };
     // seeds: vertices without out-edges, ascending id (k_shortest_walks.hpp:139-141)
     for (int32_t vb = 0; vb < g.V; vb += 32) {
         const int32_t v = vb + lane;
-        const bool seed = v < g.V && vs[v].cnt == 0;
-        tail = kahn_push(sm, q, tail, seed, v);
+        VState sx;
+        sx.sum = 0;
+        sx.anom = sx.nz = sx.tot = sx.best = 0;
+        sx.cnt = 1;
+        sx.amin_reach = 0;
+        int64_t xa = 0, xb = 0;
+        if (v < g.V) {
+            sx = vs[v];
+            xa = rev_off[v];
+            xb = rev_off[v + 1];
+        }
+        push(v < g.V && sx.cnt == 0, v, sx, xa, xb);
     }
     while (head < tail) {
-        const int32_t v = kahn_pop(sm, q, head, tail);
+        VState sv;
+        int32_t v;
+        int64_t ra, rb;
+        if (tail - head <= RRING) {
+            const int32_t s = head & (RRING - 1);
+            v = sm.v[s];
+            sv.sum = sm.sum[s];
+            sv.anom = sm.anom[s];
+            sv.nz = sm.nz[s];
+            sv.tot = sm.tot[s];
+            sv.amin_reach = sm.amin_reach[s];
+            ra = sm.ra[s];
+            rb = ra + sm.deg[s];
+        } else {  // the ring wrapped over this entry
+            v = q[head];
+            sv = vs[v];
+            ra = rev_off[v];
+            rb = rev_off[v + 1];
+        }
         head++;
-        const VState sv = vs[v];
         const bool vreach = (sv.amin_reach & 1) != 0;
         const int32_t av = sv.amin_reach >> 1;
-        const int64_t ra = rev_off[v], rb = rev_off[v + 1];
         for (int64_t kb = ra; kb < rb; kb += 32) {
             const int64_t k = kb + lane;
             bool ready = false;
             int32_t x = 0;
+            VState sx;
+            sx.sum = 0;
+            sx.anom = sx.nz = sx.tot = sx.best = sx.cnt = sx.amin_reach = 0;
+            int64_t xa = 0, xb = 0;
             if (k < rb) {
                 const RevRec r = rrec[k];
                 x = r.src;
-                VState sx = vs[x];
+                sx = vs[x];
+                xa = rev_off[x];
+                xb = rev_off[x + 1];
+                if (xb > xa) prefetch_l1(rrec + xa);  // x's own pop will start from these records
                 if (vreach) {
                     D4 cand, cur;
                     cand.sum = sv.sum + r.sum;
@@ -1187,7 +1250,7 @@ __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
                 vs[x] = sx;
                 ready = sx.cnt == 0;
             }
-            tail = kahn_push(sm, q, tail, ready, x);
+            push(ready, x, sx, xa, xb);
         }
     }
     if (lane == 0) {
@@ -1251,6 +1314,7 @@ AA_HDN void f_topo_any(const Ws &w, int64_t c, void *scratch) {
 #endif
 }
 constexpr size_t KAHN_SMEM_BYTES = 4 * 1024;
+constexpr size_t RELAX_SMEM_BYTES = 10 * 1024;
 
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------
@@ -1400,7 +1464,10 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     // ---- descent: first spine level whose key is not < k ----
                     int32_t p;
                     for (;;) {
-                        const uint32_t stop = __ballot_sync(FULL, lane < L && !key_lt(nd, k));
+                        // the sum decides unless some level ties on it (then the full PafDistance order is evaluated)
+                        const bool known = lane < L;
+                        uint32_t stop = __ballot_sync(FULL, known && nd.sum >= k.sum);
+                        if (__ballot_sync(FULL, known && nd.sum == k.sum)) stop = __ballot_sync(FULL, known && !key_lt(nd, k));
                         if (stop) {
                             p = __ffs(stop) - 1;
                             break;
@@ -1494,6 +1561,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                         hn_store(hn + nd_id, nd);
                         hn_eid[nd_id] = nd_eid;
                     }
+                    __syncwarp();  // later inserts read these nodes from other lanes
                     // ---- new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N ----
                     const int32_t nright = __shfl_sync(FULL, nd.right, sstar >= 0 ? sstar : 0);
                     const int32_t old_next = next;

@@ -475,7 +475,7 @@ struct Pipeline {
         bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
         bk.phase_end(PH_TOPO);
         bk.side_end();
-        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, KAHN_SMEM_BYTES);
+        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, RELAX_SMEM_BYTES);
         if (bk.device_kahn()) bk.for_each("relax_unpack", Vtot, FnRelaxUnpack{w});
         bk.phase_end(PH_RELAX);
         AA_BK_CHECK();

@@ -1792,13 +1792,27 @@ AA_HDN void f_enext(const Ws &w, int64_t gv) {
 }
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative K-walk enumeration (device only; the host emulation runs f_enum) ------------------------
-// The priority queue is a 32-ary min-heap under the same total order as the reference's
-// std::priority_queue<tuple<Distance, heap_t*, int64_t>> (distance, node allocation order, entry index).
-// Heap positions below ENUM_CACHE live in shared memory (root, level 1 and most of level 2), the rest in
-// global memory; one sift-down level = one coalesced 32-entry load + a warp argmin.
-constexpr int32_t ENUM_CACHE = 960;  // 30 KB of 32-B entries per warp: 7 warps per SM
+// Same pop sequence as the reference's std::priority_queue<tuple<Distance, heap_t*, int64_t>> (total order:
+// distance, node allocation order, entry index), produced in BATCHES instead of one pop at a time:
+//   * the queue is split by a threshold key T into a sorted FRONT (all entries < T; a ring in shared memory) and
+//     an unsorted BACKLOG (all entries >= T; global memory, append only);
+//   * a round takes the 32 smallest entries (one per lane), expands all of them at once (heap node, next-heap
+//     root, left / right child: the dependent loads of 32 pops overlap), and commits the longest prefix that the
+//     sequential algorithm would pop in this order: candidate j stays valid as long as no successor of
+//     candidates 0..j-1 precedes it (successors carry new, larger entry indices, so only (distance, node)
+//     decides).  Entry indices of the committed successors are the prefix sums the sequential pushes would give
+//     (next-root, left, right per pop: k_shortest_walks.hpp:245-247);
+//   * successors below T are inserted into the front, the others are appended to the backlog; when the front
+//     runs empty a new threshold is chosen from a sorted sample of the backlog and the entries below it are
+//     moved over and sorted.  Pops are monotone, so an entry crosses from the backlog to the front once.
+constexpr int32_t FCAP = 512;  // front capacity (entries of 32 B)
+constexpr int32_t FMASK = FCAP - 1;
+constexpr int32_t FKEEP = 256;         // entries that stay when a full front spills its upper part
+constexpr int32_t REFILL_ALL = 384;    // a backlog this small is moved as a whole
+constexpr int32_t REFILL_TARGET = 192;
+constexpr int32_t NSAMPLE = 512;
 struct EnumSmem {
-    PQEnt top[ENUM_CACHE];
+    PQEnt f[FCAP];
 };
 __device__ __forceinline__ PQEnt pq_ld(const PQEnt *p) {
     union {
@@ -1820,13 +1834,6 @@ __device__ __forceinline__ void pq_st(PQEnt *p, const PQEnt &e) {
     q[0] = u.v[0];
     q[1] = u.v[1];
 }
-__device__ __forceinline__ PQEnt pq_get(const EnumSmem &sm, const PQEnt *g, int32_t pos) {
-    return pos < ENUM_CACHE ? pq_ld(&sm.top[pos]) : pq_ld(g + pos);
-}
-__device__ __forceinline__ void pq_put(EnumSmem &sm, PQEnt *g, int32_t pos, const PQEnt &e) {
-    if (pos < ENUM_CACHE) pq_st(&sm.top[pos], e);
-    else pq_st(g + pos, e);
-}
 __device__ __forceinline__ PQEnt pq_bcast(const PQEnt &e, int32_t src) {
     const uint32_t FULL = 0xffffffffu;
     PQEnt r;
@@ -1836,50 +1843,34 @@ __device__ __forceinline__ PQEnt pq_bcast(const PQEnt &e, int32_t src) {
     r.tot = __shfl_sync(FULL, e.tot, src);
     r.node = __shfl_sync(FULL, e.node, src);
     r.idx = __shfl_sync(FULL, e.idx, src);
+    r.pad = __shfl_sync(FULL, e.pad, src);
+    return r;
+}
+__device__ __forceinline__ PQEnt pq_up(const PQEnt &e, int32_t d) {
+    const uint32_t FULL = 0xffffffffu;
+    PQEnt r;
+    r.sum = __shfl_up_sync(FULL, e.sum, d);
+    r.anom = __shfl_up_sync(FULL, e.anom, d);
+    r.nz = __shfl_up_sync(FULL, e.nz, d);
+    r.tot = __shfl_up_sync(FULL, e.tot, d);
+    r.node = __shfl_up_sync(FULL, e.node, d);
+    r.idx = 0;
     r.pad = 0;
     return r;
 }
-// lane holding the minimum of the valid entries under pq_less (at least one lane is valid)
-__device__ int32_t warp_argmin(const PQEnt &e, bool valid) {
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t me = 1u << (threadIdx.x & 31);
-    const int32_t hi = valid ? (int32_t)(e.sum >> 32) : 0x7fffffff;
-    const int32_t mh = __reduce_min_sync(FULL, hi);
-    const bool c1 = valid && hi == mh;
-    const uint32_t lo = c1 ? (uint32_t)e.sum : 0xffffffffu;
-    const uint32_t ml = __reduce_min_sync(FULL, lo);
-    uint32_t cand = __ballot_sync(FULL, c1 && lo == ml);
-    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
-    const int32_t an = (cand & me) ? e.anom : 0x7fffffff;
-    const int32_t ma = __reduce_min_sync(FULL, an);
-    cand = __ballot_sync(FULL, (cand & me) && e.anom == ma);
-    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
-    // mapq ratio, descending: follow strictly better leaders
-    int32_t leader = __ffs(cand) - 1;
-    int32_t nzl, totl;
-    for (;;) {
-        nzl = __shfl_sync(FULL, e.nz, leader);
-        totl = __shfl_sync(FULL, e.tot, leader);
-        const bool better = (cand & me) && (int64_t)e.nz * den(totl) > (int64_t)nzl * den(e.tot);
-        const uint32_t b = __ballot_sync(FULL, better);
-        if (!b) break;
-        leader = __ffs(b) - 1;
-    }
-    cand = __ballot_sync(FULL, (cand & me) && (int64_t)e.nz * den(totl) == (int64_t)nzl * den(e.tot));
-    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
-    const int32_t nd = (cand & me) ? e.node : 0x7fffffff;
-    const int32_t mn = __reduce_min_sync(FULL, nd);
-    cand = __ballot_sync(FULL, (cand & me) && e.node == mn);
-    if ((cand & (cand - 1)) == 0) return __ffs(cand) - 1;
-    const int32_t ix = (cand & me) ? e.idx : 0x7fffffff;
-    const int32_t mi = __reduce_min_sync(FULL, ix);
-    cand = __ballot_sync(FULL, (cand & me) && e.idx == mi);
-    return __ffs(cand) - 1;
+// (distance, node) order, strict: decides whether a NEW entry precedes an existing one
+__device__ __forceinline__ bool dn_less(const PQEnt &a, const PQEnt &b) {
+    if (a.sum != b.sum) return a.sum < b.sum;
+    if (a.anom != b.anom) return a.anom < b.anom;
+    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+    if (x != y) return x > y;
+    return a.node < b.node;
 }
 __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     EnumSmem &sm = *reinterpret_cast<EnumSmem *>(scratch);
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const uint32_t lt = (1u << lane) - 1u;
     if (w.status[c] != 0) {
         if (lane == 0) w.n_walk[c] = 0;
         return;
@@ -1892,16 +1883,21 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t *__restrict__ last = w.wlast + wo;
     int32_t *__restrict__ en = w.ent_node + 3 * wo;
     int32_t *__restrict__ ep = w.ent_prev + 3 * wo;
-    PQEnt *__restrict__ pq = w.pq + 3 * wo;
+    PQEnt *__restrict__ back = w.pq + 3 * wo;  // the backlog
     const HNode *__restrict__ hn = w.hn;
+    const ENext *__restrict__ enext = w.enext + e0;
     const int32_t K = w.K;
-    int32_t nd = 0, ne = 0, n = 0;
+    int32_t nd = 1, ne = 0;
+    int32_t head = 0, nF = 0, nR = 0;
+    bool hasT = false;  // no threshold yet: everything goes to the front
+    PQEnt T;
+    T.sum = 0;
+    T.anom = T.nz = T.tot = T.node = T.idx = T.pad = 0;
     const D4 ds = w.d[v0 + g.src];
     if (lane == 0) {
         dist[0] = ds;
         last[0] = -1;
     }
-    nd = 1;
     const int32_t hs = w.hroot[v0 + g.src];
     if (hs >= 0) {
         const HNode hr = hn_load(hn + hs);
@@ -1912,102 +1908,342 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         e.tot = ds.tot + hr.tot;
         e.node = hs;
         e.idx = 0;
-        e.pad = 0;
+        e.pad = -1;  // pad carries the entry's prev
         if (lane == 0) {
             en[0] = hs;
             ep[0] = -1;
-            pq_st(&sm.top[0], e);
+            pq_st(&sm.f[0], e);
         }
         ne = 1;
-        n = 1;
+        nF = 1;
+    }
+    __syncwarp();
+
+    // front(i): the i-th smallest entry of the front
+    auto fslot = [&](int32_t i) -> PQEnt * { return &sm.f[(head + i) & FMASK]; };
+    // a full front spills its upper part to the backlog and lowers the threshold to the first spilled key
+    auto spill = [&]() {
+        const PQEnt t0 = pq_ld(fslot(FKEEP));
+        for (int32_t i = FKEEP + lane; i < nF; i += 32) pq_st(back + nR + (i - FKEEP), pq_ld(fslot(i)));
+        nR += nF - FKEEP;
+        nF = FKEEP;
+        T = t0;
+        hasT = true;
         __syncwarp();
-        while (n > 0 && nd < K) {
-            // ---- pop the minimum ----
-            const PQEnt t = pq_ld(&sm.top[0]);
-            if (lane == 0) {
-                D4 cd;
-                cd.sum = t.sum;
-                cd.anom = t.anom;
-                cd.nz = t.nz;
-                cd.tot = t.tot;
-                cd.aux = 0;
-                dist[nd] = cd;
-                last[nd] = t.idx;
+    };
+    // sorted insert of a warp-uniform entry
+    auto front_insert = [&](const PQEnt &e) {
+        if (nF == FCAP) {
+            spill();
+            if (!pq_less(e, T)) {  // the lowered threshold sends it to the backlog after all
+                if (lane == 0) pq_st(back + nR, e);
+                nR++;
+                return;
             }
-            nd++;
-            n--;
-            // start the loads of the popped sidetrack's heap node early (consumed after the sift-down)
+        }
+        // position = number of front entries below e: 32 pivots, then inside one segment
+        const int32_t seg = (nF + 31) >> 5;  // <= 16
+        int32_t pos = 0;
+        if (nF > 0) {
+            const bool b1 = lane * seg < nF && pq_less(pq_ld(fslot(lane * seg)), e);
+            const int32_t c1 = __popc(__ballot_sync(FULL, b1));  // pivots are sorted: the lower ones are below
+            if (c1 > 0) {
+                const int32_t base = (c1 - 1) * seg + 1;
+                const bool b2 = lane < seg - 1 && base + lane < nF && pq_less(pq_ld(fslot(base + lane)), e);
+                pos = base + __popc(__ballot_sync(FULL, b2));
+            }
+        }
+        if (pos < nF - pos) {  // move the lower part one slot down (towards a new head)
+            for (int32_t i0 = 0; i0 < pos; i0 += 32) {
+                const int32_t i = i0 + lane;
+                PQEnt x;
+                if (i < pos) x = pq_ld(fslot(i));
+                __syncwarp();
+                if (i < pos) pq_st(&sm.f[(head + i - 1) & FMASK], x);
+                __syncwarp();
+            }
+            head = (head - 1) & FMASK;
+        } else {  // move the upper part one slot up
+            for (int32_t i1 = nF; i1 > pos; i1 -= 32) {
+                const int32_t i = i1 - 1 - lane;
+                PQEnt x;
+                if (i >= pos) x = pq_ld(fslot(i));
+                __syncwarp();
+                if (i >= pos) pq_st(fslot(i + 1), x);
+                __syncwarp();
+            }
+        }
+        if (lane == 0) pq_st(fslot(pos), e);
+        nF++;
+        __syncwarp();
+    };
+    // bitonic sort of sm.f[0, P) under the total order (P a power of two)
+    auto sort_front = [&](int32_t P) {
+        for (int32_t k = 2; k <= P; k <<= 1)
+            for (int32_t j = k >> 1; j > 0; j >>= 1) {
+                for (int32_t t = lane; t < (P >> 1); t += 32) {
+                    const int32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int32_t p2 = i | j;
+                    const PQEnt A = pq_ld(&sm.f[i]), B = pq_ld(&sm.f[p2]);
+                    const bool asc = (i & k) == 0;
+                    if (asc ? pq_less(B, A) : pq_less(A, B)) {
+                        pq_st(&sm.f[i], B);
+                        pq_st(&sm.f[p2], A);
+                    }
+                }
+                __syncwarp();
+            }
+    };
+    auto pad_inf = [&](int32_t from, int32_t to) {
+        PQEnt inf;
+        inf.sum = I64_MAX;
+        inf.anom = inf.nz = inf.tot = 0;
+        inf.node = inf.idx = 0x7fffffff;
+        inf.pad = 0;
+        for (int32_t i = from + lane; i < to; i += 32) pq_st(&sm.f[i], inf);
+    };
+    // the front is empty: pick a threshold, move the backlog entries below it over, sort them
+    auto refill = [&]() {
+        head = 0;
+        if (nR <= REFILL_ALL) {
+            for (int32_t i = lane; i < nR; i += 32) pq_st(&sm.f[i], pq_ld(back + i));
+            nF = nR;
+            nR = 0;
+            hasT = false;
+        } else {
+            const int32_t stride = nR / NSAMPLE > 0 ? nR / NSAMPLE : 1;
+            const int32_t ns = nR / stride < NSAMPLE ? nR / stride : NSAMPLE;
+            int32_t r = REFILL_TARGET / stride;
+            if (r > ns - 1) r = ns - 1;
+            for (;;) {
+                if (r < 1) {
+                    // last resort (a sample could not split the backlog): move the single minimum
+                    PQEnt best;
+                    int32_t bi = -1;
+                    for (int32_t i = lane; i < nR; i += 32) {
+                        const PQEnt x = pq_ld(back + i);
+                        if (bi < 0 || pq_less(x, best)) {
+                            best = x;
+                            bi = i;
+                        }
+                    }
+                    for (int32_t d = 16; d > 0; d >>= 1) {
+                        const PQEnt o = pq_bcast(best, (lane + d) & 31);
+                        const int32_t oi = __shfl_sync(FULL, bi, (lane + d) & 31);
+                        if (lane + d < 32 && oi >= 0 && (bi < 0 || pq_less(o, best))) {
+                            best = o;
+                            bi = oi;
+                        }
+                    }
+                    best = pq_bcast(best, 0);
+                    bi = __shfl_sync(FULL, bi, 0);
+                    const PQEnt tail_e = pq_ld(back + nR - 1);
+                    __syncwarp();
+                    if (lane == 0) {
+                        pq_st(back + bi, tail_e);
+                        pq_st(&sm.f[0], best);
+                    }
+                    nR--;
+                    nF = 1;
+                    T = best;
+                    T.idx = best.idx + 1;  // the smallest key above `best`
+                    hasT = true;
+                    break;
+                }
+                // threshold = r-th smallest of a strided sample
+                for (int32_t i = lane; i < ns; i += 32) pq_st(&sm.f[i], pq_ld(back + (int64_t)i * stride));
+                int32_t P = 32;
+                while (P < ns) P <<= 1;
+                pad_inf(ns, P);
+                __syncwarp();
+                sort_front(P);
+                T = pq_ld(&sm.f[r]);
+                hasT = true;
+                __syncwarp();
+                // one pass: below T -> front (unsorted for now), the rest is compacted in place
+                int32_t nb = 0, wpos = 0;
+                for (int32_t i0 = 0; i0 < nR; i0 += 32) {
+                    const int32_t i = i0 + lane;
+                    const bool valid = i < nR;
+                    PQEnt x;
+                    if (valid) x = pq_ld(back + i);
+                    const bool below = valid && pq_less(x, T);
+                    const uint32_t mb = __ballot_sync(FULL, below);
+                    const int32_t at = nb + __popc(mb & lt);
+                    const bool stage = below && at < FCAP;
+                    const uint32_t mk = __ballot_sync(FULL, valid && !stage);
+                    if (stage) pq_st(&sm.f[at], x);
+                    if (valid && !stage) pq_st(back + wpos + __popc(mk & lt), x);
+                    nb += __popc(mb);
+                    wpos += __popc(mk);
+                    __syncwarp();
+                }
+                if (nb <= FCAP) {
+                    nF = nb;
+                    nR = wpos;
+                    break;
+                }
+                // too many entries below this threshold: put the staged ones back and try a lower one
+                for (int32_t i = lane; i < FCAP; i += 32) pq_st(back + wpos + i, pq_ld(&sm.f[i]));
+                nR = wpos + FCAP;
+                __syncwarp();
+                r >>= 1;
+            }
+        }
+        if (nF > 1) {
+            int32_t P = 2;
+            while (P < nF) P <<= 1;
+            pad_inf(nF, P);
+            __syncwarp();
+            sort_front(P);
+        }
+        __syncwarp();
+    };
+
+    while (nd < K) {
+        if (nF == 0) {
+            if (nR == 0) break;
+            refill();
+            continue;
+        }
+        int32_t ncand = nF < 32 ? nF : 32;
+        if (ncand > K - nd) ncand = K - nd;
+        const bool have = lane < ncand;
+        // ---- the candidates and their successors (speculative beyond the first) ----
+        PQEnt t;
+        t.sum = 0;
+        t.anom = t.nz = t.tot = t.node = t.idx = t.pad = 0;
+        PQEnt a0, a1, a2;
+        a0.node = a1.node = a2.node = -1;
+        a0.sum = a1.sum = a2.sum = 0;
+        a0.anom = a0.nz = a0.tot = a0.idx = a0.pad = 0;
+        a1 = a0;
+        a2 = a0;
+        a1.node = a2.node = -1;
+        if (have) {
+            t = pq_ld(fslot(lane));
             const HNode ch = hn_load(hn + t.node);
             const int32_t ceid = w.hn_eid[t.node];
-            const int32_t pre = ep[t.idx];
-            if (n > 0) {
-                const PQEnt mv = pq_get(sm, pq, n);  // the last entry moves down from the root
-                int32_t pos = 0;
-                for (;;) {
-                    const int32_t first = (pos << 5) + 1;
-                    if (first >= n) break;
-                    const bool valid = first + lane < n;
-                    PQEnt mine;
-                    if (valid) mine = pq_get(sm, pq, first + lane);
-                    const int32_t ml = warp_argmin(mine, valid);
-                    const PQEnt best = pq_bcast(mine, ml);
-                    if (!pq_less(best, mv)) break;
-                    if (lane == 0) pq_put(sm, pq, pos, best);
-                    pos = first + ml;
-                }
-                if (lane == 0) pq_put(sm, pq, pos, mv);
-                __syncwarp();
+            HNode xl, xr;
+            if (ch.left >= 0) xl = hn_load(hn + ch.left);
+            if (ch.right >= 0) xr = hn_load(hn + ch.right);
+            const ENext x = enext[ceid];
+            if (x.hv >= 0) {
+                a0.sum = t.sum + x.sum;
+                a0.anom = t.anom + x.anom;
+                a0.nz = t.nz + x.nz;
+                a0.tot = t.tot + x.tot;
+                a0.node = x.hv;
+                a0.pad = t.idx;
             }
-            // ---- the (up to) three successors: lane 0 next-heap root, lane 1 left child, lane 2 right child ----
-            PQEnt a;
-            a.sum = 0;
-            a.anom = a.nz = a.tot = 0;
-            a.node = -1;
-            a.idx = 0;
-            a.pad = 0;
-            int32_t aprev = -1;
-            if (lane == 0) {
-                const ENext x = w.enext[e0 + ceid];
-                if (x.hv >= 0) {
-                    a.sum = t.sum + x.sum;
-                    a.anom = t.anom + x.anom;
-                    a.nz = t.nz + x.nz;
-                    a.tot = t.tot + x.tot;
-                    a.node = x.hv;
-                    aprev = t.idx;
-                }
-            } else if (lane <= 2) {
-                const int32_t cid = lane == 1 ? ch.left : ch.right;
-                if (cid >= 0) {
-                    const HNode x = hn_load(hn + cid);
-                    a.sum = t.sum + x.sum - ch.sum;
-                    a.anom = t.anom + x.anom - ch.anom;
-                    a.nz = t.nz + x.nz - ch.nz;
-                    a.tot = t.tot + x.tot - ch.tot;
-                    a.node = cid;
-                    aprev = pre;
+            if (ch.left >= 0) {
+                a1.sum = t.sum + xl.sum - ch.sum;
+                a1.anom = t.anom + xl.anom - ch.anom;
+                a1.nz = t.nz + xl.nz - ch.nz;
+                a1.tot = t.tot + xl.tot - ch.tot;
+                a1.node = ch.left;
+                a1.pad = t.pad;
+            }
+            if (ch.right >= 0) {
+                a2.sum = t.sum + xr.sum - ch.sum;
+                a2.anom = t.anom + xr.anom - ch.anom;
+                a2.nz = t.nz + xr.nz - ch.nz;
+                a2.tot = t.tot + xr.tot - ch.tot;
+                a2.node = ch.right;
+                a2.pad = t.pad;
+            }
+        }
+        // ---- how many candidates does the sequential order confirm? ----
+        PQEnt pm = a0;  // this lane's smallest successor under (distance, node)
+        bool pv = a0.node >= 0;
+        if (a1.node >= 0 && (!pv || dn_less(a1, pm))) {
+            pm = a1;
+            pv = true;
+        }
+        if (a2.node >= 0 && (!pv || dn_less(a2, pm))) {
+            pm = a2;
+            pv = true;
+        }
+        int32_t m = ncand;
+        if (ncand > 1) {
+            for (int32_t d = 1; d < ncand; d <<= 1) {  // inclusive prefix minimum over the lanes
+                const PQEnt o = pq_up(pm, d);
+                const bool ov = __shfl_up_sync(FULL, (int32_t)pv, d) != 0;
+                if (lane >= d && ov && (!pv || dn_less(o, pm))) {
+                    pm = o;
+                    pv = true;
                 }
             }
-            const uint32_t vm = __ballot_sync(FULL, a.node >= 0);
-            if (a.node >= 0) {
-                a.idx = ne + __popc(vm & ((1u << lane) - 1u));
-                en[a.idx] = a.node;
-                ep[a.idx] = aprev;
-            }
-            ne += __popc(vm);
-            // ---- push them in entry order ----
-            for (uint32_t m = vm; m; m &= m - 1) {
-                const PQEnt e2 = pq_bcast(a, __ffs(m) - 1);
-                int32_t pos = n++;
-                while (pos > 0) {
-                    const int32_t par = (pos - 1) >> 5;
-                    const PQEnt pe = pq_get(sm, pq, par);
-                    if (!pq_less(e2, pe)) break;
-                    if (lane == 0) pq_put(sm, pq, pos, pe);
-                    pos = par;
+            const PQEnt ex = pq_up(pm, 1);
+            const bool exv = __shfl_up_sync(FULL, (int32_t)pv, 1) != 0;
+            const bool viol = have && lane > 0 && exv && dn_less(ex, t);
+            const uint32_t vm = __ballot_sync(FULL, viol);
+            if (vm) m = __ffs(vm) - 1;
+        }
+        // ---- commit candidates 0..m-1 ----
+        const bool com = lane < m;
+        if (com) {
+            D4 cd;
+            cd.sum = t.sum;
+            cd.anom = t.anom;
+            cd.nz = t.nz;
+            cd.tot = t.tot;
+            cd.aux = 0;
+            dist[nd + lane] = cd;
+            last[nd + lane] = t.idx;
+        }
+        const int32_t v0c = com && a0.node >= 0, v1c = com && a1.node >= 0, v2c = com && a2.node >= 0;
+        const int32_t mycnt = v0c + v1c + v2c;
+        int32_t inc = mycnt;
+        for (int32_t d = 1; d < 32; d <<= 1) {
+            const int32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const int32_t total = __shfl_sync(FULL, inc, 31);
+        int32_t id = ne + inc - mycnt;
+        if (v0c) {
+            a0.idx = id;
+            en[id] = a0.node;
+            ep[id] = a0.pad;
+            id++;
+        }
+        if (v1c) {
+            a1.idx = id;
+            en[id] = a1.node;
+            ep[id] = a1.pad;
+            id++;
+        }
+        if (v2c) {
+            a2.idx = id;
+            en[id] = a2.node;
+            ep[id] = a2.pad;
+        }
+        ne += total;
+        nd += m;
+        head = (head + m) & FMASK;
+        nF -= m;
+        if (nd >= K) break;
+        // ---- the successors enter the queue: backlog appends in parallel, front inserts one by one ----
+#pragma unroll
+        for (int32_t sidx = 0; sidx < 3; sidx++) {
+            const PQEnt &a = sidx == 0 ? a0 : (sidx == 1 ? a1 : a2);
+            const bool valid = sidx == 0 ? v0c : (sidx == 1 ? v1c : v2c);
+            const bool toF = valid && (!hasT || pq_less(a, T));
+            const bool toR = valid && !toF;
+            const uint32_t mR = __ballot_sync(FULL, toR);
+            if (toR) pq_st(back + nR + __popc(mR & lt), a);
+            nR += __popc(mR);
+            uint32_t mF = __ballot_sync(FULL, toF);
+            while (mF) {
+                const int32_t l = __ffs(mF) - 1;
+                mF &= mF - 1;
+                const PQEnt e = pq_bcast(a, l);
+                if (hasT && !pq_less(e, T)) {  // the threshold dropped since toF was evaluated (a spill)
+                    if (lane == 0) pq_st(back + nR, e);
+                    nR++;
+                } else {
+                    front_insert(e);
                 }
-                if (lane == 0) pq_put(sm, pq, pos, e2);
-                __syncwarp();
             }
         }
     }
@@ -2022,7 +2258,7 @@ AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {
     f_enum(w, c);
 #endif
 }
-constexpr size_t ENUM_SMEM_BYTES = 960 * 32;
+constexpr size_t ENUM_SMEM_BYTES = 512 * 32;  // >= sizeof(EnumSmem) (device only)
 
 // phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.

@@ -1805,11 +1805,11 @@ AA_HDN void f_enext(const Ws &w, int64_t gv) {
 //   * successors below T are inserted into the front, the others are appended to the backlog; when the front
 //     runs empty a new threshold is chosen from a sorted sample of the backlog and the entries below it are
 //     moved over and sorted.  Pops are monotone, so an entry crosses from the backlog to the front once.
-constexpr int32_t FCAP = 512;  // front capacity (entries of 32 B)
+constexpr int32_t FCAP = 1024;  // front capacity (entries of 32 B)
 constexpr int32_t FMASK = FCAP - 1;
-constexpr int32_t FKEEP = 256;         // entries that stay when a full front spills its upper part
-constexpr int32_t REFILL_ALL = 384;    // a backlog this small is moved as a whole
-constexpr int32_t REFILL_TARGET = 192;
+constexpr int32_t FKEEP = 512;         // entries that stay when a full front spills its upper part
+constexpr int32_t REFILL_ALL = 768;    // a backlog this small is moved as a whole
+constexpr int32_t REFILL_TARGET = 384;
 constexpr int32_t NSAMPLE = 512;
 struct EnumSmem {
     PQEnt f[FCAP];
@@ -1865,6 +1865,20 @@ __device__ __forceinline__ bool dn_less(const PQEnt &a, const PQEnt &b) {
     const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
     if (x != y) return x > y;
     return a.node < b.node;
+}
+// branch-free forms of the two orders (lanes of a warp disagree on where a comparison is decided)
+__device__ __forceinline__ bool ent_less(const PQEnt &a, const PQEnt &b) {  // total order: == pq_less
+    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+    const int32_t tail = (a.node < b.node) | ((a.node == b.node) & (a.idx < b.idx));
+    const int32_t r = (x > y) | ((x == y) & tail);
+    const int32_t an = (a.anom < b.anom) | ((a.anom == b.anom) & r);
+    return ((a.sum < b.sum) | ((a.sum == b.sum) & an)) != 0;
+}
+__device__ __forceinline__ bool dn_less_bl(const PQEnt &a, const PQEnt &b) {  // (distance, node), strict
+    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+    const int32_t r = (x > y) | ((x == y) & (a.node < b.node));
+    const int32_t an = (a.anom < b.anom) | ((a.anom == b.anom) & r);
+    return ((a.sum < b.sum) | ((a.sum == b.sum) & an)) != 0;
 }
 __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     EnumSmem &sm = *reinterpret_cast<EnumSmem *>(scratch);
@@ -1935,21 +1949,21 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     auto front_insert = [&](const PQEnt &e) {
         if (nF == FCAP) {
             spill();
-            if (!pq_less(e, T)) {  // the lowered threshold sends it to the backlog after all
+            if (!ent_less(e, T)) {  // the lowered threshold sends it to the backlog after all
                 if (lane == 0) pq_st(back + nR, e);
                 nR++;
                 return;
             }
         }
         // position = number of front entries below e: 32 pivots, then inside one segment
-        const int32_t seg = (nF + 31) >> 5;  // <= 16
+        const int32_t seg = (nF + 31) >> 5;  // <= 32
         int32_t pos = 0;
         if (nF > 0) {
-            const bool b1 = lane * seg < nF && pq_less(pq_ld(fslot(lane * seg)), e);
+            const bool b1 = lane * seg < nF && ent_less(pq_ld(fslot(lane * seg)), e);
             const int32_t c1 = __popc(__ballot_sync(FULL, b1));  // pivots are sorted: the lower ones are below
             if (c1 > 0) {
                 const int32_t base = (c1 - 1) * seg + 1;
-                const bool b2 = lane < seg - 1 && base + lane < nF && pq_less(pq_ld(fslot(base + lane)), e);
+                const bool b2 = lane < seg - 1 && base + lane < nF && ent_less(pq_ld(fslot(base + lane)), e);
                 pos = base + __popc(__ballot_sync(FULL, b2));
             }
         }
@@ -1986,7 +2000,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                     const int32_t p2 = i | j;
                     const PQEnt A = pq_ld(&sm.f[i]), B = pq_ld(&sm.f[p2]);
                     const bool asc = (i & k) == 0;
-                    if (asc ? pq_less(B, A) : pq_less(A, B)) {
+                    if (asc ? ent_less(B, A) : ent_less(A, B)) {
                         pq_st(&sm.f[i], B);
                         pq_st(&sm.f[p2], A);
                     }
@@ -2011,7 +2025,9 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             nR = 0;
             hasT = false;
         } else {
-            const int32_t stride = nR / NSAMPLE > 0 ? nR / NSAMPLE : 1;
+            // sample stride ~ target / 4: the threshold is the 4th sample or so, the sample sort stays small
+            int32_t stride = REFILL_TARGET / 4;
+            if (nR / stride > NSAMPLE) stride = nR / NSAMPLE;
             const int32_t ns = nR / stride < NSAMPLE ? nR / stride : NSAMPLE;
             int32_t r = REFILL_TARGET / stride;
             if (r > ns - 1) r = ns - 1;
@@ -2022,7 +2038,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                     int32_t bi = -1;
                     for (int32_t i = lane; i < nR; i += 32) {
                         const PQEnt x = pq_ld(back + i);
-                        if (bi < 0 || pq_less(x, best)) {
+                        if (bi < 0 || ent_less(x, best)) {
                             best = x;
                             bi = i;
                         }
@@ -2030,7 +2046,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                     for (int32_t d = 16; d > 0; d >>= 1) {
                         const PQEnt o = pq_bcast(best, (lane + d) & 31);
                         const int32_t oi = __shfl_sync(FULL, bi, (lane + d) & 31);
-                        if (lane + d < 32 && oi >= 0 && (bi < 0 || pq_less(o, best))) {
+                        if (lane + d < 32 && oi >= 0 && (bi < 0 || ent_less(o, best))) {
                             best = o;
                             bi = oi;
                         }
@@ -2062,20 +2078,24 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 __syncwarp();
                 // one pass: below T -> front (unsorted for now), the rest is compacted in place
                 int32_t nb = 0, wpos = 0;
-                for (int32_t i0 = 0; i0 < nR; i0 += 32) {
-                    const int32_t i = i0 + lane;
-                    const bool valid = i < nR;
-                    PQEnt x;
-                    if (valid) x = pq_ld(back + i);
-                    const bool below = valid && pq_less(x, T);
-                    const uint32_t mb = __ballot_sync(FULL, below);
-                    const int32_t at = nb + __popc(mb & lt);
-                    const bool stage = below && at < FCAP;
-                    const uint32_t mk = __ballot_sync(FULL, valid && !stage);
-                    if (stage) pq_st(&sm.f[at], x);
-                    if (valid && !stage) pq_st(back + wpos + __popc(mk & lt), x);
-                    nb += __popc(mb);
-                    wpos += __popc(mk);
+                for (int32_t i0 = 0; i0 < nR; i0 += 128) {  // four chunks of loads in flight
+                    PQEnt xs[4];
+#pragma unroll
+                    for (int32_t u = 0; u < 4; u++)
+                        if (i0 + 32 * u + lane < nR) xs[u] = pq_ld(back + i0 + 32 * u + lane);
+#pragma unroll
+                    for (int32_t u = 0; u < 4; u++) {
+                        const bool valid = i0 + 32 * u + lane < nR;
+                        const bool below = valid && ent_less(xs[u], T);
+                        const uint32_t mb = __ballot_sync(FULL, below);
+                        const int32_t at = nb + __popc(mb & lt);
+                        const bool stage = below && at < FCAP;
+                        const uint32_t mk = __ballot_sync(FULL, valid && !stage);
+                        if (stage) pq_st(&sm.f[at], xs[u]);
+                        if (valid && !stage) pq_st(back + wpos + __popc(mk & lt), xs[u]);
+                        nb += __popc(mb);
+                        wpos += __popc(mk);
+                    }
                     __syncwarp();
                 }
                 if (nb <= FCAP) {
@@ -2100,13 +2120,14 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         __syncwarp();
     };
 
+    int32_t width = 32;  // candidates per round: follows the commit length (tie-heavy queues confirm few)
     while (nd < K) {
         if (nF == 0) {
             if (nR == 0) break;
             refill();
             continue;
         }
-        int32_t ncand = nF < 32 ? nF : 32;
+        int32_t ncand = nF < width ? nF : width;
         if (ncand > K - nd) ncand = K - nd;
         const bool have = lane < ncand;
         // ---- the candidates and their successors (speculative beyond the first) ----
@@ -2156,11 +2177,11 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         // ---- how many candidates does the sequential order confirm? ----
         PQEnt pm = a0;  // this lane's smallest successor under (distance, node)
         bool pv = a0.node >= 0;
-        if (a1.node >= 0 && (!pv || dn_less(a1, pm))) {
+        if (a1.node >= 0 && (!pv || dn_less_bl(a1, pm))) {
             pm = a1;
             pv = true;
         }
-        if (a2.node >= 0 && (!pv || dn_less(a2, pm))) {
+        if (a2.node >= 0 && (!pv || dn_less_bl(a2, pm))) {
             pm = a2;
             pv = true;
         }
@@ -2169,17 +2190,18 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             for (int32_t d = 1; d < ncand; d <<= 1) {  // inclusive prefix minimum over the lanes
                 const PQEnt o = pq_up(pm, d);
                 const bool ov = __shfl_up_sync(FULL, (int32_t)pv, d) != 0;
-                if (lane >= d && ov && (!pv || dn_less(o, pm))) {
+                if (lane >= d && ov && (!pv || dn_less_bl(o, pm))) {
                     pm = o;
                     pv = true;
                 }
             }
             const PQEnt ex = pq_up(pm, 1);
             const bool exv = __shfl_up_sync(FULL, (int32_t)pv, 1) != 0;
-            const bool viol = have && lane > 0 && exv && dn_less(ex, t);
+            const bool viol = have && lane > 0 && exv && dn_less_bl(ex, t);
             const uint32_t vm = __ballot_sync(FULL, viol);
             if (vm) m = __ffs(vm) - 1;
         }
+        width = m >= ncand ? (2 * width < 32 ? 2 * width : 32) : (2 * m + 2 < 32 ? 2 * m + 2 : 32);
         // ---- commit candidates 0..m-1 ----
         const bool com = lane < m;
         if (com) {
@@ -2228,7 +2250,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         for (int32_t sidx = 0; sidx < 3; sidx++) {
             const PQEnt &a = sidx == 0 ? a0 : (sidx == 1 ? a1 : a2);
             const bool valid = sidx == 0 ? v0c : (sidx == 1 ? v1c : v2c);
-            const bool toF = valid && (!hasT || pq_less(a, T));
+            const bool toF = valid && (!hasT || ent_less(a, T));
             const bool toR = valid && !toF;
             const uint32_t mR = __ballot_sync(FULL, toR);
             if (toR) pq_st(back + nR + __popc(mR & lt), a);
@@ -2238,7 +2260,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 const int32_t l = __ffs(mF) - 1;
                 mF &= mF - 1;
                 const PQEnt e = pq_bcast(a, l);
-                if (hasT && !pq_less(e, T)) {  // the threshold dropped since toF was evaluated (a spill)
+                if (hasT && !ent_less(e, T)) {  // the threshold dropped since toF was evaluated (a spill)
                     if (lane == 0) pq_st(back + nR, e);
                     nR++;
                 } else {
@@ -2258,7 +2280,7 @@ AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {
     f_enum(w, c);
 #endif
 }
-constexpr size_t ENUM_SMEM_BYTES = 512 * 32;  // >= sizeof(EnumSmem) (device only)
+constexpr size_t ENUM_SMEM_BYTES = 1024 * 32;  // >= sizeof(EnumSmem) (device only)
 
 // phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.

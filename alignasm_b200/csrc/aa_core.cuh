@@ -1794,29 +1794,43 @@ AA_HDN void f_enext(const Ws &w, int64_t gv) {
 // ---- warp-cooperative K-walk enumeration (device only; the host emulation runs f_enum) ------------------------
 // Same pop sequence as the reference's std::priority_queue<tuple<Distance, heap_t*, int64_t>> (total order:
 // distance, node allocation order, entry index), produced in BATCHES instead of one pop at a time:
-//   * the queue is split by a threshold key T into a sorted FRONT (all entries < T; a ring in shared memory) and
-//     an unsorted BACKLOG (all entries >= T; global memory, append only);
-//   * a round takes the 32 smallest entries (one per lane), expands all of them at once (heap node, next-heap
-//     root, left / right child: the dependent loads of 32 pops overlap), and commits the longest prefix that the
-//     sequential algorithm would pop in this order: candidate j stays valid as long as no successor of
-//     candidates 0..j-1 precedes it (successors carry new, larger entry indices, so only (distance, node)
-//     decides).  Entry indices of the committed successors are the prefix sums the sequential pushes would give
-//     (next-root, left, right per pop: k_shortest_walks.hpp:245-247);
-//   * successors below T are inserted into the front, the others are appended to the backlog; when the front
-//     runs empty a new threshold is chosen from a sorted sample of the backlog and the entries below it are
-//     moved over and sorted.  Pops are monotone, so an entry crosses from the backlog to the front once.
-constexpr int32_t FCAP = 1024;  // front capacity (entries of 32 B)
+//   * the queue is split by a threshold key T into a FRONT (all entries < T) and an unsorted BACKLOG (all
+//     entries >= T; global memory, append only).  The front is a sorted run in shared memory (filled by a
+//     refill, never inserted into one by one) plus up to 32 PENDING entries, sorted across the lanes in
+//     registers, which take every new entry below T (one ballot + one shuffle-shift per insert);
+//   * a round merges the heads of the two (a 64 -> 32 bitonic merge in registers), expands the candidates at
+//     once (heap node, next-heap root, left / right child: the dependent loads of up to 32 pops overlap), and
+//     commits the longest prefix that the sequential algorithm would pop in this order: candidate j stays
+//     valid as long as no successor of candidates 0..j-1 precedes it (successors carry new, larger entry
+//     indices, so only (distance, node) decides).  Entry indices of the committed successors are the prefix
+//     sums the sequential pushes would give (next-root, left, right per pop: k_shortest_walks.hpp:245-247);
+//   * full pending registers are merged into the run in one pass; when the front is empty a new threshold is
+//     chosen from a small sorted sample of the backlog and the entries below it are moved over and sorted.
+//     Pops are monotone, so an entry crosses from the backlog to the front once;
+//   * entries that can no longer be among the K walks (at least K - popped entries are known to be smaller)
+//     are dropped at the next refill and, from then on, when they are created.
+// Keys are packed for cheap comparisons: the mapq ratio nz/tot (descending) becomes the exact fixed-point
+// number RMAX - floor(nz * 2^S / tot), S = 2 * bits(V): two different fractions with denominators < 2^(S/2)
+// differ by more than 2^-S.  Contigs too large for that (V >= 2^20) compare the ratio by cross-multiplying.
+constexpr int32_t FCAP = 1024;  // run capacity (entries of 32 B)
 constexpr int32_t FMASK = FCAP - 1;
-constexpr int32_t FKEEP = 512;         // entries that stay when a full front spills its upper part
+constexpr int32_t FKEEP = 512;         // entries that stay when a full run spills its upper part
 constexpr int32_t REFILL_ALL = 768;    // a backlog this small is moved as a whole
 constexpr int32_t REFILL_TARGET = 384;
 constexpr int32_t NSAMPLE = 512;
-struct EnumSmem {
-    PQEnt f[FCAP];
+struct __attribute__((aligned(16))) QE {
+    int64_t sum;
+    uint64_t k1;  // anom << (S + 1) | ratio key        (wide mode: anom << 32)
+    uint64_t k2;  // node << 32 | entry index
+    int32_t nz, tot;
 };
-__device__ __forceinline__ PQEnt pq_ld(const PQEnt *p) {
+static_assert(sizeof(QE) == sizeof(PQEnt), "the backlog reuses the PQEnt array");
+struct EnumSmem {
+    QE f[FCAP];
+};
+__device__ __forceinline__ QE qe_ld(const QE *p) {
     union {
-        PQEnt e;
+        QE e;
         V16 v[2];
     } u;
     const V16 *q = reinterpret_cast<const V16 *>(p);
@@ -1824,9 +1838,9 @@ __device__ __forceinline__ PQEnt pq_ld(const PQEnt *p) {
     u.v[1] = q[1];
     return u.e;
 }
-__device__ __forceinline__ void pq_st(PQEnt *p, const PQEnt &e) {
+__device__ __forceinline__ void qe_st(QE *p, const QE &e) {
     union {
-        PQEnt e;
+        QE e;
         V16 v[2];
     } u;
     u.e = e;
@@ -1834,51 +1848,55 @@ __device__ __forceinline__ void pq_st(PQEnt *p, const PQEnt &e) {
     q[0] = u.v[0];
     q[1] = u.v[1];
 }
-__device__ __forceinline__ PQEnt pq_bcast(const PQEnt &e, int32_t src) {
-    const uint32_t FULL = 0xffffffffu;
-    PQEnt r;
-    r.sum = __shfl_sync(FULL, e.sum, src);
-    r.anom = __shfl_sync(FULL, e.anom, src);
-    r.nz = __shfl_sync(FULL, e.nz, src);
-    r.tot = __shfl_sync(FULL, e.tot, src);
-    r.node = __shfl_sync(FULL, e.node, src);
-    r.idx = __shfl_sync(FULL, e.idx, src);
-    r.pad = __shfl_sync(FULL, e.pad, src);
+template <class SH>
+__device__ __forceinline__ QE qe_shfl(const QE &e, SH sh) {  // sh(x) = a warp shuffle of one 32/64-bit value
+    QE r;
+    r.sum = sh(e.sum);
+    r.k1 = sh(e.k1);
+    r.k2 = sh(e.k2);
+    r.nz = sh(e.nz);
+    r.tot = sh(e.tot);
     return r;
 }
-__device__ __forceinline__ PQEnt pq_up(const PQEnt &e, int32_t d) {
-    const uint32_t FULL = 0xffffffffu;
-    PQEnt r;
-    r.sum = __shfl_up_sync(FULL, e.sum, d);
-    r.anom = __shfl_up_sync(FULL, e.anom, d);
-    r.nz = __shfl_up_sync(FULL, e.nz, d);
-    r.tot = __shfl_up_sync(FULL, e.tot, d);
-    r.node = __shfl_up_sync(FULL, e.node, d);
-    r.idx = 0;
-    r.pad = 0;
-    return r;
+struct ShIdx {
+    int32_t src;
+    template <class T>
+    __device__ __forceinline__ T operator()(T x) const { return __shfl_sync(0xffffffffu, x, src); }
+};
+struct ShUp {
+    int32_t d;
+    template <class T>
+    __device__ __forceinline__ T operator()(T x) const { return __shfl_up_sync(0xffffffffu, x, d); }
+};
+struct ShDown {
+    int32_t d;
+    template <class T>
+    __device__ __forceinline__ T operator()(T x) const { return __shfl_down_sync(0xffffffffu, x, d); }
+};
+struct ShXor {
+    int32_t m;
+    template <class T>
+    __device__ __forceinline__ T operator()(T x) const { return __shfl_xor_sync(0xffffffffu, x, m); }
+};
+// total order (distance, node, entry index); branch-free apart from the warp-uniform `wide`
+__device__ __forceinline__ bool qe_less(const QE &a, const QE &b, bool wide) {
+    int32_t t = a.k2 < b.k2;
+    if (wide) {
+        const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+        t = (x > y) | ((x == y) & t);
+    }
+    const int32_t k = (a.k1 < b.k1) | ((a.k1 == b.k1) & t);
+    return ((a.sum < b.sum) | ((a.sum == b.sum) & k)) != 0;
 }
 // (distance, node) order, strict: decides whether a NEW entry precedes an existing one
-__device__ __forceinline__ bool dn_less(const PQEnt &a, const PQEnt &b) {
-    if (a.sum != b.sum) return a.sum < b.sum;
-    if (a.anom != b.anom) return a.anom < b.anom;
-    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
-    if (x != y) return x > y;
-    return a.node < b.node;
-}
-// branch-free forms of the two orders (lanes of a warp disagree on where a comparison is decided)
-__device__ __forceinline__ bool ent_less(const PQEnt &a, const PQEnt &b) {  // total order: == pq_less
-    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
-    const int32_t tail = (a.node < b.node) | ((a.node == b.node) & (a.idx < b.idx));
-    const int32_t r = (x > y) | ((x == y) & tail);
-    const int32_t an = (a.anom < b.anom) | ((a.anom == b.anom) & r);
-    return ((a.sum < b.sum) | ((a.sum == b.sum) & an)) != 0;
-}
-__device__ __forceinline__ bool dn_less_bl(const PQEnt &a, const PQEnt &b) {  // (distance, node), strict
-    const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
-    const int32_t r = (x > y) | ((x == y) & (a.node < b.node));
-    const int32_t an = (a.anom < b.anom) | ((a.anom == b.anom) & r);
-    return ((a.sum < b.sum) | ((a.sum == b.sum) & an)) != 0;
+__device__ __forceinline__ bool qe_dn_less(const QE &a, const QE &b, bool wide) {
+    int32_t t = (a.k2 >> 32) < (b.k2 >> 32);
+    if (wide) {
+        const int64_t x = (int64_t)a.nz * den(b.tot), y = (int64_t)b.nz * den(a.tot);
+        t = (x > y) | ((x == y) & t);
+    }
+    const int32_t k = (a.k1 < b.k1) | ((a.k1 == b.k1) & t);
+    return ((a.sum < b.sum) | ((a.sum == b.sum) & k)) != 0;
 }
 __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     EnumSmem &sm = *reinterpret_cast<EnumSmem *>(scratch);
@@ -1897,16 +1915,30 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t *__restrict__ last = w.wlast + wo;
     int32_t *__restrict__ en = w.ent_node + 3 * wo;
     int32_t *__restrict__ ep = w.ent_prev + 3 * wo;
-    PQEnt *__restrict__ back = w.pq + 3 * wo;  // the backlog
+    QE *__restrict__ back = reinterpret_cast<QE *>(w.pq + 3 * wo);  // the backlog
     const HNode *__restrict__ hn = w.hn;
     const ENext *__restrict__ enext = w.enext + e0;
     const int32_t K = w.K;
+    // key packing for this contig
+    int32_t vb = 1;
+    while ((1 << vb) <= g.V) vb++;
+    const bool wide = vb > 20;
+    const int32_t S = wide ? 31 : 2 * vb;  // k1 = anom << (S + 1) | ratio key (<= 2^S)
+    auto make_k1 = [&](int32_t anom, int32_t nz, int32_t tot) -> uint64_t {
+        uint64_t rk = 0;
+        if (!wide) rk = ((uint64_t)1 << S) - (((uint64_t)(uint32_t)nz << S) / (uint64_t)(tot ? tot : 1));
+        return ((uint64_t)(uint32_t)anom << (S + 1)) | rk;
+    };
+    QE INF;
+    INF.sum = I64_MAX;
+    INF.k1 = INF.k2 = ~(uint64_t)0;
+    INF.nz = 0;
+    INF.tot = 1;
+
     int32_t nd = 1, ne = 0;
-    int32_t head = 0, nF = 0, nR = 0;
-    bool hasT = false;  // no threshold yet: everything goes to the front
-    PQEnt T;
-    T.sum = 0;
-    T.anom = T.nz = T.tot = T.node = T.idx = T.pad = 0;
+    int32_t head = 0, n0 = 0, np = 0, nR = 0;  // run ring [head, head + n0), pending lanes [0, np), backlog [0, nR)
+    bool hasT = false, hasB = false;           // threshold between front and backlog; bound of the useful keys
+    QE T = INF, B = INF, P = INF;              // P: this lane's pending entry
     const D4 ds = w.d[v0 + g.src];
     if (lane == 0) {
         dist[0] = ds;
@@ -1915,113 +1947,136 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     const int32_t hs = w.hroot[v0 + g.src];
     if (hs >= 0) {
         const HNode hr = hn_load(hn + hs);
-        PQEnt e;
+        QE e;
         e.sum = ds.sum + hr.sum;
-        e.anom = ds.anom + hr.anom;
         e.nz = ds.nz + hr.nz;
         e.tot = ds.tot + hr.tot;
-        e.node = hs;
-        e.idx = 0;
-        e.pad = -1;  // pad carries the entry's prev
+        e.k1 = make_k1(ds.anom + hr.anom, e.nz, e.tot);
+        e.k2 = (uint64_t)(uint32_t)hs << 32;
         if (lane == 0) {
             en[0] = hs;
             ep[0] = -1;
-            pq_st(&sm.f[0], e);
+            P = e;
         }
         ne = 1;
-        nF = 1;
+        np = 1;
     }
-    __syncwarp();
-
-    // front(i): the i-th smallest entry of the front
-    auto fslot = [&](int32_t i) -> PQEnt * { return &sm.f[(head + i) & FMASK]; };
-    // a full front spills its upper part to the backlog and lowers the threshold to the first spilled key
-    auto spill = [&]() {
-        const PQEnt t0 = pq_ld(fslot(FKEEP));
-        for (int32_t i = FKEEP + lane; i < nF; i += 32) pq_st(back + nR + (i - FKEEP), pq_ld(fslot(i)));
-        nR += nF - FKEEP;
-        nF = FKEEP;
-        T = t0;
-        hasT = true;
+    auto fslot = [&](int32_t i) -> QE * { return &sm.f[(head + i) & FMASK]; };
+    // number of run entries below e (per-lane binary search; the run is sorted)
+    auto run_lower_bound = [&](const QE &e) -> int32_t {
+        int32_t lo = 0, hi = n0;
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (qe_less(qe_ld(fslot(mid)), e, wide)) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    // merge the pending registers into the run (one pass over the part of the run that has to move)
+    auto flush = [&]() {
+        if (np == 0) return;
+        if (n0 + np > FCAP) {  // the run spills its upper part to the backlog; the threshold drops to the first spilled key
+            const QE t0 = qe_ld(fslot(FKEEP));
+            for (int32_t i = FKEEP + lane; i < n0; i += 32) qe_st(back + nR + (i - FKEEP), qe_ld(fslot(i)));
+            nR += n0 - FKEEP;
+            n0 = FKEEP;
+            T = t0;
+            hasT = true;
+            const uint32_t out = __ballot_sync(FULL, lane < np && !qe_less(P, T, wide));  // a suffix of the pending lanes
+            if (out & (1u << lane)) qe_st(back + nR + __popc(out & lt), P);
+            nR += __popc(out);
+            np -= __popc(out);
+            __syncwarp();
+            if (np == 0) return;
+        }
+        const int32_t pos = lane < np ? run_lower_bound(P) : 0x7fffffff;  // ascending over the lanes
+        const int32_t pos_first = __shfl_sync(FULL, pos, 0), pos_last = __shfl_sync(FULL, pos, np - 1);
+        // run element i ends up at i + #{pending l : pos_l <= i}
+        auto below_cnt = [&](int32_t i) -> int32_t {
+            int32_t lo = 0, hi = np;
+            for (int32_t s5 = 0; s5 < 5; s5++) {  // binary search over the lanes' pos (uniform trip count)
+                const int32_t mid = (lo + hi) >> 1;
+                const int32_t pm = __shfl_sync(FULL, pos, mid < 31 ? mid : 31);
+                if (lo < hi) {
+                    if (pm <= i) lo = mid + 1;
+                    else hi = mid;
+                }
+            }
+            const int32_t pm = __shfl_sync(FULL, pos, lo < 31 ? lo : 31);
+            if (lo < hi && pm <= i) lo++;
+            return lo;
+        };
+        if (pos_last <= n0 - pos_first) {  // move the lower part down: new head = head - np
+            for (int32_t i0 = 0; i0 < pos_last; i0 += 32) {
+                const int32_t i = i0 + lane;
+                const int32_t cnt = below_cnt(i);
+                QE x = INF;
+                if (i < pos_last) x = qe_ld(fslot(i));
+                __syncwarp();
+                if (i < pos_last) qe_st(&sm.f[(head - np + i + cnt) & FMASK], x);
+                __syncwarp();
+            }
+            head = (head - np) & FMASK;
+        } else {  // move the upper part up
+            for (int32_t i1 = n0; i1 > pos_first; i1 -= 32) {
+                const int32_t i = i1 - 1 - lane;
+                const int32_t cnt = below_cnt(i);
+                QE x = INF;
+                if (i >= pos_first) x = qe_ld(fslot(i));
+                __syncwarp();
+                if (i >= pos_first) qe_st(fslot(i + cnt), x);
+                __syncwarp();
+            }
+        }
+        if (lane < np) qe_st(fslot(pos + lane), P);
+        n0 += np;
+        np = 0;
+        P = INF;
         __syncwarp();
     };
-    // sorted insert of a warp-uniform entry
-    auto front_insert = [&](const PQEnt &e) {
-        if (nF == FCAP) {
-            spill();
-            if (!ent_less(e, T)) {  // the lowered threshold sends it to the backlog after all
-                if (lane == 0) pq_st(back + nR, e);
+    // sorted insert of a warp-uniform entry into the pending registers
+    auto pend_insert = [&](const QE &e) {
+        if (np == 32) {
+            flush();
+            if (hasT && !qe_less(e, T, wide)) {  // a spill lowered the threshold below e
+                if (lane == 0) qe_st(back + nR, e);
                 nR++;
                 return;
             }
         }
-        // position = number of front entries below e: 32 pivots, then inside one segment
-        const int32_t seg = (nF + 31) >> 5;  // <= 32
-        int32_t pos = 0;
-        if (nF > 0) {
-            const bool b1 = lane * seg < nF && ent_less(pq_ld(fslot(lane * seg)), e);
-            const int32_t c1 = __popc(__ballot_sync(FULL, b1));  // pivots are sorted: the lower ones are below
-            if (c1 > 0) {
-                const int32_t base = (c1 - 1) * seg + 1;
-                const bool b2 = lane < seg - 1 && base + lane < nF && ent_less(pq_ld(fslot(base + lane)), e);
-                pos = base + __popc(__ballot_sync(FULL, b2));
-            }
-        }
-        if (pos < nF - pos) {  // move the lower part one slot down (towards a new head)
-            for (int32_t i0 = 0; i0 < pos; i0 += 32) {
-                const int32_t i = i0 + lane;
-                PQEnt x;
-                if (i < pos) x = pq_ld(fslot(i));
-                __syncwarp();
-                if (i < pos) pq_st(&sm.f[(head + i - 1) & FMASK], x);
-                __syncwarp();
-            }
-            head = (head - 1) & FMASK;
-        } else {  // move the upper part one slot up
-            for (int32_t i1 = nF; i1 > pos; i1 -= 32) {
-                const int32_t i = i1 - 1 - lane;
-                PQEnt x;
-                if (i >= pos) x = pq_ld(fslot(i));
-                __syncwarp();
-                if (i >= pos) pq_st(fslot(i + 1), x);
-                __syncwarp();
-            }
-        }
-        if (lane == 0) pq_st(fslot(pos), e);
-        nF++;
-        __syncwarp();
+        const int32_t pos = __popc(__ballot_sync(FULL, lane < np && qe_less(P, e, wide)));
+        const QE up = qe_shfl(P, ShUp{1});
+        if (lane > pos) P = up;
+        if (lane == pos) P = e;
+        np++;
     };
-    // bitonic sort of sm.f[0, P) under the total order (P a power of two)
-    auto sort_front = [&](int32_t P) {
-        for (int32_t k = 2; k <= P; k <<= 1)
+    // bitonic sort of sm.f[0, n) padded to a power of two (run must be empty: head is reset by the caller)
+    auto sort_run = [&](int32_t n) {
+        int32_t Pw = 2;
+        while (Pw < n) Pw <<= 1;
+        for (int32_t i = n + lane; i < Pw; i += 32) qe_st(&sm.f[i], INF);
+        __syncwarp();
+        for (int32_t k = 2; k <= Pw; k <<= 1)
             for (int32_t j = k >> 1; j > 0; j >>= 1) {
-                for (int32_t t = lane; t < (P >> 1); t += 32) {
+                for (int32_t t = lane; t < (Pw >> 1); t += 32) {
                     const int32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const int32_t p2 = i | j;
-                    const PQEnt A = pq_ld(&sm.f[i]), B = pq_ld(&sm.f[p2]);
+                    const QE A = qe_ld(&sm.f[i]), Bq = qe_ld(&sm.f[p2]);
                     const bool asc = (i & k) == 0;
-                    if (asc ? ent_less(B, A) : ent_less(A, B)) {
-                        pq_st(&sm.f[i], B);
-                        pq_st(&sm.f[p2], A);
-                    }
+                    const bool sw = asc ? qe_less(Bq, A, wide) : qe_less(A, Bq, wide);
+                    qe_st(&sm.f[i], sw ? Bq : A);
+                    qe_st(&sm.f[p2], sw ? A : Bq);
                 }
                 __syncwarp();
             }
     };
-    auto pad_inf = [&](int32_t from, int32_t to) {
-        PQEnt inf;
-        inf.sum = I64_MAX;
-        inf.anom = inf.nz = inf.tot = 0;
-        inf.node = inf.idx = 0x7fffffff;
-        inf.pad = 0;
-        for (int32_t i = from + lane; i < to; i += 32) pq_st(&sm.f[i], inf);
-    };
-    // the front is empty: pick a threshold, move the backlog entries below it over, sort them
+    // the front is empty: pick a threshold, move the backlog entries below it into the run, sort them
     auto refill = [&]() {
         head = 0;
+        const int32_t remaining = K - nd;
         if (nR <= REFILL_ALL) {
-            for (int32_t i = lane; i < nR; i += 32) pq_st(&sm.f[i], pq_ld(back + i));
-            nF = nR;
+            for (int32_t i = lane; i < nR; i += 32) qe_st(&sm.f[i], qe_ld(back + i));
+            n0 = nR;
             nR = 0;
             hasT = false;
         } else {
@@ -2034,170 +2089,194 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             for (;;) {
                 if (r < 1) {
                     // last resort (a sample could not split the backlog): move the single minimum
-                    PQEnt best;
+                    QE best = INF;
                     int32_t bi = -1;
                     for (int32_t i = lane; i < nR; i += 32) {
-                        const PQEnt x = pq_ld(back + i);
-                        if (bi < 0 || ent_less(x, best)) {
+                        const QE x = qe_ld(back + i);
+                        if (bi < 0 || qe_less(x, best, wide)) {
                             best = x;
                             bi = i;
                         }
                     }
                     for (int32_t d = 16; d > 0; d >>= 1) {
-                        const PQEnt o = pq_bcast(best, (lane + d) & 31);
-                        const int32_t oi = __shfl_sync(FULL, bi, (lane + d) & 31);
-                        if (lane + d < 32 && oi >= 0 && (bi < 0 || ent_less(o, best))) {
+                        const QE o = qe_shfl(best, ShDown{d});
+                        const int32_t oi = __shfl_down_sync(FULL, bi, d);
+                        if (lane + d < 32 && oi >= 0 && (bi < 0 || qe_less(o, best, wide))) {
                             best = o;
                             bi = oi;
                         }
                     }
-                    best = pq_bcast(best, 0);
+                    best = qe_shfl(best, ShIdx{0});
                     bi = __shfl_sync(FULL, bi, 0);
-                    const PQEnt tail_e = pq_ld(back + nR - 1);
+                    const QE tail_e = qe_ld(back + nR - 1);
                     __syncwarp();
                     if (lane == 0) {
-                        pq_st(back + bi, tail_e);
-                        pq_st(&sm.f[0], best);
+                        qe_st(back + bi, tail_e);
+                        qe_st(&sm.f[0], best);
                     }
                     nR--;
-                    nF = 1;
+                    n0 = 1;
                     T = best;
-                    T.idx = best.idx + 1;  // the smallest key above `best`
+                    T.k2 = best.k2 + 1;  // the smallest key above `best`
                     hasT = true;
                     break;
                 }
                 // threshold = r-th smallest of a strided sample
-                for (int32_t i = lane; i < ns; i += 32) pq_st(&sm.f[i], pq_ld(back + (int64_t)i * stride));
-                int32_t P = 32;
-                while (P < ns) P <<= 1;
-                pad_inf(ns, P);
+                for (int32_t i = lane; i < ns; i += 32) qe_st(&sm.f[i], qe_ld(back + (int64_t)i * stride));
                 __syncwarp();
-                sort_front(P);
-                T = pq_ld(&sm.f[r]);
+                sort_run(ns);
+                T = qe_ld(&sm.f[r]);
                 hasT = true;
+                // candidate bound of the useful keys: about 1.25 * remaining entries are below it
+                bool tryB = false;
+                QE Bc = INF;
+                {
+                    const int64_t qb = ((int64_t)remaining * 5 / 4) / stride + 2;
+                    if (qb < ns) {
+                        Bc = qe_ld(&sm.f[qb]);
+                        tryB = !hasB || qe_less(Bc, B, wide);
+                    }
+                }
                 __syncwarp();
-                // one pass: below T -> front (unsorted for now), the rest is compacted in place
-                int32_t nb = 0, wpos = 0;
+                // one pass: below T -> run (unsorted for now), dead entries are dropped, the rest is compacted
+                int32_t nb = 0, wpos = 0, ncb = 0;
                 for (int32_t i0 = 0; i0 < nR; i0 += 128) {  // four chunks of loads in flight
-                    PQEnt xs[4];
+                    QE xs[4];
 #pragma unroll
                     for (int32_t u = 0; u < 4; u++)
-                        if (i0 + 32 * u + lane < nR) xs[u] = pq_ld(back + i0 + 32 * u + lane);
+                        if (i0 + 32 * u + lane < nR) xs[u] = qe_ld(back + i0 + 32 * u + lane);
 #pragma unroll
                     for (int32_t u = 0; u < 4; u++) {
-                        const bool valid = i0 + 32 * u + lane < nR;
-                        const bool below = valid && ent_less(xs[u], T);
+                        bool valid = i0 + 32 * u + lane < nR;
+                        if (valid && hasB && !qe_less(xs[u], B, wide)) valid = false;  // can never be popped
+                        const bool below = valid && qe_less(xs[u], T, wide);
                         const uint32_t mb = __ballot_sync(FULL, below);
                         const int32_t at = nb + __popc(mb & lt);
                         const bool stage = below && at < FCAP;
                         const uint32_t mk = __ballot_sync(FULL, valid && !stage);
-                        if (stage) pq_st(&sm.f[at], xs[u]);
-                        if (valid && !stage) pq_st(back + wpos + __popc(mk & lt), xs[u]);
+                        if (tryB) ncb += __popc(__ballot_sync(FULL, valid && qe_less(xs[u], Bc, wide)));
+                        if (stage) qe_st(&sm.f[at], xs[u]);
+                        if (valid && !stage) qe_st(back + wpos + __popc(mk & lt), xs[u]);
                         nb += __popc(mb);
                         wpos += __popc(mk);
                     }
                     __syncwarp();
                 }
                 if (nb <= FCAP) {
-                    nF = nb;
+                    n0 = nb;
                     nR = wpos;
+                    if (tryB && ncb >= remaining) {
+                        B = Bc;
+                        hasB = true;
+                    }
                     break;
                 }
                 // too many entries below this threshold: put the staged ones back and try a lower one
-                for (int32_t i = lane; i < FCAP; i += 32) pq_st(back + wpos + i, pq_ld(&sm.f[i]));
+                for (int32_t i = lane; i < FCAP; i += 32) qe_st(back + wpos + i, qe_ld(&sm.f[i]));
                 nR = wpos + FCAP;
                 __syncwarp();
                 r >>= 1;
             }
         }
-        if (nF > 1) {
-            int32_t P = 2;
-            while (P < nF) P <<= 1;
-            pad_inf(nF, P);
-            __syncwarp();
-            sort_front(P);
-        }
+        __syncwarp();
+        if (n0 > 1) sort_run(n0);
         __syncwarp();
     };
 
     int32_t width = 32;  // candidates per round: follows the commit length (tie-heavy queues confirm few)
     while (nd < K) {
-        if (nF == 0) {
+        if (n0 == 0 && np == 0) {
             if (nR == 0) break;
             refill();
             continue;
         }
-        int32_t ncand = nF < width ? nF : width;
+        // ---- candidates: the smallest entries of pending + run head, sorted over the lanes ----
+        QE t = INF;
+        int32_t from_pend = 0;
+        {
+            const int32_t nb0 = n0 < 32 ? n0 : 32;
+            if (np == 0) {
+                if (lane < nb0) t = qe_ld(fslot(lane));
+            } else if (nb0 == 0) {
+                t = P;
+                from_pend = lane < np;
+            } else {
+                QE br = INF;  // run head, reversed over the lanes
+                if (31 - lane < nb0) br = qe_ld(fslot(31 - lane));
+                t = P;
+                from_pend = 1;
+                if (qe_less(br, t, wide)) {
+                    t = br;
+                    from_pend = 0;
+                }
+#pragma unroll
+                for (int32_t j = 16; j > 0; j >>= 1) {  // sort the bitonic sequence of the 32 smallest
+                    const QE o = qe_shfl(t, ShXor{j});
+                    const int32_t of = __shfl_xor_sync(FULL, from_pend, j);
+                    const bool lower = (lane & j) == 0;
+                    const bool o_less = qe_less(o, t, wide);
+                    if (lower == o_less) {
+                        t = o;
+                        from_pend = of;
+                    }
+                }
+            }
+        }
+        int32_t ncand = n0 + np < width ? n0 + np : width;
         if (ncand > K - nd) ncand = K - nd;
         const bool have = lane < ncand;
-        // ---- the candidates and their successors (speculative beyond the first) ----
-        PQEnt t;
-        t.sum = 0;
-        t.anom = t.nz = t.tot = t.node = t.idx = t.pad = 0;
-        PQEnt a0, a1, a2;
-        a0.node = a1.node = a2.node = -1;
-        a0.sum = a1.sum = a2.sum = 0;
-        a0.anom = a0.nz = a0.tot = a0.idx = a0.pad = 0;
-        a1 = a0;
-        a2 = a0;
-        a1.node = a2.node = -1;
+        // ---- their successors (speculative beyond the first candidate) ----
+        QE a0 = INF, a1 = INF, a2 = INF;
+        int32_t p0 = -1, p12 = -1;  // prev of the successors
+        bool v0s = false, v1s = false, v2s = false;
         if (have) {
-            t = pq_ld(fslot(lane));
-            const HNode ch = hn_load(hn + t.node);
-            const int32_t ceid = w.hn_eid[t.node];
+            const int32_t node = (int32_t)(t.k2 >> 32), idx = (int32_t)(uint32_t)t.k2;
+            const int32_t anom = (int32_t)(t.k1 >> (S + 1));
+            const HNode ch = hn_load(hn + node);
+            const int32_t ceid = w.hn_eid[node];
+            p12 = ep[idx];
+            p0 = idx;
             HNode xl, xr;
             if (ch.left >= 0) xl = hn_load(hn + ch.left);
             if (ch.right >= 0) xr = hn_load(hn + ch.right);
             const ENext x = enext[ceid];
             if (x.hv >= 0) {
                 a0.sum = t.sum + x.sum;
-                a0.anom = t.anom + x.anom;
                 a0.nz = t.nz + x.nz;
                 a0.tot = t.tot + x.tot;
-                a0.node = x.hv;
-                a0.pad = t.idx;
+                a0.k1 = make_k1(anom + x.anom, a0.nz, a0.tot);
+                a0.k2 = (uint64_t)(uint32_t)x.hv << 32;
+                v0s = true;
             }
             if (ch.left >= 0) {
                 a1.sum = t.sum + xl.sum - ch.sum;
-                a1.anom = t.anom + xl.anom - ch.anom;
                 a1.nz = t.nz + xl.nz - ch.nz;
                 a1.tot = t.tot + xl.tot - ch.tot;
-                a1.node = ch.left;
-                a1.pad = t.pad;
+                a1.k1 = make_k1(anom + xl.anom - ch.anom, a1.nz, a1.tot);
+                a1.k2 = (uint64_t)(uint32_t)ch.left << 32;
+                v1s = true;
             }
             if (ch.right >= 0) {
                 a2.sum = t.sum + xr.sum - ch.sum;
-                a2.anom = t.anom + xr.anom - ch.anom;
                 a2.nz = t.nz + xr.nz - ch.nz;
                 a2.tot = t.tot + xr.tot - ch.tot;
-                a2.node = ch.right;
-                a2.pad = t.pad;
+                a2.k1 = make_k1(anom + xr.anom - ch.anom, a2.nz, a2.tot);
+                a2.k2 = (uint64_t)(uint32_t)ch.right << 32;
+                v2s = true;
             }
         }
         // ---- how many candidates does the sequential order confirm? ----
-        PQEnt pm = a0;  // this lane's smallest successor under (distance, node)
-        bool pv = a0.node >= 0;
-        if (a1.node >= 0 && (!pv || dn_less_bl(a1, pm))) {
-            pm = a1;
-            pv = true;
-        }
-        if (a2.node >= 0 && (!pv || dn_less_bl(a2, pm))) {
-            pm = a2;
-            pv = true;
-        }
         int32_t m = ncand;
         if (ncand > 1) {
+            QE pm = a0;  // this lane's smallest successor under (distance, node); INF when it has none
+            if (qe_dn_less(a1, pm, wide)) pm = a1;
+            if (qe_dn_less(a2, pm, wide)) pm = a2;
             for (int32_t d = 1; d < ncand; d <<= 1) {  // inclusive prefix minimum over the lanes
-                const PQEnt o = pq_up(pm, d);
-                const bool ov = __shfl_up_sync(FULL, (int32_t)pv, d) != 0;
-                if (lane >= d && ov && (!pv || dn_less_bl(o, pm))) {
-                    pm = o;
-                    pv = true;
-                }
+                const QE o = qe_shfl(pm, ShUp{d});
+                if (lane >= d && qe_dn_less(o, pm, wide)) pm = o;
             }
-            const PQEnt ex = pq_up(pm, 1);
-            const bool exv = __shfl_up_sync(FULL, (int32_t)pv, 1) != 0;
-            const bool viol = have && lane > 0 && exv && dn_less_bl(ex, t);
+            const QE ex = qe_shfl(pm, ShUp{1});
+            const bool viol = have && lane > 0 && ex.sum != I64_MAX && qe_dn_less(ex, t, wide);
             const uint32_t vm = __ballot_sync(FULL, viol);
             if (vm) m = __ffs(vm) - 1;
         }
@@ -2207,14 +2286,14 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         if (com) {
             D4 cd;
             cd.sum = t.sum;
-            cd.anom = t.anom;
+            cd.anom = (int32_t)(t.k1 >> (S + 1));
             cd.nz = t.nz;
             cd.tot = t.tot;
             cd.aux = 0;
             dist[nd + lane] = cd;
-            last[nd + lane] = t.idx;
+            last[nd + lane] = (int32_t)(uint32_t)t.k2;
         }
-        const int32_t v0c = com && a0.node >= 0, v1c = com && a1.node >= 0, v2c = com && a2.node >= 0;
+        const int32_t v0c = com && v0s, v1c = com && v1s, v2c = com && v2s;
         const int32_t mycnt = v0c + v1c + v2c;
         int32_t inc = mycnt;
         for (int32_t d = 1; d < 32; d <<= 1) {
@@ -2224,47 +2303,56 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         const int32_t total = __shfl_sync(FULL, inc, 31);
         int32_t id = ne + inc - mycnt;
         if (v0c) {
-            a0.idx = id;
-            en[id] = a0.node;
-            ep[id] = a0.pad;
+            a0.k2 |= (uint32_t)id;
+            en[id] = (int32_t)(a0.k2 >> 32);
+            ep[id] = p0;
             id++;
         }
         if (v1c) {
-            a1.idx = id;
-            en[id] = a1.node;
-            ep[id] = a1.pad;
+            a1.k2 |= (uint32_t)id;
+            en[id] = (int32_t)(a1.k2 >> 32);
+            ep[id] = p12;
             id++;
         }
         if (v2c) {
-            a2.idx = id;
-            en[id] = a2.node;
-            ep[id] = a2.pad;
+            a2.k2 |= (uint32_t)id;
+            en[id] = (int32_t)(a2.k2 >> 32);
+            ep[id] = p12;
         }
         ne += total;
         nd += m;
-        head = (head + m) & FMASK;
-        nF -= m;
+        {  // the committed entries leave the front: a prefix of the pending lanes and a prefix of the run
+            const int32_t na = __popc(__ballot_sync(FULL, com && from_pend));
+            if (na > 0) {
+                const QE dn = qe_shfl(P, ShDown{na});
+                P = lane + na < np ? dn : INF;
+                np -= na;
+            }
+            head = (head + (m - na)) & FMASK;
+            n0 -= m - na;
+        }
         if (nd >= K) break;
-        // ---- the successors enter the queue: backlog appends in parallel, front inserts one by one ----
+        // ---- the successors enter the queue: backlog appends in parallel, pending inserts one by one ----
 #pragma unroll
         for (int32_t sidx = 0; sidx < 3; sidx++) {
-            const PQEnt &a = sidx == 0 ? a0 : (sidx == 1 ? a1 : a2);
-            const bool valid = sidx == 0 ? v0c : (sidx == 1 ? v1c : v2c);
-            const bool toF = valid && (!hasT || ent_less(a, T));
+            const QE &a = sidx == 0 ? a0 : (sidx == 1 ? a1 : a2);
+            bool valid = sidx == 0 ? v0c : (sidx == 1 ? v1c : v2c);
+            if (valid && hasB && !qe_less(a, B, wide)) valid = false;  // beyond the K walks: dropped
+            const bool toF = valid && (!hasT || qe_less(a, T, wide));
             const bool toR = valid && !toF;
             const uint32_t mR = __ballot_sync(FULL, toR);
-            if (toR) pq_st(back + nR + __popc(mR & lt), a);
+            if (toR) qe_st(back + nR + __popc(mR & lt), a);
             nR += __popc(mR);
             uint32_t mF = __ballot_sync(FULL, toF);
             while (mF) {
                 const int32_t l = __ffs(mF) - 1;
                 mF &= mF - 1;
-                const PQEnt e = pq_bcast(a, l);
-                if (hasT && !ent_less(e, T)) {  // the threshold dropped since toF was evaluated (a spill)
-                    if (lane == 0) pq_st(back + nR, e);
+                const QE e = qe_shfl(a, ShIdx{l});
+                if (hasT && !qe_less(e, T, wide)) {  // the threshold dropped since toF was evaluated (a spill)
+                    if (lane == 0) qe_st(back + nR, e);
                     nR++;
                 } else {
-                    front_insert(e);
+                    pend_insert(e);
                 }
             }
         }

@@ -298,6 +298,7 @@ struct CudaBackend {
     template <class F>
     void for_each_contig(const char *name, int64_t n, F f, size_t smem = 0) {
         if (n <= 0 || failed) return;
+        if (smem > 48 * 1024) AA_CUDA(cudaFuncSetAttribute(k_warp_items<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_warp_items<F><<<(unsigned)n, 32, smem, stream>>>(n, f);
         n_launch++;
         mark(name);

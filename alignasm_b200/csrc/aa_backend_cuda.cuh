@@ -208,11 +208,12 @@ struct CudaBackend {
     }
     void free_persistent(void *p) { cudaFree(p); }
 
-    void begin_solve() {
+    // give the whole workspace back to the bump allocator (coalescing a fragmented pool into one block)
+    void reset_pool() {
         AA_CUDA(cudaSetDevice(device));
-        // coalesce a fragmented pool into one block so the next solve bumps through contiguous memory
         if (pool.size() > 1) {
-            AA_CUDA(cudaStreamSynchronize(stream));
+            AA_CUDA(cudaStreamSynchronize(main_stream));
+            AA_CUDA(cudaStreamSynchronize(side_stream));
             size_t total = 0;
             for (auto &b : pool) {
                 total += b.cap;
@@ -223,11 +224,15 @@ struct CudaBackend {
             if (cudaMalloc(&p, total) == cudaSuccess) pool.push_back({p, total, 0});
             else cudaGetLastError();
         }
+        for (auto &b : pool) b.top = 0;
+        log.clear();
+    }
+    void begin_solve(bool keep_pool = false) {
+        AA_CUDA(cudaSetDevice(device));
         stream = main_stream;
         if (side_pending) AA_CUDA(cudaStreamSynchronize(side_stream));
         side_pending = false;
-        for (auto &b : pool) b.top = 0;
-        log.clear();
+        if (!keep_pool) reset_pool();
         n_launch = 0;
         n_marks = 0;
         t_host0 = std::chrono::steady_clock::now();

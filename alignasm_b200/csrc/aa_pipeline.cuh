@@ -136,8 +136,10 @@ struct DevBatch {
     uint8_t *fwd = nullptr, *mapq = nullptr;
     int64_t *run_off = nullptr, *run_ql = nullptr, *run_qr = nullptr, *run_rl = nullptr;
     // host mirror of what the host-side sort needs (OC1)
-    std::vector<int64_t> h_ctg_off, h_qs, h_qe;
+    std::vector<int64_t> own_ctg_off, own_qs, own_qe;  // copies, for a batch that stays resident
+    const int64_t *h_ctg_off = nullptr, *h_qs = nullptr, *h_qe = nullptr;  // the caller's arrays for a one-shot solve
     std::vector<void *> owned;
+    bool pooled = false;  // arrays live in the solve workspace (one-shot aa_solve): nothing to free
 };
 
 inline void rows_alloc_host(aa_rows &r, int64_t n) {
@@ -257,7 +259,9 @@ struct Pipeline {
         return (T *)bk.alloc_bytes((size_t)(n > 0 ? n : 1) * sizeof(T));
     }
 
-    aa_status upload(const aa_batch *b, DevBatch *&out) {
+    // pooled: stage the batch in the workspace pool (which the caller has just reset) instead of cudaMalloc'ing it;
+    // the solve that follows must then keep the pool (solve(..., keep_pool = true))
+    aa_status upload(const aa_batch *b, DevBatch *&out, bool pooled = false) {
         std::string v = validate_batch(b);
         if (!v.empty()) {
             err = v;
@@ -267,11 +271,13 @@ struct Pipeline {
         d->C = b->n_ctg;
         d->B = b->n_blk;
         d->R = b->n_run;
+        d->pooled = pooled;
         auto up = [&](auto *&dst, const auto *src, int64_t n) {
             using T = std::remove_const_t<std::remove_pointer_t<decltype(src)>>;
-            dst = (T *)bk.alloc_persistent((size_t)(n > 0 ? n : 1) * sizeof(T));
+            const size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(T);
+            dst = (T *)(pooled ? bk.alloc_bytes(bytes) : bk.alloc_persistent(bytes));
             if (!dst) return false;
-            d->owned.push_back(dst);
+            if (!pooled) d->owned.push_back(dst);
             if (n > 0) bk.h2d(dst, src, (size_t)n * sizeof(T));
             return true;
         };
@@ -285,9 +291,18 @@ struct Pipeline {
             err = "device allocation failed while staging the batch";
             return AA_ERR_NOMEM;
         }
-        d->h_ctg_off.assign(b->ctg_off, b->ctg_off + d->C + 1);
-        d->h_qs.assign(b->qry_str, b->qry_str + d->B);
-        d->h_qe.assign(b->qry_end, b->qry_end + d->B);
+        if (pooled) {
+            d->h_ctg_off = b->ctg_off;
+            d->h_qs = b->qry_str;
+            d->h_qe = b->qry_end;
+        } else {
+            d->own_ctg_off.assign(b->ctg_off, b->ctg_off + d->C + 1);
+            d->own_qs.assign(b->qry_str, b->qry_str + d->B);
+            d->own_qe.assign(b->qry_end, b->qry_end + d->B);
+            d->h_ctg_off = d->own_ctg_off.data();
+            d->h_qs = d->own_qs.data();
+            d->h_qe = d->own_qe.data();
+        }
         bk.sync();
         out = d;
         return AA_OK;
@@ -306,8 +321,8 @@ struct Pipeline {
         }                        \
     } while (0)
     // ---- the whole hot path over a staged batch ------------------------------------------------------
-    aa_status solve(DevBatch &d, const aa_opts &opt, aa_result *res) {
-        bk.begin_solve();
+    aa_status solve(DevBatch &d, const aa_opts &opt, aa_result *res, bool keep_pool = false) {
+        bk.begin_solve(keep_pool);
         aa_stats st;
         std::memset(&st, 0, sizeof st);
         const int64_t C = d.C, B = d.B;

@@ -90,11 +90,34 @@ aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, a
 }
 aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_result *res) {
     if (!ctx || !res) return AA_ERR_INVALID;
-    aa_dev_batch *dev = nullptr;
-    aa_status st = aa_upload(ctx, batch, &dev);
-    if (st != AA_OK) return st;
-    st = aa_solve_device(ctx, dev, opts, res);
-    aa_dev_batch_free(ctx, dev);
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        return AA_ERR_CUDA;
+    }
+    // one-shot: the batch is staged in the pooled workspace, so a steady-state call makes no cudaMalloc / cudaFree
+    ctx->bk.reset_pool();
+    aa::DevBatch *d = nullptr;
+    aa_status st = ctx->pipe.upload(batch, d, /*pooled=*/true);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        return st;
+    }
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        ctx->pipe.free_batch(d);
+        return AA_ERR_CUDA;
+    }
+    aa_opts o{};
+    if (opts) o = *opts;
+    st = ctx->pipe.solve(*d, o, res, /*keep_pool=*/true);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        if (st != AA_ERR_UNSOLVABLE) {
+            aa::result_free_host(res);
+            cudaStreamSynchronize(ctx->bk.stream);
+        }
+    }
+    ctx->pipe.free_batch(d);
     return st;
 }
 void aa_result_free(aa_result *res) { aa::result_free_host(res); }

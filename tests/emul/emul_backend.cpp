@@ -79,7 +79,7 @@ struct HostBackend {
     int host_threads() { return 1; }
     int64_t max_workers() { return 3; }  // >1 so that slot indexing is exercised
     int64_t scratch_budget() { return (int64_t)1 << 30; }
-    void begin_solve() {}
+    void begin_solve(bool = false) {}
     void end_solve(aa_stats &) {
         for (void *p : blocks) std::free(p);
         blocks.clear();

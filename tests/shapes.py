@@ -10,5 +10,6 @@ SMALL = {
               "--lmax", 5000, "--gap_max", 200], [False, True]),
     "singletons": (["--contigs", 50, "--blocks", 2, "--sd", 2, "--seed", 14, "--lmin", 500, "--lmax", 5000], [False]),
     "dense200": (["--preset", "c4", "--n", 200], [False, True]),
+    "dense400": (["--preset", "c4", "--n", 400], [False, True]),
     "cancer_small": (["--preset", "c3", "--scale", 0.004], [False]),
 }

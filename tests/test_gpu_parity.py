@@ -106,6 +106,65 @@ def test_full_size_properties(solver, workdir):
     assert full_rows == [got.rows_of("out", k) for k in range(len(pick))]
 
 
+def test_cancer_full_size(solver, workdir):
+    """BASELINE config 3 (cancer karyotype: dense translocation / inversion / duplicate blocks, exact ties, the
+    alt loop active on most contigs) at full size: invariants on every contig + exact agreement with the oracle
+    on a sample of contigs, including the tie-sensitive .alt / .all lists."""
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    pf = aa.read_paf(pu.synth(os.path.join(workdir, "c3_full.paf"), "--preset", "c3"))
+    b = pf.batch
+    res = solver.solve(b, want_all=True)
+    n = np.diff(b.ctg_off)
+    assert np.all(np.diff(res.out_off) >= 1)
+    assert res.stats["n_walk"] <= 10000 * b.n_ctg and res.stats["n_task"] >= b.n_ctg - int(np.sum(n == 1))
+    for which, off in (("out", res.out_off), ("alt", res.alt_off)):
+        r = getattr(res, which)
+        ctg = np.repeat(np.arange(b.n_ctg), np.diff(off))
+        g = b.ctg_off[ctg] + r["ctg_index"]
+        assert np.all(r["ctg_index"] >= 0) and np.all(r["ctg_index"] < n[ctg])
+        assert np.all(r["qry_str"] >= b.qry_str[g]) and np.all(r["qry_end"] <= b.qry_end[g])
+        same = ctg[1:] == ctg[:-1]
+        assert np.all(r["qry_str"][1:][same] > r["qry_end"][:-1][same])
+    # the alt chain exists only where it has fewer anomalies than the primary could avoid: it is never longer than the contig
+    assert np.all(np.diff(res.alt_off) <= n)
+    pick = np.nonzero(n <= 500)[0][:80]
+    sub = b.select(pick)
+    got = solver.solve(sub, want_all=True, keep_debug=True)
+    want = oracle_py.oracle_solve(sub, threads=8, want_all=True, keep_debug=True)
+    assert pu.debug_equal(got.dbg, want.dbg) is None
+    assert pu.result_rows_equal(got, want) is None
+    assert [res.rows_of("alt", int(c)) for c in pick] == [got.rows_of("alt", k) for k in range(len(pick))]
+
+
+def test_sharded_solve_equals_whole(solver, workdir):
+    """Contig sharding: LPT shards solved one after the other on this GPU and merged in input
+    order give exactly the rows of the unsharded solve."""
+    import alignasm_b200 as aa
+    from alignasm_b200 import sharding
+    args, _ = SMALL["cancer_small"]
+    b = aa.read_paf(pu.synth(os.path.join(workdir, "shard.paf"), *args)).batch
+    whole = sharding.rows_by_contig(solver.solve(b, want_all=True))
+    for world in (2, 3, 8):
+        shards = sharding.lpt_shards(sharding.contig_costs(b), world)
+        rows = [sharding.rows_by_contig(solver.solve(b.select(ids), want_all=True)) if len(ids) else [] for ids in shards]
+        assert sharding.merge_shards(b.n_ctg, shards, rows) == whole
+
+
+def test_walk_limit_option(solver, workdir):
+    """aa_opts.max_walks (MAX_PATH_COUNT, paf_data.cpp:729): small limits exercise the early stop of the batched
+    enumeration, a large one its backlog / refill / spill paths; all against the oracle."""
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    args, _ = SMALL["ties"]
+    b = aa.read_paf(pu.synth(os.path.join(workdir, "klimit.paf"), *args)).batch
+    for k in (1, 2, 37, 1000, 60000):
+        got = solver.solve(b, want_all=True, keep_debug=True, max_walks=k)
+        want = oracle_py.oracle_solve(b, threads=8, want_all=True, keep_debug=True, max_walks=k)
+        assert pu.debug_equal(got.dbg, want.dbg) is None, k
+        assert pu.result_rows_equal(got, want) is None, k
+
+
 def test_cli_writes_reference_bytes(product_lib, workdir):
     """`alignasm <input.paf>` (the drop-in surface) reproduces the reference's three files byte for byte."""
     import shutil

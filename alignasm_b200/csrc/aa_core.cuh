@@ -2923,6 +2923,105 @@ AA_HDN void f_main_resolve(const Ws &w, int64_t c, const Slot &s) {
     w.task_cov[t0] = A.cov;
     w.task_rows[t0] = A.rows;
 }
+#if defined(__CUDA_ARCH__)
+// S2 on the device: the same chain, but the per-position records are loaded 32 at a time (coalesced, one chunk
+// ahead) and the chain walks through them by shuffles; only a failed speculation runs the real step (lane 0)
+__device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0) return;
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    const int32_t m = w.m_len[c];
+    Auto A;
+    A.cs = g.src;
+    A.cov = 0;
+    A.rows = 0;
+    Emit em;
+    em.mode = 1;
+    em.dst = 0;
+    em.base = v0;
+    em.call = 0;
+    struct Rec {
+        int32_t used, cs, rows, mw;
+        int64_t cov;
+    };
+    auto load = [&](int32_t b) -> Rec {
+        Rec r;
+        r.used = 0;
+        r.cs = r.rows = r.mw = 0;
+        r.cov = 0;
+        const int32_t i = b + lane;
+        if (i < m) {
+            r.used = w.sp_used[v0 + i];
+            r.cs = w.sp_cs[v0 + i];
+            r.rows = w.sp_rows[v0 + i];
+            r.cov = w.sp_cov[v0 + i];
+            r.mw = w.main_walk[v0 + i];
+        }
+        return r;
+    };
+    int32_t b = 0;
+    Rec cur = load(0), nxt = load(32);
+    // state of the automaton when it stood at this lane's position (stored when the chunk is left)
+    int32_t o_cs = -1, o_rows = 0;
+    int64_t o_cov = 0;
+    bool o_set = false, o_done = false;
+    auto store_chunk = [&]() {
+        const int32_t i = b + lane;
+        if (o_set && i < m) {
+            w.m_cs[v0 + i] = o_cs;
+            w.m_cov[v0 + i] = o_cov;
+            w.m_rows[v0 + i] = o_rows;
+            if (o_done) w.m_done[v0 + i] = 1;
+        }
+        o_set = o_done = false;
+    };
+    int32_t i = 0;
+    while (i < m) {
+        while (i >= b + 32) {
+            store_chunk();
+            b += 32;
+            cur = nxt;
+            nxt = load(b + 32);
+        }
+        const int32_t l = i - b;
+        if (lane == l) {
+            o_cs = A.cs;
+            o_cov = A.cov;
+            o_rows = A.rows;
+            o_set = true;
+        }
+        int32_t used = __shfl_sync(FULL, cur.used, l);
+        const int32_t mw = __shfl_sync(FULL, cur.mw, l);
+        if (used != 0 && A.cs == mw) {
+            A.cov += __shfl_sync(FULL, cur.cov, l);
+            A.rows += __shfl_sync(FULL, cur.rows, l);
+            A.cs = __shfl_sync(FULL, cur.cs, l);
+        } else {
+            if (lane == 0) {
+                const int32_t v = w.main_walk[v0 + i + 1];
+                const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
+                used = auto_step(w, g, s.buf, A, v, nv, em);
+            }
+            used = __shfl_sync(FULL, used, 0);
+            A.cs = __shfl_sync(FULL, A.cs, 0);
+            A.cov = __shfl_sync(FULL, A.cov, 0);
+            A.rows = __shfl_sync(FULL, A.rows, 0);
+            if (lane == l) o_done = true;
+        }
+        i += used;
+    }
+    store_chunk();
+    if (lane == 0) {
+        w.m_tot_cov[c] = A.cov;
+        w.m_tot_rows[c] = A.rows;
+        const int64_t t0 = w.task_off[c];
+        w.task_cov[t0] = A.cov;
+        w.task_rows[t0] = A.rows;
+    }
+}
+#endif
 // S3 (per walk-0 position, parallel): emit the rows of every state the resolve pass took from speculation
 AA_HDN void f_main_rows(const Ws &w, int64_t gv) {
     const int64_t c = upper_idx(w.vtx_off, w.C, gv);
@@ -3088,7 +3187,11 @@ AA_HDN void f_tasks_a0(const Ws &w, int64_t slot, const int32_t *ord) {
     for (;;) {
         const int64_t k = next_item(w);
         if (k >= w.C) break;
-        if (aa_lane() == 0) f_main_resolve(w, ord[k], s);
+#if defined(__CUDA_ARCH__)
+        f_main_resolve_warp(w, ord[k], s);
+#else
+        f_main_resolve(w, ord[k], s);
+#endif
     }
 }
 // pass A1: every other planned walk (coverage, row count, block marks)

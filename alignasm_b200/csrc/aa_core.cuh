@@ -2577,10 +2577,10 @@ AA_HDN void f_plan_any(const Ws &w, int64_t c) {
 }
 
 AA_HDN void f_task_compact(const Ws &w, int64_t c) {
-    if (aa_lane() != 0) return;
     int64_t o = w.task_off[c];
     const Task *t = w.task + 2 * w.walk_off[c];
-    for (int32_t k = 0; k < w.n_task[c]; k++) w.tasks[o + k] = t[k];
+    const int32_t n = w.n_task[c];
+    for (int32_t k = aa_lane(); k < n; k += AA_LANES) w.tasks[o + k] = t[k];
 }
 
 // ---- walk task: recover + mark + upgrade + rows ---------------------------------------------------

@@ -188,6 +188,8 @@ struct CudaBackend {
         b.top += n;
         return r;
     }
+    size_t alloc_mark() const { return log.size(); }
+    void release_to(size_t mark) { release_last((int)(log.size() - mark)); }
     void release_last(int k) {
         while (k-- > 0 && !log.empty()) {
             Mark m = log.back();

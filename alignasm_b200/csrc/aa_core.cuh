@@ -261,6 +261,17 @@ struct Ws {
     InsKey *ins;         // [Nins] inserts of every contig, BFS order then edge order
     int32_t *root_at;    // [Vtot] heap root by BFS position
     int32_t key_bits;    // bits of the depth / preorder fields of the sort key
+    int32_t *cdepth;     // [C] depth of the tree
+    int32_t *hmode;      // [C] 0: streaming builder (one warp per contig), 1: level-parallel builder (shallow, wide trees)
+    int32_t *lvl_overflow;  // arena / spine overflow flag of the level-parallel builder
+    uint32_t *ck_owner;  // [Hcap/64] BFS slot that owns a 64-node chunk (0xffffffff: not a level-mode chunk)
+    int32_t *ck_seq;     // [Hcap/64] running number of the chunk inside its owner
+    int32_t *ck_used;    // [Hcap/64] nodes used in the chunk
+    uint64_t *ck_key_in, *ck_key;  // chunk sort keys (owner, sequence)
+    uint32_t *ck_val_in, *ck_val;  // chunk ids in sorted order
+    int32_t *ck_cnt;     // [chunks+1] fill in sorted order
+    int64_t *ck_pre;     // [chunks+2] its exclusive prefix sum
+    int32_t *ck_new;     // [Hcap/64] new id of the chunk's first node
     ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
     // enumeration
@@ -949,6 +960,11 @@ AA_HDN void f_bfs_key(const Ws &w, int64_t gv, const Tour *__restrict__ tour) {
         depth = (uint64_t)(1 - me.sd);
         pre = (uint64_t)(root.sp - me.sp);
         if (x == dest) w.ntree[c] = root.sp;
+#if defined(__CUDA_ARCH__)
+        if (w.nchild[gv] == 0) atomicMax(&w.cdepth[c], (int32_t)depth);  // leaves suffice for the maximum
+#else
+        if ((int32_t)depth > w.cdepth[c]) w.cdepth[c] = (int32_t)depth;
+#endif
     } else {
         depth = ((uint64_t)1 << kb) - 1;
         pre = (uint64_t)x;
@@ -956,6 +972,19 @@ AA_HDN void f_bfs_key(const Ws &w, int64_t gv, const Tour *__restrict__ tour) {
     }
     w.bkey_in[gv] = ((uint64_t)c << (2 * kb)) | (depth << kb) | pre;
     w.bval_in[gv] = (uint32_t)gv;
+}
+AA_HDN void f_lvl_off(const Ws &w, int64_t item, const int32_t *ctgs, int32_t per, int64_t *out) {
+    const int64_t c = ctgs[item / per];
+    const int64_t d = item % per + 1;  // depths 1 .. per
+    const int kb = w.key_bits;
+    const uint64_t want = ((uint64_t)c << (2 * kb)) | ((uint64_t)d << kb);
+    int64_t lo = w.vtx_off[c], hi = w.vtx_off[c] + w.ntree[c];
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (w.bkey[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    out[item] = lo;
 }
 AA_HDN void f_bfs_pos(const Ws &w, int64_t i) {  // i = sorted slot; contigs keep their vertex ranges
     const int64_t c = upper_idx(w.vtx_off, w.C, i);
@@ -1067,6 +1096,9 @@ AA_HDN int32_t heap_insert(HNode *__restrict__ hn, int32_t *__restrict__ hn_eid,
     return r;
 }
 
+#if defined(__CUDACC__)
+__device__ void f_heaps_level(const Ws &w, int64_t slot);  // level-parallel builder, defined with the warp kernels below
+#endif
 // phase: sidetrack heaps (k_shortest_walks.hpp:191-215): the tree vertices in BFS order, each inserting its
 // sidetracks into the heap it inherits from its tree parent.  Sequential form (host emulation).
 AA_HDN void f_heaps(const Ws &w, int64_t c) {
@@ -1365,12 +1397,133 @@ __device__ __forceinline__ VInfo vinfo_ld(const VInfo *p) {
     u.q = *reinterpret_cast<const V16 *>(p);
     return u.v;
 }
+// ---- the working spine of one warp and the two halves of an insert (shared by the two heap builders) --------
+struct Spine {
+    HNode nd;        // spine level `lane` (valid below L)
+    int32_t nd_id, nd_eid;
+    HNode nx;        // the first unknown spine node, loaded ahead of need (valid when next >= 0)
+    int32_t nx_eid;
+    int32_t L, next;
+};
+__device__ __forceinline__ void spine_reset(Spine &sp, const HNode *__restrict__ hn, const int32_t *__restrict__ hn_eid,
+                                            int32_t root) {  // nothing known yet: the spine starts at `root`
+    sp.L = 0;
+    sp.next = root;
+    if (root >= 0) {
+        sp.nx = hn_load(hn + root);
+        sp.nx_eid = hn_eid[root];
+    }
+}
+// descent: first spine level whose key is not < k (-1: the spine would exceed the 32 lanes)
+__device__ __forceinline__ int32_t spine_descend(Spine &sp, const HNode *__restrict__ hn, const int32_t *__restrict__ hn_eid,
+                                                 const InsKey &k) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    for (;;) {
+        // the sum decides unless some level ties on it (then the full PafDistance order is evaluated)
+        const bool known = lane < sp.L;
+        uint32_t stop = __ballot_sync(FULL, known && sp.nd.sum >= k.sum);
+        if (__ballot_sync(FULL, known && sp.nd.sum == k.sum)) stop = __ballot_sync(FULL, known && !key_lt(sp.nd, k));
+        if (stop) return __ffs(stop) - 1;
+        if (sp.next < 0) return sp.L;
+        if (sp.L >= SPMAX - 1) return -1;  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
+        if (lane == sp.L) {
+            sp.nd = sp.nx;
+            sp.nd_id = sp.next;
+            sp.nd_eid = sp.nx_eid;
+        }
+        sp.L++;
+        sp.next = sp.nx.right;
+        if (sp.next >= 0) {
+            sp.nx = hn_load(hn + sp.next);  // same address on every lane: one transaction
+            sp.nx_eid = hn_eid[sp.next];
+        }
+    }
+}
+// path copy: N = nbase, the copy of level q = nbase + (p - q); returns the new root
+__device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn, int32_t *__restrict__ hn_eid, const InsKey &k,
+                                               int32_t p, int32_t nbase) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int32_t BIG = 1 << 24;
+    // ranks: suffix scan of the per-level maps r -> min(a, r + b) over levels < p
+    int32_t fa = BIG, fb = 0;
+    if (lane < p) {
+        fa = sp.nd.left < 0 ? 0 : (int32_t)sp.nd.lrank + 1;
+        fb = sp.nd.left < 0 ? BIG : 1;
+    }
+    for (int32_t d = 1; d < p; d <<= 1) {
+        const int32_t oa = __shfl_down_sync(FULL, fa, d);
+        const int32_t ob = __shfl_down_sync(FULL, fb, d);
+        if (lane + d < 32) {
+            fa = min(fa, oa + fb);
+            fb = fb + ob;
+        }
+    }
+    const int32_t my_rank = min(fa, 1 + fb);           // rank of this level's copy
+    int32_t rin = __shfl_down_sync(FULL, my_rank, 1);  // rank of its new right child
+    if (lane >= p - 1) rin = 1;                        // level p-1 gets N (rank 1)
+    const bool my_swap = lane < p && (sp.nd.left < 0 || (int32_t)sp.nd.lrank < rin);
+    const uint32_t swaps = __ballot_sync(FULL, my_swap);
+    const int32_t sstar = swaps ? __ffs(swaps) - 1 : -1;
+    // the stop node (level p, if any) becomes N's left child
+    const int32_t stop_id = __shfl_sync(FULL, sp.nd_id, p & 31);
+    const int32_t stop_rank = __shfl_sync(FULL, (int32_t)sp.nd.rank, p & 31);
+    if (lane < p) {
+        const int32_t ch = nbase + (p - 1 - lane);
+        if (my_swap) {
+            sp.nd.right = sp.nd.left;
+            sp.nd.left = ch;
+            sp.nd.lrank = (int16_t)rin;
+        } else {
+            sp.nd.right = ch;
+        }
+        sp.nd.rank = (int16_t)my_rank;
+        sp.nd_id = nbase + (p - lane);
+    } else if (lane == p) {
+        sp.nd.sum = k.sum;
+        sp.nd.anom = k.anom;
+        sp.nd.nz = k.nz;
+        sp.nd.tot = k.tot;
+        sp.nd.left = p < sp.L ? stop_id : -1;
+        sp.nd.right = -1;
+        sp.nd.rank = 1;
+        sp.nd.lrank = (int16_t)(p < sp.L ? stop_rank : 0);
+        sp.nd_id = nbase;
+        sp.nd_eid = k.eid;
+    }
+    if (lane <= p) {
+        hn_store(hn + sp.nd_id, sp.nd);
+        hn_eid[sp.nd_id] = sp.nd_eid;
+    }
+    __syncwarp();  // later inserts read these nodes from other lanes
+    // new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N
+    const int32_t nright = __shfl_sync(FULL, sp.nd.right, sstar >= 0 ? sstar : 0);
+    const int32_t old_next = sp.next;
+    sp.next = sstar >= 0 ? nright : -1;
+    sp.L = sstar >= 0 ? sstar + 1 : p + 1;
+    if (sp.next >= 0 && sp.next != old_next) {
+        sp.nx = hn_load(hn + sp.next);
+        sp.nx_eid = hn_eid[sp.next];
+    }
+    return p > 0 ? nbase + p : nbase;
+}
+__device__ __forceinline__ InsKey ins_bcast(const InsKey &kreg, int32_t src) {
+    const uint32_t FULL = 0xffffffffu;
+    InsKey k;
+    k.sum = __shfl_sync(FULL, kreg.sum, src);
+    k.anom = __shfl_sync(FULL, kreg.anom, src);
+    k.nz = __shfl_sync(FULL, kreg.nz, src);
+    k.tot = __shfl_sync(FULL, kreg.tot, src);
+    k.eid = __shfl_sync(FULL, kreg.eid, src);
+    return k;
+}
 __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
     HeapSmem &sm = *reinterpret_cast<HeapSmem *>(scratch);
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
-    const int32_t BIG = 1 << 24;
     if (w.status[c] != 0 && w.status[c] != 3) return;
+    if (w.hmode[c] != 0) return;  // a shallow, wide tree: built level by level, one warp per vertex (f_heaps_level)
     const int64_t v0 = w.vtx_off[c];
     HNode *__restrict__ hn = w.hn;
     int32_t *__restrict__ hn_eid = w.hn_eid;
@@ -1393,15 +1546,16 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
     knext.anom = knext.nz = knext.tot = knext.eid = 0;
     if (kbase + lane < kend) kreg = ins_ld(ins + kbase + lane);
     if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
-    // ---- working spine: level `lane` (valid below L); `next` = id of the first unknown spine node (or -1),
-    //      nx = that node, loaded ahead of need ----
-    HNode nd, nx;
-    nd.sum = nx.sum = 0;
-    nd.anom = nd.nz = nd.tot = nx.anom = nx.nz = nx.tot = 0;
-    nd.left = nd.right = nx.left = nx.right = -1;
-    nd.rank = nd.lrank = nx.rank = nx.lrank = 0;
-    int32_t nd_id = -1, nd_eid = 0, nx_eid = 0;
-    int32_t L = 0, next = -1, cur_root = -1;  // the working spine is the spine of heap cur_root (-1: empty heap)
+    Spine sp;
+    sp.nd.sum = sp.nx.sum = 0;
+    sp.nd.anom = sp.nd.nz = sp.nd.tot = sp.nx.anom = sp.nx.nz = sp.nx.tot = 0;
+    sp.nd.left = sp.nd.right = sp.nx.left = sp.nx.right = -1;
+    sp.nd.rank = sp.nd.lrank = sp.nx.rank = sp.nx.lrank = 0;
+    sp.nd_id = -1;
+    sp.nd_eid = sp.nx_eid = 0;
+    sp.L = 0;
+    sp.next = -1;
+    int32_t cur_root = -1;  // the working spine is the spine of heap cur_root (-1: empty heap)
     // ---- vertex stream ----
     VInfo vnext;
     vnext.x = -1;
@@ -1428,73 +1582,37 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                 int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
                 // ---- working spine := spine of `root` ----
                 if (root != cur_root) {
-                    L = 0;
-                    next = root;
                     const uint32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
                     if (root >= 0 && hit) {
                         const int32_t sl = __ffs(hit) - 1;
-                        L = sm.sL[sl];
-                        next = sm.snext[sl];
-                        if (lane < L) {
-                            nd = hn_load(&sm.snode[sl][lane]);
+                        sp.L = sm.sL[sl];
+                        sp.next = sm.snext[sl];
+                        if (lane < sp.L) {
+                            sp.nd = hn_load(&sm.snode[sl][lane]);
                             const IdEid ie = sm.sid[sl][lane];
-                            nd_id = ie.id;
-                            nd_eid = ie.eid;
+                            sp.nd_id = ie.id;
+                            sp.nd_eid = ie.eid;
                         }
-                    }
-                    if (next >= 0) {
-                        nx = hn_load(hn + next);
-                        nx_eid = hn_eid[next];
+                        if (sp.next >= 0) {
+                            sp.nx = hn_load(hn + sp.next);
+                            sp.nx_eid = hn_eid[sp.next];
+                        }
+                    } else {
+                        spine_reset(sp, hn, hn_eid, root);
                     }
                 }
                 for (int32_t t = 0; t < nins && !overflow; t++, ki++) {
-                    // ---- the key (stream position ki) ----
                     if (ki - kbase >= 32) {  // inserts are consumed in stream order: at most one chunk forward
                         kreg = knext;
                         kbase += 32;
                         if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
                     }
-                    const int32_t src = (int32_t)(ki - kbase);
-                    InsKey k;
-                    k.sum = __shfl_sync(FULL, kreg.sum, src);
-                    k.anom = __shfl_sync(FULL, kreg.anom, src);
-                    k.nz = __shfl_sync(FULL, kreg.nz, src);
-                    k.tot = __shfl_sync(FULL, kreg.tot, src);
-                    k.eid = __shfl_sync(FULL, kreg.eid, src);
-                    // ---- descent: first spine level whose key is not < k ----
-                    int32_t p;
-                    for (;;) {
-                        // the sum decides unless some level ties on it (then the full PafDistance order is evaluated)
-                        const bool known = lane < L;
-                        uint32_t stop = __ballot_sync(FULL, known && nd.sum >= k.sum);
-                        if (__ballot_sync(FULL, known && nd.sum == k.sum)) stop = __ballot_sync(FULL, known && !key_lt(nd, k));
-                        if (stop) {
-                            p = __ffs(stop) - 1;
-                            break;
-                        }
-                        if (next < 0) {
-                            p = L;
-                            break;
-                        }
-                        if (L >= SPMAX - 1) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
-                            overflow = true;
-                            p = 0;
-                            break;
-                        }
-                        if (lane == L) {
-                            nd = nx;
-                            nd_id = next;
-                            nd_eid = nx_eid;
-                        }
-                        L++;
-                        next = nx.right;
-                        if (next >= 0) {
-                            nx = hn_load(hn + next);  // same address on every lane: one transaction
-                            nx_eid = hn_eid[next];
-                        }
+                    const InsKey k = ins_bcast(kreg, (int32_t)(ki - kbase));
+                    const int32_t p = spine_descend(sp, hn, hn_eid, k);
+                    if (p < 0) {
+                        overflow = true;
+                        break;
                     }
-                    if (overflow) break;
-                    // ---- ids: N = base, level q's copy = base + (p - q) ----
                     const int32_t need = p + 1;
                     if (cur + need > end) {
                         unsigned long long at = 0;
@@ -1510,68 +1628,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     const int32_t nbase = (int32_t)cur;
                     cur += need;
                     used += need;
-                    // ---- ranks: suffix scan of the per-level maps r -> min(a, r + b) over levels < p ----
-                    int32_t fa = BIG, fb = 0;
-                    if (lane < p) {
-                        fa = nd.left < 0 ? 0 : (int32_t)nd.lrank + 1;
-                        fb = nd.left < 0 ? BIG : 1;
-                    }
-                    for (int32_t d = 1; d < p; d <<= 1) {
-                        const int32_t oa = __shfl_down_sync(FULL, fa, d);
-                        const int32_t ob = __shfl_down_sync(FULL, fb, d);
-                        if (lane + d < 32) {
-                            fa = min(fa, oa + fb);
-                            fb = fb + ob;
-                        }
-                    }
-                    const int32_t my_rank = min(fa, 1 + fb);           // rank of this level's copy
-                    int32_t rin = __shfl_down_sync(FULL, my_rank, 1);  // rank of its new right child
-                    if (lane >= p - 1) rin = 1;                        // level p-1 gets N (rank 1)
-                    const bool my_swap = lane < p && (nd.left < 0 || (int32_t)nd.lrank < rin);
-                    const uint32_t swaps = __ballot_sync(FULL, my_swap);
-                    const int32_t sstar = swaps ? __ffs(swaps) - 1 : -1;
-                    // the stop node (level p, if any) becomes N's left child
-                    const int32_t stop_id = __shfl_sync(FULL, nd_id, p & 31);
-                    const int32_t stop_rank = __shfl_sync(FULL, (int32_t)nd.rank, p & 31);
-                    // ---- build and write this lane's node ----
-                    if (lane < p) {
-                        const int32_t ch = nbase + (p - 1 - lane);
-                        if (my_swap) {
-                            nd.right = nd.left;
-                            nd.left = ch;
-                            nd.lrank = (int16_t)rin;
-                        } else {
-                            nd.right = ch;
-                        }
-                        nd.rank = (int16_t)my_rank;
-                        nd_id = nbase + (p - lane);
-                    } else if (lane == p) {
-                        nd.sum = k.sum;
-                        nd.anom = k.anom;
-                        nd.nz = k.nz;
-                        nd.tot = k.tot;
-                        nd.left = p < L ? stop_id : -1;
-                        nd.right = -1;
-                        nd.rank = 1;
-                        nd.lrank = (int16_t)(p < L ? stop_rank : 0);
-                        nd_id = nbase;
-                        nd_eid = k.eid;
-                    }
-                    if (lane <= p) {
-                        hn_store(hn + nd_id, nd);
-                        hn_eid[nd_id] = nd_eid;
-                    }
-                    __syncwarp();  // later inserts read these nodes from other lanes
-                    // ---- new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N ----
-                    const int32_t nright = __shfl_sync(FULL, nd.right, sstar >= 0 ? sstar : 0);
-                    const int32_t old_next = next;
-                    next = sstar >= 0 ? nright : -1;
-                    L = sstar >= 0 ? sstar + 1 : p + 1;
-                    root = p > 0 ? nbase + p : nbase;
-                    if (next >= 0 && next != old_next) {
-                        nx = hn_load(hn + next);
-                        nx_eid = hn_eid[next];
-                    }
+                    root = spine_apply(sp, hn, hn_eid, k, p, nbase);
                 }
                 if (overflow) break;
                 cur_root = root;
@@ -1581,17 +1638,17 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     if (!have) {
                         const int32_t sl = save_at;
                         save_at = (save_at + 1) % NSAVE;
-                        if (lane < L) {
-                            hn_store(&sm.snode[sl][lane], nd);
+                        if (lane < sp.L) {
+                            hn_store(&sm.snode[sl][lane], sp.nd);
                             IdEid ie;
-                            ie.id = nd_id;
-                            ie.eid = nd_eid;
+                            ie.id = sp.nd_id;
+                            ie.eid = sp.nd_eid;
                             sm.sid[sl][lane] = ie;
                         }
                         if (lane == 0) {
                             sm.sroot[sl] = root;
-                            sm.sL[sl] = L;
-                            sm.snext[sl] = next;
+                            sm.sL[sl] = sp.L;
+                            sm.snext[sl] = sp.next;
                         }
                         __syncwarp();
                     }
@@ -1611,7 +1668,124 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
         w.status[c] = overflow ? 3 : 0;
     }
 }
+// ---- level-parallel builder for shallow, wide trees (dense contigs: depth 4, tens of thousands of vertices per
+// level).  One warp per tree vertex of the current depth; the parent's heap is complete (previous launch), its
+// spine is fetched on demand.  Nodes come from 64-node chunks whose (owner, sequence, fill) are recorded, so that
+// f_ck_* can afterwards move the nodes to ids in the sequential allocation order (vertex by vertex in BFS order,
+// insert by insert), which is what the enumeration's tie-break compares.
+constexpr int32_t LCHUNK = 64;
+__device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of the vertex */) {
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int64_t c = upper_idx(w.vtx_off, w.C, slot);
+    const int64_t v0 = w.vtx_off[c];
+    HNode *__restrict__ hn = w.hn;
+    int32_t *__restrict__ hn_eid = w.hn_eid;
+    const VInfo vi = vinfo_ld(w.vinfo + slot);
+    int32_t root = vi.ppos < 0 ? -1 : w.root_at[v0 + vi.ppos];
+    const int32_t nins = vi.nins & (VI_KIDS - 1);
+    int64_t used = 0;
+    bool overflow = *w.lvl_overflow != 0;
+    if (nins > 0 && !overflow) {
+        const InsKey *__restrict__ ins = w.ins + vi.ins_beg;
+        Spine sp;
+        sp.nd.sum = sp.nx.sum = 0;
+        sp.nd.anom = sp.nd.nz = sp.nd.tot = sp.nx.anom = sp.nx.nz = sp.nx.tot = 0;
+        sp.nd.left = sp.nd.right = sp.nx.left = sp.nx.right = -1;
+        sp.nd.rank = sp.nd.lrank = sp.nx.rank = sp.nx.lrank = 0;
+        sp.nd_id = -1;
+        sp.nd_eid = sp.nx_eid = 0;
+        spine_reset(sp, hn, hn_eid, root);
+        int64_t cur = 0, end = 0;
+        int32_t seq = 0;
+        InsKey kreg, knext;
+        kreg.sum = knext.sum = 0;
+        kreg.anom = kreg.nz = kreg.tot = kreg.eid = 0;
+        knext.anom = knext.nz = knext.tot = knext.eid = 0;
+        if (lane < nins) kreg = ins_ld(ins + lane);
+        if (32 + lane < nins) knext = ins_ld(ins + 32 + lane);
+        for (int32_t t = 0; t < nins; t++) {
+            if (t > 0 && (t & 31) == 0) {
+                kreg = knext;
+                if (t + 32 + lane < nins) knext = ins_ld(ins + t + 32 + lane);
+            }
+            const InsKey k = ins_bcast(kreg, t & 31);
+            const int32_t p = spine_descend(sp, hn, hn_eid, k);
+            if (p < 0) {
+                overflow = true;
+                break;
+            }
+            const int32_t need = p + 1;
+            if (cur + need > end) {
+                unsigned long long at = 0;
+                if (lane == 0) {
+                    if (end > 0) w.ck_used[(end - LCHUNK) / LCHUNK] = (int32_t)(cur - (end - LCHUNK));
+                    at = atomicAdd(w.heap_top, (unsigned long long)LCHUNK);
+                }
+                at = __shfl_sync(FULL, at, 0);
+                if ((int64_t)at + LCHUNK > w.Hcap) {
+                    overflow = true;
+                    break;
+                }
+                cur = (int64_t)at;
+                end = cur + LCHUNK;
+                if (lane == 0) {
+                    w.ck_owner[at / LCHUNK] = (uint32_t)slot;
+                    w.ck_seq[at / LCHUNK] = seq;
+                }
+                seq++;
+            }
+            const int32_t nbase = (int32_t)cur;
+            cur += need;
+            used += need;
+            root = spine_apply(sp, hn, hn_eid, k, p, nbase);
+        }
+        if (lane == 0 && end > 0 && !overflow) w.ck_used[(end - LCHUNK) / LCHUNK] = (int32_t)(cur - (end - LCHUNK));
+    }
+    if (lane == 0) {
+        if (overflow) {
+            *w.lvl_overflow = 1;
+        } else {
+            w.root_at[slot] = root;
+            w.hroot[v0 + vi.x] = root;
+            if (used) atomicAdd((unsigned long long *)&w.heap_used[c], (unsigned long long)used);
+        }
+    }
+}
 #endif
+// ---- renumbering after the level-parallel build: chunks sorted by (owner slot, sequence) give the sequential order
+AA_HDN void f_ck_key(const Ws &w, int64_t k) {  // one chunk
+    const uint32_t owner = w.ck_owner[k];
+    w.ck_key_in[k] = owner == 0xffffffffu ? ~(uint64_t)0 : (((uint64_t)owner << 28) | (uint64_t)(uint32_t)w.ck_seq[k]);
+    w.ck_val_in[k] = (uint32_t)k;
+}
+AA_HDN void f_ck_cnt(const Ws &w, int64_t j) {  // sorted position j -> fill of that chunk
+    const uint64_t key = w.ck_key[j];
+    w.ck_cnt[j] = key == ~(uint64_t)0 ? 0 : w.ck_used[w.ck_val[j]];
+}
+AA_HDN void f_ck_base(const Ws &w, int64_t j, int64_t region) {  // new id of the chunk's first node
+    if (w.ck_key[j] != ~(uint64_t)0) w.ck_new[w.ck_val[j]] = (int32_t)(region + w.ck_pre[j]);
+}
+AA_HD int32_t ck_remap(const Ws &w, int32_t id) { return id < 0 ? -1 : w.ck_new[id >> 6] + (id & 63); }
+AA_HDN void f_ck_move(const Ws &w, int64_t i) {  // i = sorted chunk * 64 + offset
+    const int64_t j = i >> 6;
+    const int32_t o = (int32_t)(i & 63);
+    if (w.ck_key[j] == ~(uint64_t)0) return;
+    const int64_t k = w.ck_val[j];
+    if (o >= w.ck_used[k]) return;
+    const int64_t old = k * 64 + o;
+    HNode n = w.hn[old];
+    n.left = ck_remap(w, n.left);
+    n.right = ck_remap(w, n.right);
+    const int64_t nw = (int64_t)w.ck_new[k] + o;
+    w.hn[nw] = n;
+    w.hn_eid[nw] = w.hn_eid[old];
+}
+AA_HDN void f_ck_roots(const Ws &w, int64_t gv) {  // heap roots of the contigs that were built level by level
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.hmode[c] == 0) return;
+    w.hroot[gv] = ck_remap(w, w.hroot[gv]);
+}
 AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
 #if defined(__CUDA_ARCH__)
     f_heaps_warp(w, c, scratch);

@@ -60,6 +60,29 @@ AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
 AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
 AA_FUNCTOR(FnTourBuild, f_tour_build(w, i))
+AA_FUNCTOR(FnCkKey, f_ck_key(w, i))
+AA_FUNCTOR(FnCkCnt, f_ck_cnt(w, i))
+AA_FUNCTOR(FnCkMove, f_ck_move(w, i))
+AA_FUNCTOR(FnCkRoots, f_ck_roots(w, i))
+struct FnCkBase {
+    Ws w;
+    int64_t region;
+    AA_HD void operator()(int64_t i, void *) const { f_ck_base(w, i, region); }
+};
+struct FnLvlOff {
+    Ws w;
+    const int32_t *ctgs;
+    int32_t per;
+    int64_t *out;
+    AA_HD void operator()(int64_t i, void *) const { f_lvl_off(w, i, ctgs, per, out); }
+};
+#if defined(__CUDACC__)
+struct FnHeapsLevel {  // one warp per tree vertex of one depth (device only)
+    Ws w;
+    int64_t first;
+    __device__ void operator()(int64_t i, void *) const { f_heaps_level(w, first + i); }
+};
+#endif
 AA_FUNCTOR(FnBfsPos, f_bfs_pos(w, i))
 AA_FUNCTOR(FnVInfo, f_vinfo(w, i))
 AA_FUNCTOR(FnInsFill, f_ins_fill(w, i))
@@ -564,6 +587,10 @@ struct Pipeline {
                 return AA_ERR_NOMEM;
             }
             w.key_bits = kb;
+            w.cdepth = A<int32_t>(C);
+            w.hmode = A<int32_t>(C);
+            bk.zero(w.cdepth, (size_t)C * 4);
+            bk.zero(w.hmode, (size_t)C * 4);
             bk.for_each("tour_build", Vtot, FnTourBuild{w});
             Tour *src = w.tour_a, *dst = w.tour_b;
             for (int r = 0; r < rounds; r++) {
@@ -585,29 +612,111 @@ struct Pipeline {
             bk.for_each("ins_fill", Vtot, FnInsFill{w});
             bk.fill_ff(w.hroot, (size_t)Vtot * 4);  // vertices outside the tree have no heap
         }
-        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
+        // shallow, wide trees (dense contigs) are built level by level with one warp per vertex; everything else by the
+        // streaming builder (one warp per contig)
+        std::vector<int32_t> m1;             // contigs in level mode
+        std::vector<int64_t> h_lvl;          // [m1][depth + 1] first BFS slot of each depth (last: end of the tree)
+        int32_t lvl_per = 0;
+        if (bk.device_kahn()) {
+            std::vector<int32_t> h_depth((size_t)C);
+            bk.d2h(h_depth.data(), w.cdepth, (size_t)C * 4);
+            std::vector<int32_t> h_mode((size_t)C, 0);
+            for (int64_t k = 0; k < C && m1.size() < 64; k++) {  // largest contigs first
+                const int64_t c = ctg_order[(size_t)k];
+                const int64_t Vc = h_voff[(size_t)c + 1] - h_voff[(size_t)c];
+                if (Vc >= 8192 && h_depth[(size_t)c] >= 1 && h_depth[(size_t)c] <= 64) {
+                    h_mode[(size_t)c] = 1;
+                    m1.push_back((int32_t)c);
+                    lvl_per = std::max(lvl_per, h_depth[(size_t)c] + 1);
+                }
+            }
+            if (!m1.empty()) {
+                bk.h2d(w.hmode, h_mode.data(), (size_t)C * 4);
+                int32_t *d_m1 = A<int32_t>((int64_t)m1.size());
+                int64_t *d_lvl = A<int64_t>((int64_t)m1.size() * lvl_per);
+                bk.h2d(d_m1, m1.data(), m1.size() * 4);
+                bk.for_each("lvl_off", (int64_t)m1.size() * lvl_per, FnLvlOff{w, d_m1, lvl_per, d_lvl});
+                h_lvl.resize(m1.size() * (size_t)lvl_per);
+                bk.d2h(h_lvl.data(), d_lvl, h_lvl.size() * 8);
+            }
+        }
+        const bool any_m1 = !m1.empty();
+        w.lvl_overflow = A<int32_t>(1);
+        int64_t hcap = (any_m1 ? 12 : 6) * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
             w.Hcap = hcap;
+            const size_t arena_mark = bk.alloc_mark();
             w.hn = A<HNode>(hcap);
             w.hn_eid = A<int32_t>(hcap);
             if (!w.hn || !w.hn_eid) {
                 err = "device allocation failed (sidetrack heap arena)";
                 return AA_ERR_NOMEM;
             }
+            const int64_t nck_cap = hcap / 64 + 1;
+            if (any_m1) {
+                w.ck_owner = A<uint32_t>(nck_cap);
+                w.ck_seq = A<int32_t>(nck_cap);
+                w.ck_used = A<int32_t>(nck_cap);
+                w.ck_new = A<int32_t>(nck_cap);
+                w.ck_key_in = A<uint64_t>(nck_cap);
+                w.ck_key = A<uint64_t>(nck_cap);
+                w.ck_val_in = A<uint32_t>(nck_cap);
+                w.ck_val = A<uint32_t>(nck_cap);
+                w.ck_cnt = A<int32_t>(nck_cap + 1);
+                w.ck_pre = A<int64_t>(nck_cap + 2);
+                if (!w.ck_owner || !w.ck_seq || !w.ck_used || !w.ck_new || !w.ck_key_in || !w.ck_key || !w.ck_val_in || !w.ck_val ||
+                    !w.ck_cnt || !w.ck_pre) {
+                    err = "device allocation failed (heap chunk table)";
+                    return AA_ERR_NOMEM;
+                }
+                bk.fill_ff(w.ck_owner, (size_t)nck_cap * 4);
+            }
             bk.zero(w.heap_top, 8);
+            bk.zero(w.heap_used, (size_t)C * 8);
+            bk.zero(w.lvl_overflow, 4);
             bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, HEAP_SMEM_BYTES);
+            bool overflow = false;
+#if defined(__CUDACC__)
+            if (any_m1) {
+                for (int32_t d = 1; d < lvl_per; d++)
+                    for (size_t k = 0; k < m1.size(); k++) {
+                        const int64_t lo = h_lvl[k * (size_t)lvl_per + (size_t)d - 1], hi = h_lvl[k * (size_t)lvl_per + (size_t)d];
+                        if (hi > lo) bk.for_each_contig("heaps_level", hi - lo, FnHeapsLevel{w, lo});
+                    }
+                int32_t h_lo = 0;
+                bk.d2h(&h_lo, w.lvl_overflow, 4);
+                overflow = h_lo != 0;
+            }
+#endif
             bk.d2h(h_status.data(), w.status, (size_t)C * 4);
             AA_BK_CHECK();
-            bool overflow = false;
             for (int32_t s : h_status) overflow = overflow || s == 3;
+            if (!overflow && any_m1) {
+                // move the nodes of the level-built heaps to ids in sequential allocation order (the enumeration's tie-break)
+                const int64_t top = bk.read_i64((const int64_t *)w.heap_top);
+                const int64_t nck = top / 64;
+                bk.for_each("ck_key", nck, FnCkKey{w});
+                bk.sort_pairs_u64(w.ck_key_in, w.ck_key, w.ck_val_in, w.ck_val, nck, 64);
+                bk.for_each("ck_cnt", nck, FnCkCnt{w});
+                bk.zero(w.ck_cnt + nck, 4);
+                bk.scan_i32(w.ck_cnt, w.ck_pre, nck + 1);
+                const int64_t total = bk.read_i64(w.ck_pre + nck);
+                if (top + total > hcap) {
+                    overflow = true;
+                } else {
+                    bk.for_each("ck_base", nck, FnCkBase{w, top});
+                    bk.for_each("ck_move", nck * 64, FnCkMove{w});
+                    bk.for_each("ck_roots", Vtot, FnCkRoots{w});
+                }
+            }
             if (!overflow) break;
             if (hcap >= 0x7ffffff0LL || attempt > 8) {
                 err = "sidetrack heap arena exhausted (contig too dense for one device)";
                 return AA_ERR_NOMEM;
             }
-            bk.release_last(2);  // give the two arena arrays back before growing
+            bk.release_to(arena_mark);  // give the arena arrays (and the sort / scan scratch) back before growing
             hcap *= 4;
         }
         bk.phase_end(PH_HEAPS);

@@ -19,6 +19,8 @@ struct HostBackend {
         blocks.push_back(p);
         return p;
     }
+    size_t alloc_mark() const { return blocks.size(); }
+    void release_to(size_t mark) { release_last((int)(blocks.size() - mark)); }
     void release_last(int k) {
         while (k-- > 0 && !blocks.empty()) {
             std::free(blocks.back());

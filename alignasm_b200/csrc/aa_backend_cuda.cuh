@@ -48,6 +48,7 @@ struct CudaBackend {
     cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     bool side_pending = false;
     bool failed = false;
+    bool oom = false;  // the failure was an allocation: recoverable
     std::string errmsg;
     int64_t n_launch = 0;
     int sm_count = 148;
@@ -166,8 +167,9 @@ struct CudaBackend {
         n = (n + 255) & ~(size_t)255;
         if (n == 0) n = 256;
         if (pool.empty() || pool.back().top + n > pool.back().cap) {
+            // geometric growth up to 4 GB per block; larger requests get a block of exactly their size (no waste)
             size_t last = pool.empty() ? 0 : pool.back().cap;
-            size_t want = std::max<size_t>(n, std::max<size_t>(2 * last, (size_t)256 << 20));
+            size_t want = std::max<size_t>(n, std::max<size_t>(std::min<size_t>(2 * last, (size_t)4 << 30), (size_t)256 << 20));
             char *p = nullptr;
             cudaError_t e = cudaMalloc(&p, want);
             if (e != cudaSuccess && want > n) {
@@ -177,6 +179,7 @@ struct CudaBackend {
             }
             if (e != cudaSuccess) {
                 cudaGetLastError();
+                oom = true;  // the context stays usable: the next solve starts from an empty pool
                 fail("cudaMalloc(workspace)", e);
                 return nullptr;
             }
@@ -194,8 +197,15 @@ struct CudaBackend {
         while (k-- > 0 && !log.empty()) {
             Mark m = log.back();
             log.pop_back();
-            // only the newest block can shrink; older blocks keep their tail unused for this solve
-            if (m.block == (int)pool.size() - 1) pool[(size_t)m.block].top = m.top;
+            // allocations are a stack: the one being released lives in the newest block
+            if (m.block == (int)pool.size() - 1) {
+                pool[(size_t)m.block].top = m.top;
+                if (m.top == 0 && pool.size() > 1) {  // the block is empty again: hand it back (a regrown arena needs the room)
+                    cudaStreamSynchronize(main_stream);
+                    cudaFree(pool.back().base);
+                    pool.pop_back();
+                }
+            }
         }
     }
     void *alloc_persistent(size_t n) {
@@ -212,6 +222,14 @@ struct CudaBackend {
 
     // give the whole workspace back to the bump allocator (coalescing a fragmented pool into one block)
     void reset_pool() {
+        if (failed && oom) {  // recover from an out-of-memory solve: drop the whole pool and start over
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            for (auto &b : pool) cudaFree(b.base);
+            pool.clear();
+            failed = oom = false;
+            errmsg.clear();
+        }
         AA_CUDA(cudaSetDevice(device));
         if (pool.size() > 1) {
             AA_CUDA(cudaStreamSynchronize(main_stream));

@@ -640,7 +640,7 @@ struct Pipeline {
                 bk.d2h(h_lvl.data(), d_lvl, h_lvl.size() * 8);
             }
         }
-        const bool any_m1 = !m1.empty();
+        bool any_m1 = !m1.empty();
         w.lvl_overflow = A<int32_t>(1);
         int64_t hcap = (any_m1 ? 12 : 6) * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
@@ -712,6 +712,14 @@ struct Pipeline {
                 }
             }
             if (!overflow) break;
+            if (any_m1 && hcap >= 0x7ffffff0LL) {
+                // the level-parallel builder needs room for the nodes twice (built + moved): too many for 31-bit ids,
+                // so these contigs go through the streaming builder after all
+                any_m1 = false;
+                bk.zero(w.hmode, (size_t)C * 4);
+                bk.release_to(arena_mark);
+                continue;
+            }
             if (hcap >= 0x7ffffff0LL || attempt > 8) {
                 err = "sidetrack heap arena exhausted (contig too dense for one device)";
                 return AA_ERR_NOMEM;

@@ -72,7 +72,7 @@ void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev) {
 }
 aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, aa_result *res) {
     if (!ctx || !dev || !dev->d) return AA_ERR_INVALID;
-    if (!ctx->bk.ok()) {
+    if (!ctx->bk.ok() && !ctx->bk.oom) {  // (an out-of-memory failure is cleared by the pool reset of the next solve)
         ctx->err = ctx->bk.error();
         return AA_ERR_CUDA;
     }
@@ -90,12 +90,12 @@ aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, a
 }
 aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_result *res) {
     if (!ctx || !res) return AA_ERR_INVALID;
+    // one-shot: the batch is staged in the pooled workspace, so a steady-state call makes no cudaMalloc / cudaFree
+    ctx->bk.reset_pool();  // (also recovers a context whose last solve ran out of memory)
     if (!ctx->bk.ok()) {
         ctx->err = ctx->bk.error();
         return AA_ERR_CUDA;
     }
-    // one-shot: the batch is staged in the pooled workspace, so a steady-state call makes no cudaMalloc / cudaFree
-    ctx->bk.reset_pool();
     aa::DevBatch *d = nullptr;
     aa_status st = ctx->pipe.upload(batch, d, /*pooled=*/true);
     if (st != AA_OK) {

@@ -261,6 +261,16 @@ struct Ws {
     InsKey *ins;         // [Nins] inserts of every contig, BFS order then edge order
     int32_t *root_at;    // [Vtot] heap root by BFS position
     int32_t key_bits;    // bits of the depth / preorder fields of the sort key
+    // level-synchronous Kahn passes for wide, shallow DAGs (dense contigs)
+    int32_t *rmode;      // [C] -1: warp-per-contig Kahn passes, k >= 0: k-th contig of the level-synchronous passes
+    int32_t *kl_cnt;     // [Vtot] remaining degree
+    unsigned long long *kl_last;  // [Vtot] (contig k, position of the last-finishing neighbour, index in its list)
+    int32_t *kl_pos;     // [Vtot] FIFO position (reverse pass)
+    uint32_t *kl_front, *kl_next;  // [Vtot] current / next level (global vertex ids)
+    int32_t *kl_nnext;   // [1]
+    unsigned long long *kl_key_in, *kl_key;  // [Vtot] sort keys of the next level
+    uint32_t *kl_val;    // [Vtot] next level, sorted
+    int32_t *kl_done;    // [64] vertices positioned so far, per level-mode contig
     int32_t *cdepth;     // [C] depth of the tree
     int32_t *hmode;      // [C] 0: streaming builder (one warp per contig), 1: level-parallel builder (shallow, wide trees)
     int32_t *lvl_overflow;  // arena / spine overflow flag of the level-parallel builder
@@ -796,6 +806,7 @@ AA_HDN void f_relax_init(const Ws &w, int64_t gv) {  // one vertex
     w.cnt2[gv] = (int32_t)(w.rev_off[gv + 1] - w.rev_off[gv]);
 }
 AA_HDN void f_relax_unpack(const Ws &w, int64_t gv) {  // one vertex: VState -> d / best
+    if (w.rmode[upper_idx(w.vtx_off, w.C, gv)] >= 0) return;  // written directly by the level-synchronous pass
     const VState s = w.vs[gv];
     D4 d;
     d.sum = s.sum;
@@ -830,6 +841,173 @@ AA_HDN void f_topo(const Ws &w, int64_t c) {
         }
     }
 }
+
+// ---- level-synchronous Kahn passes (dense contigs: tens of levels, hundreds of vertices per level) -------------
+// The reference's FIFO order (k_shortest_walks.hpp:132-156) is: levels in order (level = longest path to a seed),
+// and inside a level the order in which the vertices became ready, i.e. by (FIFO position of the neighbour that
+// finished last, index in that neighbour's list).  Both are available without a queue: every list entry of a
+// finished vertex does an atomicMax of that pair on its target, the targets whose degree reaches zero form the
+// next level, one radix sort of their pairs gives their positions.  REV = reverse graph (relax), else forward.
+constexpr int KL_POSB = 27;  // bits of a position / list index
+AA_HD unsigned long long kl_key(int32_t k, int32_t pos, int32_t j) {
+    return ((unsigned long long)(uint32_t)k << (2 * KL_POSB)) | ((unsigned long long)(uint32_t)pos << KL_POSB) | (unsigned long long)(uint32_t)j;
+}
+AA_HD int32_t aa_atomic_dec(int32_t *p) {  // returns the old value
+#if defined(__CUDA_ARCH__)
+    return atomicSub(p, 1);
+#else
+    return (*p)--;
+#endif
+}
+AA_HD void aa_atomic_max64(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+AA_HD int32_t aa_atomic_inc(int32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, 1);
+#else
+    return (*p)++;
+#endif
+}
+template <bool REV>
+AA_HDN void f_kl_init(const Ws &w, int64_t gv) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int32_t k = w.rmode[c];
+    if (k < 0 || w.status[c] != 0) return;
+    const int32_t deg = REV ? (int32_t)(w.eoff[gv + 1] - w.eoff[gv]) : (int32_t)(w.rev_off[gv + 1] - w.rev_off[gv]);
+    w.kl_cnt[gv] = deg;
+    w.kl_last[gv] = 0;
+    if (deg == 0) {  // seeds in ascending id (k_shortest_walks.hpp:139-141)
+        w.kl_last[gv] = kl_key(k, 0, (int32_t)(gv - w.vtx_off[c]));
+        w.kl_next[aa_atomic_inc(w.kl_nnext)] = (uint32_t)gv;
+    }
+}
+AA_HDN void f_kl_keys(const Ws &w, int64_t i) { w.kl_key_in[i] = w.kl_last[w.kl_next[i]]; }
+// sorted slot i of the new level -> FIFO position
+template <bool REV>
+AA_HDN void f_kl_assign(const Ws &w, int64_t i, int64_t n) {
+    const unsigned long long key = w.kl_key[i];
+    const int32_t k = (int32_t)(key >> (2 * KL_POSB));
+    const unsigned long long want = (unsigned long long)(uint32_t)k << (2 * KL_POSB);
+    int64_t lo = 0, hi = n;  // first slot of contig k in this level
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (w.kl_key[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    const int64_t gv = w.kl_val[i];
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t pos = w.kl_done[k] + (int32_t)(i - lo);
+    w.kl_front[i] = (uint32_t)gv;
+    if (REV) {
+        w.kl_pos[gv] = pos;
+        w.queue[v0 + pos] = (int32_t)(gv - v0);
+    } else {
+        w.order[gv] = pos;
+        w.topo[v0 + pos] = (int32_t)(gv - v0);
+    }
+}
+AA_HDN void f_kl_count(const Ws &w, int64_t k, int64_t n) {  // level-mode contig k: vertices of this level
+    const unsigned long long a = (unsigned long long)(uint32_t)k << (2 * KL_POSB), b = (unsigned long long)(uint32_t)(k + 1) << (2 * KL_POSB);
+    int64_t lo = 0, hi = n, lo2 = 0, hi2 = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (w.kl_key[mid] < a) lo = mid + 1;
+        else hi = mid;
+    }
+    while (lo2 < hi2) {
+        const int64_t mid = (lo2 + hi2) >> 1;
+        if (w.kl_key[mid] < b) lo2 = mid + 1;
+        else hi2 = mid;
+    }
+    w.kl_done[k] += (int32_t)(lo2 - lo);
+}
+// one finished vertex (front slot i): its list entries count their targets down; lanes stride the list
+template <bool REV>
+AA_HDN void f_kl_expand(const Ws &w, int64_t i) {
+    const int64_t gv = w.kl_front[i];
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t k = w.rmode[c];
+    const int32_t pos = REV ? w.kl_pos[gv] : w.order[gv];
+    const int64_t a = REV ? w.rev_off[gv] : w.eoff[gv], b = REV ? w.rev_off[gv + 1] : w.eoff[gv + 1];
+    for (int64_t e = a + aa_lane(); e < b; e += AA_LANES) {
+        const int64_t gx = v0 + (REV ? w.e_src[w.rev_eid[e]] : e_dst(w.edge[e]));
+        aa_atomic_max64(&w.kl_last[gx], kl_key(k, pos, (int32_t)(e - a)));
+        if (aa_atomic_dec(&w.kl_cnt[gx]) == 1) w.kl_next[aa_atomic_inc(w.kl_nnext)] = (uint32_t)gx;
+    }
+}
+// relax of one vertex of the new level (reverse pass): minimum over its out-edges of d[head] + w, the first popped
+// head winning among equals (strict '<' on arrival order, k_shortest_walks.hpp:168-172); min-anom DP beside it
+AA_HDN void f_kl_pull(const Ws &w, int64_t i) {
+    const int64_t gv = w.kl_front[i];
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    const int64_t v0 = w.vtx_off[c];
+    const int32_t x = (int32_t)(gv - v0), dest = (int32_t)(w.vtx_off[c + 1] - v0) - 1;
+    D4 best;
+    best.sum = 0;
+    best.anom = best.nz = best.tot = 0;
+    best.aux = x == dest ? 1 : 0;
+    int32_t bv = -1, bpos = 0x7fffffff, am = x == dest ? 0 : 0x3fffffff;
+    for (int64_t e = w.eoff[gv] + aa_lane(); e < w.eoff[gv + 1]; e += AA_LANES) {
+        const Edge ed = w.edge[e];
+        const int32_t v = e_dst(ed);
+        const D4 dv = w.d[v0 + v];
+        if (!dv.aux) continue;
+        D4 cand;
+        cand.sum = dv.sum + ed.qry + ed.ref;
+        cand.anom = dv.anom + e_anom(ed);
+        cand.nz = dv.nz + e_nz(ed);
+        cand.tot = dv.tot + e_tot(ed);
+        cand.aux = 1;
+        const int32_t pv = w.kl_pos[v0 + v];
+        if (!best.aux || less4(cand, best) || (!less4(best, cand) && pv < bpos)) {
+            best = cand;
+            bv = v;
+            bpos = pv;
+        }
+        const int32_t na = w.amin[v0 + v] + e_anom(ed);
+        if (na < am) am = na;
+    }
+#if defined(__CUDA_ARCH__)
+    for (int32_t d = 16; d > 0; d >>= 1) {  // combine the lanes
+        D4 o;
+        o.sum = __shfl_down_sync(0xffffffffu, best.sum, d);
+        o.anom = __shfl_down_sync(0xffffffffu, best.anom, d);
+        o.nz = __shfl_down_sync(0xffffffffu, best.nz, d);
+        o.tot = __shfl_down_sync(0xffffffffu, best.tot, d);
+        o.aux = __shfl_down_sync(0xffffffffu, best.aux, d);
+        const int32_t ov = __shfl_down_sync(0xffffffffu, bv, d), op = __shfl_down_sync(0xffffffffu, bpos, d);
+        const int32_t oa = __shfl_down_sync(0xffffffffu, am, d);
+        if (o.aux && (!best.aux || less4(o, best) || (!less4(best, o) && op < bpos))) {
+            best = o;
+            bv = ov;
+            bpos = op;
+        }
+        if (oa < am) am = oa;
+    }
+    if (aa_lane() != 0) return;
+#endif
+    if (!best.aux) {
+        best.sum = 0;
+        best.anom = best.nz = best.tot = 0;
+    }
+    w.d[gv] = best;
+    w.best[gv] = bv;
+    w.amin[gv] = am;
+}
+AA_HDN void f_kl_finish(const Ws &w, int64_t c) {  // anom_dis[dest] of the reference = min anom from src (paf_data.cpp:713)
+    if (w.rmode[c] < 0 || w.status[c] != 0) return;
+    const int64_t gs = w.vtx_off[c + 1] - 2;
+    w.anom_dis[c] = w.amin[gs];
+    if (!w.d[gs].aux) w.status[c] = 2;
+}
+AA_HDN void f_ctg_edges(const Ws &w, int64_t c, int64_t *out) { out[c] = w.eoff[w.vtx_off[c]]; }  // c in [0, C]
 
 // ---- persistent leftist heap (leftist_heap.hpp:29-40) -------------------------------------------------
 struct HeapAlloc {
@@ -1176,6 +1354,7 @@ __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     if (w.status[c] != 0) return;
+    if (w.rmode[c] >= 0) return;  // level-synchronous pass
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     VState *__restrict__ vs = w.vs + v0;
@@ -1296,6 +1475,7 @@ __device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
     KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     if (w.status[c] == 1) return;  // singleton; (unsolvable contigs are not known yet: relax runs concurrently)
+    if (w.rmode[c] >= 0) return;   // level-synchronous pass
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     int32_t *__restrict__ cnt = w.cnt2 + v0;

@@ -60,6 +60,35 @@ AA_FUNCTOR(FnDegree, f_degree(w, i))
 AA_FUNCTOR(FnFill, f_fill(w, i))
 AA_FUNCTOR(FnHeapPrep, f_heap_prep(w, i))
 AA_FUNCTOR(FnTourBuild, f_tour_build(w, i))
+AA_FUNCTOR(FnKlKeys, f_kl_keys(w, i))
+AA_FUNCTOR(FnKlPull, f_kl_pull(w, i))
+AA_FUNCTOR(FnKlFinish, f_kl_finish(w, i))
+template <bool REV>
+struct FnKlInit {
+    Ws w;
+    AA_HD void operator()(int64_t i, void *) const { f_kl_init<REV>(w, i); }
+};
+template <bool REV>
+struct FnKlAssign {
+    Ws w;
+    int64_t n;
+    AA_HD void operator()(int64_t i, void *) const { f_kl_assign<REV>(w, i, n); }
+};
+template <bool REV>
+struct FnKlExpand {
+    Ws w;
+    AA_HD void operator()(int64_t i, void *) const { f_kl_expand<REV>(w, i); }
+};
+struct FnKlCount {
+    Ws w;
+    int64_t n;
+    AA_HD void operator()(int64_t i, void *) const { f_kl_count(w, i, n); }
+};
+struct FnCtgEdges {
+    Ws w;
+    int64_t *out;
+    AA_HD void operator()(int64_t i, void *) const { f_ctg_edges(w, i, out); }
+};
 AA_FUNCTOR(FnCkKey, f_ck_key(w, i))
 AA_FUNCTOR(FnCkCnt, f_ck_cnt(w, i))
 AA_FUNCTOR(FnCkMove, f_ck_move(w, i))
@@ -477,6 +506,25 @@ struct Pipeline {
         bk.phase_end(PH_REVERSE);
         AA_BK_CHECK();
 
+        // ---- which contigs take the level-synchronous Kahn passes (wide, shallow DAGs: dense contigs) ----
+        w.rmode = A<int32_t>(C);
+        bk.fill_ff(w.rmode, (size_t)C * 4);
+        int32_t n_lm = 0;
+        if (bk.device_kahn()) {
+            int64_t *d_ce = A<int64_t>(C + 1);
+            std::vector<int64_t> h_ce((size_t)C + 1);
+            bk.for_each("ctg_edges", C + 1, FnCtgEdges{w, d_ce});
+            bk.d2h(h_ce.data(), d_ce, (size_t)(C + 1) * 8);
+            h_ce[(size_t)C] = E;
+            std::vector<int32_t> h_rmode((size_t)C, -1);
+            for (int64_t k = 0; k < C && n_lm < 64; k++) {  // largest contigs first
+                const int64_t c = ctg_order[(size_t)k];
+                const int64_t Vc = h_voff[(size_t)c + 1] - h_voff[(size_t)c], Ec = h_ce[(size_t)c + 1] - h_ce[(size_t)c];
+                if (Vc >= 8192 && Vc < ((int64_t)1 << KL_POSB) && Ec >= 16 * Vc) h_rmode[(size_t)c] = n_lm++;
+            }
+            if (n_lm > 0) bk.h2d(w.rmode, h_rmode.data(), (size_t)C * 4);
+        }
+
         // ---- phase 5/6: relax + forward order ----
         w.d = A<D4>(Vtot);
         w.best = A<int32_t>(Vtot);
@@ -494,6 +542,22 @@ struct Pipeline {
         }
         // the forward Kahn order is only consumed by the walk phases: it runs on the side stream, concurrently
         // with relax / heaps / enum
+        if (n_lm > 0) {
+            w.kl_cnt = A<int32_t>(Vtot);
+            w.kl_last = (unsigned long long *)A<uint64_t>(Vtot);
+            w.kl_pos = A<int32_t>(Vtot);
+            w.kl_front = A<uint32_t>(Vtot);
+            w.kl_next = A<uint32_t>(Vtot);
+            w.kl_nnext = A<int32_t>(1);
+            w.kl_key_in = (unsigned long long *)A<uint64_t>(Vtot);
+            w.kl_key = (unsigned long long *)A<uint64_t>(Vtot);
+            w.kl_val = A<uint32_t>(Vtot);
+            w.kl_done = A<int32_t>(64);
+            if (!w.kl_cnt || !w.kl_last || !w.kl_pos || !w.kl_front || !w.kl_next || !w.kl_key_in || !w.kl_key || !w.kl_val) {
+                err = "device allocation failed (level-synchronous passes)";
+                return AA_ERR_NOMEM;
+            }
+        }
         if (bk.device_kahn()) {
             w.rrec = A<RevRec>(E);
             w.vs = A<VState>(Vtot);
@@ -514,6 +578,11 @@ struct Pipeline {
         bk.phase_end(PH_TOPO);
         bk.side_end();
         bk.for_each_contig("relax", C, FnRelax{w, d_ord}, RELAX_SMEM_BYTES);
+        if (n_lm > 0) {
+            if (!kahn_levels<true>(w, Vtot, n_lm)) return AA_ERR_CUDA;   // d, best, min anom of the dense contigs
+            bk.for_each("kl_finish", C, FnKlFinish{w});
+            if (!kahn_levels<false>(w, Vtot, n_lm)) return AA_ERR_CUDA;  // their forward order
+        }
         if (bk.device_kahn()) bk.for_each("relax_unpack", Vtot, FnRelaxUnpack{w});
         bk.phase_end(PH_RELAX);
         AA_BK_CHECK();
@@ -937,6 +1006,33 @@ struct Pipeline {
             return AA_ERR_UNSOLVABLE;
         }
         return AA_OK;
+    }
+
+    // level-synchronous Kahn pass over the contigs with rmode >= 0 (see f_kl_* in aa_core.cuh)
+    template <bool REV>
+    bool kahn_levels(const Ws &w, int64_t Vtot, int32_t n_lm) {
+        bk.zero(w.kl_nnext, 4);
+        bk.zero(w.kl_done, 64 * 4);
+        bk.for_each("kl_init", Vtot, FnKlInit<REV>{w});
+        for (;;) {
+            int32_t n = 0;
+            bk.d2h(&n, w.kl_nnext, 4);
+            if (!bk.ok()) {
+                err = bk.error();
+                return false;
+            }
+            if (n == 0) break;
+            const size_t mark = bk.alloc_mark();  // the sort scratch of one level is reused by the next (stream order)
+            bk.for_each("kl_keys", n, FnKlKeys{w});
+            bk.sort_pairs_u64((const uint64_t *)w.kl_key_in, (uint64_t *)w.kl_key, w.kl_next, w.kl_val, n, 2 * KL_POSB + 6);
+            bk.for_each("kl_assign", n, FnKlAssign<REV>{w, n});
+            bk.for_each("kl_count", n_lm, FnKlCount{w, n});
+            bk.zero(w.kl_nnext, 4);
+            if (REV) bk.for_each_contig("kl_pull", n, FnKlPull{w});
+            bk.for_each_contig("kl_expand", n, FnKlExpand<REV>{w});
+            bk.release_to(mark);
+        }
+        return true;
     }
 
     aa_stats last_stats{};

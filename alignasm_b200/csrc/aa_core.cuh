@@ -1851,8 +1851,8 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
 // ---- level-parallel builder for shallow, wide trees (dense contigs: depth 4, tens of thousands of vertices per
 // level).  One warp per tree vertex of the current depth; the parent's heap is complete (previous launch), its
 // spine is fetched on demand.  Nodes come from 64-node chunks whose (owner, sequence, fill) are recorded, so that
-// f_ck_* can afterwards move the nodes to ids in the sequential allocation order (vertex by vertex in BFS order,
-// insert by insert), which is what the enumeration's tie-break compares.
+// f_ck_* can afterwards rank every node in the sequential allocation order (vertex by vertex in BFS order, insert
+// by insert): that rank, not the build-time id, is what the enumeration's tie-break compares.
 constexpr int32_t LCHUNK = 64;
 __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of the vertex */) {
     const uint32_t FULL = 0xffffffffu;
@@ -1933,7 +1933,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
     }
 }
 #endif
-// ---- renumbering after the level-parallel build: chunks sorted by (owner slot, sequence) give the sequential order
+// ---- order keys after the level-parallel build: chunks sorted by (owner slot, sequence) give the sequential order
 AA_HDN void f_ck_key(const Ws &w, int64_t k) {  // one chunk
     const uint32_t owner = w.ck_owner[k];
     w.ck_key_in[k] = owner == 0xffffffffu ? ~(uint64_t)0 : (((uint64_t)owner << 28) | (uint64_t)(uint32_t)w.ck_seq[k]);
@@ -1943,28 +1943,8 @@ AA_HDN void f_ck_cnt(const Ws &w, int64_t j) {  // sorted position j -> fill of 
     const uint64_t key = w.ck_key[j];
     w.ck_cnt[j] = key == ~(uint64_t)0 ? 0 : w.ck_used[w.ck_val[j]];
 }
-AA_HDN void f_ck_base(const Ws &w, int64_t j, int64_t region) {  // new id of the chunk's first node
+AA_HDN void f_ck_base(const Ws &w, int64_t j, int64_t region) {  // sequential rank of the chunk's first node
     if (w.ck_key[j] != ~(uint64_t)0) w.ck_new[w.ck_val[j]] = (int32_t)(region + w.ck_pre[j]);
-}
-AA_HD int32_t ck_remap(const Ws &w, int32_t id) { return id < 0 ? -1 : w.ck_new[id >> 6] + (id & 63); }
-AA_HDN void f_ck_move(const Ws &w, int64_t i) {  // i = sorted chunk * 64 + offset
-    const int64_t j = i >> 6;
-    const int32_t o = (int32_t)(i & 63);
-    if (w.ck_key[j] == ~(uint64_t)0) return;
-    const int64_t k = w.ck_val[j];
-    if (o >= w.ck_used[k]) return;
-    const int64_t old = k * 64 + o;
-    HNode n = w.hn[old];
-    n.left = ck_remap(w, n.left);
-    n.right = ck_remap(w, n.right);
-    const int64_t nw = (int64_t)w.ck_new[k] + o;
-    w.hn[nw] = n;
-    w.hn_eid[nw] = w.hn_eid[old];
-}
-AA_HDN void f_ck_roots(const Ws &w, int64_t gv) {  // heap roots of the contigs that were built level by level
-    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
-    if (w.hmode[c] == 0) return;
-    w.hroot[gv] = ck_remap(w, w.hroot[gv]);
 }
 AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
 #if defined(__CUDA_ARCH__)
@@ -2277,6 +2257,12 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t vb = 1;
     while ((1 << vb) <= g.V) vb++;
     const bool wide = vb > 20;
+    // heaps built level by level keep their build-time node ids; their order key (the sequential allocation order
+    // that the reference's pointer comparison sees) comes from the chunk table, the id from ent_node[]
+    const bool keyed = w.hmode[c] != 0;
+    auto okey = [&](int32_t id) -> uint64_t {
+        return (uint64_t)(uint32_t)(keyed ? w.ck_new[id >> 6] + (id & 63) : id) << 32;
+    };
     const int32_t S = wide ? 31 : 2 * vb;  // k1 = anom << (S + 1) | ratio key (<= 2^S)
     auto make_k1 = [&](int32_t anom, int32_t nz, int32_t tot) -> uint64_t {
         uint64_t rk = 0;
@@ -2306,7 +2292,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         e.nz = ds.nz + hr.nz;
         e.tot = ds.tot + hr.tot;
         e.k1 = make_k1(ds.anom + hr.anom, e.nz, e.tot);
-        e.k2 = (uint64_t)(uint32_t)hs << 32;
+        e.k2 = okey(hs);
         if (lane == 0) {
             en[0] = hs;
             ep[0] = -1;
@@ -2340,6 +2326,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             if (out & (1u << lane)) qe_st(back + nR + __popc(out & lt), P);
             nR += __popc(out);
             np -= __popc(out);
+            if (lane >= np) P = INF;  // the lanes that went to the backlog are free again
             __syncwarp();
             if (np == 0) return;
         }
@@ -2583,8 +2570,10 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         QE a0 = INF, a1 = INF, a2 = INF;
         int32_t p0 = -1, p12 = -1;  // prev of the successors
         bool v0s = false, v1s = false, v2s = false;
+        int32_t sn0 = -1, sn1 = -1, sn2 = -1;  // node ids of the successors
         if (have) {
-            const int32_t node = (int32_t)(t.k2 >> 32), idx = (int32_t)(uint32_t)t.k2;
+            const int32_t idx = (int32_t)(uint32_t)t.k2;
+            const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
             const int32_t anom = (int32_t)(t.k1 >> (S + 1));
             const HNode ch = hn_load(hn + node);
             const int32_t ceid = w.hn_eid[node];
@@ -2599,7 +2588,8 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 a0.nz = t.nz + x.nz;
                 a0.tot = t.tot + x.tot;
                 a0.k1 = make_k1(anom + x.anom, a0.nz, a0.tot);
-                a0.k2 = (uint64_t)(uint32_t)x.hv << 32;
+                a0.k2 = okey(x.hv);
+                sn0 = x.hv;
                 v0s = true;
             }
             if (ch.left >= 0) {
@@ -2607,7 +2597,8 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 a1.nz = t.nz + xl.nz - ch.nz;
                 a1.tot = t.tot + xl.tot - ch.tot;
                 a1.k1 = make_k1(anom + xl.anom - ch.anom, a1.nz, a1.tot);
-                a1.k2 = (uint64_t)(uint32_t)ch.left << 32;
+                a1.k2 = okey(ch.left);
+                sn1 = ch.left;
                 v1s = true;
             }
             if (ch.right >= 0) {
@@ -2615,7 +2606,8 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 a2.nz = t.nz + xr.nz - ch.nz;
                 a2.tot = t.tot + xr.tot - ch.tot;
                 a2.k1 = make_k1(anom + xr.anom - ch.anom, a2.nz, a2.tot);
-                a2.k2 = (uint64_t)(uint32_t)ch.right << 32;
+                a2.k2 = okey(ch.right);
+                sn2 = ch.right;
                 v2s = true;
             }
         }
@@ -2658,19 +2650,19 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         int32_t id = ne + inc - mycnt;
         if (v0c) {
             a0.k2 |= (uint32_t)id;
-            en[id] = (int32_t)(a0.k2 >> 32);
+            en[id] = sn0;
             ep[id] = p0;
             id++;
         }
         if (v1c) {
             a1.k2 |= (uint32_t)id;
-            en[id] = (int32_t)(a1.k2 >> 32);
+            en[id] = sn1;
             ep[id] = p12;
             id++;
         }
         if (v2c) {
             a2.k2 |= (uint32_t)id;
-            en[id] = (int32_t)(a2.k2 >> 32);
+            en[id] = sn2;
             ep[id] = p12;
         }
         ne += total;

@@ -91,8 +91,6 @@ struct FnCtgEdges {
 };
 AA_FUNCTOR(FnCkKey, f_ck_key(w, i))
 AA_FUNCTOR(FnCkCnt, f_ck_cnt(w, i))
-AA_FUNCTOR(FnCkMove, f_ck_move(w, i))
-AA_FUNCTOR(FnCkRoots, f_ck_roots(w, i))
 struct FnCkBase {
     Ws w;
     int64_t region;
@@ -711,7 +709,7 @@ struct Pipeline {
         }
         bool any_m1 = !m1.empty();
         w.lvl_overflow = A<int32_t>(1);
-        int64_t hcap = (any_m1 ? 12 : 6) * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
+        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
@@ -763,7 +761,8 @@ struct Pipeline {
             AA_BK_CHECK();
             for (int32_t s : h_status) overflow = overflow || s == 3;
             if (!overflow && any_m1) {
-                // move the nodes of the level-built heaps to ids in sequential allocation order (the enumeration's tie-break)
+                // order keys of the level-built nodes: chunks sorted by (owner's BFS slot, sequence) and prefix-summed give
+                // every node its rank in the sequential allocation order (what the enumeration's tie-break compares)
                 const int64_t top = bk.read_i64((const int64_t *)w.heap_top);
                 const int64_t nck = top / 64;
                 bk.for_each("ck_key", nck, FnCkKey{w});
@@ -771,24 +770,9 @@ struct Pipeline {
                 bk.for_each("ck_cnt", nck, FnCkCnt{w});
                 bk.zero(w.ck_cnt + nck, 4);
                 bk.scan_i32(w.ck_cnt, w.ck_pre, nck + 1);
-                const int64_t total = bk.read_i64(w.ck_pre + nck);
-                if (top + total > hcap) {
-                    overflow = true;
-                } else {
-                    bk.for_each("ck_base", nck, FnCkBase{w, top});
-                    bk.for_each("ck_move", nck * 64, FnCkMove{w});
-                    bk.for_each("ck_roots", Vtot, FnCkRoots{w});
-                }
+                bk.for_each("ck_base", nck, FnCkBase{w, 0});
             }
             if (!overflow) break;
-            if (any_m1 && hcap >= 0x7ffffff0LL) {
-                // the level-parallel builder needs room for the nodes twice (built + moved): too many for 31-bit ids,
-                // so these contigs go through the streaming builder after all
-                any_m1 = false;
-                bk.zero(w.hmode, (size_t)C * 4);
-                bk.release_to(arena_mark);
-                continue;
-            }
             if (hcap >= 0x7ffffff0LL || attempt > 8) {
                 err = "sidetrack heap arena exhausted (contig too dense for one device)";
                 return AA_ERR_NOMEM;

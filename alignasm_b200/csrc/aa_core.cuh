@@ -151,10 +151,12 @@ struct __attribute__((aligned(16))) VState {
     int32_t amin_reach;  // bit 0: reaches dest; bits 1..: min anom sum to dest
 };
 // per edge (u,v): root of v's sidetrack heap and its key, so that a pop needs one load instead of three
-struct __attribute__((aligned(8))) ENext {
+struct __attribute__((aligned(16))) ENext {
     int64_t sum;
     int32_t anom, nz, tot;
-    int32_t hv;  // hroot[v] or -1
+    int32_t hv;     // hroot[v] or -1
+    int32_t hrank;  // its rank in the sequential allocation order (device path)
+    int32_t pad;
 };
 // ---- BFS order of the shortest-path tree, computed in parallel (Euler tour + list ranking), and the
 // flat stream of sidetrack inserts in that order (k_shortest_walks.hpp:196-215) -------------------------------
@@ -274,14 +276,15 @@ struct Ws {
     int32_t *cdepth;     // [C] depth of the tree
     int32_t *hmode;      // [C] 0: streaming builder (one warp per contig), 1: level-parallel builder (shallow, wide trees)
     int32_t *lvl_overflow;  // arena / spine overflow flag of the level-parallel builder
-    uint32_t *ck_owner;  // [Hcap/64] BFS slot that owns a 64-node chunk (0xffffffff: not a level-mode chunk)
-    int32_t *ck_seq;     // [Hcap/64] running number of the chunk inside its owner
-    int32_t *ck_used;    // [Hcap/64] nodes used in the chunk
-    uint64_t *ck_key_in, *ck_key;  // chunk sort keys (owner, sequence)
-    uint32_t *ck_val_in, *ck_val;  // chunk ids in sorted order
-    int32_t *ck_cnt;     // [chunks+1] fill in sorted order
-    int64_t *ck_pre;     // [chunks+2] its exclusive prefix sum
-    int32_t *ck_new;     // [Hcap/64] new id of the chunk's first node
+    // order of the heap nodes: the reference's queue breaks ties by node address = allocation order.  Nodes are
+    // built out of that order (leaves and dense contigs in parallel), so every node records (owner's BFS slot, running
+    // number inside the owner); after the build that pair is replaced by the node's rank in the sequential order
+    unsigned long long *hn_key;  // [Hcap] slot << 32 | number, then the rank
+    int32_t *vcnt;       // [Vtot+1] nodes allocated by the vertex at each BFS slot
+    int64_t *vbase;      // [Vtot+2] exclusive prefix sum of vcnt
+    int32_t *leaf_flag;  // [Vtot+1] 1: tree leaf with inserts of a streaming-mode contig (built by f_heaps_level)
+    int64_t *leaf_off;   // [Vtot+2]
+    uint32_t *leaf_list; // [n_leaf] their BFS slots
     ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
     // enumeration
@@ -1621,8 +1624,9 @@ __device__ __forceinline__ int32_t spine_descend(Spine &sp, const HNode *__restr
     }
 }
 // path copy: N = nbase, the copy of level q = nbase + (p - q); returns the new root
-__device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn, int32_t *__restrict__ hn_eid, const InsKey &k,
-                                               int32_t p, int32_t nbase) {
+__device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn, int32_t *__restrict__ hn_eid,
+                                               unsigned long long *__restrict__ hn_key, const InsKey &k, int32_t p, int32_t nbase,
+                                               unsigned long long keybase /* owner slot << 32 | nodes it has so far */) {
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     const int32_t BIG = 1 << 24;
@@ -1675,6 +1679,7 @@ __device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn
     if (lane <= p) {
         hn_store(hn + sp.nd_id, sp.nd);
         hn_eid[sp.nd_id] = sp.nd_eid;
+        hn_key[sp.nd_id] = keybase + (unsigned long long)(sp.nd_id - nbase);
     }
     __syncwarp();  // later inserts read these nodes from other lanes
     // new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N
@@ -1707,6 +1712,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
     const int64_t v0 = w.vtx_off[c];
     HNode *__restrict__ hn = w.hn;
     int32_t *__restrict__ hn_eid = w.hn_eid;
+    unsigned long long *__restrict__ hn_key = w.hn_key;
     const VInfo *__restrict__ vinfo = w.vinfo + v0;
     const InsKey *__restrict__ ins = w.ins;
     int32_t *__restrict__ hroot = w.hroot + v0;
@@ -1749,7 +1755,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
         // roots of parents that were finished in earlier batches (parents inside this batch come by shuffle)
         int32_t proot = -1;
         if (base + lane < nt && vi.ppos >= 0 && vi.ppos < base) proot = root_at[vi.ppos];
-        int32_t myroot = -1;
+        int32_t myroot = -1, mycnt = 0;
         const int32_t cnt = nt - base < 32 ? nt - base : 32;
         for (int32_t j = 0; j < cnt && !overflow; j++) {
             const int32_t nins_f = __shfl_sync(FULL, vi.nins, j);
@@ -1758,7 +1764,9 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
             const int32_t inb = __shfl_sync(FULL, myroot, ppos >= base ? ppos - base : 0);
             int32_t root = ppos >= base ? inb : pr;
             const int32_t nins = nins_f & (VI_KIDS - 1);
-            if (nins > 0) {
+            int32_t vseq = 0;  // nodes this vertex has allocated
+            // a leaf of the tree feeds no other heap: its inserts are done by f_heaps_level, off this serial chain
+            if (nins > 0 && (nins_f & VI_KIDS)) {
                 int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
                 // ---- working spine := spine of `root` ----
                 if (root != cur_root) {
@@ -1782,9 +1790,14 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     }
                 }
                 for (int32_t t = 0; t < nins && !overflow; t++, ki++) {
-                    if (ki - kbase >= 32) {  // inserts are consumed in stream order: at most one chunk forward
-                        kreg = knext;
-                        kbase += 32;
+                    if (ki - kbase >= 32) {  // inserts are consumed in stream order; skipped leaves may jump over chunks
+                        if (ki - kbase < 64) {
+                            kreg = knext;
+                            kbase += 32;
+                        } else {
+                            kbase += ((ki - kbase) >> 5) << 5;
+                            if (kbase + lane < kend) kreg = ins_ld(ins + kbase + lane);
+                        }
                         if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
                     }
                     const InsKey k = ins_bcast(kreg, (int32_t)(ki - kbase));
@@ -1808,12 +1821,14 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     const int32_t nbase = (int32_t)cur;
                     cur += need;
                     used += need;
-                    root = spine_apply(sp, hn, hn_eid, k, p, nbase);
+                    root = spine_apply(sp, hn, hn_eid, hn_key, k, p, nbase,
+                                       ((unsigned long long)(uint32_t)(v0 + base + j) << 32) | (uint32_t)vseq);
+                    vseq += need;
                 }
                 if (overflow) break;
                 cur_root = root;
                 // ---- remember the spine for the children ----
-                if ((nins_f & VI_KIDS) && root >= 0) {
+                if (root >= 0) {
                     const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
                     if (!have) {
                         const int32_t sl = save_at;
@@ -1834,12 +1849,16 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     }
                 }
             }
-            if (lane == j) myroot = root;
+            if (lane == j) {
+                myroot = root;
+                mycnt = vseq;
+            }
         }
         if (overflow) break;
         if (base + lane < nt) {
             root_at[base + lane] = myroot;
-            hroot[vi.x] = myroot;
+            hroot[vi.x] = myroot;  // (an active leaf: the inherited root for now, its own after f_heaps_level)
+            w.vcnt[v0 + base + lane] = mycnt;
         }
         __syncwarp();
     }
@@ -1848,11 +1867,10 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
         w.status[c] = overflow ? 3 : 0;
     }
 }
-// ---- level-parallel builder for shallow, wide trees (dense contigs: depth 4, tens of thousands of vertices per
-// level).  One warp per tree vertex of the current depth; the parent's heap is complete (previous launch), its
-// spine is fetched on demand.  Nodes come from 64-node chunks whose (owner, sequence, fill) are recorded, so that
-// f_ck_* can afterwards rank every node in the sequential allocation order (vertex by vertex in BFS order, insert
-// by insert): that rank, not the build-time id, is what the enumeration's tie-break compares.
+// ---- one warp per tree vertex: the builder of (a) shallow, wide trees (dense contigs: depth 4, tens of thousands of
+// vertices per level), launched depth by depth, and (b) the leaves of every other tree, which feed no other heap
+// and therefore need not wait in the serial chain of f_heaps_warp.  The parent's heap is complete (earlier launch);
+// its spine is fetched on demand.  Nodes come from 64-node chunks of the arena.
 constexpr int32_t LCHUNK = 64;
 __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of the vertex */) {
     const uint32_t FULL = 0xffffffffu;
@@ -1864,7 +1882,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
     const VInfo vi = vinfo_ld(w.vinfo + slot);
     int32_t root = vi.ppos < 0 ? -1 : w.root_at[v0 + vi.ppos];
     const int32_t nins = vi.nins & (VI_KIDS - 1);
-    int64_t used = 0;
+    int32_t used = 0;
     bool overflow = *w.lvl_overflow != 0;
     if (nins > 0 && !overflow) {
         const InsKey *__restrict__ ins = w.ins + vi.ins_beg;
@@ -1877,7 +1895,6 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
         sp.nd_eid = sp.nx_eid = 0;
         spine_reset(sp, hn, hn_eid, root);
         int64_t cur = 0, end = 0;
-        int32_t seq = 0;
         InsKey kreg, knext;
         kreg.sum = knext.sum = 0;
         kreg.anom = kreg.nz = kreg.tot = kreg.eid = 0;
@@ -1898,10 +1915,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
             const int32_t need = p + 1;
             if (cur + need > end) {
                 unsigned long long at = 0;
-                if (lane == 0) {
-                    if (end > 0) w.ck_used[(end - LCHUNK) / LCHUNK] = (int32_t)(cur - (end - LCHUNK));
-                    at = atomicAdd(w.heap_top, (unsigned long long)LCHUNK);
-                }
+                if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)LCHUNK);
                 at = __shfl_sync(FULL, at, 0);
                 if ((int64_t)at + LCHUNK > w.Hcap) {
                     overflow = true;
@@ -1909,18 +1923,12 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
                 }
                 cur = (int64_t)at;
                 end = cur + LCHUNK;
-                if (lane == 0) {
-                    w.ck_owner[at / LCHUNK] = (uint32_t)slot;
-                    w.ck_seq[at / LCHUNK] = seq;
-                }
-                seq++;
             }
             const int32_t nbase = (int32_t)cur;
             cur += need;
+            root = spine_apply(sp, hn, hn_eid, w.hn_key, k, p, nbase, ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)used);
             used += need;
-            root = spine_apply(sp, hn, hn_eid, k, p, nbase);
         }
-        if (lane == 0 && end > 0 && !overflow) w.ck_used[(end - LCHUNK) / LCHUNK] = (int32_t)(cur - (end - LCHUNK));
     }
     if (lane == 0) {
         if (overflow) {
@@ -1928,23 +1936,29 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
         } else {
             w.root_at[slot] = root;
             w.hroot[v0 + vi.x] = root;
+            w.vcnt[slot] = used;
             if (used) atomicAdd((unsigned long long *)&w.heap_used[c], (unsigned long long)used);
         }
     }
 }
 #endif
-// ---- order keys after the level-parallel build: chunks sorted by (owner slot, sequence) give the sequential order
-AA_HDN void f_ck_key(const Ws &w, int64_t k) {  // one chunk
-    const uint32_t owner = w.ck_owner[k];
-    w.ck_key_in[k] = owner == 0xffffffffu ? ~(uint64_t)0 : (((uint64_t)owner << 28) | (uint64_t)(uint32_t)w.ck_seq[k]);
-    w.ck_val_in[k] = (uint32_t)k;
+// ---- which vertices f_heaps_level takes from the streaming builder: tree leaves with inserts
+AA_HDN void f_leaf_flag(const Ws &w, int64_t i) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    int32_t f = 0;
+    if (w.hmode[c] == 0 && (w.status[c] == 0 || w.status[c] == 3) && i - w.vtx_off[c] < w.ntree[c]) {
+        const int32_t nf = w.vinfo[i].nins;
+        f = (nf & (VI_KIDS - 1)) > 0 && !(nf & VI_KIDS);
+    }
+    w.leaf_flag[i] = f;
 }
-AA_HDN void f_ck_cnt(const Ws &w, int64_t j) {  // sorted position j -> fill of that chunk
-    const uint64_t key = w.ck_key[j];
-    w.ck_cnt[j] = key == ~(uint64_t)0 ? 0 : w.ck_used[w.ck_val[j]];
+AA_HDN void f_leaf_list(const Ws &w, int64_t i) {
+    if (w.leaf_flag[i]) w.leaf_list[w.leaf_off[i]] = (uint32_t)i;
 }
-AA_HDN void f_ck_base(const Ws &w, int64_t j, int64_t region) {  // sequential rank of the chunk's first node
-    if (w.ck_key[j] != ~(uint64_t)0) w.ck_new[w.ck_val[j]] = (int32_t)(region + w.ck_pre[j]);
+// ---- after the build: (owner slot, number) -> rank in the sequential allocation order
+AA_HDN void f_node_rank(const Ws &w, int64_t id) {
+    const unsigned long long key = w.hn_key[id];
+    if (key != ~0ull) w.hn_key[id] = (unsigned long long)(w.vbase[key >> 32] + (int64_t)(uint32_t)key);
 }
 AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
 #if defined(__CUDA_ARCH__)
@@ -2112,6 +2126,8 @@ AA_HDN void f_enext(const Ws &w, int64_t gv) {
         const int32_t hv = w.hroot[v0 + v];
         ENext n;
         n.hv = hv;
+        n.pad = 0;
+        n.hrank = (hv >= 0 && w.hn_key) ? (int32_t)(uint32_t)w.hn_key[hv] : hv;
         n.sum = 0;
         n.anom = n.nz = n.tot = 0;
         if (hv >= 0) {
@@ -2257,12 +2273,10 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t vb = 1;
     while ((1 << vb) <= g.V) vb++;
     const bool wide = vb > 20;
-    // heaps built level by level keep their build-time node ids; their order key (the sequential allocation order
-    // that the reference's pointer comparison sees) comes from the chunk table, the id from ent_node[]
-    const bool keyed = w.hmode[c] != 0;
-    auto okey = [&](int32_t id) -> uint64_t {
-        return (uint64_t)(uint32_t)(keyed ? w.ck_new[id >> 6] + (id & 63) : id) << 32;
-    };
+    // node ids are build-time ids (leaves and dense contigs are built in parallel); the tie-break of the queue is the
+    // node's rank in the sequential allocation order (what the reference's pointer comparison sees); the
+    // id itself comes back from ent_node[]
+    auto okey = [&](int32_t id) -> uint64_t { return (uint64_t)(uint32_t)w.hn_key[id] << 32; };
     const int32_t S = wide ? 31 : 2 * vb;  // k1 = anom << (S + 1) | ratio key (<= 2^S)
     auto make_k1 = [&](int32_t anom, int32_t nz, int32_t tot) -> uint64_t {
         uint64_t rk = 0;
@@ -2573,7 +2587,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         int32_t sn0 = -1, sn1 = -1, sn2 = -1;  // node ids of the successors
         if (have) {
             const int32_t idx = (int32_t)(uint32_t)t.k2;
-            const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
+            const int32_t node = en[idx];
             const int32_t anom = (int32_t)(t.k1 >> (S + 1));
             const HNode ch = hn_load(hn + node);
             const int32_t ceid = w.hn_eid[node];
@@ -2588,7 +2602,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 a0.nz = t.nz + x.nz;
                 a0.tot = t.tot + x.tot;
                 a0.k1 = make_k1(anom + x.anom, a0.nz, a0.tot);
-                a0.k2 = okey(x.hv);
+                a0.k2 = (uint64_t)(uint32_t)x.hrank << 32;
                 sn0 = x.hv;
                 v0s = true;
             }

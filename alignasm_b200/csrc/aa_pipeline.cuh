@@ -89,13 +89,9 @@ struct FnCtgEdges {
     int64_t *out;
     AA_HD void operator()(int64_t i, void *) const { f_ctg_edges(w, i, out); }
 };
-AA_FUNCTOR(FnCkKey, f_ck_key(w, i))
-AA_FUNCTOR(FnCkCnt, f_ck_cnt(w, i))
-struct FnCkBase {
-    Ws w;
-    int64_t region;
-    AA_HD void operator()(int64_t i, void *) const { f_ck_base(w, i, region); }
-};
+AA_FUNCTOR(FnLeafFlag, f_leaf_flag(w, i))
+AA_FUNCTOR(FnLeafList, f_leaf_list(w, i))
+AA_FUNCTOR(FnNodeRank, f_node_rank(w, i))
 struct FnLvlOff {
     Ws w;
     const int32_t *ctgs;
@@ -108,6 +104,10 @@ struct FnHeapsLevel {  // one warp per tree vertex of one depth (device only)
     Ws w;
     int64_t first;
     __device__ void operator()(int64_t i, void *) const { f_heaps_level(w, first + i); }
+};
+struct FnHeapsLeaf {  // one warp per tree leaf with inserts (device only)
+    Ws w;
+    __device__ void operator()(int64_t i, void *) const { f_heaps_level(w, (int64_t)w.leaf_list[i]); }
 };
 #endif
 AA_FUNCTOR(FnBfsPos, f_bfs_pos(w, i))
@@ -707,9 +707,23 @@ struct Pipeline {
                 bk.d2h(h_lvl.data(), d_lvl, h_lvl.size() * 8);
             }
         }
-        bool any_m1 = !m1.empty();
+        const bool any_m1 = !m1.empty();
         w.lvl_overflow = A<int32_t>(1);
-        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + ((int64_t)1 << 20);
+        // tree leaves with inserts leave the serial builder (they feed no other heap): one warp each, after it
+        int64_t n_leaf = 0;
+        if (bk.device_kahn()) {
+            w.vcnt = A<int32_t>(Vtot + 1);
+            w.vbase = A<int64_t>(Vtot + 2);
+            w.leaf_flag = A<int32_t>(Vtot + 1);
+            w.leaf_off = A<int64_t>(Vtot + 2);
+            bk.zero(w.leaf_flag + Vtot, 4);
+            bk.for_each("leaf_flag", Vtot, FnLeafFlag{w});
+            bk.scan_i32(w.leaf_flag, w.leaf_off, Vtot + 1);
+            n_leaf = bk.read_i64(w.leaf_off + Vtot);
+            w.leaf_list = A<uint32_t>(n_leaf);
+            bk.for_each("leaf_list", Vtot, FnLeafList{w});
+        }
+        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 64 * (n_leaf + (any_m1 ? Vtot : 0)) + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
@@ -721,24 +735,14 @@ struct Pipeline {
                 err = "device allocation failed (sidetrack heap arena)";
                 return AA_ERR_NOMEM;
             }
-            const int64_t nck_cap = hcap / 64 + 1;
-            if (any_m1) {
-                w.ck_owner = A<uint32_t>(nck_cap);
-                w.ck_seq = A<int32_t>(nck_cap);
-                w.ck_used = A<int32_t>(nck_cap);
-                w.ck_new = A<int32_t>(nck_cap);
-                w.ck_key_in = A<uint64_t>(nck_cap);
-                w.ck_key = A<uint64_t>(nck_cap);
-                w.ck_val_in = A<uint32_t>(nck_cap);
-                w.ck_val = A<uint32_t>(nck_cap);
-                w.ck_cnt = A<int32_t>(nck_cap + 1);
-                w.ck_pre = A<int64_t>(nck_cap + 2);
-                if (!w.ck_owner || !w.ck_seq || !w.ck_used || !w.ck_new || !w.ck_key_in || !w.ck_key || !w.ck_val_in || !w.ck_val ||
-                    !w.ck_cnt || !w.ck_pre) {
-                    err = "device allocation failed (heap chunk table)";
+            if (bk.device_kahn()) {
+                w.hn_key = (unsigned long long *)A<uint64_t>(hcap);
+                if (!w.hn_key) {
+                    err = "device allocation failed (heap node order keys)";
                     return AA_ERR_NOMEM;
                 }
-                bk.fill_ff(w.ck_owner, (size_t)nck_cap * 4);
+                bk.fill_ff(w.hn_key, (size_t)hcap * 8);
+                bk.zero(w.vcnt, (size_t)(Vtot + 1) * 4);
             }
             bk.zero(w.heap_top, 8);
             bk.zero(w.heap_used, (size_t)C * 8);
@@ -746,12 +750,14 @@ struct Pipeline {
             bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, HEAP_SMEM_BYTES);
             bool overflow = false;
 #if defined(__CUDACC__)
-            if (any_m1) {
+            if (n_leaf > 0) bk.for_each_contig("heaps_leaf", n_leaf, FnHeapsLeaf{w});
+            if (any_m1)
                 for (int32_t d = 1; d < lvl_per; d++)
                     for (size_t k = 0; k < m1.size(); k++) {
                         const int64_t lo = h_lvl[k * (size_t)lvl_per + (size_t)d - 1], hi = h_lvl[k * (size_t)lvl_per + (size_t)d];
                         if (hi > lo) bk.for_each_contig("heaps_level", hi - lo, FnHeapsLevel{w, lo});
                     }
+            if (n_leaf > 0 || any_m1) {
                 int32_t h_lo = 0;
                 bk.d2h(&h_lo, w.lvl_overflow, 4);
                 overflow = h_lo != 0;
@@ -760,24 +766,18 @@ struct Pipeline {
             bk.d2h(h_status.data(), w.status, (size_t)C * 4);
             AA_BK_CHECK();
             for (int32_t s : h_status) overflow = overflow || s == 3;
-            if (!overflow && any_m1) {
-                // order keys of the level-built nodes: chunks sorted by (owner's BFS slot, sequence) and prefix-summed give
-                // every node its rank in the sequential allocation order (what the enumeration's tie-break compares)
+            if (!overflow && bk.device_kahn()) {
+                // (owner slot, number) of every node -> its rank in the sequential allocation order
                 const int64_t top = bk.read_i64((const int64_t *)w.heap_top);
-                const int64_t nck = top / 64;
-                bk.for_each("ck_key", nck, FnCkKey{w});
-                bk.sort_pairs_u64(w.ck_key_in, w.ck_key, w.ck_val_in, w.ck_val, nck, 64);
-                bk.for_each("ck_cnt", nck, FnCkCnt{w});
-                bk.zero(w.ck_cnt + nck, 4);
-                bk.scan_i32(w.ck_cnt, w.ck_pre, nck + 1);
-                bk.for_each("ck_base", nck, FnCkBase{w, 0});
+                bk.scan_i32(w.vcnt, w.vbase, Vtot + 1);
+                bk.for_each("node_rank", top, FnNodeRank{w});
             }
             if (!overflow) break;
             if (hcap >= 0x7ffffff0LL || attempt > 8) {
                 err = "sidetrack heap arena exhausted (contig too dense for one device)";
                 return AA_ERR_NOMEM;
             }
-            bk.release_to(arena_mark);  // give the arena arrays (and the sort / scan scratch) back before growing
+            bk.release_to(arena_mark);  // give the arena arrays (and the scan scratch) back before growing
             hcap *= 4;
         }
         bk.phase_end(PH_HEAPS);

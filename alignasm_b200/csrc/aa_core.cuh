@@ -48,7 +48,7 @@ constexpr int64_t SV_TRANS_PENALTY = 2000;
 constexpr int64_t SV_INV_PENALTY = 500;
 constexpr int64_t SV_FRONT_END = 2;
 constexpr int64_t REF_NEG_PENALTY = 2;
-constexpr int32_t HEAP_CHUNK = 1024;  // leftist-heap nodes handed to a contig per arena grab
+constexpr int32_t HEAP_CHUNK = 4096;  // leftist-heap nodes handed to a contig per arena grab
 constexpr int64_t I64_MAX = 0x7fffffffffffffffLL;
 
 // ---- distance types -----------------------------------------------------------------------------
@@ -285,6 +285,7 @@ struct Ws {
     int32_t *leaf_flag;  // [Vtot+1] 1: tree leaf with inserts of a streaming-mode contig (built by f_heaps_level)
     int64_t *leaf_off;   // [Vtot+2]
     uint32_t *leaf_list; // [n_leaf] their BFS slots
+    int32_t *leaf_base;  // [Vtot] first of the 32 * nins node ids the streaming builder reserved for a leaf (keeps ids in order)
     ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
     // enumeration
@@ -1546,6 +1547,7 @@ constexpr size_t RELAX_SMEM_BYTES = 10 * 1024;
 // Spines of finished vertices with children are kept in shared memory (keyed by root id): BFS visits siblings
 // and then their children, all of which start from a heap built a few vertices earlier.
 constexpr int32_t SPMAX = 32;
+constexpr int32_t LEAF_MAX_INS = 32;  // a leaf's reserved ids (32 per insert) fit one arena chunk
 constexpr int32_t NSAVE = 8;
 struct __attribute__((aligned(8))) IdEid {
     int32_t id, eid;
@@ -1755,7 +1757,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
         // roots of parents that were finished in earlier batches (parents inside this batch come by shuffle)
         int32_t proot = -1;
         if (base + lane < nt && vi.ppos >= 0 && vi.ppos < base) proot = root_at[vi.ppos];
-        int32_t myroot = -1, mycnt = 0;
+        int32_t myroot = -1, mycnt = 0, mybase = -1;
         const int32_t cnt = nt - base < 32 ? nt - base : 32;
         for (int32_t j = 0; j < cnt && !overflow; j++) {
             const int32_t nins_f = __shfl_sync(FULL, vi.nins, j);
@@ -1765,8 +1767,24 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
             int32_t root = ppos >= base ? inb : pr;
             const int32_t nins = nins_f & (VI_KIDS - 1);
             int32_t vseq = 0;  // nodes this vertex has allocated
-            // a leaf of the tree feeds no other heap: its inserts are done by f_heaps_level, off this serial chain
-            if (nins > 0 && (nins_f & VI_KIDS)) {
+            // a leaf of the tree feeds no other heap: its inserts are done by f_heaps_level, off this serial chain.  It gets
+            // its node ids here, in sequence (32 per insert is the most a spine can copy), so that ids stay in allocation order
+            if (nins > 0 && nins <= LEAF_MAX_INS && !(nins_f & VI_KIDS)) {
+                const int32_t need = nins * 32;
+                if (cur + need > end) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+                    at = __shfl_sync(FULL, at, 0);
+                    if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
+                        overflow = true;
+                        break;
+                    }
+                    cur = (int64_t)at;
+                    end = cur + HEAP_CHUNK;
+                }
+                if (lane == j) mybase = (int32_t)cur;
+                cur += need;
+            } else if (nins > 0) {
                 int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
                 // ---- working spine := spine of `root` ----
                 if (root != cur_root) {
@@ -1859,6 +1877,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
             root_at[base + lane] = myroot;
             hroot[vi.x] = myroot;  // (an active leaf: the inherited root for now, its own after f_heaps_level)
             w.vcnt[v0 + base + lane] = mycnt;
+            w.leaf_base[v0 + base + lane] = mybase;
         }
         __syncwarp();
     }
@@ -1895,6 +1914,10 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
         sp.nd_eid = sp.nx_eid = 0;
         spine_reset(sp, hn, hn_eid, root);
         int64_t cur = 0, end = 0;
+        if (w.hmode[c] == 0) {  // a leaf of a streaming-mode contig: ids reserved in sequence by f_heaps_warp
+            cur = w.leaf_base[slot];
+            end = cur + (int64_t)nins * 32;
+        }
         InsKey kreg, knext;
         kreg.sum = knext.sum = 0;
         kreg.anom = kreg.nz = kreg.tot = kreg.eid = 0;
@@ -1948,7 +1971,7 @@ AA_HDN void f_leaf_flag(const Ws &w, int64_t i) {
     int32_t f = 0;
     if (w.hmode[c] == 0 && (w.status[c] == 0 || w.status[c] == 3) && i - w.vtx_off[c] < w.ntree[c]) {
         const int32_t nf = w.vinfo[i].nins;
-        f = (nf & (VI_KIDS - 1)) > 0 && !(nf & VI_KIDS);
+        f = (nf & (VI_KIDS - 1)) > 0 && (nf & (VI_KIDS - 1)) <= 32 && !(nf & VI_KIDS);
     }
     w.leaf_flag[i] = f;
 }
@@ -2273,10 +2296,11 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t vb = 1;
     while ((1 << vb) <= g.V) vb++;
     const bool wide = vb > 20;
-    // node ids are build-time ids (leaves and dense contigs are built in parallel); the tie-break of the queue is the
-    // node's rank in the sequential allocation order (what the reference's pointer comparison sees); the
-    // id itself comes back from ent_node[]
-    auto okey = [&](int32_t id) -> uint64_t { return (uint64_t)(uint32_t)w.hn_key[id] << 32; };
+    // the tie-break of the queue is the node's place in the sequential allocation order (what the reference's pointer
+    // comparison sees).  Streaming-mode contigs have their node ids in that order (leaves get reserved id
+    // ranges); heaps built level by level do not: there the rank recorded per node is compared and ent_node[] keeps the id
+    const bool keyed = w.hmode[c] != 0;
+    auto okey = [&](int32_t id) -> uint64_t { return (uint64_t)(uint32_t)(keyed ? (int32_t)(uint32_t)w.hn_key[id] : id) << 32; };
     const int32_t S = wide ? 31 : 2 * vb;  // k1 = anom << (S + 1) | ratio key (<= 2^S)
     auto make_k1 = [&](int32_t anom, int32_t nz, int32_t tot) -> uint64_t {
         uint64_t rk = 0;
@@ -2587,7 +2611,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         int32_t sn0 = -1, sn1 = -1, sn2 = -1;  // node ids of the successors
         if (have) {
             const int32_t idx = (int32_t)(uint32_t)t.k2;
-            const int32_t node = en[idx];
+            const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
             const int32_t anom = (int32_t)(t.k1 >> (S + 1));
             const HNode ch = hn_load(hn + node);
             const int32_t ceid = w.hn_eid[node];
@@ -2602,7 +2626,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 a0.nz = t.nz + x.nz;
                 a0.tot = t.tot + x.tot;
                 a0.k1 = make_k1(anom + x.anom, a0.nz, a0.tot);
-                a0.k2 = (uint64_t)(uint32_t)x.hrank << 32;
+                a0.k2 = (uint64_t)(uint32_t)(keyed ? x.hrank : x.hv) << 32;
                 sn0 = x.hv;
                 v0s = true;
             }

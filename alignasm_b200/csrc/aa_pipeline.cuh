@@ -721,9 +721,11 @@ struct Pipeline {
             bk.scan_i32(w.leaf_flag, w.leaf_off, Vtot + 1);
             n_leaf = bk.read_i64(w.leaf_off + Vtot);
             w.leaf_list = A<uint32_t>(n_leaf);
+            w.leaf_base = A<int32_t>(Vtot);
             bk.for_each("leaf_list", Vtot, FnLeafList{w});
         }
-        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 64 * (n_leaf + (any_m1 ? Vtot : 0)) + ((int64_t)1 << 20);
+        // (a leaf of a streaming-mode contig reserves 32 ids per insert, at most a chunk; level mode wastes < 64 per vertex)
+        int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 256 * n_leaf + 64 * (any_m1 ? Vtot : 0) + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;

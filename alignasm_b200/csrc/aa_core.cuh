@@ -2304,7 +2304,16 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     const int32_t S = wide ? 31 : 2 * vb;  // k1 = anom << (S + 1) | ratio key (<= 2^S)
     auto make_k1 = [&](int32_t anom, int32_t nz, int32_t tot) -> uint64_t {
         uint64_t rk = 0;
-        if (!wide) rk = ((uint64_t)1 << S) - (((uint64_t)(uint32_t)nz << S) / (uint64_t)(tot ? tot : 1));
+        if (!wide) {
+            // floor(nz * 2^S / tot) without a 64-bit integer division: an fp64 quotient (error < 2^-13 after scaling, since
+            // nz <= tot < 2^20 and S <= 40) corrected by one exact integer step
+            const uint64_t dn = (uint64_t)(tot ? tot : 1), num = (uint64_t)(uint32_t)nz << S;
+            uint64_t q = (uint64_t)(__ddiv_rn((double)nz, (double)dn) * (double)((uint64_t)1 << S));
+            const uint64_t prod = q * dn;
+            if (prod > num) q--;
+            else if (prod + dn <= num) q++;
+            rk = ((uint64_t)1 << S) - q;
+        }
         return ((uint64_t)(uint32_t)anom << (S + 1)) | rk;
     };
     QE INF;

@@ -978,7 +978,7 @@ struct Pipeline {
             a[PH_REVERSE] = 2.0 * 8.0 * Ed * 4.0 + 8.0 * Vd;   // 4 radix passes over (key,val), offsets
             a[PH_RELAX] = (16.0 + 4.0 + 4.0) * Ed + (24.0 + 4.0) * Vd;      // edge, rev id, src read; d + best write
             a[PH_TOPO] = 16.0 * Ed + 8.0 * Vd;
-            a[PH_HEAPS] = 16.0 * Ed + 24.0 * Vd + 36.0 * Hd;
+            a[PH_HEAPS] = 16.0 * Ed + 24.0 * Vd + 44.0 * Hd;  // node 32 + edge id 4 + order key 8
             a[PH_ENUM] = Kd * (32.0 + 36.0 + 3.0 * (32.0 + 32.0 + 8.0) + 28.0);  // pop, node, <=3 (node read, push, entry), out
             a[PH_PLAN] = 24.0 * Kd;
             a[PH_WALKS_A] = 0;  // data dependent; reported as time only

@@ -18,8 +18,8 @@ import numpy as np
 from . import _abi
 from ._abi import aa_batch, aa_opts, aa_result, np_from, ptr_of
 
-__all__ = ["Batch", "PafFile", "Result", "Solver", "AlignasmError", "read_paf", "solve_ctg_read", "lib_path",
-           "load_library"]
+__all__ = ["Batch", "PafFile", "Result", "Solver", "AlignasmError", "read_paf", "solve_ctg_read", "solve_multi",
+           "shard_contigs", "lib_path", "load_library"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -76,6 +76,12 @@ def load_library():
     lib.aa_paf_write.restype = C.c_int
     lib.aa_paf_free.argtypes = [vp]
     lib.aa_paf_free.restype = None
+    lib.aa_solve_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(aa_batch), C.POINTER(aa_opts), C.POINTER(aa_result)]
+    lib.aa_solve_multi.restype = C.c_int
+    lib.aa_shard_contigs.argtypes = [C.POINTER(aa_batch), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.aa_shard_contigs.restype = None
+    lib.aa_multi_last_error.argtypes = []
+    lib.aa_multi_last_error.restype = C.c_char_p
     _LIB = lib
     return lib
 
@@ -331,6 +337,27 @@ class _DevBatch:
             self.free()
         except Exception:
             pass
+
+
+def solve_multi(batch, devices, **kw):
+    """The batch sharded by contig over several GPUs of this box (aa_solve_multi: LPT shards, one host thread and
+    one context per device, rows merged in input order; no collective)."""
+    lib = load_library()
+    dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    res = aa_result()
+    o = _opts(**kw)
+    st = lib.aa_solve_multi(dev, len(devices), C.byref(batch.c_struct()), C.byref(o), C.byref(res))
+    if st != 0:
+        raise AlignasmError(st, (lib.aa_multi_last_error() or b"").decode())
+    return Result(res, batch.n_blk, lib.aa_result_free)
+
+
+def shard_contigs(batch, n_shards, max_walks=0):
+    """Shard id of every contig under the library's cost model (aa_shard_contigs)."""
+    lib = load_library()
+    out = np.zeros(batch.n_ctg, dtype=np.int32)
+    lib.aa_shard_contigs(C.byref(batch.c_struct()), int(max_walks), int(n_shards), ptr_of(out, C.c_int32))
+    return out
 
 
 def solve_ctg_read(blocks, solver=None, non_skip_linkable=False):

@@ -1,0 +1,238 @@
+// aa_multi.cpp — contig sharding across the GPUs of one box (host side only, no CUDA in this file).
+// The reference parallelises over contigs with tbb::parallel_for (src/alignasm.cpp:351-359); contigs are
+// independent, so here they are partitioned by a cost estimate (longest processing time first), every shard is
+// solved by its own aa_ctx on its own device from its own host thread, and the per-contig row lists are merged
+// back in input order.  No collective, no NCCL: the only inter-GPU "traffic" is the host scattering the
+// structure-of-arrays shards and gathering a few hundred bytes of rows per contig.
+#include "../../include/alignasm_b200.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+thread_local std::string g_multi_err;
+
+struct Shard {
+    std::vector<int64_t> ctgs;  // input contig ids, ascending
+    std::vector<int64_t> ctg_off, qs, qe, rs, re, qt, run_off, ql, qr, rl;
+    std::vector<int32_t> chr;
+    std::vector<uint8_t> fwd, mq;
+    aa_batch batch{};
+    aa_result res{};
+    aa_status st = AA_OK;
+    std::string err;
+};
+
+void build_shard(const aa_batch *b, Shard &s) {
+    s.ctg_off.push_back(0);
+    s.run_off.push_back(0);
+    for (int64_t c : s.ctgs) {
+        const int64_t b0 = b->ctg_off[c], b1 = b->ctg_off[c + 1];
+        s.qs.insert(s.qs.end(), b->qry_str + b0, b->qry_str + b1);
+        s.qe.insert(s.qe.end(), b->qry_end + b0, b->qry_end + b1);
+        s.rs.insert(s.rs.end(), b->ref_str + b0, b->ref_str + b1);
+        s.re.insert(s.re.end(), b->ref_end + b0, b->ref_end + b1);
+        s.qt.insert(s.qt.end(), b->qry_total + b0, b->qry_total + b1);
+        s.chr.insert(s.chr.end(), b->ref_chr + b0, b->ref_chr + b1);
+        s.fwd.insert(s.fwd.end(), b->aln_fwd + b0, b->aln_fwd + b1);
+        s.mq.insert(s.mq.end(), b->map_qul + b0, b->map_qul + b1);
+        const int64_t r0 = b->run_off[b0], r1 = b->run_off[b1];
+        const int64_t shift = (int64_t)s.ql.size() - r0;
+        for (int64_t i = b0; i < b1; i++) s.run_off.push_back(b->run_off[i + 1] + shift);
+        if (r1 > r0) {
+            s.ql.insert(s.ql.end(), b->run_ql + r0, b->run_ql + r1);
+            s.qr.insert(s.qr.end(), b->run_qr + r0, b->run_qr + r1);
+            s.rl.insert(s.rl.end(), b->run_rl + r0, b->run_rl + r1);
+        }
+        s.ctg_off.push_back((int64_t)s.qs.size());
+    }
+    aa_batch &o = s.batch;
+    o.n_ctg = (int64_t)s.ctgs.size();
+    o.n_blk = (int64_t)s.qs.size();
+    o.n_run = (int64_t)s.ql.size();
+    o.ctg_off = s.ctg_off.data();
+    o.qry_str = s.qs.data();
+    o.qry_end = s.qe.data();
+    o.ref_str = s.rs.data();
+    o.ref_end = s.re.data();
+    o.qry_total = s.qt.data();
+    o.ref_chr = s.chr.data();
+    o.aln_fwd = s.fwd.data();
+    o.map_qul = s.mq.data();
+    o.run_off = s.run_off.data();
+    o.run_ql = s.ql.data();
+    o.run_qr = s.qr.data();
+    o.run_rl = s.rl.data();
+}
+
+template <class T>
+T *host_n(int64_t n) {
+    return (T *)std::calloc((size_t)(n > 0 ? n : 1), sizeof(T));
+}
+void rows_alloc(aa_rows &r, int64_t n) {
+    r.n = n;
+    r.ctg_index = host_n<int32_t>(n);
+    r.qry_str = host_n<int64_t>(n);
+    r.qry_end = host_n<int64_t>(n);
+    r.ref_str = host_n<int64_t>(n);
+    r.ref_end = host_n<int64_t>(n);
+    r.is_alt = host_n<uint8_t>(n);
+}
+void rows_copy(aa_rows &dst, int64_t at, const aa_rows &src, int64_t from, int64_t n) {
+    if (n <= 0) return;
+    std::memcpy(dst.ctg_index + at, src.ctg_index + from, (size_t)n * 4);
+    std::memcpy(dst.qry_str + at, src.qry_str + from, (size_t)n * 8);
+    std::memcpy(dst.qry_end + at, src.qry_end + from, (size_t)n * 8);
+    std::memcpy(dst.ref_str + at, src.ref_str + from, (size_t)n * 8);
+    std::memcpy(dst.ref_end + at, src.ref_end + from, (size_t)n * 8);
+    std::memcpy(dst.is_alt + at, src.is_alt + from, (size_t)n);
+}
+}  // namespace
+
+extern "C" {
+
+const char *aa_multi_last_error(void) { return g_multi_err.c_str(); }
+
+/* cost model of one contig: the fixed K-walk enumeration plus the serial per-block chain (relax / heaps / walk 0) */
+void aa_shard_contigs(const aa_batch *b, int32_t max_walks, int32_t n_shards, int32_t *shard_of) {
+    const int64_t C = b->n_ctg;
+    const double K = max_walks > 0 ? std::min<double>(max_walks, 10000) : 10000.0;
+    std::vector<double> cost((size_t)C);
+    std::vector<int64_t> order((size_t)C);
+    for (int64_t c = 0; c < C; c++) {
+        const double n = (double)(b->ctg_off[c + 1] - b->ctg_off[c]);
+        cost[(size_t)c] = (n > 1 ? 0.4 * K : 0.0) + 14.0 * n;
+        order[(size_t)c] = c;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
+    std::vector<double> load((size_t)std::max(1, n_shards), 0.0);
+    for (int64_t c : order) {
+        const size_t k = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard_of[c] = (int32_t)k;
+        load[k] += cost[(size_t)c];
+    }
+}
+
+aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *b, const aa_opts *opts, aa_result *res) {
+    if (!devices || n_dev <= 0 || !b || !res || b->n_ctg <= 0) {
+        g_multi_err = "aa_solve_multi: bad arguments";
+        return AA_ERR_INVALID;
+    }
+    const int64_t C = b->n_ctg;
+    aa_opts o{};
+    if (opts) o = *opts;
+    if (o.keep_debug) {
+        g_multi_err = "aa_solve_multi: keep_debug is only available on a single device";
+        return AA_ERR_INVALID;
+    }
+    std::vector<int32_t> shard_of((size_t)C);
+    aa_shard_contigs(b, o.max_walks, n_dev, shard_of.data());
+    std::vector<Shard> sh((size_t)n_dev);
+    for (int64_t c = 0; c < C; c++) sh[(size_t)shard_of[(size_t)c]].ctgs.push_back(c);
+    std::vector<std::thread> pool;
+    for (int32_t k = 0; k < n_dev; k++)
+        pool.emplace_back([&, k]() {
+            Shard &s = sh[(size_t)k];
+            if (s.ctgs.empty()) return;
+            build_shard(b, s);
+            aa_ctx *ctx = nullptr;
+            s.st = aa_create(&ctx, devices[k]);
+            if (s.st != AA_OK) {
+                s.err = aa_last_error(nullptr);
+                return;
+            }
+            s.st = aa_solve(ctx, &s.batch, &o, &s.res);
+            if (s.st != AA_OK) s.err = aa_last_error(ctx);
+            aa_destroy(ctx);
+        });
+    for (auto &t : pool) t.join();
+    aa_status st = AA_OK;
+    for (auto &s : sh)
+        if (s.st != AA_OK && s.st != AA_ERR_UNSOLVABLE) {
+            st = s.st;
+            g_multi_err = s.err;
+        }
+    if (st == AA_OK)
+        for (auto &s : sh)
+            if (s.st == AA_ERR_UNSOLVABLE) {
+                st = s.st;
+                g_multi_err = s.err;
+            }
+    if (st != AA_OK && st != AA_ERR_UNSOLVABLE) {
+        for (auto &s : sh) aa_result_free(&s.res);
+        return st;
+    }
+    // ---- merge in input contig order ----
+    std::memset(res, 0, sizeof *res);
+    res->n_ctg = C;
+    res->out_off = host_n<int64_t>(C + 1);
+    res->alt_off = host_n<int64_t>(C + 1);
+    res->all_path_off = host_n<int64_t>(C + 1);
+    res->sorted_index = host_n<int32_t>(b->n_blk);
+    std::vector<int64_t> local((size_t)C);  // position of every contig inside its shard
+    for (auto &s : sh)
+        for (size_t i = 0; i < s.ctgs.size(); i++) local[(size_t)s.ctgs[i]] = (int64_t)i;
+    int64_t n_out = 0, n_alt = 0, n_paths = 0, n_all = 0;
+    for (int64_t c = 0; c < C; c++) {
+        const aa_result &r = sh[(size_t)shard_of[(size_t)c]].res;
+        const int64_t l = local[(size_t)c];
+        n_out += r.out_off[l + 1] - r.out_off[l];
+        n_alt += r.alt_off[l + 1] - r.alt_off[l];
+        const int64_t p0 = r.all_path_off[l], p1 = r.all_path_off[l + 1];
+        n_paths += p1 - p0;
+        n_all += r.all_row_off[p1] - r.all_row_off[p0];
+        res->out_off[c + 1] = n_out;
+        res->alt_off[c + 1] = n_alt;
+        res->all_path_off[c + 1] = n_paths;
+    }
+    res->all_row_off = host_n<int64_t>(n_paths + 1);
+    rows_alloc(res->out, n_out);
+    rows_alloc(res->alt, n_alt);
+    rows_alloc(res->all, n_all);
+    int64_t at_all = 0, at_path = 0;
+    for (int64_t c = 0; c < C; c++) {
+        const Shard &s = sh[(size_t)shard_of[(size_t)c]];
+        const aa_result &r = s.res;
+        const int64_t l = local[(size_t)c];
+        rows_copy(res->out, res->out_off[c], r.out, r.out_off[l], r.out_off[l + 1] - r.out_off[l]);
+        rows_copy(res->alt, res->alt_off[c], r.alt, r.alt_off[l], r.alt_off[l + 1] - r.alt_off[l]);
+        for (int64_t p = r.all_path_off[l]; p < r.all_path_off[l + 1]; p++) {
+            const int64_t n = r.all_row_off[p + 1] - r.all_row_off[p];
+            rows_copy(res->all, at_all, r.all, r.all_row_off[p], n);
+            at_all += n;
+            res->all_row_off[++at_path] = at_all;
+        }
+        const int64_t nb = b->ctg_off[c + 1] - b->ctg_off[c];
+        std::memcpy(res->sorted_index + b->ctg_off[c], r.sorted_index + s.ctg_off[(size_t)l], (size_t)nb * 4);
+    }
+    // statistics: sizes add up, times are the slowest shard's
+    aa_stats &t = res->stats;
+    for (auto &s : sh) {
+        if (s.ctgs.empty()) continue;
+        const aa_stats &x = s.res.stats;
+        t.n_ctg += x.n_ctg;
+        t.n_blk += x.n_blk;
+        t.n_run += x.n_run;
+        t.n_pair += x.n_pair;
+        t.n_vtx += x.n_vtx;
+        t.n_edge += x.n_edge;
+        t.n_heap += x.n_heap;
+        t.n_walk += x.n_walk;
+        t.n_task += x.n_task;
+        t.n_launch += x.n_launch;
+        t.algo_bytes += x.algo_bytes;
+        if (x.ms_total > t.ms_total) {
+            t.ms_total = x.ms_total;
+            std::memcpy(t.ms_phase, x.ms_phase, sizeof t.ms_phase);
+        }
+        for (int p = 0; p < 16; p++) t.algo_bytes_phase[p] += x.algo_bytes_phase[p];
+    }
+    for (auto &s : sh) aa_result_free(&s.res);
+    return st;
+}
+
+}  // extern "C"

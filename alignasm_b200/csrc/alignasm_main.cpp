@@ -7,11 +7,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 static void usage(FILE *f) {
     std::fputs(
         "Usage: alignasm [--help] [--version] [--thread THREAD] [--alt PAF_ALT_LOC] [--alt_baseline ALT_BASELINE]\n"
-        "                [--non_skip_linkable] [--device N] [--no_all] PAF_LOC\n\n"
+        "                [--non_skip_linkable] [--device N] [--devices A,B,...] [--no_all] PAF_LOC\n\n"
         "Positional arguments:\n  PAF_LOC                        Location of PAF file [required]\n\n"
         "Optional arguments:\n"
         "  -h, --help                     shows help message and exits\n"
@@ -21,6 +22,7 @@ static void usage(FILE *f) {
         "  -b, --alt_baseline ALT_BASELINE  Baseline for coverage of alternative PAF file [default: 0.5]\n"
         "  --non_skip_linkable            no edge a -> b when a -> c -> b exists\n"
         "  --device N                     CUDA device ordinal [default: 0]\n"
+        "  --devices A,B,...              shard the contigs over several CUDA devices (cost-balanced, merged in input order)\n"
         "  --no_all                       do not materialise <input>.aln.all.paf (written empty)\n",
         f);
 }
@@ -28,6 +30,7 @@ static void usage(FILE *f) {
 int main(int argc, char **argv) {
     std::string paf_loc, alt_loc;
     int threads = 1, device = 0;
+    std::vector<int32_t> devices;
     bool nsl = false, want_all = true;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -54,6 +57,14 @@ int main(int argc, char **argv) {
             const char *v = val("--device");
             if (!v) { usage(stderr); return 1; }
             device = std::atoi(v);
+        } else if (a == "--devices") {
+            const char *v = val("--devices");
+            if (!v) { usage(stderr); return 1; }
+            for (const char *p = v; *p;) {
+                devices.push_back((int32_t)std::strtol(p, const_cast<char **>(&p), 10));
+                if (*p == ',') p++;
+                else if (*p) { usage(stderr); return 1; }
+            }
         } else if (a == "--no_all") {
             want_all = false;
         } else if (!a.empty() && a[0] == '-') {
@@ -90,30 +101,40 @@ int main(int argc, char **argv) {
     const aa_batch *b = aa_paf_batch(paf);
     if (threads > 1) std::printf("Analyze PAF %lld data in parallel\n", (long long)b->n_ctg);
     std::fflush(stdout);
-    aa_ctx *ctx = nullptr;
-    st = aa_create(&ctx, device);
-    if (st != AA_OK) {
-        std::fprintf(stderr, "alignasm: %s (this build has no CPU path)\n", aa_last_error(nullptr));
-        aa_paf_free(paf);
-        return 1;
-    }
     aa_opts opt{};
     opt.non_skip_linkable = nsl;
     opt.want_all = want_all;
     aa_result res{};
-    st = aa_solve(ctx, b, &opt, &res);
-    if (st != AA_OK) {
-        std::fprintf(stderr, "alignasm: %s\n", aa_last_error(ctx));
+    if (devices.size() > 1) {
+        st = aa_solve_multi(devices.data(), (int32_t)devices.size(), b, &opt, &res);
+        if (st != AA_OK) {
+            std::fprintf(stderr, "alignasm: %s (this build has no CPU path)\n", aa_multi_last_error());
+            aa_paf_free(paf);
+            return 1;
+        }
+    } else {
+        if (devices.size() == 1) device = devices[0];
+        aa_ctx *ctx = nullptr;
+        st = aa_create(&ctx, device);
+        if (st != AA_OK) {
+            std::fprintf(stderr, "alignasm: %s (this build has no CPU path)\n", aa_last_error(nullptr));
+            aa_paf_free(paf);
+            return 1;
+        }
+        st = aa_solve(ctx, b, &opt, &res);
+        if (st != AA_OK) {
+            std::fprintf(stderr, "alignasm: %s\n", aa_last_error(ctx));
+            aa_destroy(ctx);
+            aa_paf_free(paf);
+            return 1;
+        }
         aa_destroy(ctx);
-        aa_paf_free(paf);
-        return 1;
     }
     std::puts("Write output PAF file");
     std::string prefix = paf_loc.substr(0, paf_loc.size() - 4);
     st = aa_paf_write(paf, &res, prefix.c_str(), err, sizeof err);
     if (st != AA_OK) std::fprintf(stderr, "alignasm: %s\n", err);
     aa_result_free(&res);
-    aa_destroy(ctx);
     aa_paf_free(paf);
     return st == AA_OK ? 0 : 1;
 }

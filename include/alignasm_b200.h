@@ -146,6 +146,13 @@ aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, a
 void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev);
 
 void aa_result_free(aa_result *res);
+
+/* ---- the same over several GPUs of one box: contigs are independent (tbb::parallel_for over contigs, alignasm.cpp:351-359),
+ * so they are partitioned by a cost estimate (longest processing time first), every shard is solved on its own device from
+ * its own host thread, and the rows are merged back in input order.  No collective.  `devices` may name a device twice. */
+aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *batch, const aa_opts *opts, aa_result *res);
+void aa_shard_contigs(const aa_batch *batch, int32_t max_walks, int32_t n_shards, int32_t *shard_of /* [n_ctg] */);
+const char *aa_multi_last_error(void);
 /* statistics (sizes, per-phase CUDA-event times, algorithmic bytes) of the last solve on this context */
 aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats);
 const char *aa_phase_name(int phase); /* NULL past the last phase */

@@ -151,6 +151,22 @@ def test_sharded_solve_equals_whole(solver, workdir):
         assert sharding.merge_shards(b.n_ctg, shards, rows) == whole
 
 
+def test_native_sharded_solve(solver, workdir):
+    """aa_solve_multi (C ABI): contigs sharded over several contexts (here all on device 0, which exercises the
+    partition, the per-shard host threads and the merge) return exactly the rows of the single-device solve."""
+    import alignasm_b200 as aa
+    args, _ = SMALL["cancer_small"]
+    b = aa.read_paf(pu.synth(os.path.join(workdir, "multi.paf"), *args)).batch
+    whole = solver.solve(b, want_all=True)
+    for devs in ([0, 0], [0, 0, 0, 0, 0]):
+        got = aa.solve_multi(b, devs, want_all=True)
+        assert pu.result_rows_equal(got, whole) is None
+        for k in ("n_ctg", "n_blk", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task"):
+            assert got.stats[k] == whole.stats[k], k
+    shard = aa.shard_contigs(b, 4)
+    assert shard.min() == 0 and shard.max() == 3 and len(shard) == b.n_ctg
+
+
 def test_walk_limit_option(solver, workdir):
     """aa_opts.max_walks (MAX_PATH_COUNT, paf_data.cpp:729): small limits exercise the early stop of the batched
     enumeration, a large one its backlog / refill / spill paths; all against the oracle."""
@@ -178,3 +194,10 @@ def test_cli_writes_reference_bytes(product_lib, workdir):
     for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
         assert pu.files_equal(paf[:-4] + "." + ext, os.path.join(pu.GOLDEN, "ties." + ext)), ext
     assert subprocess.run([exe, os.path.join(workdir, "nope.txt")], capture_output=True).returncode == 1
+    # the same through the sharded path (two contexts on device 0)
+    paf2 = os.path.join(workdir, "cli_ties2.paf")
+    shutil.copy(os.path.join(pu.GOLDEN, "ties.paf"), paf2)
+    out = subprocess.run([exe, "--devices", "0,0", paf2], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(paf2[:-4] + "." + ext, os.path.join(pu.GOLDEN, "ties." + ext)), ext

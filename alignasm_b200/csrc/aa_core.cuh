@@ -1626,6 +1626,7 @@ __device__ __forceinline__ int32_t spine_descend(Spine &sp, const HNode *__restr
     }
 }
 // path copy: N = nbase, the copy of level q = nbase + (p - q); returns the new root
+template <bool KEYS>
 __device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn, int32_t *__restrict__ hn_eid,
                                                unsigned long long *__restrict__ hn_key, const InsKey &k, int32_t p, int32_t nbase,
                                                unsigned long long keybase /* owner slot << 32 | nodes it has so far */) {
@@ -1681,7 +1682,7 @@ __device__ __forceinline__ int32_t spine_apply(Spine &sp, HNode *__restrict__ hn
     if (lane <= p) {
         hn_store(hn + sp.nd_id, sp.nd);
         hn_eid[sp.nd_id] = sp.nd_eid;
-        hn_key[sp.nd_id] = keybase + (unsigned long long)(sp.nd_id - nbase);
+        if (KEYS) hn_key[sp.nd_id] = keybase + (unsigned long long)(sp.nd_id - nbase);
     }
     __syncwarp();  // later inserts read these nodes from other lanes
     // new known spine: copies 0..sstar (then the old left of sstar), or copies 0..p-1 and N
@@ -1839,8 +1840,7 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                     const int32_t nbase = (int32_t)cur;
                     cur += need;
                     used += need;
-                    root = spine_apply(sp, hn, hn_eid, hn_key, k, p, nbase,
-                                       ((unsigned long long)(uint32_t)(v0 + base + j) << 32) | (uint32_t)vseq);
+                    root = spine_apply<false>(sp, hn, hn_eid, hn_key, k, p, nbase, 0);  // ids are in order here: no key
                     vseq += need;
                 }
                 if (overflow) break;
@@ -1949,7 +1949,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
             }
             const int32_t nbase = (int32_t)cur;
             cur += need;
-            root = spine_apply(sp, hn, hn_eid, w.hn_key, k, p, nbase, ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)used);
+            root = spine_apply<true>(sp, hn, hn_eid, w.hn_key, k, p, nbase, ((unsigned long long)(uint32_t)slot << 32) | (uint32_t)used);
             used += need;
         }
     }

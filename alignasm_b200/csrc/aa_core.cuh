@@ -2572,8 +2572,12 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     };
 
     int32_t width = 32;  // candidates per round: follows the commit length (tie-heavy queues confirm few)
+    // a successor that precedes the next candidate is the next pop itself: it is recorded at once and carried into the
+    // following round as candidate 0 (already popped; only its successors are still to come)
+    bool carry = false;
+    QE cy = INF;
     while (nd < K) {
-        if (n0 == 0 && np == 0) {
+        if (n0 == 0 && np == 0 && !carry) {
             if (nR == 0) break;
             refill();
             continue;
@@ -2610,8 +2614,17 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 }
             }
         }
-        int32_t ncand = n0 + np < width ? n0 + np : width;
-        if (ncand > K - nd) ncand = K - nd;
+        const int32_t cr = carry ? 1 : 0;
+        if (carry) {  // the carried entry takes lane 0, the queue candidates move up
+            t = qe_shfl(t, ShUp{1});
+            from_pend = __shfl_up_sync(FULL, from_pend, 1);
+            if (lane == 0) {
+                t = cy;
+                from_pend = 0;
+            }
+        }
+        int32_t ncand = n0 + np + cr < width ? n0 + np + cr : width;
+        if (ncand > K - nd + cr) ncand = K - nd + cr;
         const bool have = lane < ncand;
         // ---- their successors (speculative beyond the first candidate) ----
         QE a0 = INF, a1 = INF, a2 = INF;
@@ -2660,6 +2673,8 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         }
         // ---- how many candidates does the sequential order confirm? ----
         int32_t m = ncand;
+        bool violated = false;
+        QE star = INF;  // the successor that precedes candidate m (valid when violated)
         if (ncand > 1) {
             QE pm = a0;  // this lane's smallest successor under (distance, node); INF when it has none
             if (qe_dn_less(a1, pm, wide)) pm = a1;
@@ -2671,20 +2686,24 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             const QE ex = qe_shfl(pm, ShUp{1});
             const bool viol = have && lane > 0 && ex.sum != I64_MAX && qe_dn_less(ex, t, wide);
             const uint32_t vm = __ballot_sync(FULL, viol);
-            if (vm) m = __ffs(vm) - 1;
+            if (vm) {
+                m = __ffs(vm) - 1;
+                violated = true;
+                star = qe_shfl(pm, ShIdx{m - 1});  // minimum over the successors of candidates 0..m-1
+            }
         }
         width = m >= ncand ? (2 * width < 32 ? 2 * width : 32) : (2 * m + 2 < 32 ? 2 * m + 2 : 32);
         // ---- commit candidates 0..m-1 ----
         const bool com = lane < m;
-        if (com) {
+        if (com && !(carry && lane == 0)) {
             D4 cd;
             cd.sum = t.sum;
             cd.anom = (int32_t)(t.k1 >> (S + 1));
             cd.nz = t.nz;
             cd.tot = t.tot;
             cd.aux = 0;
-            dist[nd + lane] = cd;
-            last[nd + lane] = (int32_t)(uint32_t)t.k2;
+            dist[nd + lane - cr] = cd;
+            last[nd + lane - cr] = (int32_t)(uint32_t)t.k2;
         }
         const int32_t v0c = com && v0s, v1c = com && v1s, v2c = com && v2s;
         const int32_t mycnt = v0c + v1c + v2c;
@@ -2713,7 +2732,37 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             ep[id] = p12;
         }
         ne += total;
-        nd += m;
+        nd += m - cr;
+        // ---- the preceding successor, if any, is the next pop: record it, keep it out of the queue, carry it over ----
+        bool s0 = v0c, s1 = v1c, s2 = v2c;  // successors that enter the queue
+        carry = false;
+        if (violated && nd < K && !wide) {  // (packed keys: equal (sum, k1, node) is equality in (distance, node))
+            const uint64_t sn = star.k2 >> 32;
+            const bool e0 = v0c && a0.sum == star.sum && a0.k1 == star.k1 && (a0.k2 >> 32) == sn;
+            const bool e1 = v1c && a1.sum == star.sum && a1.k1 == star.k1 && (a1.k2 >> 32) == sn;
+            const bool e2 = v2c && a2.sum == star.sum && a2.k1 == star.k1 && (a2.k2 >> 32) == sn;
+            const uint32_t em = __ballot_sync(FULL, e0 || e1 || e2);  // equal (distance, node): the smallest entry index wins
+            const int32_t L = __ffs(em) - 1;
+            const QE mine = e0 ? a0 : (e1 ? a1 : a2);
+            cy = qe_shfl(mine, ShIdx{L});
+            if (lane == L) {
+                if (e0) s0 = false;
+                else if (e1) s1 = false;
+                else s2 = false;
+            }
+            if (lane == 0) {
+                D4 cd;
+                cd.sum = cy.sum;
+                cd.anom = (int32_t)(cy.k1 >> (S + 1));
+                cd.nz = cy.nz;
+                cd.tot = cy.tot;
+                cd.aux = 0;
+                dist[nd] = cd;
+                last[nd] = (int32_t)(uint32_t)cy.k2;
+            }
+            nd++;
+            carry = true;
+        }
         {  // the committed entries leave the front: a prefix of the pending lanes and a prefix of the run
             const int32_t na = __popc(__ballot_sync(FULL, com && from_pend));
             if (na > 0) {
@@ -2721,15 +2770,15 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 P = lane + na < np ? dn : INF;
                 np -= na;
             }
-            head = (head + (m - na)) & FMASK;
-            n0 -= m - na;
+            head = (head + (m - cr - na)) & FMASK;
+            n0 -= m - cr - na;
         }
         if (nd >= K) break;
         // ---- the successors enter the queue: backlog appends in parallel, pending inserts one by one ----
 #pragma unroll
         for (int32_t sidx = 0; sidx < 3; sidx++) {
             const QE &a = sidx == 0 ? a0 : (sidx == 1 ? a1 : a2);
-            bool valid = sidx == 0 ? v0c : (sidx == 1 ? v1c : v2c);
+            bool valid = sidx == 0 ? s0 : (sidx == 1 ? s1 : s2);
             if (valid && hasB && !qe_less(a, B, wide)) valid = false;  // beyond the K walks: dropped
             const bool toF = valid && (!hasT || qe_less(a, T, wide));
             const bool toR = valid && !toF;

@@ -7,6 +7,8 @@
 #include "../../include/alignasm_b200.h"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -15,6 +17,29 @@
 
 namespace {
 thread_local std::string g_multi_err;
+
+// contexts are kept between calls (a context owns its pooled workspace: a warm one makes no cudaMalloc); the key
+// is (device, how many times the device was named before in the list), so naming a device twice gives two contexts
+std::mutex g_ctx_mutex;
+std::map<std::pair<int32_t, int32_t>, aa_ctx *> g_ctx_cache;
+
+aa_status cached_ctx(int32_t device, int32_t nth, aa_ctx **out, std::string &err) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    auto it = g_ctx_cache.find({device, nth});
+    if (it != g_ctx_cache.end()) {
+        *out = it->second;
+        return AA_OK;
+    }
+    aa_ctx *ctx = nullptr;
+    aa_status st = aa_create(&ctx, device);
+    if (st != AA_OK) {
+        err = aa_last_error(nullptr);
+        return st;
+    }
+    g_ctx_cache[{device, nth}] = ctx;
+    *out = ctx;
+    return AA_OK;
+}
 
 struct Shard {
     std::vector<int64_t> ctgs;  // input contig ids, ascending
@@ -97,6 +122,13 @@ extern "C" {
 
 const char *aa_multi_last_error(void) { return g_multi_err.c_str(); }
 
+/* release the contexts aa_solve_multi keeps between calls */
+void aa_multi_release(void) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    for (auto &kv : g_ctx_cache) aa_destroy(kv.second);
+    g_ctx_cache.clear();
+}
+
 /* cost model of one contig: the fixed K-walk enumeration plus the serial per-block chain (relax / heaps / walk 0) */
 void aa_shard_contigs(const aa_batch *b, int32_t max_walks, int32_t n_shards, int32_t *shard_of) {
     const int64_t C = b->n_ctg;
@@ -139,15 +171,13 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
             Shard &s = sh[(size_t)k];
             if (s.ctgs.empty()) return;
             build_shard(b, s);
+            int32_t nth = 0;
+            for (int32_t q = 0; q < k; q++) nth += devices[q] == devices[k];
             aa_ctx *ctx = nullptr;
-            s.st = aa_create(&ctx, devices[k]);
-            if (s.st != AA_OK) {
-                s.err = aa_last_error(nullptr);
-                return;
-            }
+            s.st = cached_ctx(devices[k], nth, &ctx, s.err);
+            if (s.st != AA_OK) return;
             s.st = aa_solve(ctx, &s.batch, &o, &s.res);
             if (s.st != AA_OK) s.err = aa_last_error(ctx);
-            aa_destroy(ctx);
         });
     for (auto &t : pool) t.join();
     aa_status st = AA_OK;

@@ -153,6 +153,7 @@ void aa_result_free(aa_result *res);
 aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *batch, const aa_opts *opts, aa_result *res);
 void aa_shard_contigs(const aa_batch *batch, int32_t max_walks, int32_t n_shards, int32_t *shard_of /* [n_ctg] */);
 const char *aa_multi_last_error(void);
+void aa_multi_release(void); /* aa_solve_multi keeps one warm context per (device, repetition) between calls: free them */
 /* statistics (sizes, per-phase CUDA-event times, algorithmic bytes) of the last solve on this context */
 aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats);
 const char *aa_phase_name(int phase); /* NULL past the last phase */

@@ -3490,15 +3490,42 @@ AA_HDN void f_main_rows(const Ws &w, int64_t gv) {
 // copy rows [r0, r1) of the main chain into the task's output (lanes stride the range)
 AA_HD void copy_main_rows(const Ws &w, const Ctg &g, int32_t r0, int32_t r1, const Emit &em, int32_t rows_before) {
     if (em.mode != 2) return;
-    for (int32_t r = r0 + aa_lane(); r < r1; r += AA_LANES) {
-        const int64_t src = g.v0 + r, o = em.base + rows_before + (r - r0);
-        const int64_t gb = g.b0 + w.mr_blk[src];
-        w.r_idx[em.dst][o] = w.orig[gb];
-        w.r_qs[em.dst][o] = w.mr_qs[src];
-        w.r_qe[em.dst][o] = w.mr_qe[src];
-        w.r_rs[em.dst][o] = w.mr_rs[src];
-        w.r_re[em.dst][o] = w.mr_re[src];
-        w.r_alt[em.dst][o] = w.first_call[gb] > em.call ? 1 : 0;
+    // four rows per lane and step: the dependent gathers (row -> block -> original index / first call) of the four
+    // overlap instead of queueing up behind one another
+    for (int32_t rb = r0 + aa_lane(); rb < r1; rb += 4 * AA_LANES) {
+        int64_t gb[4], qs_[4], qe_[4], rs_[4], re_[4];
+        int32_t oi[4], fc[4];
+#pragma unroll
+        for (int32_t u = 0; u < 4; u++) {
+            const int32_t r = rb + u * AA_LANES;
+            if (r < r1) {
+                const int64_t src = g.v0 + r;
+                gb[u] = g.b0 + w.mr_blk[src];
+                qs_[u] = w.mr_qs[src];
+                qe_[u] = w.mr_qe[src];
+                rs_[u] = w.mr_rs[src];
+                re_[u] = w.mr_re[src];
+            }
+        }
+#pragma unroll
+        for (int32_t u = 0; u < 4; u++)
+            if (rb + u * AA_LANES < r1) {
+                oi[u] = w.orig[gb[u]];
+                fc[u] = w.first_call[gb[u]];
+            }
+#pragma unroll
+        for (int32_t u = 0; u < 4; u++) {
+            const int32_t r = rb + u * AA_LANES;
+            if (r < r1) {
+                const int64_t o = em.base + rows_before + (r - r0);
+                w.r_idx[em.dst][o] = oi[u];
+                w.r_qs[em.dst][o] = qs_[u];
+                w.r_qe[em.dst][o] = qe_[u];
+                w.r_rs[em.dst][o] = rs_[u];
+                w.r_re[em.dst][o] = re_[u];
+                w.r_alt[em.dst][o] = fc[u] > em.call ? 1 : 0;
+            }
+        }
     }
 }
 

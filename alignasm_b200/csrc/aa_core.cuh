@@ -332,6 +332,9 @@ struct Ws {
     int32_t *mr_blk;     // [Vtot] contig-local sorted block
     int64_t *mr_qs, *mr_qe, *mr_rs, *mr_re;
     int64_t n_tasks_total;
+    int32_t *fb_list;     // [Ntask] tasks the one-thread-per-task pass handed back
+    int32_t *fb_n;        // [1]
+    int64_t fb_count;
     // selection + output
     int32_t *win_out, *win_alt;  // [C] compacted task index (or -1)
     int32_t *out_cnt, *alt_cnt, *all_cnt;  // [C] rows / rows / paths
@@ -3532,17 +3535,23 @@ AA_HD void copy_main_rows(const Ws &w, const Ctg &g, int32_t r0, int32_t r1, con
 // One edge_path_to_paf_path call (paf_data.cpp:1489-1568) for an arbitrary planned walk: follow the main
 // chain by prefix-sum differences (and block copies of its rows), simulate only around the walk's sidetracks.
 // mark: record the blocks of the un-upgraded walk (pass A).  All lanes of the warp call this; lane 0 drives.
-AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit &em, bool mark, int64_t *cov_out,
-                          int32_t *rows_out) {
+// SOLO: one thread per task (pass A only: nothing is copied), small private scratch; returns false when the task
+// does not fit it (the caller hands it to the warp version).  !SOLO: one warp per task, lane 0 drives, all lanes copy.
+template <bool SOLO>
+AA_HDN bool walk_task_inc_t(const Ws &w, const Task &t, int32_t *side, int32_t side_cap, const DPBuf &buf, const Emit &em, bool mark,
+                            int64_t *cov_out, int32_t *rows_out) {
     const int64_t c = t.ctg;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0, e0 = w.eoff[v0], wo = w.walk_off[c];
     const int32_t *en = w.ent_node + 3 * wo;
     const int32_t *ep = w.ent_prev + 3 * wo;
-    const bool lead = aa_lane() == 0;
+    const bool lead = SOLO || aa_lane() == 0;
     int32_t ns = 0;
     if (lead)
-        for (int32_t cur = w.wlast[wo + t.walk]; cur != -1; cur = ep[cur]) s.side[ns++] = w.hn_eid[en[cur]];
+        for (int32_t cur = w.wlast[wo + t.walk]; cur != -1; cur = ep[cur]) {
+            if (SOLO && ns == side_cap) return false;
+            side[ns++] = w.hn_eid[en[cur]];
+        }
     int32_t si = ns - 1;  // side[] is last-to-first
     Auto A;
     A.cs = g.src;
@@ -3562,7 +3571,7 @@ AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit 
                     A.rows += r1 - r0;
                     finished = 1;
                 } else {
-                    const int32_t p = w.main_pos[v0 + w.e_src[e0 + s.side[si]]];
+                    const int32_t p = w.main_pos[v0 + w.e_src[e0 + side[si]]];
                     // main states at positions <= p-2 never look past the tail of the next sidetrack
                     int32_t j = p - 1 > i ? p - 1 : i;
                     if (w.m_cs[v0 + j] == -1) j++;
@@ -3578,27 +3587,30 @@ AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit 
             }
         }
 #if defined(__CUDA_ARCH__)
-        if (em.mode == 2) {
-            r0 = __shfl_sync(0xffffffffu, r0, 0);
-            r1 = __shfl_sync(0xffffffffu, r1, 0);
-            rows_before = __shfl_sync(0xffffffffu, rows_before, 0);
+        if (!SOLO) {
+            if (em.mode == 2) {
+                r0 = __shfl_sync(0xffffffffu, r0, 0);
+                r1 = __shfl_sync(0xffffffffu, r1, 0);
+                rows_before = __shfl_sync(0xffffffffu, rows_before, 0);
+            }
+            finished = __shfl_sync(0xffffffffu, finished, 0);
         }
-        finished = __shfl_sync(0xffffffffu, finished, 0);
 #endif
-        if (r1 > r0) copy_main_rows(w, g, r0, r1, em, rows_before);
+        if (!SOLO && r1 > r0) copy_main_rows(w, g, r0, r1, em, rows_before);
         if (finished) break;
         // ---- one simulated step from walk vertex a (lane 0) ----
         if (lead) {
             int32_t si1 = si, si2;
             int32_t v, nv = -1;
-            if (si1 >= 0 && a == w.e_src[e0 + s.side[si1]]) v = e_dst(w.edge[e0 + s.side[si1--]]);
+            if (si1 >= 0 && a == w.e_src[e0 + side[si1]]) v = e_dst(w.edge[e0 + side[si1--]]);
             else v = w.best[v0 + a];
             si2 = si1;
             if (v != g.dest) {
-                if (si2 >= 0 && v == w.e_src[e0 + s.side[si2]]) nv = e_dst(w.edge[e0 + s.side[si2--]]);
+                if (si2 >= 0 && v == w.e_src[e0 + side[si2]]) nv = e_dst(w.edge[e0 + side[si2--]]);
                 else nv = w.best[v0 + v];
             }
-            const int32_t used = auto_step(w, g, s.buf, A, v, nv, em);
+            const int32_t used = auto_step(w, g, buf, A, v, nv, em);
+            if (SOLO && used < 0) return false;  // the gap-filling DP does not fit the private scratch
             if (mark && v != g.dest && w.main_pos[v0 + v] < 0) {
                 int32_t x, y;
                 vtx_xy(w, g, v, x, y);
@@ -3629,7 +3641,7 @@ AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit 
             }
         }
 #if defined(__CUDA_ARCH__)
-        finished = __shfl_sync(0xffffffffu, finished, 0);
+        if (!SOLO) finished = __shfl_sync(0xffffffffu, finished, 0);
 #endif
         if (finished) break;
     }
@@ -3637,6 +3649,11 @@ AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit 
         if (cov_out) *cov_out = A.cov;
         if (rows_out) *rows_out = A.rows;
     }
+    return true;
+}
+AA_HDN void walk_task_inc(const Ws &w, const Task &t, const Slot &s, const Emit &em, bool mark, int64_t *cov_out,
+                          int32_t *rows_out) {
+    walk_task_inc_t<false>(w, t, s.side, 0x7fffffff, s.buf, em, mark, cov_out, rows_out);
 }
 
 // worker loops (dynamic scheduling); slot = worker index.  All lanes run the loop, lane 0 pulls the work.
@@ -3663,7 +3680,23 @@ AA_HDN void f_tasks_a0(const Ws &w, int64_t slot, const int32_t *ord) {
 #endif
     }
 }
-// pass A1: every other planned walk (coverage, row count, block marks)
+// pass A1: every other planned walk (coverage, row count, block marks).  The tasks are independent and each is a
+// chain of dependent loads, so they run one per THREAD with a small private scratch; the few whose gap-filling DP or
+// sidetrack list does not fit go to the warp version below.
+constexpr int32_t SOLO_SIDE = 32;
+AA_HDN void f_tasks_a1_solo(const Ws &w, int64_t t) {
+    const Task tk = w.tasks[t];
+    if (tk.call == 0) return;
+    LocalDP loc;
+    int32_t side[SOLO_SIDE];
+    Emit em;
+    em.mode = 0;
+    em.dst = 0;
+    em.base = 0;
+    em.call = 0;
+    if (!walk_task_inc_t<true>(w, tk, side, SOLO_SIDE, loc.buf(), em, true, &w.task_cov[t], &w.task_rows[t]))
+        w.fb_list[aa_atomic_inc(w.fb_n)] = (int32_t)t;
+}
 AA_HDN void f_tasks_a1(const Ws &w, int64_t slot) {
     Slot s = slot_view(w, slot);
     Emit em;
@@ -3672,10 +3705,10 @@ AA_HDN void f_tasks_a1(const Ws &w, int64_t slot) {
     em.base = 0;
     em.call = 0;
     for (;;) {
-        const int64_t t = next_item(w);
-        if (t >= w.n_tasks_total) break;
+        const int64_t k = next_item(w);
+        if (k >= w.fb_count) break;
+        const int64_t t = w.fb_list[k];
         const Task tk = w.tasks[t];
-        if (tk.call == 0) continue;
         walk_task_inc(w, tk, s, em, true, &w.task_cov[t], &w.task_rows[t]);
     }
 }

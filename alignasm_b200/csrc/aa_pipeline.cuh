@@ -130,6 +130,7 @@ AA_FUNCTOR(FnRelaxUnpack, f_relax_unpack(w, i))
 AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
 AA_FUNCTOR(FnMainRows, f_main_rows(w, i))
 AA_FUNCTOR(FnTasksA1, f_tasks_a1(w, i))
+AA_FUNCTOR(FnTasksA1Solo, f_tasks_a1_solo(w, i))
 struct FnTasksA0 {
     Ws w;
     const int32_t *ord;
@@ -858,8 +859,19 @@ struct Pipeline {
         bk.workers("main_resolve", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});
         bk.for_each("main_rows", Vtot, FnMainRows{w});
         // every other planned walk
-        bk.zero(w.task_next, 8);
-        if (NT > C) bk.workers("walksA1", std::min<int64_t>(S, NT), FnTasksA1{w});
+        if (NT > C) {
+            w.fb_list = A<int32_t>(NT);
+            w.fb_n = A<int32_t>(1);
+            bk.zero(w.fb_n, 4);
+            bk.for_each("walksA1_solo", NT, FnTasksA1Solo{w});  // one thread per task
+            int32_t n_fb = 0;
+            bk.d2h(&n_fb, w.fb_n, 4);
+            w.fb_count = n_fb;
+            if (n_fb > 0) {  // the tasks that did not fit the private scratch: one warp each, big scratch
+                bk.zero(w.task_next, 8);
+                bk.workers("walksA1", std::min<int64_t>(S, n_fb), FnTasksA1{w});
+            }
+        }
         bk.phase_end(PH_WALKS_A);
         AA_BK_CHECK();
 

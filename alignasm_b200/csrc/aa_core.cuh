@@ -3394,7 +3394,8 @@ __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
     auto load = [&](int32_t b) -> Rec {
         Rec r;
         r.used = 0;
-        r.cs = r.rows = r.mw = 0;
+        r.cs = r.rows = 0;
+        r.mw = -1;
         r.cov = 0;
         const int32_t i = b + lane;
         if (i < m) {
@@ -3402,8 +3403,8 @@ __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
             r.cs = w.sp_cs[v0 + i];
             r.rows = w.sp_rows[v0 + i];
             r.cov = w.sp_cov[v0 + i];
-            r.mw = w.main_walk[v0 + i];
         }
+        if (i <= m) r.mw = w.main_walk[v0 + i];
         return r;
     };
     int32_t b = 0;
@@ -3430,20 +3431,57 @@ __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
             cur = nxt;
             nxt = load(b + 32);
         }
-        const int32_t l = i - b;
-        if (lane == l) {
-            o_cs = A.cs;
-            o_cov = A.cov;
-            o_rows = A.rows;
-            o_set = true;
-        }
-        int32_t used = __shfl_sync(FULL, cur.used, l);
-        const int32_t mw = __shfl_sync(FULL, cur.mw, l);
-        if (used != 0 && A.cs == mw) {
-            A.cov += __shfl_sync(FULL, cur.cov, l);
-            A.rows += __shfl_sync(FULL, cur.rows, l);
-            A.cs = __shfl_sync(FULL, cur.cs, l);
+        const int32_t e = i - b;
+        // which positions of this chunk can take their speculated step, and where that step leads
+        const int32_t tgt = lane + cur.used;
+        const int32_t mw_a = __shfl_sync(FULL, cur.mw, tgt & 31), mw_b = __shfl_sync(FULL, nxt.mw, tgt & 31);
+        const int32_t mwt = tgt < 32 ? mw_a : mw_b;                           // walk vertex at the position after the step
+        const uint32_t U0 = __ballot_sync(FULL, cur.used != 0);               // speculated
+        const uint32_t U2 = __ballot_sync(FULL, cur.used == 2);
+        const uint32_t NX = __ballot_sync(FULL, cur.used != 0 && cur.cs == mwt);  // ... and the next position's assumption holds
+        const int32_t mw_e = __shfl_sync(FULL, cur.mw, e);
+        if ((U0 >> e & 1u) && A.cs == mw_e) {
+            // follow the chain of speculated steps through the chunk (warp-uniform bit arithmetic, no memory)
+            uint32_t vis = 0;
+            int32_t l = e, last;
+            for (;;) {
+                vis |= 1u << l;
+                last = l;
+                const int32_t nl = l + 1 + (int32_t)(U2 >> l & 1u);
+                if (!(NX >> l & 1u) || nl >= 32 || !(U0 >> nl & 1u)) break;
+                l = nl;
+            }
+            const bool mine = (vis >> lane & 1u) != 0;
+            int64_t icov = mine ? cur.cov : 0;
+            int32_t irows = mine ? cur.rows : 0;
+            for (int32_t d = 1; d < 32; d <<= 1) {  // inclusive prefix sums over the visited positions
+                const int64_t oc = __shfl_up_sync(FULL, icov, d);
+                const int32_t orr = __shfl_up_sync(FULL, irows, d);
+                if (lane >= d) {
+                    icov += oc;
+                    irows += orr;
+                }
+            }
+            if (mine) {
+                o_cs = cur.mw;
+                o_cov = A.cov + icov - cur.cov;
+                o_rows = A.rows + irows - cur.rows;
+                o_set = true;
+            }
+            A.cov += __shfl_sync(FULL, icov, 31);
+            A.rows += __shfl_sync(FULL, irows, 31);
+            A.cs = __shfl_sync(FULL, cur.cs, last);
+            i = b + last + 1 + (int32_t)(U2 >> last & 1u);
         } else {
+            // the assumption fails here (or nothing was speculated): the real step, by lane 0
+            if (lane == e) {
+                o_cs = A.cs;
+                o_cov = A.cov;
+                o_rows = A.rows;
+                o_set = true;
+                o_done = true;
+            }
+            int32_t used = 0;
             if (lane == 0) {
                 const int32_t v = w.main_walk[v0 + i + 1];
                 const int32_t nv = (i + 2 <= m) ? w.main_walk[v0 + i + 2] : -1;
@@ -3453,9 +3491,8 @@ __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
             A.cs = __shfl_sync(FULL, A.cs, 0);
             A.cov = __shfl_sync(FULL, A.cov, 0);
             A.rows = __shfl_sync(FULL, A.rows, 0);
-            if (lane == l) o_done = true;
+            i += used;
         }
-        i += used;
     }
     store_chunk();
     if (lane == 0) {

@@ -329,7 +329,10 @@ struct Pipeline {
             dst = (T *)(pooled ? bk.alloc_bytes(bytes) : bk.alloc_persistent(bytes));
             if (!dst) return false;
             if (!pooled) d->owned.push_back(dst);
-            if (n > 0) bk.h2d(dst, src, (size_t)n * sizeof(T));
+            if (n > 0) {
+                if (pooled) bk.stage(dst, src, (size_t)n * sizeof(T));  // one-shot solve: all arrays go up together
+                else bk.h2d(dst, src, (size_t)n * sizeof(T));
+            }
             return true;
         };
         bool ok = up(d->ctg_off, b->ctg_off, d->C + 1) && up(d->qs, b->qry_str, d->B) && up(d->qe, b->qry_end, d->B) &&
@@ -342,6 +345,7 @@ struct Pipeline {
             err = "device allocation failed while staging the batch";
             return AA_ERR_NOMEM;
         }
+        if (pooled) bk.flush_staged();
         if (pooled) {
             d->h_ctg_off = b->ctg_off;
             d->h_qs = b->qry_str;
@@ -354,7 +358,7 @@ struct Pipeline {
             d->h_qs = d->own_qs.data();
             d->h_qe = d->own_qe.data();
         }
-        bk.sync();
+        if (!pooled) bk.sync();  // (the staged copies of a one-shot solve are ordered before its kernels on the stream)
         out = d;
         return AA_OK;
     }

@@ -30,6 +30,8 @@ struct HostBackend {
     void *alloc_persistent(size_t n) { return std::malloc(n ? n : 1); }
     void free_persistent(void *p) { std::free(p); }
     void h2d(void *d, const void *h, size_t n) { std::memcpy(d, h, n); }
+    void stage(void *d, const void *h, size_t n) { std::memcpy(d, h, n); }
+    void flush_staged() {}
     void d2h(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
     void zero(void *p, size_t n) { std::memset(p, 0, n); }
     void sync() {}

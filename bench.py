@@ -202,6 +202,9 @@ def main():
         torch.cuda.set_device(local)
         dist = None
         if world > 1:
+            # NCCL prints its version banner on stdout at the VERSION level: keep stdout to the one JSON line
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

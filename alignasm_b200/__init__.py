@@ -70,6 +70,8 @@ def load_library():
     lib.aa_version.restype = C.c_char_p
     lib.aa_paf_read.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_int64]
     lib.aa_paf_read.restype = C.c_int
+    lib.aa_paf_read_alt.argtypes = [vp, C.c_char_p, C.c_double, C.c_char_p, C.c_int64]
+    lib.aa_paf_read_alt.restype = C.c_int
     lib.aa_paf_batch.argtypes = [vp]
     lib.aa_paf_batch.restype = C.POINTER(aa_batch)
     lib.aa_paf_write.argtypes = [vp, C.POINTER(aa_result), C.c_char_p, C.c_char_p, C.c_int64]
@@ -211,7 +213,8 @@ class Result:
 class PafFile:
     """A parsed PAF (reader + bucketing + cs:Z: -> runs), owned by the C library."""
 
-    def __init__(self, path):
+    def __init__(self, path, alt=None, alt_baseline=0.5):
+        """`alt`: an alternative PAF (reference CLI `--alt`, `--alt_baseline`; alignasm.cpp:186-332)."""
         lib = load_library()
         self._lib = lib
         h = C.c_void_p()
@@ -222,6 +225,12 @@ class PafFile:
         self._h = h
         self.path = path
         self._batch = None
+        if alt is not None:
+            st = lib.aa_paf_read_alt(h, os.fsencode(alt), float(alt_baseline), err, 512)
+            if st != 0:
+                lib.aa_paf_free(h)
+                self._h = None
+                raise AlignasmError(st, err.value.decode())
 
     @property
     def batch(self):
@@ -247,8 +256,8 @@ class PafFile:
             pass
 
 
-def read_paf(path):
-    return PafFile(path)
+def read_paf(path, alt=None, alt_baseline=0.5):
+    return PafFile(path, alt=alt, alt_baseline=alt_baseline)
 
 
 def _opts(non_skip_linkable=False, want_all=False, max_walks=0, keep_debug=False):

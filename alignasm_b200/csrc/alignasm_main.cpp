@@ -18,7 +18,7 @@ static void usage(FILE *f) {
         "  -h, --help                     shows help message and exits\n"
         "  -v, --version                  prints version information and exits\n"
         "  -t, --thread THREAD            Number of threads (accepted for compatibility; contigs run on the GPU) [default: 1]\n"
-        "  -a, --alt PAF_ALT_LOC          Location of alternative PAF file (not supported by this build)\n"
+        "  -a, --alt PAF_ALT_LOC          Location of alternative PAF file\n"
         "  -b, --alt_baseline ALT_BASELINE  Baseline for coverage of alternative PAF file [default: 0.5]\n"
         "  --non_skip_linkable            no edge a -> b when a -> c -> b exists\n"
         "  --device N                     CUDA device ordinal [default: 0]\n"
@@ -30,6 +30,7 @@ static void usage(FILE *f) {
 int main(int argc, char **argv) {
     std::string paf_loc, alt_loc;
     int threads = 1, device = 0;
+    double alt_baseline = 0.5;
     std::vector<int32_t> devices;
     bool nsl = false, want_all = true;
     for (int i = 1; i < argc; i++) {
@@ -50,7 +51,10 @@ int main(int argc, char **argv) {
             if (!v) { usage(stderr); return 1; }
             alt_loc = v;
         } else if (a == "-b" || a == "--alt_baseline") {
-            if (!val("-b")) { usage(stderr); return 1; }
+            const char *v = val("-b");
+            char *e = nullptr;
+            if (v) alt_baseline = std::strtod(v, &e);
+            if (!v || e == v || *e) { usage(stderr); return 1; }
         } else if (a == "--non_skip_linkable") {
             nsl = true;
         } else if (a == "--device") {
@@ -86,8 +90,9 @@ int main(int argc, char **argv) {
         usage(stderr);
         return 1;
     }
-    if (!alt_loc.empty()) {
-        std::fputs("--alt ingestion (reference alignasm.cpp:186-332) is outside this build's scope (SURVEY.md §8(f))\n", stderr);
+    if (!alt_loc.empty() && (alt_loc.size() < 4 || alt_loc.compare(alt_loc.size() - 4, 4, ".paf") != 0)) {  // alignasm.cpp:191-195
+        std::fprintf(stderr, "Wrong PAF file : \"%s\"", alt_loc.c_str());
+        usage(stderr);
         return 1;
     }
     char err[512] = {0};
@@ -96,6 +101,14 @@ int main(int argc, char **argv) {
     if (st != AA_OK) {
         std::fprintf(stderr, "%s\n", err);
         return 1;
+    }
+    if (!alt_loc.empty()) {  // alignasm.cpp:186-332
+        st = aa_paf_read_alt(paf, alt_loc.c_str(), alt_baseline, err, sizeof err);
+        if (st != AA_OK) {
+            std::fprintf(stderr, "%s\n", err);
+            aa_paf_free(paf);
+            return 1;
+        }
     }
     std::puts("File read complete");
     const aa_batch *b = aa_paf_batch(paf);

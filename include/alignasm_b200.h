@@ -163,6 +163,11 @@ const char *aa_version(void);
 typedef struct aa_paf aa_paf;
 /* reader + contig bucketing + get_overlap_range (alignasm.cpp:110-181, paf_data.cpp:90-123) */
 aa_status aa_paf_read(const char *path, aa_paf **paf, char *err, int64_t err_cap);
+/* --alt ingestion (alignasm.cpp:186-332): rows of an alternative PAF whose query names are `<contig>:<START>-<END>`
+ * segments are shifted into contig coordinates and appended to that contig's blocks (every row of a segment whose
+ * aln_len / segment length exceeds `alt_baseline`, else the segment's best row); they are written back with
+ * `xi:Z:A_<row>`.  Call between aa_paf_read and aa_paf_batch; pointers from an earlier aa_paf_batch are invalidated. */
+aa_status aa_paf_read_alt(aa_paf *paf, const char *alt_path, double alt_baseline, char *err, int64_t err_cap);
 const aa_batch *aa_paf_batch(const aa_paf *paf);
 /* writers incl. get_edited_paf_data (alignasm.cpp:398-490, paf_data.cpp:125-220); writes
  * <prefix>.aln.paf, <prefix>.aln.alt.paf, <prefix>.aln.all.paf */

@@ -71,7 +71,7 @@ def ref_binary(variant="canon"):
 
 
 def run_ref(paf_path, out_prefix, variant="canon", non_skip_linkable=False, threads=1, dump=None, no_write=False,
-            limit_contigs=None, timeout=None):
+            limit_contigs=None, timeout=None, alt=None, alt_baseline=None):
     """Run the compiled reference on a PAF file; returns its timing JSON."""
     exe = ref_binary(variant)
     if exe is None:
@@ -85,6 +85,10 @@ def run_ref(paf_path, out_prefix, variant="canon", non_skip_linkable=False, thre
         cmd += ["--dump", dump]
     if limit_contigs is not None:
         cmd += ["--limit-contigs", str(limit_contigs)]
+    if alt is not None:
+        cmd += ["--alt", alt]
+    if alt_baseline is not None:
+        cmd += ["--alt_baseline", repr(float(alt_baseline))]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError(f"{exe} failed ({out.returncode}): {out.stderr[-2000:]}")

@@ -5,6 +5,7 @@
 // parts of /root/reference/src/alignasm.cpp that need the absent third-party libraries
 // (csv-parser, argparse, TBB, indicators):
 //   * the PAF reader + contig bucketing            alignasm.cpp:110-181
+//   * --alt ingestion                             alignasm.cpp:186-332
 //   * the solve loop over contigs                  alignasm.cpp:346-379   (std::thread pool stands in for TBB)
 //   * the three writers                            alignasm.cpp:398-490
 //
@@ -130,7 +131,8 @@ double now_s() {
 }  // namespace
 
 int main(int argc, char **argv) {
-    std::string in_path, out_prefix;
+    std::string in_path, out_prefix, alt_path;
+    double alt_baseline = 0.5;
     int threads = 1;
     bool no_write = false;
     int64_t limit_contigs = -1;
@@ -138,6 +140,8 @@ int main(int argc, char **argv) {
         std::string a = argv[i];
         if (a == "--non_skip_linkable") NON_SKIP_LINKABLE = true;
         else if ((a == "-t" || a == "--thread") && i + 1 < argc) threads = std::atoi(argv[++i]);
+        else if ((a == "-a" || a == "--alt") && i + 1 < argc) alt_path = argv[++i];
+        else if ((a == "-b" || a == "--alt_baseline") && i + 1 < argc) alt_baseline = std::atof(argv[++i]);
         else if (a == "--no-write") no_write = true;
         else if (a == "--out-prefix" && i + 1 < argc) out_prefix = argv[++i];
         else if (a == "--limit-contigs" && i + 1 < argc) limit_contigs = std::atoll(argv[++i]);
@@ -164,6 +168,39 @@ int main(int argc, char **argv) {
     std::vector<PafReadData> cur;
     std::vector<std::string> ctg_names;
     std::string ctg_chr;
+    std::unordered_map<std::string, int32_t> paf_map;
+    // one row -> PafReadData (alignasm.cpp:138-176 and 259-300 share this shape); q_off shifts the query interval
+    auto fill_row = [&](const std::vector<std::string_view> &f, int64_t q_off, bool alt_row, PafReadData &d) -> bool {
+        std::string ref_chr(f[PAF_REF_CHR]);
+        if (!chr_map.count(ref_chr)) {
+            chr_map[ref_chr] = (int32_t)chr_rev.size();
+            chr_rev.push_back(ref_chr);
+        }
+        d.qry_str = to_i64(f[PAF_QRY_STR]) + q_off;
+        d.qry_end = to_i64(f[PAF_QRY_END]) + q_off - 1;
+        d.ref_total_length = to_i64(f[PAF_REF_TOT]);
+        d.ref_str = to_i64(f[PAF_REF_STR]);
+        d.ref_end = to_i64(f[PAF_REF_END]) - 1;
+        d.ref_chr = chr_map[ref_chr];
+        d.aln_fwd = f[PAF_ALN_FWD][0] == '+';
+        if (!d.aln_fwd) std::swap(d.ref_str, d.ref_end);
+        d.map_qul = (uint8_t)to_i64(f[PAF_MAT_QUL]);
+        std::string_view cs;
+        for (size_t k = PAF_MAT_QUL + 1; k < f.size(); k++)
+            if (f[k].size() >= 5 && f[k].substr(0, 5) == "cs:Z:") {
+                cs = f[k];
+                break;
+            }
+        if (cs.empty()) {
+            std::cerr << "Missing cs:Z tag in " << (alt_row ? "alternative " : "") << "PAF record for query '" << f[PAF_QRY_CHR] << "'\n";
+            return false;
+        }
+        d.cs_string = cs;
+        d.mat_num = (int32_t)to_i64(f[PAF_MAT_NUM]);
+        d.aln_len = (int32_t)to_i64(f[PAF_ALN_LEN]);
+        get_overlap_range(d, cs);
+        return true;
+    };
     {
         std::ifstream in(in_path);
         if (!in) {
@@ -183,10 +220,6 @@ int main(int argc, char **argv) {
             }
             std::string qry_chr(f[PAF_QRY_CHR]), ref_chr(f[PAF_REF_CHR]);
             if (ctg_chr.empty()) ctg_chr = qry_chr;
-            if (!chr_map.count(ref_chr)) {
-                chr_map[ref_chr] = (int32_t)chr_rev.size();
-                chr_rev.push_back(ref_chr);
-            }
             if (ctg_chr != qry_chr) {
                 paf_data.push_back(cur);
                 ctg_names.push_back(ctg_chr);
@@ -196,37 +229,86 @@ int main(int argc, char **argv) {
                 paf_index++;
             }
             PafReadData d{};
+            paf_map[qry_chr] = paf_index;
             d.paf_index = paf_index;
             d.ctg_index = ctg_index++;
             d.qry_total_length = to_i64(f[PAF_QRY_TOT]);
-            d.qry_str = to_i64(f[PAF_QRY_STR]);
-            d.qry_end = to_i64(f[PAF_QRY_END]) - 1;
-            d.ref_total_length = to_i64(f[PAF_REF_TOT]);
-            d.ref_str = to_i64(f[PAF_REF_STR]);
-            d.ref_end = to_i64(f[PAF_REF_END]) - 1;
-            d.ref_chr = chr_map[ref_chr];
-            d.aln_fwd = f[PAF_ALN_FWD][0] == '+';
-            if (!d.aln_fwd) std::swap(d.ref_str, d.ref_end);
-            d.map_qul = (uint8_t)to_i64(f[PAF_MAT_QUL]);
-            std::string_view cs;
-            for (size_t k = PAF_MAT_QUL + 1; k < f.size(); k++)
-                if (f[k].size() >= 5 && f[k].substr(0, 5) == "cs:Z:") {
-                    cs = f[k];
-                    break;
-                }
-            if (cs.empty()) {
-                std::cerr << "Missing cs:Z tag in PAF record for query '" << qry_chr << "'\n";
-                return 1;
-            }
-            d.cs_string = cs;
-            d.mat_num = (int32_t)to_i64(f[PAF_MAT_NUM]);
-            d.aln_len = (int32_t)to_i64(f[PAF_ALN_LEN]);
             d.original_cord = {TYPE_MAIN, row_global++};
-            get_overlap_range(d, cs);
+            if (!fill_row(f, 0, false, d)) return 1;
             cur.push_back(d);
         }
         ctg_names.push_back(ctg_chr);
         paf_data.push_back(cur);
+    }
+    // ---- --alt: alignasm.cpp:186-332 ----
+    if (!alt_path.empty()) {
+        if (alt_path.size() < 4 || alt_path.substr(alt_path.size() - 4) != ".paf") {
+            std::fprintf(stderr, "Wrong PAF file : %s\n", alt_path.c_str());
+            return 1;
+        }
+        std::ifstream in(alt_path);
+        if (!in) {
+            std::fprintf(stderr, "cannot open %s\n", alt_path.c_str());
+            return 1;
+        }
+        std::string line, grp_ctg;
+        std::vector<std::string_view> f;
+        int64_t grp_off = -1;
+        bool grp_open = false, grp_hit = false;
+        double grp_ratio = 0;
+        PafReadData grp_best{};
+        auto close_group = [&]() {  // :247-255
+            if (!grp_open || grp_hit) return;
+            auto &dst = paf_data[(size_t)paf_map[grp_ctg]];
+            grp_best.ctg_index = (int32_t)dst.size();
+            dst.push_back(grp_best);
+        };
+        int32_t alt_row = 0;
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty()) continue;
+            split_tabs(line, f);
+            if (f.size() < 12) {
+                std::fprintf(stderr, "short PAF row\n");
+                return 1;
+            }
+            // "<contig>:<START>-<END>" (:211-234)
+            std::string qname(f[PAF_QRY_CHR]);
+            size_t colon = qname.find(':');
+            if (colon == std::string::npos) throw std::invalid_argument("Invalid input string format");
+            size_t dash = qname.find('-', colon + 1);
+            if (dash == std::string::npos) dash = qname.size();
+            int64_t q_off = to_i64(std::string_view(qname).substr(colon + 1, dash - colon - 1)) - 1;
+            std::string real = qname.substr(0, colon);
+            auto &tail = paf_data[(size_t)paf_map[real]].back();
+            PafReadData d{};
+            d.paf_index = tail.paf_index;
+            d.qry_total_length = tail.qry_total_length;
+            d.original_cord = {TYPE_ALT, alt_row};
+            if (!fill_row(f, q_off, true, d)) return 1;
+            if (!grp_open || grp_off != q_off || grp_ctg != real) {
+                close_group();
+                grp_open = true;
+                grp_hit = false;
+                grp_ratio = 0;
+                grp_off = q_off;
+                grp_ctg = real;
+                grp_best = {};
+            }
+            double ratio = std::atof(std::string(f[PAF_ALN_LEN]).c_str()) / std::atof(std::string(f[PAF_QRY_TOT]).c_str());
+            if (ratio > grp_ratio) {
+                grp_ratio = ratio;
+                grp_best = d;
+            }
+            if (ratio > alt_baseline) {
+                auto &dst = paf_data[(size_t)paf_map[real]];
+                d.ctg_index = (int32_t)dst.size();
+                dst.push_back(d);
+                grp_hit = true;
+            }
+            alt_row++;
+        }
+        close_group();
     }
     if (limit_contigs >= 0 && (size_t)limit_contigs < paf_data.size()) {
         paf_data.resize((size_t)limit_contigs);

@@ -5,6 +5,7 @@ Run here (container with /root/reference):   python tests/golden/make_golden.py
 It needs oracle/_ref (built by `make -C oracle ref` from the reference sources where they lie) and writes, per case
 and per mode (default / --non_skip_linkable):
     <case>.paf                               input (hand-built micro cases or tools/synth_paf.cpp output)
+    <case>.altin.paf                         (case `withalt`) the alternative PAF given as `--alt` (tests/alt_util.py)
     <case>[.nsl].aln.paf / .aln.alt.paf / .aln.all.paf   reference outputs, canonical allocator
     <case>[.nsl].dump.npz                    graph edges / d / best / forward order / walk distances / anom_dis of the
                                              first DUMP_CONTIGS contigs, from the hook build (oracle/ref_dump_tu.cpp)
@@ -24,6 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import oracle_py  # noqa: E402
 import parity_util as pu  # noqa: E402
+import alt_util  # noqa: E402
 
 DUMP_CONTIGS = 6
 CHR = {"chr1": 248956422, "chr2": 242193529, "chr3": 198295559}
@@ -105,14 +107,16 @@ def micro_cases():
 
 
 def gen_outputs(case, paf, tmp):
+    alt = paf[:-4] + ".altin.paf"
+    alt = alt if os.path.exists(alt) else None
     for nsl in (False, True):
         tag = case + (".nsl" if nsl else "")
         pre = os.path.join(tmp, tag)
-        oracle_py.run_ref(paf, pre, variant="canon", non_skip_linkable=nsl)
+        oracle_py.run_ref(paf, pre, variant="canon", non_skip_linkable=nsl, alt=alt)
         for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
             shutil.copy(pre + "." + ext, os.path.join(HERE, tag + "." + ext))
         dump = pre + ".dump"
-        oracle_py.run_ref(paf, pre + "_d", variant="dump", non_skip_linkable=nsl, dump=dump, limit_contigs=DUMP_CONTIGS)
+        oracle_py.run_ref(paf, pre + "_d", variant="dump", non_skip_linkable=nsl, dump=dump, limit_contigs=DUMP_CONTIGS, alt=alt)
         ctgs = oracle_py.parse_dump(dump)
         arrays = {"n": np.array([c["n"] for c in ctgs], dtype=np.int64)}
         for i, c in enumerate(ctgs):
@@ -140,6 +144,9 @@ def main():
         cases["ties"] = pu.synth(os.path.join(HERE, "ties.paf"), "--contigs", 10, "--blocks", 30, "--sd", 10, "--p_dup", 0.15,
                                  "--p_trans", 0.15, "--p_inv", 0.15, "--seed", 11, "--lmin", 2000, "--lmax", 9000)
         cases["dense"] = pu.synth(os.path.join(HERE, "dense.paf"), "--preset", "c4", "--n", 40, "--lmin", 2000, "--lmax", 20000)
+        cases["withalt"] = pu.synth(os.path.join(HERE, "withalt.paf"), "--contigs", 12, "--blocks", 14, "--sd", 6, "--p_dup", 0.1,
+                                    "--p_trans", 0.15, "--p_inv", 0.15, "--seed", 17, "--lmin", 1500, "--lmax", 8000)
+        alt_util.make_alt(cases["withalt"], os.path.join(HERE, "withalt.altin.paf"), seed=5)
         for case, paf in cases.items():
             gen_outputs(case, paf, tmp)
             print("golden", case, os.path.getsize(paf), "bytes")

@@ -5,7 +5,14 @@ import numpy as np
 
 import parity_util as pu
 
-CASES = ["micro", "tiny", "ties", "dense"]
+CASES = ["micro", "tiny", "ties", "dense", "withalt"]
+
+
+def open_case(case):
+    """The golden input as a parsed PafFile; case `withalt` carries an alternative PAF (`--alt`, alignasm.cpp:186-332)."""
+    import alignasm_b200 as aa
+    alt = os.path.join(pu.GOLDEN, case + ".altin.paf")
+    return aa.read_paf(os.path.join(pu.GOLDEN, case + ".paf"), alt=alt if os.path.exists(alt) else None)
 
 
 def check_against_golden(case, nsl, solve_fn, paf_file, workdir):

@@ -100,3 +100,38 @@ def test_minus_strand_runs(product_lib, workdir):
     # query order: :150 +a :50 *ag -tt :100
     assert b.run_ql.tolist() == [100, 251, 302] and b.run_qr.tolist() == [249, 300, 401]
     assert b.run_rl.tolist() == [1302, 1152, 1099]
+
+
+def test_alt_reader(product_lib, workdir):
+    """aa_paf_read_alt: rows land behind their contig's own rows in contig coordinates; grouping by segment; errors."""
+    import alignasm_b200 as aa
+    main = os.path.join(workdir, "altr.paf")
+    cs = "cs:Z::1000"
+    with open(main, "w") as f:
+        f.write(f"a\t9000\t0\t1000\t+\tchr1\t100000\t500\t1500\t1000\t1000\t60\ttp:A:P\t{cs}\n")
+        f.write(f"b\t9000\t100\t1100\t+\tchr1\t100000\t500\t1500\t1000\t1000\t60\ttp:A:P\t{cs}\n")
+    alt = os.path.join(workdir, "altr.altin.paf")
+    seg = lambda q, qlen, s, e, n: f"{q}\t{qlen}\t{s}\t{e}\t-\tchr9\t100000\t700\t{700 + n}\t{n}\t{n}\t30\ttp:A:P\tcs:Z::{n}\n"
+    with open(alt, "w") as f:
+        f.write(seg("b:2001-4000", 2000, 0, 1500, 1500))    # above 0.5: taken
+        f.write(seg("b:2001-4000", 2000, 1600, 1900, 300))  # below: dropped, the group already took a row
+        f.write(seg("a:5001-7000", 2000, 100, 400, 300))    # group without a row above 0.5 ...
+        f.write(seg("a:5001-7000", 2000, 500, 1300, 800))   # ... contributes its best row
+        f.write(seg("zzz:11-2010", 2000, 0, 2000, 2000))    # unknown contig: bucket 0 (paf_map default, alignasm.cpp:258)
+    pf = aa.read_paf(main, alt=alt)
+    b = pf.batch
+    assert b.ctg_off.tolist() == [0, 3, 5]
+    assert b.qry_str.tolist() == [0, 5500, 10, 100, 2000] and b.qry_end.tolist() == [999, 6299, 2009, 1099, 3499]
+    assert b.qry_total.tolist() == [9000] * 5
+    assert b.aln_fwd.tolist() == [1, 0, 0, 1, 0] and b.ref_str[1] == 700 + 800 - 1 and b.ref_end[1] == 700
+    assert aa.read_paf(main, alt=alt, alt_baseline=0.1).batch.n_blk == 7
+    bad = os.path.join(workdir, "altbad.paf")
+    with open(bad, "w") as f:
+        f.write(seg("no_segment_name", 2000, 0, 1500, 1500))
+    with pytest.raises(aa.AlignasmError):
+        aa.read_paf(main, alt=bad)
+    with pytest.raises(aa.AlignasmError):
+        aa.read_paf(main, alt=os.path.join(workdir, "altr.txt"))
+    empty = os.path.join(workdir, "altempty.paf")
+    open(empty, "w").close()
+    assert aa.read_paf(main, alt=empty).batch.n_blk == 2

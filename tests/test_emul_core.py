@@ -7,7 +7,7 @@ import os
 import pytest
 
 import parity_util as pu
-from golden_util import CASES, check_against_golden
+from golden_util import CASES, check_against_golden, open_case
 from shapes import SMALL
 
 
@@ -16,7 +16,7 @@ from shapes import SMALL
 def test_core_matches_reference_golden(case, nsl, product_lib, workdir):
     import alignasm_b200 as aa
     import emul_py
-    pf = aa.read_paf(os.path.join(pu.GOLDEN, case + ".paf"))
+    pf = open_case(case)
     check_against_golden(case, nsl, emul_py.emul_solve, pf, workdir)
 
 

@@ -35,12 +35,12 @@ def test_matches_oracle(name, solver, workdir):
 
 
 @pytest.mark.parametrize("nsl", [False, True])
-@pytest.mark.parametrize("case", ["micro", "tiny", "ties", "dense"])
+@pytest.mark.parametrize("case", ["micro", "tiny", "ties", "dense", "withalt"])
 def test_matches_reference_golden(case, nsl, solver, workdir):
     """The CUDA path against the golden vectors the reference itself produced (tests/golden/make_golden.py)."""
     import alignasm_b200 as aa
-    from golden_util import check_against_golden
-    pf = aa.read_paf(os.path.join(pu.GOLDEN, case + ".paf"))
+    from golden_util import check_against_golden, open_case
+    pf = open_case(case)
     res = check_against_golden(case, nsl, solver.solve, pf, workdir)
     assert res.stats["n_launch"] > 0
 
@@ -201,3 +201,36 @@ def test_cli_writes_reference_bytes(product_lib, workdir):
     assert out.returncode == 0, out.stderr
     for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
         assert pu.files_equal(paf2[:-4] + "." + ext, os.path.join(pu.GOLDEN, "ties." + ext)), ext
+
+
+def test_cli_alt_ingestion(product_lib, workdir):
+    """`alignasm --alt ALT.paf [--alt_baseline B] <input.paf>` (alignasm.cpp:186-332): byte-identical to the reference,
+    against the committed golden (baseline 0.5) and against the oracle on a fresh seeded case (baseline 0.25)."""
+    import shutil
+    import subprocess
+    import alignasm_b200 as aa
+    import alt_util
+    from oracle import oracle_py
+    exe = os.path.join(pu.ROOT, "alignasm_b200", "alignasm")
+    paf, alt = os.path.join(workdir, "cli_withalt.paf"), os.path.join(workdir, "cli_withalt.altin.paf")
+    shutil.copy(os.path.join(pu.GOLDEN, "withalt.paf"), paf)
+    shutil.copy(os.path.join(pu.GOLDEN, "withalt.altin.paf"), alt)
+    out = subprocess.run([exe, "--alt", alt, paf], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(paf[:-4] + "." + ext, os.path.join(pu.GOLDEN, "withalt." + ext)), ext
+    with open(paf[:-4] + ".aln.paf") as f:
+        assert any("\txi:Z:A_" in line for line in f)
+    assert subprocess.run([exe, "--alt", os.path.join(workdir, "nope.txt"), paf], capture_output=True).returncode == 1
+    # fresh case, other baseline, --non_skip_linkable: CLI bytes == reader + oracle + writer
+    paf = pu.synth(os.path.join(workdir, "cli_alt2.paf"), "--contigs", 40, "--blocks", 30, "--sd", 10, "--p_dup", 0.15,
+                   "--p_trans", 0.15, "--p_inv", 0.15, "--seed", 21)
+    alt = alt_util.make_alt(paf, os.path.join(workdir, "cli_alt2.altin.paf"), seed=3)
+    out = subprocess.run([exe, "-a", alt, "-b", "0.25", "--non_skip_linkable", paf], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    pf = aa.read_paf(paf, alt=alt, alt_baseline=0.25)
+    want = oracle_py.oracle_solve(pf.batch, threads=8, non_skip_linkable=True, want_all=True)
+    pre = os.path.join(workdir, "cli_alt2_want")
+    pf.write(want, pre)
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(paf[:-4] + "." + ext, pre + "." + ext), pu.first_diff(paf[:-4] + "." + ext, pre + "." + ext)

@@ -5,7 +5,7 @@ import os
 import pytest
 
 import parity_util as pu
-from golden_util import CASES, check_against_golden
+from golden_util import CASES, check_against_golden, open_case
 
 
 @pytest.mark.parametrize("nsl", [False, True])
@@ -13,7 +13,7 @@ from golden_util import CASES, check_against_golden
 def test_oracle_matches_reference_golden(case, nsl, product_lib, workdir):
     import alignasm_b200 as aa
     from oracle import oracle_py
-    pf = aa.read_paf(os.path.join(pu.GOLDEN, case + ".paf"))
+    pf = open_case(case)
     check_against_golden(case, nsl, oracle_py.oracle_solve, pf, workdir)
 
 

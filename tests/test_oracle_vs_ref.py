@@ -34,6 +34,25 @@ def test_port_equals_reference(name, product_lib, workdir):
         assert pu.debug_vs_dump(res.dbg, op.parse_dump(pre + ".dump")) is None
 
 
+@pytest.mark.parametrize("baseline", [0.5, 0.25, 0.9])
+def test_alt_ingestion_equals_reference(baseline, product_lib, workdir):
+    """`--alt` (alignasm.cpp:186-332): the product's reader + merge, solved by the port, against the reference run with
+    the same alternative PAF — output files byte-identical (xi:Z:A_ rows included)."""
+    import alignasm_b200 as aa
+    import alt_util
+    op = _ref()
+    paf = pu.synth(os.path.join(workdir, "alt_main.paf"), "--contigs", 40, "--blocks", 30, "--sd", 10, "--p_dup", 0.15,
+                   "--p_trans", 0.15, "--p_inv", 0.15, "--seed", 21)
+    alt = alt_util.make_alt(paf, os.path.join(workdir, "alt_main.altin.paf"), seed=3)
+    pf = aa.read_paf(paf, alt=alt, alt_baseline=baseline)
+    assert pf.batch.n_blk > aa.read_paf(paf).batch.n_blk
+    pre = os.path.join(workdir, f"alt_{baseline}")
+    pf.write(op.oracle_solve(pf.batch, threads=4, want_all=True), pre + "_port")
+    op.run_ref(paf, pre + "_ref", variant="canon", alt=alt, alt_baseline=baseline)
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(pre + "_port." + ext, pre + "_ref." + ext), pu.first_diff(pre + "_port." + ext, pre + "_ref." + ext)
+
+
 def test_reference_asserts_hold_on_generator_output(workdir):
     """The assert-enabled reference build accepts the generator's PAF (cs consistent, cuts possible, DAG)."""
     op = _ref()

@@ -140,8 +140,9 @@ struct __attribute__((aligned(16))) PQEnt {
 struct __attribute__((aligned(16))) RevRec {
     int64_t sum;   // qry + ref
     int32_t src;   // contig-local source vertex
-    uint32_t fl;   // bits 0..1 anom, 2 qul_nonzero, 3 qul_total
+    uint32_t fl;   // bits 0..1 anom, 2 qul_nonzero, 3 qul_total, 4..31 out-degree of src (saturating; its initial Kahn count)
 };
+constexpr uint32_t RR_DEG_SAT = (1u << 28) - 1u;
 // relax state of one vertex, 32 B: d[v] (CALC_SUM view), best[v], remaining out-degree, min anom to dest
 struct __attribute__((aligned(16))) VState {
     int64_t sum;
@@ -798,6 +799,9 @@ AA_HDN void f_rev_pack(const Ws &w, int64_t k) {  // one reverse slot
     r.sum = e.qry + e.ref;
     r.src = w.e_src[eid];
     r.fl = (uint32_t)e_anom(e) | ((uint32_t)e_nz(e) << 2) | ((uint32_t)e_tot(e) << 3);
+    const int64_t gs = upper_idx(w.eoff, w.vtx_off[w.C], eid);  // global source vertex: the one whose edge range holds eid
+    const int64_t deg = w.eoff[gs + 1] - w.eoff[gs];
+    r.fl |= (uint32_t)(deg < (int64_t)RR_DEG_SAT ? deg : (int64_t)RR_DEG_SAT) << 4;
     w.rrec[k] = r;
 }
 AA_HDN void f_relax_init(const Ws &w, int64_t gv) {  // one vertex
@@ -1477,6 +1481,239 @@ __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
         if (!(ss.amin_reach & 1)) w.status[c] = 2;
     }
 }
+// ---- relax with the open-vertex state on chip --------------------------------------------------------------------
+// A vertex is *open* from the first time one of its out-neighbours is popped until its own count reaches zero.  Its
+// state is revisited once per out-edge, and a store to global memory invalidates the line in L1, so keeping the open
+// states in HBM costs one L2 round trip per pop on the critical path.  In a chain-like contig the open vertices are
+// the few vertices of the parts next to the frontier, and vertex ids are local (singles in sorted block order, pair
+// vertices in (i, j) discovery order), so two direct-mapped shared-memory tables (singles / pairs and src / dest,
+// indexed by id mod RC_SLOTS) hold them without conflicts.  A first touch initialises the entry from the in-edge
+// record itself (RevRec carries the source's initial count), a vertex whose count reaches zero is written to vs[]
+// once, with its final state, and leaves the table.  Two open vertices that map to one slot make the warp give up:
+// the contig is flagged (status 4) and redone by the global-memory form above (f_relax_redo_warp).
+// The first 32 in-edge records of the next queue entry are loaded one pop ahead whenever the queue holds one.
+constexpr int32_t RC_SLOTS = 512;  // per table
+struct __attribute__((aligned(16))) RCEnt {
+    int64_t sum;
+    int32_t anom, nz;
+    int32_t tot, best, cnt, amin_reach;
+    uint32_t ra;
+    int32_t deg;
+    int32_t tag;  // vertex held by the slot, -1: free
+    int32_t pad;
+};
+struct RelaxSmemC {
+    RelaxSmem ring;
+    RCEnt tab[2 * RC_SLOTS];
+};
+static_assert(sizeof(RelaxSmemC) <= 58 * 1024, "RelaxSmemC does not fit its shared-memory allotment");
+__device__ __forceinline__ RevRec rrec_ld(const RevRec *p) {
+    const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+    RevRec r;
+    r.sum = (int64_t)(((uint64_t)(uint32_t)t.y << 32) | (uint32_t)t.x);
+    r.src = t.z;
+    r.fl = (uint32_t)t.w;
+    return r;
+}
+__device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
+    RelaxSmemC &smc = *reinterpret_cast<RelaxSmemC *>(scratch);
+    RelaxSmem &sm = smc.ring;
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0) return;
+    if (w.rmode[c] >= 0) return;  // level-synchronous pass
+    Ctg g = ctg_view(w, c);
+    const int64_t v0 = g.v0;
+    VState *__restrict__ vs = w.vs + v0;
+    const RevRec *__restrict__ rrec = w.rrec;
+    const int64_t *__restrict__ rev_off = w.rev_off + v0;
+    int32_t *__restrict__ q = w.queue + v0;
+    int32_t head = 0, tail = 0;
+    for (int32_t i = lane; i < 2 * RC_SLOTS; i += 32) smc.tab[i].tag = -1;
+    __syncwarp();
+    auto push = [&](bool ready, int32_t x, const VState &sx, uint32_t xa, int32_t xdeg) {
+        const uint32_t m = __ballot_sync(FULL, ready);
+        if (ready) {
+            const int32_t pos = tail + __popc(m & ((1u << lane) - 1u));
+            const int32_t s = pos & (RRING - 1);
+            q[pos] = x;
+            sm.v[s] = x;
+            sm.sum[s] = sx.sum;
+            sm.anom[s] = sx.anom;
+            sm.nz[s] = sx.nz;
+            sm.tot[s] = sx.tot;
+            sm.amin_reach[s] = sx.amin_reach;
+            sm.ra[s] = xa;
+            sm.deg[s] = xdeg;
+        }
+        __syncwarp();
+        tail += __popc(m);
+    };
+    for (int32_t vb = 0; vb < g.V; vb += 32) {  // seeds: vertices without out-edges, ascending id
+        const int32_t v = vb + lane;
+        VState sx;
+        sx.sum = 0;
+        sx.anom = sx.nz = sx.tot = sx.best = 0;
+        sx.cnt = 1;
+        sx.amin_reach = 0;
+        int64_t xa = 0, xb = 0;
+        if (v < g.V) {
+            sx = vs[v];
+            xa = rev_off[v];
+            xb = rev_off[v + 1];
+        }
+        push(v < g.V && sx.cnt == 0, v, sx, (uint32_t)xa, (int32_t)(xb - xa));
+    }
+    RevRec pre;
+    pre.sum = 0;
+    pre.src = 0;
+    pre.fl = 0;
+    int32_t pre_for = -1;  // queue position whose first 32 records are in `pre`
+    bool clash = false;
+    while (head < tail) {
+        VState sv;
+        int32_t v;
+        int64_t ra, rb;
+        if (tail - head <= RRING) {
+            const int32_t s = head & (RRING - 1);
+            v = sm.v[s];
+            sv.sum = sm.sum[s];
+            sv.anom = sm.anom[s];
+            sv.nz = sm.nz[s];
+            sv.tot = sm.tot[s];
+            sv.amin_reach = sm.amin_reach[s];
+            ra = sm.ra[s];
+            rb = ra + sm.deg[s];
+        } else {  // the ring wrapped over this entry: its final state is in vs[]
+            v = q[head];
+            sv = vs[v];
+            ra = rev_off[v];
+            rb = rev_off[v + 1];
+        }
+        const bool have = pre_for == head;
+        const RevRec r0 = pre;
+        head++;
+        if (head < tail && tail - head <= RRING) {  // records of the next pop, one pop ahead
+            const int32_t s2 = head & (RRING - 1);
+            const uint32_t nra = sm.ra[s2];
+            if (lane < sm.deg[s2]) pre = rrec_ld(rrec + nra + lane);
+            pre_for = head;
+        }
+        const bool vreach = (sv.amin_reach & 1) != 0;
+        const int32_t av = sv.amin_reach >> 1;
+        for (int64_t kb = ra; kb < rb; kb += 32) {
+            const int64_t k = kb + lane;
+            bool ready = false, bad = false;
+            int32_t x = 0, xdeg = 0;
+            uint32_t xa = 0;
+            VState sx;
+            sx.sum = 0;
+            sx.anom = sx.nz = sx.tot = sx.best = sx.cnt = sx.amin_reach = 0;
+            if (k < rb) {
+                const RevRec r = (have && kb == ra) ? r0 : rrec_ld(rrec + k);
+                x = r.src;
+                RCEnt &e = smc.tab[(x < g.n ? 0 : RC_SLOTS) + (x & (RC_SLOTS - 1))];
+                const int32_t old = atomicCAS(&e.tag, -1, x);
+                if (old == x) {
+                    sx.sum = e.sum;
+                    sx.anom = e.anom;
+                    sx.nz = e.nz;
+                    sx.tot = e.tot;
+                    sx.best = e.best;
+                    sx.cnt = e.cnt;
+                    sx.amin_reach = e.amin_reach;
+                    xa = e.ra;
+                    xdeg = e.deg;
+                } else if (old < 0 && (r.fl >> 4) != RR_DEG_SAT) {  // first touch: the state relax_init gave it
+                    sx.best = -1;
+                    sx.cnt = (int32_t)(r.fl >> 4);
+                    sx.amin_reach = 0x3fffffff << 1;
+                    const int64_t a = __ldg(rev_off + x), b = __ldg(rev_off + x + 1);
+                    xa = (uint32_t)a;
+                    xdeg = (int32_t)(b - a);
+                } else {
+                    bad = true;
+                }
+                if (!bad) {
+                    if (vreach) {
+                        D4 cand, cur;
+                        cand.sum = sv.sum + r.sum;
+                        cand.anom = sv.anom + (int32_t)(r.fl & 3u);
+                        cand.nz = sv.nz + (int32_t)((r.fl >> 2) & 1u);
+                        cand.tot = sv.tot + (int32_t)((r.fl >> 3) & 1u);
+                        cur.sum = sx.sum;
+                        cur.anom = sx.anom;
+                        cur.nz = sx.nz;
+                        cur.tot = sx.tot;
+                        int32_t am = sx.amin_reach >> 1;
+                        const int32_t na = av + (int32_t)(r.fl & 3u);
+                        if (!(sx.amin_reach & 1) || less4(cand, cur)) {  // strict: the first relaxer wins among equals
+                            sx.sum = cand.sum;
+                            sx.anom = cand.anom;
+                            sx.nz = cand.nz;
+                            sx.tot = cand.tot;
+                            sx.best = v;
+                        }
+                        if (na < am) am = na;
+                        sx.amin_reach = (am << 1) | 1;
+                    }
+                    sx.cnt -= 1;
+                    ready = sx.cnt == 0;
+                    if (ready) {
+                        vs[x] = sx;  // final
+                        e.tag = -1;
+                    } else {
+                        e.sum = sx.sum;
+                        e.anom = sx.anom;
+                        e.nz = sx.nz;
+                        e.tot = sx.tot;
+                        e.best = sx.best;
+                        e.cnt = sx.cnt;
+                        e.amin_reach = sx.amin_reach;
+                        e.ra = xa;
+                        e.deg = xdeg;
+                    }
+                }
+            }
+            if (__any_sync(FULL, bad)) {
+                clash = true;
+                break;
+            }
+            push(ready, x, sx, xa, xdeg);
+        }
+        if (clash) break;
+    }
+    if (clash) {  // two open vertices on one slot: redo this contig with the states in global memory
+        if (lane == 0) w.status[c] = 4;
+        return;
+    }
+    if (lane == 0) {
+        const VState ss = vs[g.src];
+        w.anom_dis[c] = ss.amin_reach >> 1;
+        if (!(ss.amin_reach & 1)) w.status[c] = 2;
+    }
+}
+// second launch: the contigs the on-chip form gave up on (status 4) start over from the initial states
+__device__ void f_relax_redo_warp(const Ws &w, int64_t c, void *scratch) {
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 4) return;
+    __syncwarp();
+    Ctg g = ctg_view(w, c);
+    for (int32_t v = lane; v < g.V; v += 32) {
+        const int64_t gv = g.v0 + v;
+        VState s;
+        s.sum = 0;
+        s.anom = s.nz = s.tot = 0;
+        s.best = -1;
+        s.cnt = (int32_t)(w.eoff[gv + 1] - w.eoff[gv]);
+        s.amin_reach = v == g.dest ? 1 : (0x3fffffff << 1);
+        w.vs[gv] = s;
+    }
+    if (lane == 0) w.status[c] = 0;
+    __threadfence_block();
+    __syncwarp();
+    f_relax_warp(w, c, scratch);
+}
 // forward Kahn order (paf_data.cpp:742-746)
 __device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
     KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
@@ -1518,10 +1755,19 @@ __device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
 #endif
 AA_HDN void f_relax_any(const Ws &w, int64_t c, void *scratch) {
 #if defined(__CUDA_ARCH__)
-    f_relax_warp(w, c, scratch);
+    f_relax_warp_cached(w, c, scratch);
 #else
     (void)scratch;
     f_relax(w, c);
+#endif
+}
+AA_HDN void f_relax_redo_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_relax_redo_warp(w, c, scratch);
+#else
+    (void)w;
+    (void)c;
+    (void)scratch;
 #endif
 }
 AA_HDN void f_topo_any(const Ws &w, int64_t c, void *scratch) {
@@ -1533,7 +1779,8 @@ AA_HDN void f_topo_any(const Ws &w, int64_t c, void *scratch) {
 #endif
 }
 constexpr size_t KAHN_SMEM_BYTES = 4 * 1024;
-constexpr size_t RELAX_SMEM_BYTES = 10 * 1024;
+constexpr size_t RELAX_SMEM_BYTES = 10 * 1024;        // global-state form (redo launch)
+constexpr size_t RELAX_SMEM_C_BYTES = 10 * 1024 + 48 * 1024;  // ring + open-vertex tables
 
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------

@@ -164,6 +164,7 @@ struct FnTasksB {
     };
 AA_CTG_FUNCTOR(FnParts, f_parts_any(w, c))
 AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
+AA_CTG_FUNCTOR(FnRelaxRedo, f_relax_redo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnTopo, f_topo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnEnum, f_enum_any(w, c, scratch))
@@ -580,7 +581,8 @@ struct Pipeline {
         bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
         bk.phase_end(PH_TOPO);
         bk.side_end();
-        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, RELAX_SMEM_BYTES);
+        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, bk.device_kahn() ? RELAX_SMEM_C_BYTES : RELAX_SMEM_BYTES);
+        if (bk.device_kahn()) bk.for_each_contig("relax_redo", C, FnRelaxRedo{w, d_ord}, RELAX_SMEM_BYTES);
         if (n_lm > 0) {
             if (!kahn_levels<true>(w, Vtot, n_lm)) return AA_ERR_CUDA;   // d, best, min anom of the dense contigs
             bk.for_each("kl_finish", C, FnKlFinish{w});

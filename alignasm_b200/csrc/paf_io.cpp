@@ -14,27 +14,109 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <charconv>
+#include <chrono>
+#include <memory>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the joined tables are sized once and
+// filled by all host threads, so the pages are first touched in parallel instead of being zeroed by one thread
+template <class T>
+struct NoInit : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = NoInit<U>;
+    };
+    template <class U>
+    void construct(U *p) noexcept {
+        ::new ((void *)p) U;
+    }
+    template <class U, class... A>
+    void construct(U *p, A &&...a) {
+        ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T>
+using Vec = std::vector<T, NoInit<T>>;
+
+// a PAF file as read: mapped when possible, else read into memory
+struct Image {
+    const char *data = nullptr;
+    size_t size = 0;
+    bool mapped = false;
+    std::string own;
+    Image() = default;
+    Image(const Image &) = delete;
+    Image &operator=(const Image &) = delete;
+    ~Image() {
+        if (mapped) munmap(const_cast<char *>(data), size);
+    }
+    bool open(const char *path) {
+        int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat sb;
+        if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                data = (const char *)m;
+                size = (size_t)sb.st_size;
+                mapped = true;
+                ::close(fd);
+                return true;
+            }
+        }
+        char buf[1 << 16];
+        ssize_t got;
+        while ((got = ::read(fd, buf, sizeof buf)) > 0) own.append(buf, (size_t)got);
+        ::close(fd);
+        data = own.data();
+        size = own.size();
+        return true;
+    }
+};
+
 // one table of parsed rows, structure-of-arrays (the main PAF, and the rows of the alternative PAF before the merge)
 struct Rows {
-    std::vector<int64_t> qs, qe, rs, re, qtot, rtot, run_off{0}, run_ql, run_qr, run_rl;
-    std::vector<int32_t> chr, mat_num, aln_len, orig_idx;
-    std::vector<uint8_t> fwd, mapq, orig_alt;  // orig_alt: TYPE_ALT row (xi:Z:A_<row>), else TYPE_MAIN (xi:Z:P_<row>)
-    std::vector<std::string> cs;               // original cs:Z: field per row (needed to re-cut for output)
+    Vec<int64_t> qs, qe, rs, re, qtot, rtot, run_off{0}, run_ql, run_qr, run_rl;
+    Vec<int32_t> chr, mat_num, aln_len, orig_idx;
+    Vec<uint8_t> fwd, mapq, orig_alt;  // orig_alt: TYPE_ALT row (xi:Z:A_<row>), else TYPE_MAIN (xi:Z:P_<row>)
+    Vec<std::string_view> cs;          // original cs:Z: field per row (a view into the file image; re-cut for output)
     size_t size() const { return qs.size(); }
+};
+
+// target names in order of first appearance (chr_map / chr_rev_map, alignasm.cpp:119-123)
+struct ChrTable {
+    std::unordered_map<std::string, int32_t> map;
+    std::vector<std::string> names;
+    int32_t id(std::string_view name) {
+        std::string key(name);
+        auto it = map.find(key);
+        if (it != map.end()) return it->second;
+        const int32_t k = (int32_t)names.size();
+        map.emplace(key, k);
+        names.push_back(std::move(key));
+        return k;
+    }
 };
 
 struct aa_paf {
     aa_batch batch{};
     Rows r;
     std::vector<int64_t> ctg_off;
-    std::vector<std::string> ctg_name, chr_name;
-    std::unordered_map<std::string, int32_t> chr_map;
+    std::vector<std::string> ctg_name;
+    ChrTable chrs;
     std::unordered_map<std::string, int32_t> paf_map;  // query name -> last bucket of that name (alignasm.cpp:136)
+    std::vector<std::unique_ptr<Image>> images;  // the files as read: Rows::cs points into them
     void bind();
 };
 
@@ -146,22 +228,13 @@ namespace {
 // One PAF row -> one entry of `t` (alignasm.cpp:138-176 / 270-300): closed intervals, ref_str > ref_end on the minus
 // strand, exact-match runs from the cs tag (get_overlap_range, paf_data.cpp:90-123).  `q_off` shifts the query
 // coordinates (rows of the alternative PAF are relative to their `ctg:START-END` segment, alignasm.cpp:266-268).
-aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t q_off, const char *what, aa_paf &p, Rows &t,
+aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t q_off, const char *what, ChrTable &chrs, Rows &t,
                     std::vector<CsOp> &ops, std::string &why) {
     if (f.size() < 12) {
         why = std::string(what) + " row " + std::to_string(row) + " has fewer than 12 columns";
         return AA_ERR_FORMAT;
     }
-    std::string ref_chr(f[5]);
-    auto it = p.chr_map.find(ref_chr);
-    int32_t chr_id;
-    if (it == p.chr_map.end()) {
-        chr_id = (int32_t)p.chr_name.size();
-        p.chr_map.emplace(ref_chr, chr_id);
-        p.chr_name.push_back(ref_chr);
-    } else {
-        chr_id = it->second;
-    }
+    const int32_t chr_id = chrs.id(f[5]);
     int64_t qtot, qs, qe, rtot, rs, re, mat, aln, mq;
     if (!to_i64(f[1], qtot) || !to_i64(f[2], qs) || !to_i64(f[3], qe) || !to_i64(f[6], rtot) || !to_i64(f[7], rs) ||
         !to_i64(f[8], re) || !to_i64(f[9], mat) || !to_i64(f[10], aln) || !to_i64(f[11], mq) || f[4].empty()) {
@@ -224,9 +297,66 @@ aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t
     t.mapq.push_back((uint8_t)mq);
     t.mat_num.push_back((int32_t)mat);
     t.aln_len.push_back((int32_t)aln);
-    t.cs.emplace_back(cs);
+    t.cs.push_back(cs);
     return AA_OK;
 }
+
+// next non-empty line of [pos, end): trailing '\r' / '\n' stripped; false at the end
+inline bool next_line(const char *base, size_t &pos, size_t end, std::string_view &line) {
+    while (pos < end) {
+        const char *nl = (const char *)std::memchr(base + pos, '\n', end - pos);
+        size_t stop = nl ? (size_t)(nl - base) : end, len = stop - pos;
+        while (len > 0 && (base[pos + len - 1] == '\r' || base[pos + len - 1] == '\n')) len--;
+        line = std::string_view(base + pos, len);
+        pos = nl ? stop + 1 : end;
+        if (len > 0) return true;
+    }
+    return false;
+}
+
+int host_threads(size_t bytes) {
+    if (bytes < (1u << 20)) return 1;
+    int n = 0;
+    if (const char *e = std::getenv("AA_HOST_THREADS")) n = std::atoi(e);
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    if (n <= 0) n = 1;
+    return n > 64 ? 64 : n;
+}
+
+// AA_IO_TRACE=1: stage times of the reader / writer on stderr
+struct IoTrace {
+    bool on = std::getenv("AA_IO_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[aa_io] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+template <class F>
+void run_parallel(int n, F f) {
+    if (n <= 1) {
+        f(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n; t++) pool.emplace_back(f, t);
+    f(0);
+    for (auto &t : pool) t.join();
+}
+
+// what one reader thread produces from its slice of the file
+struct Chunk {
+    size_t beg = 0, end = 0;
+    int64_t row_base = 0, n_rows = 0;
+    Rows rows;
+    ChrTable chrs;                                             // slice-local target ids
+    std::vector<std::pair<int64_t, std::string_view>> names;  // (local row, query name) wherever the name changes
+    aa_status st = AA_OK;
+    std::string why;
+};
 
 // the reference's `aln_len / qry_total` as doubles (csv-parser get<double>, alignasm.cpp:310)
 bool to_f64(std::string_view s, double &v) {
@@ -263,54 +393,126 @@ extern "C" {
 aa_status aa_paf_read(const char *path, aa_paf **out, char *err, int64_t err_cap) {
     if (!path || !out) return AA_ERR_INVALID;
     *out = nullptr;
-    FILE *fp = std::fopen(path, "rb");
-    if (!fp) {
+    IoTrace tr;
+    auto img = std::make_unique<Image>();
+    if (!img->open(path)) {
         set_err(err, err_cap, std::string("cannot open ") + path);
         return AA_ERR_IO;
     }
-    aa_paf *p = new aa_paf();
-    std::string ctg_chr;
-    std::vector<std::string_view> f;
-    std::vector<CsOp> ops;
-    std::string why;
-    char *line = nullptr;
-    size_t cap = 0;
-    ssize_t got;
-    int64_t row = 0;
-    aa_status st = AA_OK;
-    while ((got = getline(&line, &cap, fp)) >= 0) {
-        while (got > 0 && (line[got - 1] == '\n' || line[got - 1] == '\r')) got--;
-        if (got == 0) continue;
-        std::string_view lv(line, (size_t)got);
-        split_tabs(lv, f);
-        st = parse_row(f, row, 0, "PAF", *p, p->r, ops, why);
-        if (st != AA_OK) {
-            set_err(err, err_cap, why);
-            break;
+    tr.mark("read file");
+    // The file is cut into one slice per host thread at line boundaries.  Every slice is parsed on its own (rows, runs,
+    // slice-local target ids, places where the query name changes); the slices are then joined in file order, which
+    // gives the row numbers, target ids (first appearance) and contig buckets (change of name, alignasm.cpp:115-133)
+    // of a sequential read, and the first error in file order.
+    const char *base = img->data;
+    const size_t size = img->size;
+    const int T = host_threads(size);
+    std::vector<Chunk> ch((size_t)T);
+    for (int t = 0; t < T; t++) {
+        size_t b = size * (size_t)t / (size_t)T;
+        if (t > 0 && b < size) {
+            const char *nl = (const char *)std::memchr(base + b - 1, '\n', size - b + 1);
+            b = nl ? (size_t)(nl - base) + 1 : size;
         }
-        // bucket by *change* of the query name (alignasm.cpp:115-133): a name that re-appears later
-        // opens a new contig, exactly as the reference does
-        if (p->ctg_off.empty() || ctg_chr != f[0]) {
-            p->ctg_off.push_back(row);
-            p->ctg_name.emplace_back(f[0]);
-            ctg_chr.assign(f[0]);
-        }
-        p->paf_map[ctg_chr] = (int32_t)p->ctg_off.size() - 1;
-        p->r.orig_idx.push_back((int32_t)row);  // original_cord = {TYPE_MAIN, row_global_index} (alignasm.cpp:172)
-        p->r.orig_alt.push_back(0);
-        row++;
+        ch[(size_t)t].beg = b;
+        if (t > 0) ch[(size_t)t - 1].end = b;
     }
-    std::free(line);
-    std::fclose(fp);
-    if (st == AA_OK && row == 0) {
+    ch[(size_t)T - 1].end = size;
+    run_parallel(T, [&](int t) {  // pass 1: rows per slice
+        Chunk &c = ch[(size_t)t];
+        size_t pos = c.beg;
+        std::string_view line;
+        while (next_line(base, pos, c.end, line)) c.n_rows++;
+    });
+    for (int t = 1; t < T; t++) ch[(size_t)t].row_base = ch[(size_t)t - 1].row_base + ch[(size_t)t - 1].n_rows;
+    tr.mark("count rows");
+    run_parallel(T, [&](int t) {  // pass 2: parse
+        Chunk &c = ch[(size_t)t];
+        std::vector<std::string_view> f;
+        std::vector<CsOp> ops;
+        std::string_view line, cur;
+        size_t pos = c.beg;
+        int64_t row = 0;
+        c.rows.qs.reserve((size_t)c.n_rows);
+        while (next_line(base, pos, c.end, line)) {
+            split_tabs(line, f);
+            c.st = parse_row(f, c.row_base + row, 0, "PAF", c.chrs, c.rows, ops, c.why);
+            if (c.st != AA_OK) return;
+            if (row == 0 || cur != f[0]) {
+                cur = f[0];
+                c.names.emplace_back(row, cur);
+            }
+            row++;
+        }
+    });
+    tr.mark("parse");
+    const int64_t n_rows = ch[(size_t)T - 1].row_base + ch[(size_t)T - 1].n_rows;
+    for (int t = 0; t < T; t++)
+        if (ch[(size_t)t].st != AA_OK) {
+            set_err(err, err_cap, ch[(size_t)t].why);
+            return ch[(size_t)t].st;
+        }
+    if (n_rows == 0) {
         set_err(err, err_cap, "PAF file holds no rows");
-        st = AA_ERR_FORMAT;
+        return AA_ERR_FORMAT;
     }
-    if (st != AA_OK) {
-        delete p;
-        return st;
+    aa_paf *p = new aa_paf();
+    std::vector<std::vector<int32_t>> remap((size_t)T);
+    std::vector<int64_t> run_base((size_t)T + 1, 0);
+    std::string_view cur;
+    for (int t = 0; t < T; t++) {
+        Chunk &c = ch[(size_t)t];
+        for (const std::string &name : c.chrs.names) remap[(size_t)t].push_back(p->chrs.id(name));
+        // bucket by *change* of the query name: a name that re-appears later opens a new contig, as in the reference
+        for (auto &nm : c.names)
+            if (p->ctg_off.empty() || cur != nm.second) {
+                cur = nm.second;
+                p->ctg_off.push_back(c.row_base + nm.first);
+                p->ctg_name.emplace_back(cur);
+                p->paf_map[p->ctg_name.back()] = (int32_t)p->ctg_off.size() - 1;
+            }
+        run_base[(size_t)t + 1] = run_base[(size_t)t] + (int64_t)c.rows.run_ql.size();
     }
-    p->ctg_off.push_back(row);
+    p->ctg_off.push_back(n_rows);
+    Rows &r = p->r;
+    const size_t N = (size_t)n_rows, R = (size_t)run_base[(size_t)T];
+    for (auto *v : {&r.qs, &r.qe, &r.rs, &r.re, &r.qtot, &r.rtot}) v->resize(N);
+    for (auto *v : {&r.run_ql, &r.run_qr, &r.run_rl}) v->resize(R);
+    for (auto *v : {&r.chr, &r.mat_num, &r.aln_len, &r.orig_idx}) v->resize(N);
+    for (auto *v : {&r.fwd, &r.mapq, &r.orig_alt}) v->resize(N);
+    r.run_off.resize(N + 1);
+    r.cs.resize(N);
+    run_parallel(T, [&](int t) {
+        const Chunk &c = ch[(size_t)t];
+        const Rows &s = c.rows;
+        const size_t at = (size_t)c.row_base, n = s.size(), rat = (size_t)run_base[(size_t)t], rn = s.run_ql.size();
+        auto put = [&](auto &dst, const auto &src, size_t where, size_t cnt) {
+            if (cnt) std::memcpy(dst.data() + where, src.data(), cnt * sizeof(src[0]));
+        };
+        put(r.qs, s.qs, at, n);
+        put(r.qe, s.qe, at, n);
+        put(r.rs, s.rs, at, n);
+        put(r.re, s.re, at, n);
+        put(r.qtot, s.qtot, at, n);
+        put(r.rtot, s.rtot, at, n);
+        put(r.mat_num, s.mat_num, at, n);
+        put(r.aln_len, s.aln_len, at, n);
+        put(r.fwd, s.fwd, at, n);
+        put(r.mapq, s.mapq, at, n);
+        put(r.cs, s.cs, at, n);
+        put(r.run_ql, s.run_ql, rat, rn);
+        put(r.run_qr, s.run_qr, rat, rn);
+        put(r.run_rl, s.run_rl, rat, rn);
+        for (size_t i = 0; i < n; i++) {
+            r.chr[at + i] = remap[(size_t)t][(size_t)s.chr[i]];
+            r.orig_idx[at + i] = (int32_t)(at + i);  // original_cord = {TYPE_MAIN, row_global_index} (alignasm.cpp:172)
+            r.orig_alt[at + i] = 0;
+            r.run_off[at + i] = s.run_off[i] + (int64_t)rat;
+        }
+    });
+    r.run_off[N] = (int64_t)R;
+    tr.mark("join");
+    p->images.push_back(std::move(img));
     p->bind();
     *out = p;
     return AA_OK;
@@ -328,8 +530,8 @@ aa_status aa_paf_read_alt(aa_paf *p, const char *alt_path, double alt_baseline, 
         set_err(err, err_cap, "Wrong PAF file : \"" + ap + "\"");
         return AA_ERR_INVALID;
     }
-    FILE *fp = std::fopen(alt_path, "rb");
-    if (!fp) {
+    auto img = std::make_unique<Image>();
+    if (!img->open(alt_path)) {
         set_err(err, err_cap, std::string("cannot open ") + alt_path);
         return AA_ERR_IO;
     }
@@ -345,15 +547,11 @@ aa_status aa_paf_read_alt(aa_paf *p, const char *alt_path, double alt_baseline, 
         if (!grouped || group_took) return;
         if (best_row >= 0) taken.emplace_back((int32_t)best_row, p->paf_map[seg_ctg]);
     };
-    char *line = nullptr;
-    size_t cap = 0;
-    ssize_t got;
     int64_t row = 0;
     aa_status st = AA_OK;
-    while ((got = getline(&line, &cap, fp)) >= 0) {
-        while (got > 0 && (line[got - 1] == '\n' || line[got - 1] == '\r')) got--;
-        if (got == 0) continue;
-        std::string_view lv(line, (size_t)got);
+    std::string_view lv;
+    size_t pos = 0;
+    while (next_line(img->data, pos, img->size, lv)) {
         split_tabs(lv, f);
         // parseString (alignasm.cpp:211-234): "<contig>:<START>[-...]" -> (contig, START - 1)
         std::string_view qn = f[0];
@@ -373,7 +571,7 @@ aa_status aa_paf_read_alt(aa_paf *p, const char *alt_path, double alt_baseline, 
         std::string real(qn.substr(0, colon));
         int64_t q_off = start1 - 1;
         int32_t c = p->paf_map[real];
-        st = parse_row(f, row, q_off, "alternative PAF", *p, alt, ops, why);
+        st = parse_row(f, row, q_off, "alternative PAF", p->chrs, alt, ops, why);
         double aln_len, seg_len;
         if (st == AA_OK && (!to_f64(f[10], aln_len) || !to_f64(f[1], seg_len))) {
             why = "alternative PAF row " + std::to_string(row) + ": non-numeric length field";
@@ -407,11 +605,10 @@ aa_status aa_paf_read_alt(aa_paf *p, const char *alt_path, double alt_baseline, 
         }
         row++;
     }
-    std::free(line);
-    std::fclose(fp);
     if (st != AA_OK) return st;
     flush();
     if (taken.empty()) return AA_OK;
+    p->images.push_back(std::move(img));
     // merge: every contig keeps its own rows, then the taken rows in the order the reference appended them
     int64_t n_ctg = (int64_t)p->ctg_off.size() - 1;
     std::vector<std::vector<int32_t>> add((size_t)n_ctg);
@@ -463,12 +660,12 @@ namespace {
 bool edit_row(const aa_paf &p, int64_t g, int64_t eqs, int64_t eqe, int64_t ers, int64_t ere, std::string &cs_out,
               int32_t &mat, int32_t &aln, std::vector<CsOp> &ops, std::vector<CsOp> &kept, std::string &why) {
     if (eqs == p.r.qs[(size_t)g] && eqe == p.r.qe[(size_t)g]) {
-        cs_out = p.r.cs[(size_t)g];
+        cs_out.assign(p.r.cs[(size_t)g]);
         mat = p.r.mat_num[(size_t)g];
         aln = p.r.aln_len[(size_t)g];
         return true;
     }
-    const std::string &cs = p.r.cs[(size_t)g];
+    const std::string_view cs = p.r.cs[(size_t)g];
     if (!parse_cs(cs, ops, why)) return false;
     bool fwd = p.r.fwd[(size_t)g] != 0;
     kept.clear();
@@ -513,7 +710,7 @@ bool edit_row(const aa_paf &p, int64_t g, int64_t eqs, int64_t eqe, int64_t ers,
             qb += o.len;
             rb += o.len;
         } else {
-            cs_out.append(cs, o.at, o.n);
+            cs_out.append(cs.substr(o.at, o.n));
             aln += (int32_t)o.len;
             if (o.type == '+') qb += o.len;
             else if (o.type == '-') rb += o.len;
@@ -542,53 +739,100 @@ extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const
         return AA_ERR_INVALID;
     }
     std::string pre(out_prefix);
-    FILE *f1 = std::fopen((pre + ".aln.paf").c_str(), "wb");
-    FILE *f2 = std::fopen((pre + ".aln.alt.paf").c_str(), "wb");
-    FILE *f3 = std::fopen((pre + ".aln.all.paf").c_str(), "wb");
-    if (!f1 || !f2 || !f3) {
-        if (f1) std::fclose(f1);
-        if (f2) std::fclose(f2);
-        if (f3) std::fclose(f3);
+    FILE *fo[3] = {std::fopen((pre + ".aln.paf").c_str(), "wb"), std::fopen((pre + ".aln.alt.paf").c_str(), "wb"),
+                   std::fopen((pre + ".aln.all.paf").c_str(), "wb")};
+    if (!fo[0] || !fo[1] || !fo[2]) {
+        for (FILE *f : fo)
+            if (f) std::fclose(f);
         set_err(err, err_cap, "cannot open output files for " + pre);
         return AA_ERR_IO;
     }
-    std::vector<CsOp> ops, kept;
-    std::string cs_out, why;
-    aa_status st = AA_OK;
-    // one output row (alignasm.cpp:426-440 / 467-481)
-    auto put = [&](FILE *fp, int64_t c, const std::string &qname, const aa_rows &rows, int64_t k) -> bool {
-        int64_t g = p.ctg_off[(size_t)c] + rows.ctg_index[k];
-        int32_t mat, aln;
-        int64_t qs = rows.qry_str[k], qe = rows.qry_end[k], rs = rows.ref_str[k], re = rows.ref_end[k];
-        if (!edit_row(p, g, qs, qe, rs, re, cs_out, mat, aln, ops, kept, why)) return false;
-        bool fwd = p.r.fwd[(size_t)g] != 0;
-        std::fprintf(fp,
-                     "%s\t%" PRId64 "\t%" PRId64 "\t%" PRId64 "\t%s\t%s\t%" PRId64 "\t%" PRId64 "\t%" PRId64
-                     "\t%d\t%d\t%d\t%s\txi:Z:%s%d\t%s\n",
-                     qname.c_str(), p.r.qtot[(size_t)g], qs, qe + 1, fwd ? "+" : "-", p.chr_name[(size_t)p.r.chr[(size_t)g]].c_str(),
-                     p.r.rtot[(size_t)g], fwd ? rs : re, (fwd ? re : rs) + 1, mat, aln, (int)p.r.mapq[(size_t)g],
-                     rows.is_alt[k] ? "tp:A:S" : "tp:A:P", p.r.orig_alt[(size_t)g] ? "A_" : "P_", (int)p.r.orig_idx[(size_t)g],
-                     cs_out.c_str());
-        return true;
-    };
-    for (int64_t c = 0; c < res->n_ctg && st == AA_OK; c++) {
-        const std::string &name = p.ctg_name[(size_t)c];
-        for (int64_t k = res->out_off[c]; k < res->out_off[c + 1]; k++)
-            if (!put(f1, c, name, res->out, k)) st = AA_ERR_FORMAT;
-        for (int64_t k = res->alt_off[c]; k < res->alt_off[c + 1]; k++)
-            if (!put(f2, c, name, res->alt, k)) st = AA_ERR_FORMAT;
-        if (res->all_path_off && res->all_row_off) {
-            int32_t cnt = 0;
-            for (int64_t m = res->all_path_off[c]; m < res->all_path_off[c + 1]; m++) {
-                std::string qn = name + "." + std::to_string(++cnt);
-                for (int64_t k = res->all_row_off[m]; k < res->all_row_off[m + 1]; k++)
-                    if (!put(f3, c, qn, res->all, k)) st = AA_ERR_FORMAT;
+    // Contigs are formatted by all host threads (dynamic, one contig at a time) into per-contig text, which is then
+    // written in input-contig order (alignasm.cpp:417-441, 456-482).
+    const int64_t C = res->n_ctg;
+    std::vector<std::string> text[3];
+    for (auto &t : text) t.resize((size_t)C);
+    std::vector<uint8_t> bad((size_t)C, 0);
+    std::vector<std::string> bad_why((size_t)C);
+    std::atomic<int64_t> next{0};
+    const int T = host_threads((size_t)(res->out_off[C] + res->alt_off[C]) * 64);
+    run_parallel(T, [&](int) {
+        std::vector<CsOp> ops, kept;
+        std::string cs_out, why;
+        char num[24];
+        auto put_i = [&](std::string &dst, int64_t v) {
+            auto r = std::to_chars(num, num + sizeof num, v);
+            dst.append(num, (size_t)(r.ptr - num));
+            dst.push_back('\t');
+        };
+        // one output row (alignasm.cpp:426-440 / 467-481)
+        auto put = [&](std::string &dst, int64_t c, const std::string &qname, const aa_rows &rows, int64_t k) -> bool {
+            const size_t g = (size_t)(p.ctg_off[(size_t)c] + rows.ctg_index[k]);
+            int32_t mat, aln;
+            const int64_t qs = rows.qry_str[k], qe = rows.qry_end[k], rs = rows.ref_str[k], re = rows.ref_end[k];
+            if (!edit_row(p, (int64_t)g, qs, qe, rs, re, cs_out, mat, aln, ops, kept, why)) return false;
+            const bool fwd = p.r.fwd[g] != 0;
+            dst.append(qname);
+            dst.push_back('\t');
+            put_i(dst, p.r.qtot[g]);
+            put_i(dst, qs);
+            put_i(dst, qe + 1);
+            dst.append(fwd ? "+\t" : "-\t");
+            dst.append(p.chrs.names[(size_t)p.r.chr[g]]);
+            dst.push_back('\t');
+            put_i(dst, p.r.rtot[g]);
+            put_i(dst, fwd ? rs : re);
+            put_i(dst, (fwd ? re : rs) + 1);
+            put_i(dst, mat);
+            put_i(dst, aln);
+            put_i(dst, (int64_t)p.r.mapq[g]);
+            dst.append(rows.is_alt[k] ? "tp:A:S\txi:Z:" : "tp:A:P\txi:Z:");
+            dst.append(p.r.orig_alt[g] ? "A_" : "P_");  // cord_to_index_string (alignasm.cpp:398-405)
+            put_i(dst, (int64_t)p.r.orig_idx[g]);
+            dst.append(cs_out);
+            dst.push_back('\n');
+            return true;
+        };
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= C) break;
+            const std::string &name = p.ctg_name[(size_t)c];
+            bool ok = true;
+            for (int64_t k = res->out_off[c]; k < res->out_off[c + 1] && ok; k++) ok = put(text[0][(size_t)c], c, name, res->out, k);
+            for (int64_t k = res->alt_off[c]; k < res->alt_off[c + 1] && ok; k++) ok = put(text[1][(size_t)c], c, name, res->alt, k);
+            if (res->all_path_off && res->all_row_off) {
+                int32_t cnt = 0;
+                for (int64_t m = res->all_path_off[c]; m < res->all_path_off[c + 1] && ok; m++) {
+                    const std::string qn = name + "." + std::to_string(++cnt);
+                    for (int64_t k = res->all_row_off[m]; k < res->all_row_off[m + 1] && ok; k++)
+                        ok = put(text[2][(size_t)c], c, qn, res->all, k);
+                }
+            }
+            if (!ok) {
+                bad[(size_t)c] = 1;
+                bad_why[(size_t)c] = why;
             }
         }
+    });
+    aa_status st = AA_OK;
+    for (int64_t c = 0; c < C; c++) {
+        for (int k = 0; k < 3; k++) {
+            const std::string &t = text[k][(size_t)c];
+            if (!t.empty() && std::fwrite(t.data(), 1, t.size(), fo[k]) != t.size() && st == AA_OK) {
+                st = AA_ERR_IO;
+                set_err(err, err_cap, "short write to the output files of " + pre);
+            }
+        }
+        if (bad[(size_t)c] && st == AA_OK) {  // rows up to the first bad one are on disk, like the reference's throw mid-write
+            st = AA_ERR_FORMAT;
+            set_err(err, err_cap, bad_why[(size_t)c]);
+            break;
+        }
     }
-    std::fclose(f1);
-    std::fclose(f2);
-    std::fclose(f3);
-    if (st != AA_OK) set_err(err, err_cap, why);
+    for (FILE *f : fo)
+        if (std::fclose(f) != 0 && st == AA_OK) {
+            st = AA_ERR_IO;
+            set_err(err, err_cap, "cannot finish the output files of " + pre);
+        }
     return st;
 }

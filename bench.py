@@ -12,6 +12,7 @@ Prints ONE JSON line (rank 0):
   value     blocks/s with the batch already resident in HBM (aa_solve_device), max over ranks
   e2e       blocks/s through the public host-buffer call aa_solve (H2D of the batch + D2H of the rows inside)
   roofline  the dominant kernel (phase) of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
+  cli       the stages of the drop-in command line: host reader (all host threads), solve, host writers
   cpu_baseline  the reference's own solve_ctg_read (oracle/_ref, built from the reference sources) on this
             box's host cores, on a bounded sample of the same workload
 --impl reference times that CPU arm alone (no GPU code on its path).
@@ -253,6 +254,23 @@ def main():
         wall_e2e = time.perf_counter() - t1
         h2d = sum(getattr(batch, n).nbytes for n, _ in aa.Batch.FIELDS) + 4 * batch.n_blk
 
+        # ---- drop-in CLI stages (parse + write reported separately): host reader, solve, host writers ----
+        cli = None
+        if rank == 0:
+            t2 = time.perf_counter()
+            pf2 = aa.read_paf(paf)
+            t3 = time.perf_counter()
+            r = solver.solve(pf2.batch, want_all=True)
+            t4 = time.perf_counter()
+            pf2.write(r, os.path.join(tmp, "cli_out"))
+            t5 = time.perf_counter()
+            out_bytes = sum(os.path.getsize(os.path.join(tmp, "cli_out" + e)) for e in (".aln.paf", ".aln.alt.paf", ".aln.all.paf"))
+            r.close()
+            pf2.close()
+            cli = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": batch.n_blk / (t5 - t2),
+                   "paf_bytes": os.path.getsize(paf), "out_bytes": out_bytes, "host_threads": os.cpu_count(),
+                   "note": "aa_paf_read + aa_solve(want_all) + aa_paf_write as the alignasm CLI chains them; process and CUDA start-up excluded"}
+
         # max over ranks
         tv = torch.tensor([wall, wall_e2e, ev_ms / 1e3], dtype=torch.float64, device="cuda")
         nb = torch.tensor([batch.n_blk], dtype=torch.float64, device="cuda")
@@ -292,6 +310,7 @@ def main():
                          "note": "latency-bound integer graph work: see DESIGN.md for the per-phase byte model"},
             "phases_ms": {n: round(m, 3) for n, m in zip(names, ph)},
             "sizes": {k: st[k] for k in ("n_ctg", "n_blk", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task")},
+            "cli": cli,
         }
         if not a.no_cpu_baseline and world == 1:
             cb = cpu_reference(paf, tmp)

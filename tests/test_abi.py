@@ -135,3 +135,42 @@ def test_alt_reader(product_lib, workdir):
     empty = os.path.join(workdir, "altempty.paf")
     open(empty, "w").close()
     assert aa.read_paf(main, alt=empty).batch.n_blk == 2
+
+
+def test_parallel_reader_equals_sequential(product_lib, workdir, monkeypatch):
+    """The reader cuts the file into one slice per host thread: row numbers, target ids, contig buckets, runs and the
+    first error in file order must be those of a sequential read; the writers give the same bytes at any thread count."""
+    import numpy as np
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    paf = pu.synth(os.path.join(workdir, "par.paf"), "--preset", "c1", "--scale", 0.08, "--seed", 9)
+    assert os.path.getsize(paf) > (1 << 20)
+    batches = {}
+    for thr in ("1", "5", "16"):
+        monkeypatch.setenv("AA_HOST_THREADS", thr)
+        pf = aa.read_paf(paf)
+        batches[thr] = pf.batch
+        if thr != "1":
+            for name, _ in aa.Batch.FIELDS:
+                assert np.array_equal(getattr(batches["1"], name), getattr(batches[thr], name)), (thr, name)
+        res = oracle_py.oracle_solve(pf.batch, threads=4, want_all=True)
+        pf.write(res, os.path.join(workdir, "par_out" + thr))
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        for thr in ("5", "16"):
+            assert pu.files_equal(os.path.join(workdir, "par_out1." + ext), os.path.join(workdir, "par_out" + thr + "." + ext))
+    # two malformed rows, one per half of the file: every thread count reports the first one
+    lines = open(paf).read().split("\n")
+    n = len(lines)
+    lines[n // 4] = lines[n // 4].replace("cs:Z:", "cs:Z:~", 1)
+    cols = lines[3 * n // 4].split("\t")
+    cols[2] = "x"
+    lines[3 * n // 4] = "\t".join(cols)
+    bad = os.path.join(workdir, "par_bad.paf")
+    open(bad, "w").write("\n".join(lines))
+    msgs = set()
+    for thr in ("1", "7"):
+        monkeypatch.setenv("AA_HOST_THREADS", thr)
+        with pytest.raises(aa.AlignasmError) as e:
+            aa.read_paf(bad)
+        msgs.add(str(e.value))
+    assert len(msgs) == 1 and "Unsupported operation" in msgs.pop()

@@ -151,6 +151,14 @@ struct __attribute__((aligned(16))) VState {
     int32_t cnt;
     int32_t amin_reach;  // bit 0: reaches dest; bits 1..: min anom sum to dest
 };
+// distance from a segment's upper articulation vertex to dest: added to the segment-local states
+struct __attribute__((aligned(16))) SegShift {
+    int64_t sum;
+    int32_t anom, nz, tot;
+    int32_t amin_reach;  // bit 0: the articulation vertex reaches dest; bits 1..: its min anom sum
+    int32_t pad[2];
+};
+constexpr int32_t SEG_BLOCKS = 256;
 // per edge (u,v): root of v's sidetrack heap and its key, so that a pop needs one load instead of three
 struct __attribute__((aligned(16))) ENext {
     int64_t sum;
@@ -264,6 +272,13 @@ struct Ws {
     InsKey *ins;         // [Nins] inserts of every contig, BFS order then edge order
     int32_t *root_at;    // [Vtot] heap root by BFS position
     int32_t key_bits;    // bits of the depth / preorder fields of the sort key
+    // segment-parallel relax of chain-like contigs (see f_relax_seg_warp)
+    int64_t *seg_boff;   // [C+1] first bucket (SEG_BLOCKS sorted blocks) of every contig
+    int32_t *seg_bnd;    // [TB] first articulation block of the bucket (contig-local) or -1; bucket 0 of a contig: -1
+    int32_t *seg_flag;   // [TB] the segment compared two distances that tie on (sum, anom): its result depends on the shift
+    struct SegShift *seg_shift;  // [TB] what relax_unpack adds to the segment's local distances
+    int32_t *seg_mode;   // [C] 1: vs[] holds segment-local states
+    int64_t TB;
     // level-synchronous Kahn passes for wide, shallow DAGs (dense contigs)
     int32_t *rmode;      // [C] -1: warp-per-contig Kahn passes, k >= 0: k-th contig of the level-synchronous passes
     int32_t *kl_cnt;     // [Vtot] remaining degree
@@ -816,9 +831,43 @@ AA_HDN void f_relax_init(const Ws &w, int64_t gv) {  // one vertex
     w.vs[gv] = s;
     w.cnt2[gv] = (int32_t)(w.rev_off[gv + 1] - w.rev_off[gv]);
 }
+// bucket that owns the segment of sorted block i of contig c (largest boundary <= i)
+AA_HD int64_t seg_owner(const Ws &w, int64_t c, int32_t i) {
+    const int64_t bo = w.seg_boff[c];
+    int64_t m = i / SEG_BLOCKS;
+    while (m > 0) {
+        const int32_t b = w.seg_bnd[bo + m];
+        if (b >= 0 && b <= i) break;
+        m--;
+    }
+    return bo + m;
+}
+// local state of a segment + the distance of its upper articulation vertex = the state the unsegmented pass computes
+AA_HD VState seg_compose(VState s, const SegShift &sh) {
+    if (!(s.amin_reach & 1) || !(sh.amin_reach & 1)) {
+        s.sum = 0;
+        s.anom = s.nz = s.tot = 0;
+        s.best = -1;
+        s.amin_reach = 0x3fffffff << 1;
+        return s;
+    }
+    s.sum += sh.sum;
+    s.anom += sh.anom;
+    s.nz += sh.nz;
+    s.tot += sh.tot;
+    s.amin_reach = (((s.amin_reach >> 1) + (sh.amin_reach >> 1)) << 1) | 1;
+    return s;
+}
 AA_HDN void f_relax_unpack(const Ws &w, int64_t gv) {  // one vertex: VState -> d / best
-    if (w.rmode[upper_idx(w.vtx_off, w.C, gv)] >= 0) return;  // written directly by the level-synchronous pass
-    const VState s = w.vs[gv];
+    const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (w.rmode[c] >= 0) return;  // written directly by the level-synchronous pass
+    VState s = w.vs[gv];
+    if (w.seg_mode && w.seg_mode[c]) {
+        const Ctg g = ctg_view(w, c);
+        const int32_t v = (int32_t)(gv - g.v0);
+        const int32_t blk = v < g.n ? v : v < g.n + g.P ? w.pair[g.p0 + (v - g.n)].j : v == g.src ? 0 : g.n - 1;
+        s = seg_compose(s, w.seg_shift[seg_owner(w, c, blk)]);
+    }
     D4 d;
     d.sum = s.sum;
     d.anom = s.anom;
@@ -1515,28 +1564,37 @@ __device__ __forceinline__ RevRec rrec_ld(const RevRec *p) {
     r.fl = (uint32_t)t.w;
     return r;
 }
-__device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
-    RelaxSmemC &smc = *reinterpret_cast<RelaxSmemC *>(scratch);
+struct SegRun {
+    int32_t pops;  // vertices this run finalised
+    bool clash;    // two open vertices on one table slot (or a saturated count): the run is void
+    bool tie;      // two distances tied on (sum, anom) with different qul counts: the choice depends on the shift
+};
+// One run of the reverse Kahn + relax over the vertices between two articulation blocks lo < hi (lo = -1: down to src,
+// hi = g.n: from dest).  A block that is a part of its own is an articulation vertex of the DAG: edges leave a part only
+// for the single vertices of the next part (paf_data.cpp:653-695), so every walk from an earlier part to dest passes
+// through it, the FIFO holds nothing else when it is popped, and what happens below it depends on what is above only
+// through its own distance, which shifts every distance below by the same amount.  Shifts do not change a comparison
+// of (sum, anom); they can change the mapq-ratio tie-break (paf_data.hpp:152-158), so a run in the local frame reports
+// whether it ever got that far (tie) and the sweep redoes those runs with the true distance of hi as the seed.
+// seed_scan: whole contig in one run, seeds = every vertex without out-edges (k_shortest_walks.hpp:139-141).
+__device__ SegRun relax_segment(const Ws &w, const Ctg &g, int32_t lo, int32_t hi, bool seed_scan, const VState &seed_state,
+                                RelaxSmemC &smc, int32_t *__restrict__ q) {
     RelaxSmem &sm = smc.ring;
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
-    if (w.status[c] != 0) return;
-    if (w.rmode[c] >= 0) return;  // level-synchronous pass
-    Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     VState *__restrict__ vs = w.vs + v0;
     const RevRec *__restrict__ rrec = w.rrec;
     const int64_t *__restrict__ rev_off = w.rev_off + v0;
-    int32_t *__restrict__ q = w.queue + v0;
     int32_t head = 0, tail = 0;
     for (int32_t i = lane; i < 2 * RC_SLOTS; i += 32) smc.tab[i].tag = -1;
     __syncwarp();
-    auto push = [&](bool ready, int32_t x, const VState &sx, uint32_t xa, int32_t xdeg) {
+    auto push = [&](bool ready, int32_t x, const VState &sx, uint32_t xa, int32_t xdeg, bool to_q) {
         const uint32_t m = __ballot_sync(FULL, ready);
         if (ready) {
             const int32_t pos = tail + __popc(m & ((1u << lane) - 1u));
             const int32_t s = pos & (RRING - 1);
-            q[pos] = x;
+            if (to_q) q[pos] = x;
             sm.v[s] = x;
             sm.sum[s] = sx.sum;
             sm.anom[s] = sx.anom;
@@ -1549,27 +1607,36 @@ __device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
         __syncwarp();
         tail += __popc(m);
     };
-    for (int32_t vb = 0; vb < g.V; vb += 32) {  // seeds: vertices without out-edges, ascending id
-        const int32_t v = vb + lane;
-        VState sx;
-        sx.sum = 0;
-        sx.anom = sx.nz = sx.tot = sx.best = 0;
-        sx.cnt = 1;
-        sx.amin_reach = 0;
-        int64_t xa = 0, xb = 0;
-        if (v < g.V) {
-            sx = vs[v];
-            xa = rev_off[v];
-            xb = rev_off[v + 1];
+    const bool top = hi == g.n;
+    if (seed_scan) {
+        for (int32_t vb = 0; vb < g.V; vb += 32) {
+            const int32_t v = vb + lane;
+            VState sx;
+            sx.sum = 0;
+            sx.anom = sx.nz = sx.tot = sx.best = 0;
+            sx.cnt = 1;
+            sx.amin_reach = 0;
+            int64_t xa = 0, xb = 0;
+            if (v < g.V) {
+                sx = vs[v];
+                xa = rev_off[v];
+                xb = rev_off[v + 1];
+            }
+            push(v < g.V && sx.cnt == 0, v, sx, (uint32_t)xa, (int32_t)(xb - xa), true);
         }
-        push(v < g.V && sx.cnt == 0, v, sx, (uint32_t)xa, (int32_t)(xb - xa));
+    } else {  // the vertex above the segment: dest, or the articulation vertex hi with the given state
+        const int32_t v = top ? g.dest : hi;
+        VState sx = seed_state;
+        if (top) sx = vs[v];
+        const int64_t xa = rev_off[v], xb = rev_off[v + 1];
+        push(lane == 0, v, sx, (uint32_t)xa, (int32_t)(xb - xa), top);
     }
     RevRec pre;
     pre.sum = 0;
     pre.src = 0;
     pre.fl = 0;
     int32_t pre_for = -1;  // queue position whose first 32 records are in `pre`
-    bool clash = false;
+    bool clash = false, tie = false;
     while (head < tail) {
         VState sv;
         int32_t v;
@@ -1596,9 +1663,10 @@ __device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
         if (head < tail && tail - head <= RRING) {  // records of the next pop, one pop ahead
             const int32_t s2 = head & (RRING - 1);
             const uint32_t nra = sm.ra[s2];
-            if (lane < sm.deg[s2]) pre = rrec_ld(rrec + nra + lane);
+            if (lane < sm.deg[s2] && sm.v[s2] != lo) pre = rrec_ld(rrec + nra + lane);
             pre_for = head;
         }
+        if (v == lo) continue;  // the lower articulation vertex: its in-edges belong to the next segment
         const bool vreach = (sv.amin_reach & 1) != 0;
         const int32_t av = sv.amin_reach >> 1;
         for (int64_t kb = ra; kb < rb; kb += 32) {
@@ -1647,6 +1715,8 @@ __device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
                         cur.tot = sx.tot;
                         int32_t am = sx.amin_reach >> 1;
                         const int32_t na = av + (int32_t)(r.fl & 3u);
+                        if ((sx.amin_reach & 1) && cand.sum == cur.sum && cand.anom == cur.anom && (cand.nz != cur.nz || cand.tot != cur.tot))
+                            tie = true;
                         if (!(sx.amin_reach & 1) || less4(cand, cur)) {  // strict: the first relaxer wins among equals
                             sx.sum = cand.sum;
                             sx.anom = cand.anom;
@@ -1679,16 +1749,136 @@ __device__ void f_relax_warp_cached(const Ws &w, int64_t c, void *scratch) {
                 clash = true;
                 break;
             }
-            push(ready, x, sx, xa, xdeg);
+            push(ready, x, sx, xa, xdeg, true);
         }
         if (clash) break;
     }
-    if (clash) {  // two open vertices on one slot: redo this contig with the states in global memory
-        if (lane == 0) w.status[c] = 4;
-        return;
+    SegRun out;
+    out.pops = tail - ((seed_scan || top) ? 0 : 1);
+    out.clash = clash;
+    out.tie = __any_sync(FULL, tie);
+    return out;
+}
+// the segment of one bucket: [its boundary, the next boundary of the contig)
+struct SegSpan {
+    int32_t lo, hi;     // articulation blocks (lo = -1: bottom segment, hi = n: top segment)
+    int32_t expect;     // vertices the run must finalise
+    int64_t qoff;       // its slice of the scratch queue
+    bool whole;         // the contig has no boundary
+};
+__device__ SegSpan seg_span(const Ws &w, const Ctg &g, int64_t bo, int64_t nb, int64_t m) {
+    SegSpan sp;
+    sp.lo = m == 0 ? -1 : w.seg_bnd[bo + m];
+    sp.hi = g.n;
+    for (int64_t k = m + 1; k < nb; k++) {
+        const int32_t b = w.seg_bnd[bo + k];
+        if (b >= 0) {
+            sp.hi = b;
+            break;
+        }
+    }
+    const int32_t l0 = sp.lo < 0 ? 0 : sp.lo;
+    const int64_t pl = w.pair_beg[g.b0 + l0] - g.p0, ph = w.pair_beg[g.b0 + sp.hi] - g.p0;
+    sp.expect = (sp.hi - l0) + (int32_t)(ph - pl) + (sp.lo < 0 ? 1 : 0) + (sp.hi == g.n ? 1 : 0);
+    sp.qoff = l0 + pl + (sp.lo >= 0 ? 1 : 0);
+    sp.whole = sp.lo < 0 && sp.hi == g.n;
+    return sp;
+}
+// first articulation block (a block that is a part of its own) of every bucket but the first of its contig
+__device__ void f_seg_bounds_warp(const Ws &w, int64_t bk) {
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int64_t c = upper_idx(w.seg_boff, w.C, bk);
+    const int64_t m = bk - w.seg_boff[c];
+    int32_t res = -1;
+    if (m > 0 && w.status[c] == 0 && w.rmode[c] < 0) {
+        const int64_t b0 = w.ctg_off[c];
+        const int32_t n = (int32_t)(w.ctg_off[c + 1] - b0);
+        const int32_t end = (int32_t)((m + 1) * SEG_BLOCKS) < n ? (int32_t)((m + 1) * SEG_BLOCKS) : n;
+        for (int32_t base = (int32_t)(m * SEG_BLOCKS); base < end && res < 0; base += 32) {
+            const int32_t i = base + lane;
+            const bool art = i < end && w.part_r[b0 + i] - w.part_l[b0 + i] == 1;
+            const uint32_t mk = __ballot_sync(0xffffffffu, art);
+            if (mk) res = base + (__ffs(mk) - 1);
+        }
     }
     if (lane == 0) {
-        const VState ss = vs[g.src];
+        w.seg_bnd[bk] = res;
+        w.seg_flag[bk] = 0;
+        if (m == 0) w.seg_mode[c] = 1;
+    }
+}
+// pass 1: every segment in the local frame (distance of its upper articulation vertex := 0)
+__device__ void f_relax_seg_warp(const Ws &w, int64_t bk, void *scratch) {
+    RelaxSmemC &smc = *reinterpret_cast<RelaxSmemC *>(scratch);
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int64_t c = upper_idx(w.seg_boff, w.C, bk);
+    if (w.status[c] != 0 && w.status[c] != 4) return;
+    if (w.rmode[c] >= 0) return;  // level-synchronous pass
+    const int64_t bo = w.seg_boff[c], m = bk - bo;
+    if (m > 0 && w.seg_bnd[bk] < 0) return;  // this bucket starts no segment
+    const Ctg g = ctg_view(w, c);
+    const SegSpan sp = seg_span(w, g, bo, w.seg_boff[c + 1] - bo, m);
+    VState seed;
+    seed.sum = 0;
+    seed.anom = seed.nz = seed.tot = 0;
+    seed.best = -1;
+    seed.cnt = 0;
+    seed.amin_reach = 1;
+    const SegRun run = relax_segment(w, g, sp.lo, sp.hi, sp.whole, seed, smc, w.queue + g.v0 + sp.qoff - ((sp.whole || sp.hi == g.n) ? 0 : 1));
+    if (lane == 0) {
+        if (run.clash || run.pops != sp.expect) w.status[c] = 4;  // redo the contig in one piece with the states in global memory
+        w.seg_flag[bk] = run.tie ? 1 : 0;
+    }
+}
+// pass 2, one warp per contig: from dest down, hand every segment the distance of its upper articulation vertex; a
+// segment whose run met a (sum, anom) tie is redone with that distance as the seed (its states are then global already)
+__device__ void f_relax_sweep_warp(const Ws &w, int64_t c, void *scratch) {
+    RelaxSmemC &smc = *reinterpret_cast<RelaxSmemC *>(scratch);
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    if (w.status[c] != 0) return;  // singletons; status 4 goes to the redo launch
+    if (w.rmode[c] >= 0) return;
+    const Ctg g = ctg_view(w, c);
+    const int64_t bo = w.seg_boff[c], nb = w.seg_boff[c + 1] - bo;
+    SegShift D;
+    D.sum = 0;
+    D.anom = D.nz = D.tot = 0;
+    D.amin_reach = 1;
+    D.pad[0] = D.pad[1] = 0;
+    SegShift zero = D;
+    for (int64_t m = nb - 1; m >= 0; m--) {
+        if (m > 0 && w.seg_bnd[bo + m] < 0) continue;
+        const SegSpan sp = seg_span(w, g, bo, nb, m);
+        SegShift sh = D;
+        if (sp.hi != g.n && w.seg_flag[bo + m] && (D.amin_reach & 1) && (D.nz != 0 || D.tot != 0)) {
+            VState seed;
+            seed.sum = D.sum;
+            seed.anom = D.anom;
+            seed.nz = D.nz;
+            seed.tot = D.tot;
+            seed.best = -1;
+            seed.cnt = 0;
+            seed.amin_reach = D.amin_reach;
+            const SegRun run = relax_segment(w, g, sp.lo, sp.hi, false, seed, smc, w.queue + g.v0 + sp.qoff - 1);
+            if (run.clash || run.pops != sp.expect) {
+                if (lane == 0) w.status[c] = 4;
+                return;
+            }
+            sh = zero;
+            __threadfence_block();
+            __syncwarp();
+        }
+        if (lane == 0) w.seg_shift[bo + m] = sh;
+        if (sp.lo >= 0) {
+            const VState s = seg_compose(w.vs[g.v0 + sp.lo], sh);
+            D.sum = s.sum;
+            D.anom = s.anom;
+            D.nz = s.nz;
+            D.tot = s.tot;
+            D.amin_reach = (s.amin_reach & 1) ? s.amin_reach : 0;
+        }
+    }
+    if (lane == 0) {
+        const VState ss = seg_compose(w.vs[g.v0 + g.src], w.seg_shift[bo]);
         w.anom_dis[c] = ss.amin_reach >> 1;
         if (!(ss.amin_reach & 1)) w.status[c] = 2;
     }
@@ -1709,7 +1899,10 @@ __device__ void f_relax_redo_warp(const Ws &w, int64_t c, void *scratch) {
         s.amin_reach = v == g.dest ? 1 : (0x3fffffff << 1);
         w.vs[gv] = s;
     }
-    if (lane == 0) w.status[c] = 0;
+    if (lane == 0) {
+        w.status[c] = 0;
+        w.seg_mode[c] = 0;  // vs[] will hold global states
+    }
     __threadfence_block();
     __syncwarp();
     f_relax_warp(w, c, scratch);
@@ -1753,12 +1946,38 @@ __device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
     }
 }
 #endif
-AA_HDN void f_relax_any(const Ws &w, int64_t c, void *scratch) {
+AA_HDN void f_relax_any(const Ws &w, int64_t c, void *scratch) {  // host emulation: the sequential form, whole contig
 #if defined(__CUDA_ARCH__)
-    f_relax_warp_cached(w, c, scratch);
+    f_relax_warp(w, c, scratch);
 #else
     (void)scratch;
     f_relax(w, c);
+#endif
+}
+AA_HDN void f_seg_bounds_any(const Ws &w, int64_t bk) {
+#if defined(__CUDA_ARCH__)
+    f_seg_bounds_warp(w, bk);
+#else
+    (void)w;
+    (void)bk;
+#endif
+}
+AA_HDN void f_relax_seg_any(const Ws &w, int64_t bk, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_relax_seg_warp(w, bk, scratch);
+#else
+    (void)w;
+    (void)bk;
+    (void)scratch;
+#endif
+}
+AA_HDN void f_relax_sweep_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_relax_sweep_warp(w, c, scratch);
+#else
+    (void)w;
+    (void)c;
+    (void)scratch;
 #endif
 }
 AA_HDN void f_relax_redo_any(const Ws &w, int64_t c, void *scratch) {

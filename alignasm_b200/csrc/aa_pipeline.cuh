@@ -165,6 +165,15 @@ struct FnTasksB {
 AA_CTG_FUNCTOR(FnParts, f_parts_any(w, c))
 AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnRelaxRedo, f_relax_redo_any(w, c, scratch))
+AA_CTG_FUNCTOR(FnRelaxSweep, f_relax_sweep_any(w, c, scratch))
+struct FnSegBounds {  // one bucket of SEG_BLOCKS sorted blocks
+    Ws w;
+    AA_HD void operator()(int64_t i, void *) const { f_seg_bounds_any(w, i); }
+};
+struct FnRelaxSeg {
+    Ws w;
+    AA_HD void operator()(int64_t i, void *scratch) const { f_relax_seg_any(w, i, scratch); }
+};
 AA_CTG_FUNCTOR(FnTopo, f_topo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnHeaps, f_heaps_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnEnum, f_enum_any(w, c, scratch))
@@ -562,14 +571,30 @@ struct Pipeline {
                 return AA_ERR_NOMEM;
             }
         }
+        w.seg_mode = nullptr;
+        w.TB = 0;
         if (bk.device_kahn()) {
             w.rrec = A<RevRec>(E);
             w.vs = A<VState>(Vtot);
             w.cnt2 = A<int32_t>(Vtot);
-            if (!w.rrec || !w.vs || !w.cnt2) {
+            // buckets of SEG_BLOCKS sorted blocks: the units of the segment-parallel relax
+            std::vector<int64_t> h_boff((size_t)C + 1, 0);
+            for (int64_t c = 0; c < C; c++) {
+                const int64_t n = d.h_ctg_off[(size_t)c + 1] - d.h_ctg_off[(size_t)c];
+                h_boff[(size_t)c + 1] = h_boff[(size_t)c] + (n + SEG_BLOCKS - 1) / SEG_BLOCKS;
+            }
+            w.TB = h_boff[(size_t)C];
+            w.seg_boff = A<int64_t>(C + 1);
+            w.seg_bnd = A<int32_t>(w.TB);
+            w.seg_flag = A<int32_t>(w.TB);
+            w.seg_shift = A<SegShift>(w.TB);
+            w.seg_mode = A<int32_t>(C);
+            if (!w.rrec || !w.vs || !w.cnt2 || !w.seg_boff || !w.seg_bnd || !w.seg_flag || !w.seg_shift || !w.seg_mode) {
                 err = "device allocation failed (relax records)";
                 return AA_ERR_NOMEM;
             }
+            bk.h2d(w.seg_boff, h_boff.data(), (size_t)(C + 1) * 8);
+            bk.zero(w.seg_mode, (size_t)C * 4);
         }
         bk.phase_begin(PH_RELAX);
         if (bk.device_kahn()) {
@@ -581,8 +606,15 @@ struct Pipeline {
         bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
         bk.phase_end(PH_TOPO);
         bk.side_end();
-        bk.for_each_contig("relax", C, FnRelax{w, d_ord}, bk.device_kahn() ? RELAX_SMEM_C_BYTES : RELAX_SMEM_BYTES);
-        if (bk.device_kahn()) bk.for_each_contig("relax_redo", C, FnRelaxRedo{w, d_ord}, RELAX_SMEM_BYTES);
+        if (bk.device_kahn()) {
+            // chain-like contigs are cut at articulation blocks and every segment is relaxed by its own warp
+            bk.for_each_contig("seg_bounds", w.TB, FnSegBounds{w});
+            bk.for_each_contig("relax_seg", w.TB, FnRelaxSeg{w}, RELAX_SMEM_C_BYTES);
+            bk.for_each_contig("relax_sweep", C, FnRelaxSweep{w, d_ord}, RELAX_SMEM_C_BYTES);
+            bk.for_each_contig("relax_redo", C, FnRelaxRedo{w, d_ord}, RELAX_SMEM_BYTES);
+        } else {
+            bk.for_each_contig("relax", C, FnRelax{w, d_ord}, RELAX_SMEM_BYTES);
+        }
         if (n_lm > 0) {
             if (!kahn_levels<true>(w, Vtot, n_lm)) return AA_ERR_CUDA;   // d, best, min anom of the dense contigs
             bk.for_each("kl_finish", C, FnKlFinish{w});

@@ -158,7 +158,16 @@ struct __attribute__((aligned(16))) SegShift {
     int32_t amin_reach;  // bit 0: the articulation vertex reaches dest; bits 1..: its min anom sum
     int32_t pad[2];
 };
+// one mapq-ratio tie-break of a segment run: with the true counts (N, T) of the upper articulation vertex the compare
+// cand < cur reads c0 + T * c1 + N * c2 > 0 (cross-multiplied ratios, paf_data.hpp:152-158); the run stands iff that
+// still gives `out`
+struct __attribute__((aligned(8))) SegCon {
+    int64_t c0;
+    int32_t c1, c2;
+    int32_t out, pad;
+};
 constexpr int32_t SEG_BLOCKS = 256;
+constexpr int32_t SEG_MAXCON = 16;
 // per edge (u,v): root of v's sidetrack heap and its key, so that a pop needs one load instead of three
 struct __attribute__((aligned(16))) ENext {
     int64_t sum;
@@ -275,7 +284,9 @@ struct Ws {
     // segment-parallel relax of chain-like contigs (see f_relax_seg_warp)
     int64_t *seg_boff;   // [C+1] first bucket (SEG_BLOCKS sorted blocks) of every contig
     int32_t *seg_bnd;    // [TB] first articulation block of the bucket (contig-local) or -1; bucket 0 of a contig: -1
-    int32_t *seg_flag;   // [TB] the segment compared two distances that tie on (sum, anom): its result depends on the shift
+    int32_t *seg_ncon;   // [TB] mapq-ratio tie-breaks the segment's run decided (each one a condition on the true shift)
+    struct SegCon *seg_con;  // [TB * SEG_MAXCON] those conditions
+    int32_t *seg_seed;   // [TB * 2] (qul_nonzero, qul_total) the run assumed for its upper articulation vertex
     struct SegShift *seg_shift;  // [TB] what relax_unpack adds to the segment's local distances
     int32_t *seg_mode;   // [C] 1: vs[] holds segment-local states
     int64_t TB;
@@ -1578,7 +1589,7 @@ struct SegRun {
 // whether it ever got that far (tie) and the sweep redoes those runs with the true distance of hi as the seed.
 // seed_scan: whole contig in one run, seeds = every vertex without out-edges (k_shortest_walks.hpp:139-141).
 __device__ SegRun relax_segment(const Ws &w, const Ctg &g, int32_t lo, int32_t hi, bool seed_scan, const VState &seed_state,
-                                RelaxSmemC &smc, int32_t *__restrict__ q) {
+                                RelaxSmemC &smc, int32_t *__restrict__ q, int64_t rec_bucket) {
     RelaxSmem &sm = smc.ring;
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
@@ -1715,9 +1726,25 @@ __device__ SegRun relax_segment(const Ws &w, const Ctg &g, int32_t lo, int32_t h
                         cur.tot = sx.tot;
                         int32_t am = sx.amin_reach >> 1;
                         const int32_t na = av + (int32_t)(r.fl & 3u);
-                        if ((sx.amin_reach & 1) && cand.sum == cur.sum && cand.anom == cur.anom && (cand.nz != cur.nz || cand.tot != cur.tot))
+                        const bool lt = !(sx.amin_reach & 1) || less4(cand, cur);
+                        if ((sx.amin_reach & 1) && cand.sum == cur.sum && cand.anom == cur.anom && (cand.nz != cur.nz || cand.tot != cur.tot)) {
                             tie = true;
-                        if (!(sx.amin_reach & 1) || less4(cand, cur)) {  // strict: the first relaxer wins among equals
+                            if (rec_bucket >= 0) {  // the outcome as a condition on the counts of the seed
+                                const int32_t slot = atomicAdd(w.seg_ncon + rec_bucket, 1);
+                                if (slot < SEG_MAXCON) {
+                                    const int64_t anz = cand.nz - seed_state.nz, atot = cand.tot - seed_state.tot;
+                                    const int64_t bnz = cur.nz - seed_state.nz, btot = cur.tot - seed_state.tot;
+                                    SegCon sc;
+                                    sc.c0 = anz * btot - bnz * atot;
+                                    sc.c1 = (int32_t)(anz - bnz);
+                                    sc.c2 = (int32_t)(btot - atot);
+                                    sc.out = lt ? 1 : 0;
+                                    sc.pad = 0;
+                                    w.seg_con[rec_bucket * SEG_MAXCON + slot] = sc;
+                                }
+                            }
+                        }
+                        if (lt) {  // strict: the first relaxer wins among equals
                             sx.sum = cand.sum;
                             sx.anom = cand.anom;
                             sx.nz = cand.nz;
@@ -1803,7 +1830,7 @@ __device__ void f_seg_bounds_warp(const Ws &w, int64_t bk) {
     }
     if (lane == 0) {
         w.seg_bnd[bk] = res;
-        w.seg_flag[bk] = 0;
+        w.seg_ncon[bk] = 0;
         if (m == 0) w.seg_mode[c] = 1;
     }
 }
@@ -1818,20 +1845,28 @@ __device__ void f_relax_seg_warp(const Ws &w, int64_t bk, void *scratch) {
     if (m > 0 && w.seg_bnd[bk] < 0) return;  // this bucket starts no segment
     const Ctg g = ctg_view(w, c);
     const SegSpan sp = seg_span(w, g, bo, w.seg_boff[c + 1] - bo, m);
+    // The run assumes plausible qul counts for its upper articulation vertex (about 5/8 hop per block above it, 5/7 of
+    // them with mapq != 0), so that most ratio tie-breaks come out as they will with the true counts; every one of them
+    // is recorded and checked by the sweep.
+    const bool local = !(sp.whole || sp.hi == g.n);
     VState seed;
     seed.sum = 0;
-    seed.anom = seed.nz = seed.tot = 0;
+    seed.anom = 0;
+    seed.tot = local ? 1 + (int32_t)(((int64_t)(g.n - sp.hi) * 5) >> 3) : 0;
+    seed.nz = local ? (int32_t)(((int64_t)seed.tot * 5) / 7) : 0;
     seed.best = -1;
     seed.cnt = 0;
     seed.amin_reach = 1;
-    const SegRun run = relax_segment(w, g, sp.lo, sp.hi, sp.whole, seed, smc, w.queue + g.v0 + sp.qoff - ((sp.whole || sp.hi == g.n) ? 0 : 1));
+    const SegRun run = relax_segment(w, g, sp.lo, sp.hi, sp.whole, seed, smc, w.queue + g.v0 + sp.qoff - (local ? 1 : 0), local ? bk : -1);
     if (lane == 0) {
         if (run.clash || run.pops != sp.expect) w.status[c] = 4;  // redo the contig in one piece with the states in global memory
-        w.seg_flag[bk] = run.tie ? 1 : 0;
+        w.seg_seed[2 * bk] = seed.nz;
+        w.seg_seed[2 * bk + 1] = seed.tot;
     }
 }
 // pass 2, one warp per contig: from dest down, hand every segment the distance of its upper articulation vertex; a
-// segment whose run met a (sum, anom) tie is redone with that distance as the seed (its states are then global already)
+// segment whose recorded tie-breaks do not all stand with the true counts is redone with that distance as the seed (its
+// states are then global already)
 __device__ void f_relax_sweep_warp(const Ws &w, int64_t c, void *scratch) {
     RelaxSmemC &smc = *reinterpret_cast<RelaxSmemC *>(scratch);
     const int32_t lane = (int32_t)(threadIdx.x & 31);
@@ -1848,8 +1883,21 @@ __device__ void f_relax_sweep_warp(const Ws &w, int64_t c, void *scratch) {
     for (int64_t m = nb - 1; m >= 0; m--) {
         if (m > 0 && w.seg_bnd[bo + m] < 0) continue;
         const SegSpan sp = seg_span(w, g, bo, nb, m);
-        SegShift sh = D;
-        if (sp.hi != g.n && w.seg_flag[bo + m] && (D.amin_reach & 1) && (D.nz != 0 || D.tot != 0)) {
+        SegShift sh = D;  // states of the run + sh = global states
+        sh.nz -= w.seg_seed[2 * (bo + m)];
+        sh.tot -= w.seg_seed[2 * (bo + m) + 1];
+        const int32_t ncon = sp.hi != g.n ? w.seg_ncon[bo + m] : 0;
+        bool stands = true;
+        if (ncon > 0 && (D.amin_reach & 1)) {  // do the recorded tie-breaks come out the same with the true counts?
+            stands = ncon <= SEG_MAXCON && D.tot >= 1;
+            for (int32_t k = lane; stands && k < ncon; k += 32) {
+                const SegCon sc = w.seg_con[(bo + m) * SEG_MAXCON + k];
+                const int64_t L = sc.c0 + (int64_t)D.tot * sc.c1 + (int64_t)D.nz * sc.c2;
+                if ((L > 0) != (sc.out != 0)) stands = false;
+            }
+            stands = __all_sync(0xffffffffu, stands);
+        }
+        if (!stands) {
             VState seed;
             seed.sum = D.sum;
             seed.anom = D.anom;
@@ -1858,7 +1906,7 @@ __device__ void f_relax_sweep_warp(const Ws &w, int64_t c, void *scratch) {
             seed.best = -1;
             seed.cnt = 0;
             seed.amin_reach = D.amin_reach;
-            const SegRun run = relax_segment(w, g, sp.lo, sp.hi, false, seed, smc, w.queue + g.v0 + sp.qoff - 1);
+            const SegRun run = relax_segment(w, g, sp.lo, sp.hi, false, seed, smc, w.queue + g.v0 + sp.qoff - 1, -1);
             if (run.clash || run.pops != sp.expect) {
                 if (lane == 0) w.status[c] = 4;
                 return;

@@ -573,12 +573,13 @@ struct Pipeline {
         }
         w.seg_mode = nullptr;
         w.TB = 0;
+        std::vector<int64_t> h_boff;
         if (bk.device_kahn()) {
             w.rrec = A<RevRec>(E);
             w.vs = A<VState>(Vtot);
             w.cnt2 = A<int32_t>(Vtot);
             // buckets of SEG_BLOCKS sorted blocks: the units of the segment-parallel relax
-            std::vector<int64_t> h_boff((size_t)C + 1, 0);
+            h_boff.assign((size_t)C + 1, 0);
             for (int64_t c = 0; c < C; c++) {
                 const int64_t n = d.h_ctg_off[(size_t)c + 1] - d.h_ctg_off[(size_t)c];
                 h_boff[(size_t)c + 1] = h_boff[(size_t)c] + (n + SEG_BLOCKS - 1) / SEG_BLOCKS;
@@ -586,10 +587,12 @@ struct Pipeline {
             w.TB = h_boff[(size_t)C];
             w.seg_boff = A<int64_t>(C + 1);
             w.seg_bnd = A<int32_t>(w.TB);
-            w.seg_flag = A<int32_t>(w.TB);
+            w.seg_ncon = A<int32_t>(w.TB);
+            w.seg_con = A<SegCon>(w.TB * SEG_MAXCON);
+            w.seg_seed = A<int32_t>(w.TB * 2);
             w.seg_shift = A<SegShift>(w.TB);
             w.seg_mode = A<int32_t>(C);
-            if (!w.rrec || !w.vs || !w.cnt2 || !w.seg_boff || !w.seg_bnd || !w.seg_flag || !w.seg_shift || !w.seg_mode) {
+            if (!w.rrec || !w.vs || !w.cnt2 || !w.seg_boff || !w.seg_bnd || !w.seg_ncon || !w.seg_con || !w.seg_seed || !w.seg_shift || !w.seg_mode) {
                 err = "device allocation failed (relax records)";
                 return AA_ERR_NOMEM;
             }
@@ -612,6 +615,26 @@ struct Pipeline {
             bk.for_each_contig("relax_seg", w.TB, FnRelaxSeg{w}, RELAX_SMEM_C_BYTES);
             bk.for_each_contig("relax_sweep", C, FnRelaxSweep{w, d_ord}, RELAX_SMEM_C_BYTES);
             bk.for_each_contig("relax_redo", C, FnRelaxRedo{w, d_ord}, RELAX_SMEM_BYTES);
+            if (std::getenv("AA_SEG_DEBUG")) {
+                std::vector<int32_t> hb((size_t)w.TB), hf((size_t)w.TB);
+                bk.d2h(hb.data(), w.seg_bnd, (size_t)w.TB * 4);
+                bk.d2h(hf.data(), w.seg_ncon, (size_t)w.TB * 4);
+                int64_t nseg = 0, nflag = 0;
+                for (int64_t i = 0; i < w.TB; i++) {
+                    nflag += hf[(size_t)i] != 0;
+                }
+                for (int64_t c = 0; c < C; c++)
+                    for (int64_t m = 0; m < h_boff[(size_t)c + 1] - h_boff[(size_t)c]; m++)
+                        nseg += (m == 0 || hb[(size_t)(h_boff[(size_t)c] + m)] >= 0);
+                const int64_t cb = ctg_order[0];
+                int64_t bs = 0, bf = 0;
+                for (int64_t m = 0; m < h_boff[(size_t)cb + 1] - h_boff[(size_t)cb]; m++) {
+                    bs += (m == 0 || hb[(size_t)(h_boff[(size_t)cb] + m)] >= 0);
+                    bf += hf[(size_t)(h_boff[(size_t)cb] + m)] != 0;
+                }
+                std::fprintf(stderr, "[aa_seg] buckets %lld segments %lld flagged %lld | largest contig: segments %lld flagged %lld\n",
+                             (long long)w.TB, (long long)nseg, (long long)nflag, (long long)bs, (long long)bf);
+            }
         } else {
             bk.for_each_contig("relax", C, FnRelax{w, d_ord}, RELAX_SMEM_BYTES);
         }

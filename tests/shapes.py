@@ -11,5 +11,8 @@ SMALL = {
     "singletons": (["--contigs", 50, "--blocks", 2, "--sd", 2, "--seed", 14, "--lmin", 500, "--lmax", 5000], [False]),
     "dense200": (["--preset", "c4", "--n", 200], [False, True]),
     "dense400": (["--preset", "c4", "--n", 400], [False, True]),
+    # contigs of several buckets of 256 blocks: the segment-parallel relax (articulation blocks, tie-break conditions, sweep)
+    "segments": (["--contigs", 6, "--blocks", 1500, "--sd", 300, "--p_dup", 0.1, "--p_trans", 0.1, "--p_inv", 0.1, "--seed", 31], [False, True]),
+    "segments_long": (["--contigs", 3, "--blocks", 5000, "--sd", 1500, "--p_trans", 0.01, "--p_inv", 0.01, "--seed", 32], [False, True]),
     "cancer_small": (["--preset", "c3", "--scale", 0.004], [False]),
 }

@@ -289,6 +289,7 @@ struct Ws {
     int32_t *seg_seed;   // [TB * 2] (qul_nonzero, qul_total) the run assumed for its upper articulation vertex
     struct SegShift *seg_shift;  // [TB] what relax_unpack adds to the segment's local distances
     int32_t *seg_mode;   // [C] 1: vs[] holds segment-local states
+    int32_t *topo_redo;  // [C] 1: the segmented forward pass did not cover the contig, redo it in one piece
     int64_t TB;
     // level-synchronous Kahn passes for wide, shallow DAGs (dense contigs)
     int32_t *rmode;      // [C] -1: warp-per-contig Kahn passes, k >= 0: k-th contig of the level-synchronous passes
@@ -1993,7 +1994,88 @@ __device__ void f_topo_warp(const Ws &w, int64_t c, void *scratch) {
         }
     }
 }
+// forward Kahn order, one warp per segment: an articulation block is alone in the FIFO when it is popped in this direction
+// as well (every earlier vertex has a walk to it, so all of them are popped before it becomes ready), which makes the order
+// below and above it independent; positions are local pop numbers + the number of vertices before the segment
+__device__ void f_topo_seg_warp(const Ws &w, int64_t bk, void *scratch) {
+    KahnSmem &sm = *reinterpret_cast<KahnSmem *>(scratch);
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const int64_t c = upper_idx(w.seg_boff, w.C, bk);
+    if (w.status[c] == 1) return;
+    if (w.rmode[c] >= 0) return;  // level-synchronous pass
+    const int64_t bo = w.seg_boff[c], m = bk - bo;
+    if (m > 0 && w.seg_bnd[bk] < 0) return;  // this bucket starts no segment
+    const Ctg g = ctg_view(w, c);
+    const SegSpan sp = seg_span(w, g, bo, w.seg_boff[c + 1] - bo, m);
+    const int64_t v0 = g.v0;
+    const int32_t base = sp.lo < 0 ? 0 : (int32_t)sp.qoff;  // src, the blocks before lo and their pair vertices
+    int32_t *__restrict__ cnt = w.cnt2 + v0;
+    const int64_t *__restrict__ eoff = w.eoff + v0;
+    const Edge *__restrict__ edge = w.edge;
+    int32_t *__restrict__ q = w.topo + v0 + base;
+    int32_t *__restrict__ order = w.order + v0;
+    const int32_t stop = sp.hi == g.n ? -1 : sp.hi;  // popped here, numbered and expanded by the segment it starts
+    int32_t head = 0, tail = 0;
+    if (sp.whole) {
+        for (int32_t vb = 0; vb < g.V; vb += 32) {
+            const int32_t v = vb + lane;
+            tail = kahn_push(sm, q, tail, v < g.V && cnt[v] == 0, v);
+        }
+    } else {
+        tail = kahn_push(sm, q, tail, lane == 0, sp.lo < 0 ? g.src : sp.lo);
+    }
+    while (head < tail) {
+        const int32_t u = kahn_pop(sm, q, head, tail);
+        if (u == stop) {
+            head++;
+            continue;
+        }
+        if (lane == 0) order[u] = base + head;
+        head++;
+        const int64_t ea = eoff[u], eb = eoff[u + 1];
+        for (int64_t kb = ea; kb < eb; kb += 32) {
+            const int64_t k = kb + lane;
+            bool ready = false;
+            int32_t x = 0;
+            if (k < eb) {
+                x = e_dst(edge[k]);
+                const int32_t left = cnt[x] - 1;  // out-edges of u have distinct heads: no conflict inside the warp
+                cnt[x] = left;
+                ready = left == 0;
+            }
+            tail = kahn_push(sm, q, tail, ready, x);
+        }
+    }
+    if (lane == 0 && tail - (stop >= 0 ? 1 : 0) != sp.expect) w.topo_redo[c] = 1;
+}
+__device__ void f_topo_redo_warp(const Ws &w, int64_t c, void *scratch) {
+    if (!w.topo_redo[c]) return;
+    const int32_t lane = (int32_t)(threadIdx.x & 31);
+    const Ctg g = ctg_view(w, c);
+    for (int32_t v = lane; v < g.V; v += 32) w.cnt2[g.v0 + v] = (int32_t)(w.rev_off[g.v0 + v + 1] - w.rev_off[g.v0 + v]);
+    __threadfence_block();
+    __syncwarp();
+    f_topo_warp(w, c, scratch);
+}
 #endif
+AA_HDN void f_topo_seg_any(const Ws &w, int64_t bk, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_topo_seg_warp(w, bk, scratch);
+#else
+    (void)w;
+    (void)bk;
+    (void)scratch;
+#endif
+}
+AA_HDN void f_topo_redo_any(const Ws &w, int64_t c, void *scratch) {
+#if defined(__CUDA_ARCH__)
+    f_topo_redo_warp(w, c, scratch);
+#else
+    (void)w;
+    (void)c;
+    (void)scratch;
+#endif
+}
 AA_HDN void f_relax_any(const Ws &w, int64_t c, void *scratch) {  // host emulation: the sequential form, whole contig
 #if defined(__CUDA_ARCH__)
     f_relax_warp(w, c, scratch);

@@ -170,6 +170,11 @@ struct FnSegBounds {  // one bucket of SEG_BLOCKS sorted blocks
     Ws w;
     AA_HD void operator()(int64_t i, void *) const { f_seg_bounds_any(w, i); }
 };
+struct FnTopoSeg {
+    Ws w;
+    AA_HD void operator()(int64_t i, void *scratch) const { f_topo_seg_any(w, i, scratch); }
+};
+AA_CTG_FUNCTOR(FnTopoRedo, f_topo_redo_any(w, c, scratch))
 struct FnRelaxSeg {
     Ws w;
     AA_HD void operator()(int64_t i, void *scratch) const { f_relax_seg_any(w, i, scratch); }
@@ -592,26 +597,33 @@ struct Pipeline {
             w.seg_seed = A<int32_t>(w.TB * 2);
             w.seg_shift = A<SegShift>(w.TB);
             w.seg_mode = A<int32_t>(C);
-            if (!w.rrec || !w.vs || !w.cnt2 || !w.seg_boff || !w.seg_bnd || !w.seg_ncon || !w.seg_con || !w.seg_seed || !w.seg_shift || !w.seg_mode) {
+            w.topo_redo = A<int32_t>(C);
+            if (!w.rrec || !w.vs || !w.cnt2 || !w.seg_boff || !w.seg_bnd || !w.seg_ncon || !w.seg_con || !w.seg_seed || !w.seg_shift || !w.seg_mode || !w.topo_redo) {
                 err = "device allocation failed (relax records)";
                 return AA_ERR_NOMEM;
             }
             bk.h2d(w.seg_boff, h_boff.data(), (size_t)(C + 1) * 8);
             bk.zero(w.seg_mode, (size_t)C * 4);
+            bk.zero(w.topo_redo, (size_t)C * 4);
         }
         bk.phase_begin(PH_RELAX);
         if (bk.device_kahn()) {
             bk.for_each("rev_pack", E, FnRevPack{w});
             bk.for_each("relax_init", Vtot, FnRelaxInit{w});
         }
+        // chain-like contigs are cut at articulation blocks; every segment is ordered / relaxed by its own warp
+        if (bk.device_kahn()) bk.for_each_contig("seg_bounds", w.TB, FnSegBounds{w});
         bk.side_begin();
         bk.phase_begin(PH_TOPO);
-        bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
+        if (bk.device_kahn()) {
+            bk.for_each_contig("topo_seg", w.TB, FnTopoSeg{w}, KAHN_SMEM_BYTES);
+            bk.for_each_contig("topo_redo", C, FnTopoRedo{w, d_ord}, KAHN_SMEM_BYTES);
+        } else {
+            bk.for_each_contig("topo", C, FnTopo{w, d_ord}, KAHN_SMEM_BYTES);
+        }
         bk.phase_end(PH_TOPO);
         bk.side_end();
         if (bk.device_kahn()) {
-            // chain-like contigs are cut at articulation blocks and every segment is relaxed by its own warp
-            bk.for_each_contig("seg_bounds", w.TB, FnSegBounds{w});
             bk.for_each_contig("relax_seg", w.TB, FnRelaxSeg{w}, RELAX_SMEM_C_BYTES);
             bk.for_each_contig("relax_sweep", C, FnRelaxSweep{w, d_ord}, RELAX_SMEM_C_BYTES);
             bk.for_each_contig("relax_redo", C, FnRelaxRedo{w, d_ord}, RELAX_SMEM_BYTES);

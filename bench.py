@@ -260,7 +260,7 @@ def main():
             t2 = time.perf_counter()
             pf2 = aa.read_paf(paf)
             t3 = time.perf_counter()
-            r = solver.solve(pf2.batch, want_all=True)
+            r = solver.solve(pf2.batch)
             t4 = time.perf_counter()
             pf2.write(r, os.path.join(tmp, "cli_out"))
             t5 = time.perf_counter()
@@ -269,7 +269,8 @@ def main():
             pf2.close()
             cli = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": batch.n_blk / (t5 - t2),
                    "paf_bytes": os.path.getsize(paf), "out_bytes": out_bytes, "host_threads": os.cpu_count(),
-                   "note": "aa_paf_read + aa_solve(want_all) + aa_paf_write as the alignasm CLI chains them; process and CUDA start-up excluded"}
+                   "note": "aa_paf_read + aa_solve + aa_paf_write as `alignasm --no_all` chains them (the .aln.all.paf of this workload, every tied "
+                           "max-coverage walk of every contig, is 25.7 GB and is left out); process and CUDA start-up excluded"}
 
         # max over ranks
         tv = torch.tensor([wall, wall_e2e, ev_ms / 1e3], dtype=torch.float64, device="cuda")
@@ -291,7 +292,7 @@ def main():
         achieved = algo / (ph[dom] * 1e-3) / 1e9 if ph[dom] > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and a.workload == "c2":  # the ncu capture is of this workload
             try:
                 traffic = json.load(open(tpath)).get(names[dom])
             except ValueError:

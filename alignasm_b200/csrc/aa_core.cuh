@@ -1832,7 +1832,7 @@ __device__ void f_seg_bounds_warp(const Ws &w, int64_t bk) {
     if (lane == 0) {
         w.seg_bnd[bk] = res;
         w.seg_ncon[bk] = 0;
-        if (m == 0) w.seg_mode[c] = 1;
+        if (m == 0) w.seg_mode[c] = (w.status[c] == 0 && w.rmode[c] < 0) ? 1 : 0;  // singletons keep their initial states
     }
 }
 // pass 1: every segment in the local frame (distance of its upper articulation vertex := 0)

@@ -357,6 +357,61 @@ struct CudaBackend {
         pieces.clear();
         staged_bytes = 0;
     }
+    // ---- staged download (result rows): asynchronous copies into the pinned buffer, one synchronisation, then a parallel
+    // memcpy into the caller's (fresh, pageable) arrays: their pages are first touched by all host threads
+    std::vector<Piece> dpieces;
+    size_t dstaged_bytes = 0;
+    void stage_d2h(void *h, const void *d, size_t n) {
+        if (!n) return;
+        dpieces.push_back({h, d, n, dstaged_bytes});
+        dstaged_bytes += (n + 255) & ~(size_t)255;
+    }
+    void flush_d2h() {
+        if (failed || dpieces.empty()) {
+            dpieces.clear();
+            dstaged_bytes = 0;
+            return;
+        }
+        if (dstaged_bytes > pinned_cap) {
+            AA_CUDA(cudaStreamSynchronize(stream));  // the upload of this solve may still read the old buffer
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr;
+            pinned_cap = 0;
+            const size_t want = dstaged_bytes + dstaged_bytes / 4;
+            if (cudaHostAlloc((void **)&pinned, want, cudaHostAllocDefault) == cudaSuccess) pinned_cap = want;
+            else cudaGetLastError();
+        }
+        if (!pinned) {
+            for (auto &p : dpieces) d2h(p.dst, p.src, p.n);
+        } else {
+            for (auto &p : dpieces) AA_CUDA(cudaMemcpyAsync(pinned + p.off, p.src, p.n, cudaMemcpyDeviceToHost, stream));
+            AA_CUDA(cudaStreamSynchronize(stream));
+            const size_t CH = (size_t)2 << 20;
+            struct Item {
+                char *d;
+                const char *s;
+                size_t n;
+            };
+            std::vector<Item> items;
+            for (auto &p : dpieces)
+                for (size_t o = 0; o < p.n; o += CH) items.push_back({(char *)p.dst + o, pinned + p.off + o, std::min(CH, p.n - o)});
+            const int nt = (int)std::min<size_t>((size_t)std::min(host_threads(), 8), items.size());
+            std::atomic<size_t> next{0};
+            auto work = [&]() {
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= items.size()) break;
+                    std::memcpy(items[i].d, items[i].s, items[i].n);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nt; t++) pool.emplace_back(work);
+            work();
+            for (auto &t : pool) t.join();
+        }
+        dpieces.clear();
+        dstaged_bytes = 0;
+    }
     void h2d(void *d, const void *h, size_t n) {
         if (n && !failed) AA_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream));
     }

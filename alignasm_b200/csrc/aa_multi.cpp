@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -53,6 +54,18 @@ struct Shard {
 };
 
 void build_shard(const aa_batch *b, Shard &s) {
+    int64_t nb = 0, nr = 0;
+    for (int64_t c : s.ctgs) {
+        nb += b->ctg_off[c + 1] - b->ctg_off[c];
+        nr += b->run_off[b->ctg_off[c + 1]] - b->run_off[b->ctg_off[c]];
+    }
+    for (auto *v : {&s.qs, &s.qe, &s.rs, &s.re, &s.qt}) v->reserve((size_t)nb);
+    for (auto *v : {&s.ql, &s.qr, &s.rl}) v->reserve((size_t)nr);
+    s.chr.reserve((size_t)nb);
+    s.fwd.reserve((size_t)nb);
+    s.mq.reserve((size_t)nb);
+    s.run_off.reserve((size_t)nb + 1);
+    s.ctg_off.reserve(s.ctgs.size() + 1);
     s.ctg_off.push_back(0);
     s.run_off.push_back(0);
     for (int64_t c : s.ctgs) {
@@ -98,14 +111,18 @@ template <class T>
 T *host_n(int64_t n) {
     return (T *)std::calloc((size_t)(n > 0 ? n : 1), sizeof(T));
 }
+template <class T>
+T *host_raw(int64_t n) {  // every element is written by the merge
+    return (T *)std::malloc((size_t)(n > 0 ? n : 1) * sizeof(T));
+}
 void rows_alloc(aa_rows &r, int64_t n) {
     r.n = n;
-    r.ctg_index = host_n<int32_t>(n);
-    r.qry_str = host_n<int64_t>(n);
-    r.qry_end = host_n<int64_t>(n);
-    r.ref_str = host_n<int64_t>(n);
-    r.ref_end = host_n<int64_t>(n);
-    r.is_alt = host_n<uint8_t>(n);
+    r.ctg_index = host_raw<int32_t>(n);
+    r.qry_str = host_raw<int64_t>(n);
+    r.qry_end = host_raw<int64_t>(n);
+    r.ref_str = host_raw<int64_t>(n);
+    r.ref_end = host_raw<int64_t>(n);
+    r.is_alt = host_raw<uint8_t>(n);
 }
 void rows_copy(aa_rows &dst, int64_t at, const aa_rows &src, int64_t from, int64_t n) {
     if (n <= 0) return;
@@ -202,7 +219,7 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
     res->out_off = host_n<int64_t>(C + 1);
     res->alt_off = host_n<int64_t>(C + 1);
     res->all_path_off = host_n<int64_t>(C + 1);
-    res->sorted_index = host_n<int32_t>(b->n_blk);
+    res->sorted_index = host_raw<int32_t>(b->n_blk);
     std::vector<int64_t> local((size_t)C);  // position of every contig inside its shard
     for (auto &s : sh)
         for (size_t i = 0; i < s.ctgs.size(); i++) local[(size_t)s.ctgs[i]] = (int64_t)i;
@@ -223,21 +240,43 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
     rows_alloc(res->out, n_out);
     rows_alloc(res->alt, n_alt);
     rows_alloc(res->all, n_all);
-    int64_t at_all = 0, at_path = 0;
+    // where the .all paths / rows of every contig start (sequential, cheap), then the copies on several host threads
+    std::vector<int64_t> all_at((size_t)C + 1, 0);
     for (int64_t c = 0; c < C; c++) {
-        const Shard &s = sh[(size_t)shard_of[(size_t)c]];
-        const aa_result &r = s.res;
-        const int64_t l = local[(size_t)c];
-        rows_copy(res->out, res->out_off[c], r.out, r.out_off[l], r.out_off[l + 1] - r.out_off[l]);
-        rows_copy(res->alt, res->alt_off[c], r.alt, r.alt_off[l], r.alt_off[l + 1] - r.alt_off[l]);
-        for (int64_t p = r.all_path_off[l]; p < r.all_path_off[l + 1]; p++) {
-            const int64_t n = r.all_row_off[p + 1] - r.all_row_off[p];
-            rows_copy(res->all, at_all, r.all, r.all_row_off[p], n);
-            at_all += n;
-            res->all_row_off[++at_path] = at_all;
-        }
-        const int64_t nb = b->ctg_off[c + 1] - b->ctg_off[c];
-        std::memcpy(res->sorted_index + b->ctg_off[c], r.sorted_index + s.ctg_off[(size_t)l], (size_t)nb * 4);
+        const aa_result &r = sh[(size_t)shard_of[(size_t)c]].res;
+        const int64_t l = local[(size_t)c], p0 = r.all_path_off[l], p1 = r.all_path_off[l + 1];
+        all_at[(size_t)c + 1] = all_at[(size_t)c] + (r.all_row_off[p1] - r.all_row_off[p0]);
+    }
+    {
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 16, C}));
+        std::atomic<int64_t> next{0};
+        auto work = [&]() {
+            const int64_t CH = 16;
+            for (;;) {
+                const int64_t c0 = next.fetch_add(CH);
+                if (c0 >= C) break;
+                for (int64_t c = c0; c < std::min(C, c0 + CH); c++) {
+                    const Shard &s = sh[(size_t)shard_of[(size_t)c]];
+                    const aa_result &r = s.res;
+                    const int64_t l = local[(size_t)c];
+                    rows_copy(res->out, res->out_off[c], r.out, r.out_off[l], r.out_off[l + 1] - r.out_off[l]);
+                    rows_copy(res->alt, res->alt_off[c], r.alt, r.alt_off[l], r.alt_off[l + 1] - r.alt_off[l]);
+                    int64_t at_all = all_at[(size_t)c], at_path = res->all_path_off[c];
+                    for (int64_t p = r.all_path_off[l]; p < r.all_path_off[l + 1]; p++) {
+                        const int64_t n = r.all_row_off[p + 1] - r.all_row_off[p];
+                        rows_copy(res->all, at_all, r.all, r.all_row_off[p], n);
+                        at_all += n;
+                        res->all_row_off[++at_path] = at_all;
+                    }
+                    const int64_t nb = b->ctg_off[c + 1] - b->ctg_off[c];
+                    std::memcpy(res->sorted_index + b->ctg_off[c], r.sorted_index + s.ctg_off[(size_t)l], (size_t)nb * 4);
+                }
+            }
+        };
+        std::vector<std::thread> mpool;
+        for (int t = 1; t < nt; t++) mpool.emplace_back(work);
+        work();
+        for (auto &t : mpool) t.join();
     }
     // statistics: sizes add up, times are the slowest shard's
     aa_stats &t = res->stats;

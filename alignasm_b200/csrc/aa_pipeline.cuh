@@ -1038,14 +1038,15 @@ struct Pipeline {
             for (int k = 0; k < 3; k++) {
                 rows_alloc_host(*dst[k], nrow[k]);
                 if (nrow[k] > 0) {
-                    bk.d2h(dst[k]->ctg_index, w.r_idx[k], (size_t)nrow[k] * 4);
-                    bk.d2h(dst[k]->qry_str, w.r_qs[k], (size_t)nrow[k] * 8);
-                    bk.d2h(dst[k]->qry_end, w.r_qe[k], (size_t)nrow[k] * 8);
-                    bk.d2h(dst[k]->ref_str, w.r_rs[k], (size_t)nrow[k] * 8);
-                    bk.d2h(dst[k]->ref_end, w.r_re[k], (size_t)nrow[k] * 8);
-                    bk.d2h(dst[k]->is_alt, w.r_alt[k], (size_t)nrow[k]);
+                    bk.stage_d2h(dst[k]->ctg_index, w.r_idx[k], (size_t)nrow[k] * 4);
+                    bk.stage_d2h(dst[k]->qry_str, w.r_qs[k], (size_t)nrow[k] * 8);
+                    bk.stage_d2h(dst[k]->qry_end, w.r_qe[k], (size_t)nrow[k] * 8);
+                    bk.stage_d2h(dst[k]->ref_str, w.r_rs[k], (size_t)nrow[k] * 8);
+                    bk.stage_d2h(dst[k]->ref_end, w.r_re[k], (size_t)nrow[k] * 8);
+                    bk.stage_d2h(dst[k]->is_alt, w.r_alt[k], (size_t)nrow[k]);
                 }
             }
+            bk.flush_d2h();
             if (opt.keep_debug) download_debug(w, res, h_status, h_voff, h_nwalk, E, Vtot);
         }
         bk.phase_end(PH_D2H);

@@ -33,6 +33,8 @@ struct HostBackend {
     void stage(void *d, const void *h, size_t n) { std::memcpy(d, h, n); }
     void flush_staged() {}
     void d2h(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
+    void stage_d2h(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
+    void flush_d2h() {}
     void zero(void *p, size_t n) { std::memset(p, 0, n); }
     void sync() {}
     template <class F>

@@ -289,6 +289,8 @@ struct Ws {
     int32_t *seg_seed;   // [TB * 2] (qul_nonzero, qul_total) the run assumed for its upper articulation vertex
     struct SegShift *seg_shift;  // [TB] what relax_unpack adds to the segment's local distances
     int32_t *seg_mode;   // [C] 1: vs[] holds segment-local states
+    int32_t seg_guess;   // test knob (AA_SEG_GUESS): 0 = plausible counts, 1 = (0, 1): most tie-break conditions then fail and
+                         // the sweep's redo path runs, 2 = also refuse every condition (every tied segment is redone)
     int32_t *topo_redo;  // [C] 1: the segmented forward pass did not cover the contig, redo it in one piece
     int64_t TB;
     // level-synchronous Kahn passes for wide, shallow DAGs (dense contigs)
@@ -1855,6 +1857,10 @@ __device__ void f_relax_seg_warp(const Ws &w, int64_t bk, void *scratch) {
     seed.anom = 0;
     seed.tot = local ? 1 + (int32_t)(((int64_t)(g.n - sp.hi) * 5) >> 3) : 0;
     seed.nz = local ? (int32_t)(((int64_t)seed.tot * 5) / 7) : 0;
+    if (local && w.seg_guess) {
+        seed.tot = 1;
+        seed.nz = 0;
+    }
     seed.best = -1;
     seed.cnt = 0;
     seed.amin_reach = 1;
@@ -1890,7 +1896,7 @@ __device__ void f_relax_sweep_warp(const Ws &w, int64_t c, void *scratch) {
         const int32_t ncon = sp.hi != g.n ? w.seg_ncon[bo + m] : 0;
         bool stands = true;
         if (ncon > 0 && (D.amin_reach & 1)) {  // do the recorded tie-breaks come out the same with the true counts?
-            stands = ncon <= SEG_MAXCON && D.tot >= 1;
+            stands = ncon <= SEG_MAXCON && D.tot >= 1 && w.seg_guess < 2;
             for (int32_t k = lane; stands && k < ncon; k += 32) {
                 const SegCon sc = w.seg_con[(bo + m) * SEG_MAXCON + k];
                 const int64_t L = sc.c0 + (int64_t)D.tot * sc.c1 + (int64_t)D.nz * sc.c2;

@@ -578,6 +578,7 @@ struct Pipeline {
         }
         w.seg_mode = nullptr;
         w.TB = 0;
+        if (const char *sg = std::getenv("AA_SEG_GUESS")) w.seg_guess = std::atoi(sg);
         std::vector<int64_t> h_boff;
         if (bk.device_kahn()) {
             w.rrec = A<RevRec>(E);

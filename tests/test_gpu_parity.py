@@ -234,3 +234,20 @@ def test_cli_alt_ingestion(product_lib, workdir):
     pf.write(want, pre)
     for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
         assert pu.files_equal(paf[:-4] + "." + ext, pre + "." + ext), pu.first_diff(paf[:-4] + "." + ext, pre + "." + ext)
+
+
+@pytest.mark.parametrize("guess", ["1", "2"])
+def test_segment_sweep_redo_paths(guess, solver, workdir, monkeypatch):
+    """The segmented relax guesses the qul counts above each segment and checks its ratio tie-breaks afterwards
+    (DESIGN.md 3.1).  AA_SEG_GUESS=1 makes the guess useless, =2 also refuses every recorded condition: tied segments are
+    then redone by the sweep with the true seed — the result must not change."""
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    args, variants = SMALL["segments"]
+    pf = aa.read_paf(pu.synth(os.path.join(workdir, "segredo.paf"), *args))
+    monkeypatch.setenv("AA_SEG_GUESS", guess)
+    for nsl in variants:
+        got = solver.solve(pf.batch, non_skip_linkable=nsl, want_all=True, keep_debug=True)
+        want = oracle_py.oracle_solve(pf.batch, threads=8, non_skip_linkable=nsl, want_all=True, keep_debug=True)
+        assert pu.debug_equal(got.dbg, want.dbg) is None
+        assert pu.result_rows_equal(got, want) is None

@@ -2394,6 +2394,29 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                 int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
                 // ---- working spine := spine of `root` ----
                 if (root != cur_root) {
+                    // the spine being left is remembered first: its heap may be the parent of a vertex that comes later
+                    // (the main chain comes back to it after a side branch); a heap that is not in the ring is
+                    // rebuilt from its nodes
+                    if (cur_root >= 0) {
+                        const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == cur_root);
+                        if (!have) {
+                            const int32_t sl = save_at;
+                            save_at = (save_at + 1) % NSAVE;
+                            if (lane < sp.L) {
+                                hn_store(&sm.snode[sl][lane], sp.nd);
+                                IdEid ie;
+                                ie.id = sp.nd_id;
+                                ie.eid = sp.nd_eid;
+                                sm.sid[sl][lane] = ie;
+                            }
+                            if (lane == 0) {
+                                sm.sroot[sl] = cur_root;
+                                sm.sL[sl] = sp.L;
+                                sm.snext[sl] = sp.next;
+                            }
+                            __syncwarp();
+                        }
+                    }
                     const uint32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
                     if (root >= 0 && hit) {
                         const int32_t sl = __ffs(hit) - 1;
@@ -2450,27 +2473,6 @@ __device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
                 }
                 if (overflow) break;
                 cur_root = root;
-                // ---- remember the spine for the children ----
-                if (root >= 0) {
-                    const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
-                    if (!have) {
-                        const int32_t sl = save_at;
-                        save_at = (save_at + 1) % NSAVE;
-                        if (lane < sp.L) {
-                            hn_store(&sm.snode[sl][lane], sp.nd);
-                            IdEid ie;
-                            ie.id = sp.nd_id;
-                            ie.eid = sp.nd_eid;
-                            sm.sid[sl][lane] = ie;
-                        }
-                        if (lane == 0) {
-                            sm.sroot[sl] = root;
-                            sm.sL[sl] = sp.L;
-                            sm.snext[sl] = sp.next;
-                        }
-                        __syncwarp();
-                    }
-                }
             }
             if (lane == j) {
                 myroot = root;

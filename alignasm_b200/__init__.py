@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import aa_batch, aa_opts, aa_result, np_from, ptr_of
+from ._abi import aa_batch, aa_opts, aa_result, np_from, np_view, ptr_of
 
 __all__ = ["Batch", "PafFile", "Result", "Solver", "AlignasmError", "read_paf", "solve_ctg_read", "solve_multi",
            "shard_contigs", "lib_path", "load_library"]
@@ -139,10 +139,11 @@ class Batch:
         return Batch(**arrays)
 
 
-def _rows(r):
+def _rows(r, get=None):
     n = r.n
-    return {"ctg_index": np_from(r.ctg_index, n), "qry_str": np_from(r.qry_str, n), "qry_end": np_from(r.qry_end, n),
-            "ref_str": np_from(r.ref_str, n), "ref_end": np_from(r.ref_end, n), "is_alt": np_from(r.is_alt, n)}
+    get = get or np_from
+    return {"ctg_index": get(r.ctg_index, n), "qry_str": get(r.qry_str, n), "qry_end": get(r.qry_end, n),
+            "ref_str": get(r.ref_str, n), "ref_end": get(r.ref_end, n), "is_alt": get(r.is_alt, n)}
 
 
 def _stats_dict(st):
@@ -156,16 +157,18 @@ def _stats_dict(st):
 class Result:
     """Host copy of an aa_result: three per-contig CSR lists of PafOutputData rows + statistics."""
 
-    def __init__(self, cres, n_blk, free_fn=None):
+    def __init__(self, cres, n_blk, free_fn=None, copy=True):
+        """copy=False: the row arrays are views of the library's buffers (as a C caller sees them), valid until close()."""
         nc = cres.n_ctg
+        get = np_from if copy else np_view
         self.n_ctg = nc
-        self.out_off = np_from(cres.out_off, nc + 1)
-        self.alt_off = np_from(cres.alt_off, nc + 1)
-        self.all_path_off = np_from(cres.all_path_off, nc + 1)
+        self.out_off = get(cres.out_off, nc + 1)
+        self.alt_off = get(cres.alt_off, nc + 1)
+        self.all_path_off = get(cres.all_path_off, nc + 1)
         npaths = int(self.all_path_off[-1]) if nc >= 0 and len(self.all_path_off) else 0
-        self.all_row_off = np_from(cres.all_row_off, npaths + 1)
-        self.out, self.alt, self.all = _rows(cres.out), _rows(cres.alt), _rows(cres.all)
-        self.sorted_index = np_from(cres.sorted_index, n_blk)
+        self.all_row_off = get(cres.all_row_off, npaths + 1)
+        self.out, self.alt, self.all = _rows(cres.out, get), _rows(cres.alt, get), _rows(cres.all, get)
+        self.sorted_index = get(cres.sorted_index, n_blk)
         self.stats = _stats_dict(cres.stats)
         self.dbg = None
         if cres.dbg:
@@ -283,12 +286,12 @@ class Solver:
         if st != 0:
             raise AlignasmError(st, self._lib.aa_last_error(self._h).decode())
 
-    def solve(self, batch, **kw):
-        """Host buffers in, host result out (the e2e path: H2D + kernels + D2H)."""
+    def solve(self, batch, copy=True, **kw):
+        """Host buffers in, host result out (the e2e path: H2D + kernels + D2H).  copy=False: see Result."""
         res = aa_result()
         o = _opts(**kw)
         self._check(self._lib.aa_solve(self._h, C.byref(batch.c_struct()), C.byref(o), C.byref(res)))
-        return Result(res, batch.n_blk, self._lib.aa_result_free)
+        return Result(res, batch.n_blk, self._lib.aa_result_free, copy=copy)
 
     def upload(self, batch):
         d = C.c_void_p()

@@ -82,5 +82,13 @@ def np_from(ptr, n):
     return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dt, copy=True)
 
 
+def np_view(ptr, n):
+    """n elements behind a ctypes pointer as a numpy array WITHOUT copying: valid only while the C memory lives."""
+    dt = _NP[ptr._type_]
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dt)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),))
+
+
 def ptr_of(arr, ctype):
     return arr.ctypes.data_as(C.POINTER(ctype))

@@ -251,3 +251,33 @@ def test_segment_sweep_redo_paths(guess, solver, workdir, monkeypatch):
         want = oracle_py.oracle_solve(pf.batch, threads=8, non_skip_linkable=nsl, want_all=True, keep_debug=True)
         assert pu.debug_equal(got.dbg, want.dbg) is None
         assert pu.result_rows_equal(got, want) is None
+
+
+@pytest.mark.parametrize("p_dup", [0, 0.05])
+def test_big_contig_in_shuffled_row_order(p_dup, solver, workdir):
+    """Rows of a large contig in arbitrary file order, without and with equal (qry_str, qry_end) keys: the sorted order is
+    the one the reference's own unstable std::sort leaves (OC1 / H2), whatever order the file had."""
+    import random
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    src = pu.synth(os.path.join(workdir, f"shuf_src_{p_dup}.paf"), "--contigs", 2, "--blocks", 20000, "--sd", 100, "--p_dup", p_dup,
+                   "--p_trans", 0.02, "--p_inv", 0.02, "--seed", 41)
+    groups, order = {}, []
+    with open(src) as f:
+        for line in f:
+            q = line.split("\t", 1)[0]
+            if q not in groups:
+                groups[q] = []
+                order.append(q)
+            groups[q].append(line)
+    rng = random.Random(7)
+    paf = os.path.join(workdir, f"shuf_{p_dup}.paf")
+    with open(paf, "w") as f:
+        for q in order:
+            rng.shuffle(groups[q])
+            f.writelines(groups[q])
+    pf = aa.read_paf(paf)
+    assert int(np.diff(pf.batch.ctg_off).max()) >= 16384
+    got = solver.solve(pf.batch, want_all=False)
+    want = oracle_py.oracle_solve(pf.batch, threads=8, want_all=False)
+    assert pu.result_rows_equal(got, want, check_all=False) is None

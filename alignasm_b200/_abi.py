@@ -68,7 +68,7 @@ STATUS = {0: "AA_OK", 1: "AA_ERR_INVALID", 2: "AA_ERR_NO_DEVICE", 3: "AA_ERR_CUD
 # every symbol include/alignasm_b200.h declares (tests check that the built library exports them all)
 EXPORTS = ["aa_create", "aa_destroy", "aa_last_error", "aa_solve", "aa_upload", "aa_solve_device",
            "aa_dev_batch_free", "aa_result_free", "aa_get_stats", "aa_phase_name", "aa_version",
-           "aa_paf_read", "aa_paf_read_alt", "aa_paf_batch", "aa_paf_write", "aa_paf_free", "aa_solve_multi", "aa_shard_contigs",
+           "aa_paf_read", "aa_paf_read_alt", "aa_paf_batch", "aa_paf_write", "aa_paf_free", "aa_solve_subset", "aa_solve_multi", "aa_shard_contigs",
            "aa_multi_last_error", "aa_multi_release"]
 
 _NP = {C.c_int64: np.int64, C.c_int32: np.int32, C.c_uint8: np.uint8}

@@ -43,69 +43,12 @@ aa_status cached_ctx(int32_t device, int32_t nth, aa_ctx **out, std::string &err
 }
 
 struct Shard {
-    std::vector<int64_t> ctgs;  // input contig ids, ascending
-    std::vector<int64_t> ctg_off, qs, qe, rs, re, qt, run_off, ql, qr, rl;
-    std::vector<int32_t> chr;
-    std::vector<uint8_t> fwd, mq;
-    aa_batch batch{};
+    std::vector<int64_t> ctgs;     // input contig ids, ascending
+    std::vector<int64_t> ctg_off;  // block offsets of those contigs inside the shard
     aa_result res{};
     aa_status st = AA_OK;
     std::string err;
 };
-
-void build_shard(const aa_batch *b, Shard &s) {
-    int64_t nb = 0, nr = 0;
-    for (int64_t c : s.ctgs) {
-        nb += b->ctg_off[c + 1] - b->ctg_off[c];
-        nr += b->run_off[b->ctg_off[c + 1]] - b->run_off[b->ctg_off[c]];
-    }
-    for (auto *v : {&s.qs, &s.qe, &s.rs, &s.re, &s.qt}) v->reserve((size_t)nb);
-    for (auto *v : {&s.ql, &s.qr, &s.rl}) v->reserve((size_t)nr);
-    s.chr.reserve((size_t)nb);
-    s.fwd.reserve((size_t)nb);
-    s.mq.reserve((size_t)nb);
-    s.run_off.reserve((size_t)nb + 1);
-    s.ctg_off.reserve(s.ctgs.size() + 1);
-    s.ctg_off.push_back(0);
-    s.run_off.push_back(0);
-    for (int64_t c : s.ctgs) {
-        const int64_t b0 = b->ctg_off[c], b1 = b->ctg_off[c + 1];
-        s.qs.insert(s.qs.end(), b->qry_str + b0, b->qry_str + b1);
-        s.qe.insert(s.qe.end(), b->qry_end + b0, b->qry_end + b1);
-        s.rs.insert(s.rs.end(), b->ref_str + b0, b->ref_str + b1);
-        s.re.insert(s.re.end(), b->ref_end + b0, b->ref_end + b1);
-        s.qt.insert(s.qt.end(), b->qry_total + b0, b->qry_total + b1);
-        s.chr.insert(s.chr.end(), b->ref_chr + b0, b->ref_chr + b1);
-        s.fwd.insert(s.fwd.end(), b->aln_fwd + b0, b->aln_fwd + b1);
-        s.mq.insert(s.mq.end(), b->map_qul + b0, b->map_qul + b1);
-        const int64_t r0 = b->run_off[b0], r1 = b->run_off[b1];
-        const int64_t shift = (int64_t)s.ql.size() - r0;
-        for (int64_t i = b0; i < b1; i++) s.run_off.push_back(b->run_off[i + 1] + shift);
-        if (r1 > r0) {
-            s.ql.insert(s.ql.end(), b->run_ql + r0, b->run_ql + r1);
-            s.qr.insert(s.qr.end(), b->run_qr + r0, b->run_qr + r1);
-            s.rl.insert(s.rl.end(), b->run_rl + r0, b->run_rl + r1);
-        }
-        s.ctg_off.push_back((int64_t)s.qs.size());
-    }
-    aa_batch &o = s.batch;
-    o.n_ctg = (int64_t)s.ctgs.size();
-    o.n_blk = (int64_t)s.qs.size();
-    o.n_run = (int64_t)s.ql.size();
-    o.ctg_off = s.ctg_off.data();
-    o.qry_str = s.qs.data();
-    o.qry_end = s.qe.data();
-    o.ref_str = s.rs.data();
-    o.ref_end = s.re.data();
-    o.qry_total = s.qt.data();
-    o.ref_chr = s.chr.data();
-    o.aln_fwd = s.fwd.data();
-    o.map_qul = s.mq.data();
-    o.run_off = s.run_off.data();
-    o.run_ql = s.ql.data();
-    o.run_qr = s.qr.data();
-    o.run_rl = s.rl.data();
-}
 
 template <class T>
 T *host_n(int64_t n) {
@@ -187,13 +130,14 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
         pool.emplace_back([&, k]() {
             Shard &s = sh[(size_t)k];
             if (s.ctgs.empty()) return;
-            build_shard(b, s);
+            s.ctg_off.assign(1, 0);
+            for (int64_t c : s.ctgs) s.ctg_off.push_back(s.ctg_off.back() + (b->ctg_off[c + 1] - b->ctg_off[c]));
             int32_t nth = 0;
             for (int32_t q = 0; q < k; q++) nth += devices[q] == devices[k];
             aa_ctx *ctx = nullptr;
             s.st = cached_ctx(devices[k], nth, &ctx, s.err);
             if (s.st != AA_OK) return;
-            s.st = aa_solve(ctx, &s.batch, &o, &s.res);
+            s.st = aa_solve_subset(ctx, b, s.ctgs.data(), (int64_t)s.ctgs.size(), &o, &s.res);  // staged from the caller's arrays
             if (s.st != AA_OK) s.err = aa_last_error(ctx);
         });
     for (auto &t : pool) t.join();

@@ -202,7 +202,8 @@ struct DevBatch {
     uint8_t *fwd = nullptr, *mapq = nullptr;
     int64_t *run_off = nullptr, *run_ql = nullptr, *run_qr = nullptr, *run_rl = nullptr;
     // host mirror of what the host-side sort needs (OC1)
-    std::vector<int64_t> own_ctg_off, own_qs, own_qe;  // copies, for a batch that stays resident
+    std::vector<int64_t> own_ctg_off, own_qs, own_qe;  // copies, for a batch that stays resident (or a staged subset)
+    std::vector<int64_t> own_run_off;                  // rebased run offsets of a staged subset
     const int64_t *h_ctg_off = nullptr, *h_qs = nullptr, *h_qe = nullptr;  // the caller's arrays for a one-shot solve
     std::vector<void *> owned;
     bool pooled = false;  // arrays live in the solve workspace (one-shot aa_solve): nothing to free
@@ -374,6 +375,82 @@ struct Pipeline {
             d->h_qe = d->own_qe.data();
         }
         if (!pooled) bk.sync();  // (the staged copies of a one-shot solve are ordered before its kernels on the stream)
+        out = d;
+        return AA_OK;
+    }
+    // One-shot staging of a SUBSET of the batch's contigs (ascending ids), straight from the caller's arrays: what a
+    // shard of aa_solve_multi solves.  The pieces of every contig go into the pinned buffer one after the other, so the
+    // shard is never materialised on the host; only its offsets and sort keys (needed by the host sort) are built here.
+    aa_status upload_subset(const aa_batch *b, const int64_t *ctgs, int64_t n_ctgs, DevBatch *&out) {
+        std::string v = validate_batch(b);
+        if (v.empty() && (!ctgs || n_ctgs <= 0)) v = "empty contig subset";
+        for (int64_t k = 0; v.empty() && k < n_ctgs; k++)
+            if (ctgs[k] < 0 || ctgs[k] >= b->n_ctg || (k > 0 && ctgs[k] <= ctgs[k - 1])) v = "contig subset not ascending / out of range";
+        if (!v.empty()) {
+            err = v;
+            return AA_ERR_INVALID;
+        }
+        DevBatch *d = new DevBatch();
+        d->pooled = true;
+        d->C = n_ctgs;
+        d->own_ctg_off.resize((size_t)n_ctgs + 1);
+        int64_t B = 0, R = 0;
+        for (int64_t k = 0; k < n_ctgs; k++) {
+            const int64_t b0 = b->ctg_off[ctgs[k]], b1 = b->ctg_off[ctgs[k] + 1];
+            d->own_ctg_off[(size_t)k] = B;
+            B += b1 - b0;
+            R += b->run_off[b1] - b->run_off[b0];
+        }
+        d->own_ctg_off[(size_t)n_ctgs] = B;
+        d->B = B;
+        d->R = R;
+        d->own_qs.resize((size_t)B);
+        d->own_qe.resize((size_t)B);
+        std::vector<int64_t> &roff = d->own_run_off;
+        roff.resize((size_t)B + 1);
+        auto dev = [&](auto *&dst, int64_t n) {
+            using T = std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>;
+            dst = (T *)bk.alloc_bytes((size_t)(n > 0 ? n : 1) * sizeof(T));
+            return dst != nullptr;
+        };
+        bool ok = dev(d->ctg_off, d->C + 1) && dev(d->qs, B) && dev(d->qe, B) && dev(d->rs, B) && dev(d->re, B) && dev(d->qtot, B) &&
+                  dev(d->chr, B) && dev(d->fwd, B) && dev(d->mapq, B) && dev(d->run_off, B + 1) && dev(d->run_ql, R) &&
+                  dev(d->run_qr, R) && dev(d->run_rl, R);
+        if (!ok) {
+            free_batch(d);
+            err = "device allocation failed while staging the batch";
+            return AA_ERR_NOMEM;
+        }
+        int64_t at = 0, rat = 0;
+        for (int64_t k = 0; k < n_ctgs; k++) {
+            const int64_t b0 = b->ctg_off[ctgs[k]], b1 = b->ctg_off[ctgs[k] + 1], n = b1 - b0;
+            const int64_t r0 = b->run_off[b0], r1 = b->run_off[b1], nr = r1 - r0;
+            std::memcpy(d->own_qs.data() + at, b->qry_str + b0, (size_t)n * 8);
+            std::memcpy(d->own_qe.data() + at, b->qry_end + b0, (size_t)n * 8);
+            for (int64_t i = 0; i < n; i++) roff[(size_t)(at + i)] = b->run_off[b0 + i] - r0 + rat;
+            bk.stage(d->rs + at, b->ref_str + b0, (size_t)n * 8);
+            bk.stage(d->re + at, b->ref_end + b0, (size_t)n * 8);
+            bk.stage(d->qtot + at, b->qry_total + b0, (size_t)n * 8);
+            bk.stage(d->chr + at, b->ref_chr + b0, (size_t)n * 4);
+            bk.stage(d->fwd + at, b->aln_fwd + b0, (size_t)n);
+            bk.stage(d->mapq + at, b->map_qul + b0, (size_t)n);
+            if (nr > 0) {
+                bk.stage(d->run_ql + rat, b->run_ql + r0, (size_t)nr * 8);
+                bk.stage(d->run_qr + rat, b->run_qr + r0, (size_t)nr * 8);
+                bk.stage(d->run_rl + rat, b->run_rl + r0, (size_t)nr * 8);
+            }
+            at += n;
+            rat += nr;
+        }
+        roff[(size_t)B] = R;
+        bk.stage(d->ctg_off, d->own_ctg_off.data(), (size_t)(d->C + 1) * 8);
+        bk.stage(d->qs, d->own_qs.data(), (size_t)B * 8);
+        bk.stage(d->qe, d->own_qe.data(), (size_t)B * 8);
+        bk.stage(d->run_off, roff.data(), (size_t)(B + 1) * 8);
+        bk.flush_staged();
+        d->h_ctg_off = d->own_ctg_off.data();
+        d->h_qs = d->own_qs.data();
+        d->h_qe = d->own_qe.data();
         out = d;
         return AA_OK;
     }

@@ -120,6 +120,40 @@ aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_r
     ctx->pipe.free_batch(d);
     return st;
 }
+
+aa_status aa_solve_subset(aa_ctx *ctx, const aa_batch *batch, const int64_t *ctgs, int64_t n_ctgs, const aa_opts *opts,
+                          aa_result *res) {
+    if (!ctx || !res) return AA_ERR_INVALID;
+    // one-shot: the batch is staged in the pooled workspace, so a steady-state call makes no cudaMalloc / cudaFree
+    ctx->bk.reset_pool();  // (also recovers a context whose last solve ran out of memory)
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        return AA_ERR_CUDA;
+    }
+    aa::DevBatch *d = nullptr;
+    aa_status st = ctx->pipe.upload_subset(batch, ctgs, n_ctgs, d);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        return st;
+    }
+    if (!ctx->bk.ok()) {
+        ctx->err = ctx->bk.error();
+        ctx->pipe.free_batch(d);
+        return AA_ERR_CUDA;
+    }
+    aa_opts o{};
+    if (opts) o = *opts;
+    st = ctx->pipe.solve(*d, o, res, /*keep_pool=*/true);
+    if (st != AA_OK) {
+        ctx->err = ctx->pipe.err;
+        if (st != AA_ERR_UNSOLVABLE) {
+            aa::result_free_host(res);
+            cudaStreamSynchronize(ctx->bk.stream);
+        }
+    }
+    ctx->pipe.free_batch(d);
+    return st;
+}
 void aa_result_free(aa_result *res) { aa::result_free_host(res); }
 aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats) {
     if (!ctx || !stats) return AA_ERR_INVALID;

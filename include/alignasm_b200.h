@@ -147,6 +147,10 @@ void aa_dev_batch_free(aa_ctx *ctx, aa_dev_batch *dev);
 
 void aa_result_free(aa_result *res);
 
+/* The same for a subset of the batch's contigs (ascending contig ids; rows of the result are indexed by position in
+ * `ctgs`): the blocked_range a TBB worker gets (alignasm.cpp:354-359).  Staged straight from the caller's arrays. */
+aa_status aa_solve_subset(aa_ctx *ctx, const aa_batch *batch, const int64_t *ctgs, int64_t n_ctgs, const aa_opts *opts,
+                          aa_result *res);
 /* ---- the same over several GPUs of one box: contigs are independent (tbb::parallel_for over contigs, alignasm.cpp:351-359),
  * so they are partitioned by a cost estimate (longest processing time first), every shard is solved on its own device from
  * its own host thread, and the rows are merged back in input order.  No collective.  `devices` may name a device twice. */

@@ -48,6 +48,7 @@ constexpr int64_t SV_TRANS_PENALTY = 2000;
 constexpr int64_t SV_INV_PENALTY = 500;
 constexpr int64_t SV_FRONT_END = 2;
 constexpr int64_t REF_NEG_PENALTY = 2;
+constexpr size_t HEAP2_FIXED_BYTES = 16 * 1024;  // f_heaps_chain: saved spines + op ring (>= sizeof(ChainSmem))
 constexpr int32_t HEAP_CHUNK = 4096;  // leftist-heap nodes handed to a contig per arena grab
 constexpr int64_t I64_MAX = 0x7fffffffffffffffLL;
 
@@ -197,6 +198,16 @@ struct __attribute__((aligned(8))) InsKey {  // one sidetrack to insert: key c =
     int32_t anom, nz, tot;
     int32_t eid;  // contig-local edge id
 };
+struct __attribute__((aligned(16))) HOp {  // one operation of the serial heap builder (f_heaps_chain), 32 B
+    int64_t sum;
+    int32_t anom, nz, tot;  // insert: the sidetrack key (reservation: anom = number of node ids)
+    int32_t eid;
+    int32_t ctl;            // HOP_FIRST: first insert of its vertex, HOP_LAST: last one, HOP_RESERVE: id reservation for a leaf
+    int32_t aux;            // FIRST: chain ordinal (within the contig) of the vertex whose heap is inherited, -1: empty heap;
+                            // RESERVE: contig-local BFS slot of the leaf
+};
+constexpr int32_t HOP_FIRST = 1, HOP_LAST = 2, HOP_RESERVE = 4;
+constexpr int32_t LEAF_MAX_INS = 32;  // a leaf's reserved ids (32 per insert) fit one arena chunk
 struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
     int32_t i, j;        // contig-local sorted block indices
     int64_t pe_q, pe_r;  // edited_loc_pre_end[i][j]
@@ -318,6 +329,16 @@ struct Ws {
     int32_t *leaf_base;  // [Vtot] first of the 32 * nins node ids the streaming builder reserved for a leaf (keeps ids in order)
     ENext *enext;        // [E] (device enumeration only)
     int64_t *heap_used;  // [C]
+    // streaming builder, flat form (f_heaps_chain): the serial warp reads one stream of operations per contig
+    HOp *ops;            // [n_ops] inserts of the chain vertices (tree vertices whose heap others inherit) + one id reservation per leaf
+    int32_t *op_cnt;     // [Vtot+1] operations of the vertex at each BFS slot
+    int64_t *op_off;     // [Vtot+2]
+    int32_t *chain_flag; // [Vtot+1] 1: chain vertex
+    int64_t *chain_ord;  // [Vtot+2] exclusive prefix sum of chain_flag
+    int32_t *owner;      // [Vtot] contig-local BFS slot of the nearest chain vertex among the vertex and its tree ancestors (-1: none)
+    int32_t *chain_root; // [n_chain] heap root of every chain vertex, written by the serial warp
+    int32_t heap_cache_bits;  // log2 of the on-chip node cache of f_heaps_chain (entries of 40 B); 0: none
+    int32_t heaps_variant;    // tuning switch (tools/heap_lab)
     // enumeration
     int64_t *walk_off;   // [C+1] = c*K
     int32_t *n_walk;     // [C]
@@ -1286,6 +1307,80 @@ AA_HDN void f_ins_fill(const Ws &w, int64_t i) {  // the inserts of the vertex a
     }
 }
 
+// ---- flat operation stream of the serial heap builder (f_heaps_chain) ---------------------------------------------
+// Tree vertices fall in three classes: CHAIN (has inserts and either tree children or more than LEAF_MAX_INS inserts: its heap
+// is inherited or too big for the leaf builder), LEAF (has inserts, no children: built off the chain by f_heaps_level) and the
+// rest (no inserts: the heap is the parent's).  The serial warp sees only the inserts of the chain vertices, in BFS order, and
+// one id reservation per leaf (so that node ids stay in allocation order); which heap a vertex starts from is
+// resolved here, in parallel, by pointer jumping to the nearest chain ancestor.
+AA_HDN void f_ops_class(const Ws &w, int64_t i) {
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    int32_t cls = 0, n = 0, own = -1;
+    if (w.hmode[c] == 0 && (w.status[c] == 0 || w.status[c] == 3) && i - v0 < w.ntree[c]) {
+        const VInfo vi = w.vinfo[i];
+        n = vi.nins & (VI_KIDS - 1);
+        if (n > 0) cls = (n <= LEAF_MAX_INS && !(vi.nins & VI_KIDS)) ? 2 : 1;
+        own = cls == 1 ? (int32_t)(i - v0) : vi.ppos;
+    }
+    w.op_cnt[i] = cls == 1 ? n : (cls == 2 ? 1 : 0);
+    w.chain_flag[i] = cls == 1;
+    w.owner[i] = own;
+}
+AA_HDN void f_owner_jump(const Ws &w, int64_t i) {  // one round; in place (a racing read sees another ancestor on the same path)
+    const int32_t o = w.owner[i];
+    if (o < 0) return;
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    if (w.chain_flag[v0 + o]) return;
+    w.owner[i] = w.owner[v0 + o];
+}
+AA_HDN void f_ops_fill(const Ws &w, int64_t i) {
+    const int32_t cnt = w.op_cnt[i];
+    if (cnt == 0) return;
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    const VInfo vi = w.vinfo[i];
+    const int64_t o = w.op_off[i];
+    const int32_t n = vi.nins & (VI_KIDS - 1);
+    if (w.chain_flag[i]) {
+        int32_t src = -1;
+        if (vi.ppos >= 0) {
+            const int32_t po = w.owner[v0 + vi.ppos];
+            if (po >= 0) src = (int32_t)(w.chain_ord[v0 + po] - w.chain_ord[v0]);
+        }
+        for (int32_t k = 0; k < n; k++) {
+            const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
+            HOp op;
+            op.sum = ik.sum;
+            op.anom = ik.anom;
+            op.nz = ik.nz;
+            op.tot = ik.tot;
+            op.eid = ik.eid;
+            op.ctl = (k == 0 ? HOP_FIRST : 0) | (k == n - 1 ? HOP_LAST : 0);
+            op.aux = k == 0 ? src : 0;
+            w.ops[o + k] = op;
+        }
+    } else {
+        HOp op;
+        op.sum = 0;
+        op.anom = 32 * n;
+        op.nz = op.tot = op.eid = 0;
+        op.ctl = HOP_RESERVE;
+        op.aux = (int32_t)(i - v0);
+        w.ops[o] = op;
+    }
+}
+AA_HDN void f_root_fill(const Ws &w, int64_t i) {  // after the serial warp: every tree vertex takes the heap of its owner
+    const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    const int64_t v0 = w.vtx_off[c];
+    if (w.hmode[c] != 0 || w.status[c] != 0 || i - v0 >= w.ntree[c]) return;
+    const int32_t o = w.owner[i];
+    const int32_t root = o < 0 ? -1 : w.chain_root[w.chain_ord[v0 + o]];
+    w.root_at[i] = root;
+    w.hroot[v0 + w.vinfo[i].x] = root;
+}
+
 // insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on arena overflow).
 // leftist_heap.hpp:29-40 made iterative: walk down the right spine while a->key < k (ties stop: the new key
 // goes on top), then copy the spine bottom-up.  Nodes are immutable, 32 B, moved with 128-bit accesses.
@@ -1351,42 +1446,77 @@ AA_HDN int32_t heap_insert(HNode *__restrict__ hn, int32_t *__restrict__ hn_eid,
 #if defined(__CUDACC__)
 __device__ void f_heaps_level(const Ws &w, int64_t slot);  // level-parallel builder, defined with the warp kernels below
 #endif
-// phase: sidetrack heaps (k_shortest_walks.hpp:191-215): the tree vertices in BFS order, each inserting its
-// sidetracks into the heap it inherits from its tree parent.  Sequential form (host emulation).
-AA_HDN void f_heaps(const Ws &w, int64_t c) {
+// phase: sidetrack heaps (k_shortest_walks.hpp:191-215): the tree vertices in BFS order, each inserting its sidetracks into the
+// heap it inherits from its tree parent.
+// Sequential forms of the flat builder (host emulation): the operation stream of one contig, then one leaf.
+AA_HDN void f_heaps_ops(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
     if (w.status[c] != 0 && w.status[c] != 3) return;
-    w.status[c] = 0;
+    if (w.hmode[c] != 0) return;
     const int64_t v0 = w.vtx_off[c];
-    const VInfo *vinfo = w.vinfo + v0;
-    int32_t *root_at = w.root_at + v0;
-    int32_t *hroot = w.hroot + v0;
+    const int32_t nt = w.ntree[c];
+    const HOp *ops = w.ops + w.op_off[v0];
+    const int64_t nops = w.op_off[v0 + nt] - w.op_off[v0];
+    int32_t *chain_root = w.chain_root + w.chain_ord[v0];
     HeapAlloc ha;
     ha.cur = ha.end = 0;
     ha.used = 0;
     ha.overflow = false;
-    const int32_t nt = w.ntree[c];
-    for (int32_t pos = 0; pos < nt && !ha.overflow; pos++) {
-        const VInfo vi = vinfo[pos];
-        int32_t root = vi.ppos < 0 ? -1 : root_at[vi.ppos];
-        const int32_t n = vi.nins & (VI_KIDS - 1);
-        for (int32_t k = 0; k < n; k++) {
-            const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
-            SKey sk;
-            sk.sum = ik.sum;
-            sk.anom = ik.anom;
-            sk.nz = ik.nz;
-            sk.tot = ik.tot;
-            sk.use = 1;
-            root = heap_insert(w.hn, w.hn_eid, w, ha, root, sk, ik.eid);
-            if (root < 0) break;
+    int32_t root = -1, cv = 0;
+    for (int64_t i = 0; i < nops && !ha.overflow; i++) {
+        const HOp op = ops[i];
+        if (op.ctl & HOP_RESERVE) {
+            if (ha.cur + op.anom > ha.end) {  // the reservation is one piece of one chunk
+                ha.cur = ha.end;
+                const int64_t keep = ha.used;
+                if (heap_new(w, ha) < 0) break;
+                ha.cur--;
+                ha.used = keep;
+            }
+            w.leaf_base[v0 + op.aux] = (int32_t)ha.cur;
+            ha.cur += op.anom;
+            continue;
         }
-        if (ha.overflow) break;
-        root_at[pos] = root;
-        hroot[vi.x] = root;
+        if (op.ctl & HOP_FIRST) root = op.aux < 0 ? -1 : chain_root[op.aux];
+        SKey sk;
+        sk.sum = op.sum;
+        sk.anom = op.anom;
+        sk.nz = op.nz;
+        sk.tot = op.tot;
+        sk.use = 1;
+        root = heap_insert(w.hn, w.hn_eid, w, ha, root, sk, op.eid);
+        if (root < 0) break;
+        if (op.ctl & HOP_LAST) chain_root[cv++] = root;
     }
     w.heap_used[c] = ha.used;
-    if (ha.overflow) w.status[c] = 3;
+    w.status[c] = ha.overflow ? 3 : 0;
+}
+AA_HDN void f_heaps_leaf_host(const Ws &w, int64_t slot) {  // a leaf of a streaming-mode contig, ids from its reservation
+    if (aa_lane() != 0) return;
+    const int64_t c = upper_idx(w.vtx_off, w.C, slot);
+    if (w.status[c] != 0) return;
+    const int64_t v0 = w.vtx_off[c];
+    const VInfo vi = w.vinfo[slot];
+    const int32_t n = vi.nins & (VI_KIDS - 1);
+    int32_t root = vi.ppos < 0 ? -1 : w.root_at[v0 + vi.ppos];
+    HeapAlloc ha;
+    ha.cur = w.leaf_base[slot];
+    ha.end = ha.cur + 32 * (int64_t)n;
+    ha.used = 0;
+    ha.overflow = false;
+    for (int32_t k = 0; k < n; k++) {
+        const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
+        SKey sk;
+        sk.sum = ik.sum;
+        sk.anom = ik.anom;
+        sk.nz = ik.nz;
+        sk.tot = ik.tot;
+        sk.use = 1;
+        root = heap_insert(w.hn, w.hn_eid, w, ha, root, sk, ik.eid);
+    }
+    w.root_at[slot] = root;
+    w.hroot[v0 + vi.x] = root;
+    w.heap_used[c] += ha.used;
 }
 
 #if defined(__CUDA_ARCH__)
@@ -2152,17 +2282,10 @@ constexpr size_t RELAX_SMEM_C_BYTES = 10 * 1024 + 48 * 1024;  // ring + open-ver
 // Spines of finished vertices with children are kept in shared memory (keyed by root id): BFS visits siblings
 // and then their children, all of which start from a heap built a few vertices earlier.
 constexpr int32_t SPMAX = 32;
-constexpr int32_t LEAF_MAX_INS = 32;  // a leaf's reserved ids (32 per insert) fit one arena chunk
 constexpr int32_t NSAVE = 8;
 struct __attribute__((aligned(8))) IdEid {
     int32_t id, eid;
 };
-struct HeapSmem {
-    HNode snode[NSAVE][SPMAX];
-    IdEid sid[NSAVE][SPMAX];
-    int32_t sroot[NSAVE], sL[NSAVE], snext[NSAVE];
-};
-static_assert(sizeof(HeapSmem) <= 12 * 1024, "HeapSmem does not fit its shared-memory allotment");
 __device__ __forceinline__ bool key_lt(const HNode &an, const InsKey &k) {  // a->key < k (paf_data.hpp:142-159)
     if (an.sum != k.sum) return an.sum < k.sum;
     if (an.anom != k.anom) return an.anom < k.anom;
@@ -2311,183 +2434,379 @@ __device__ __forceinline__ InsKey ins_bcast(const InsKey &kreg, int32_t src) {
     k.eid = __shfl_sync(FULL, kreg.eid, src);
     return k;
 }
-__device__ void f_heaps_warp(const Ws &w, int64_t c, void *scratch) {
-    HeapSmem &sm = *reinterpret_cast<HeapSmem *>(scratch);
+// ---- the serial heap builder, flat form ------------------------------------------------------------------------------
+// One warp per contig walks the contig's operation stream (f_ops_fill).  Same node ids, same nodes as f_heaps_warp; what is
+// different is the length of the instruction chain of one insert (a lone warp issues a dependent instruction every 5-6
+// cycles, so the chain length IS the time):
+//   * no vertex loop: vertices without inserts never reach the warp, parents are resolved by the pre-pass;
+//   * ranks.  With a_j = (left_j ? lrank_j : -1) + j + 1 for the copied levels j < p and a_p = p + 1 for the new node, the copy
+//     of level i gets rank min_{j in [i,p]} a_j - i, and level i swaps iff a_i < min_{j in (i,p]} a_j (leftist_heap.hpp:34-38
+//     unrolled).  The topmost swap m, which alone decides the next spine, is the LAST position of the minimum of a over
+//     [0,p]: one redux.min over (a << 5 | 31 - lane).  Levels above m take rank amin - i; only the levels between m and p
+//     (usually none or one) need a suffix scan;
+//   * the whole right spine is always in registers (level i on lane i): after a swap the spine of the old left child is
+//     read at once, from a direct-mapped shared-memory cache of the nodes this warp created (tag = node id; a global store
+//     invalidates the line in L1, so re-reading one's own nodes from memory costs an L2 round trip per level);
+//   * operations come through a shared-memory ring filled by cp.async three chunks ahead, and the next operation is read
+//     while the current one is worked on.
+constexpr int32_t OPRING = 128;
+struct ChainSmem {
+    HNode snode[NSAVE][SPMAX];
+    IdEid sid[NSAVE][SPMAX];
+    int32_t sord[NSAVE], sL[NSAVE];
+    HOp oring[OPRING];
+    // at HEAP2_FIXED_BYTES: HNode cnode[1 << bits]; IdEid ctag[1 << bits]
+};
+static_assert(sizeof(ChainSmem) <= HEAP2_FIXED_BYTES, "ChainSmem does not fit its shared-memory allotment");
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ HOp hop_lds(const HOp *p) {
+    union {
+        HOp o;
+        V16 v[2];
+    } u;
+    const volatile V16 *q = reinterpret_cast<const volatile V16 *>(p);
+    u.v[0].a = q[0].a;
+    u.v[0].b = q[0].b;
+    u.v[1].a = q[1].a;
+    u.v[1].b = q[1].b;
+    return u.o;
+}
+#ifdef AA_HEAP_TIMERS
+#define HT_DECL long long ht_t = clock64(), ht_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ht_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HT(i) do { const long long ht_now = clock64(); ht_acc[i] += ht_now - ht_t; ht_n[i]++; ht_t = ht_now; } while (0)
+#define HT_COUNT(i) ht_n[i]++
+#else
+#define HT_DECL
+#define HT(i)
+#define HT_COUNT(i)
+#endif
+__device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
+    HT_DECL
+    ChainSmem &sm = *reinterpret_cast<ChainSmem *>(scratch);
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     if (w.status[c] != 0 && w.status[c] != 3) return;
-    if (w.hmode[c] != 0) return;  // a shallow, wide tree: built level by level, one warp per vertex (f_heaps_level)
+    if (w.hmode[c] != 0) return;  // a shallow, wide tree: built level by level (f_heaps_level)
     const int64_t v0 = w.vtx_off[c];
+    const int32_t nt = w.ntree[c];
     HNode *__restrict__ hn = w.hn;
     int32_t *__restrict__ hn_eid = w.hn_eid;
-    unsigned long long *__restrict__ hn_key = w.hn_key;
-    const VInfo *__restrict__ vinfo = w.vinfo + v0;
-    const InsKey *__restrict__ ins = w.ins;
-    int32_t *__restrict__ hroot = w.hroot + v0;
-    int32_t *__restrict__ root_at = w.root_at + v0;
-    const int32_t nt = w.ntree[c];
-    if (lane < NSAVE) sm.sroot[lane] = -2;
+    // node cache
+    HNode *cnode = nullptr;
+    IdEid *ctag = nullptr;
+    int32_t cmask = -1;
+    if (w.heap_cache_bits > 0) {
+        unsigned char *base = reinterpret_cast<unsigned char *>(scratch) + HEAP2_FIXED_BYTES;
+        const int32_t n = 1 << w.heap_cache_bits;
+        cnode = reinterpret_cast<HNode *>(base);
+        ctag = reinterpret_cast<IdEid *>(base + (size_t)n * sizeof(HNode));
+        cmask = n - 1;
+        for (int32_t i = lane; i < n; i += 32) ctag[i].id = -1;
+    }
+    if (lane < NSAVE) sm.sord[lane] = -2;
+    // ---- operation stream ----
+    const HOp *__restrict__ ops = w.ops + w.op_off[v0];
+    const int32_t nops = (int32_t)(w.op_off[v0 + nt] - w.op_off[v0]);
+    int32_t *__restrict__ chain_root = w.chain_root + w.chain_ord[v0];
+    auto issue_chunk = [&](int32_t ch) {  // ops [32 ch, 32 ch + 32) -> ring (one cp.async group, possibly empty)
+        const int32_t i = ch * 32 + lane;
+        if (i < nops) {
+            const V16 *src = reinterpret_cast<const V16 *>(ops + i);
+            V16 *dst = reinterpret_cast<V16 *>(&sm.oring[i & (OPRING - 1)]);
+            cp_async16(dst, src);
+            cp_async16(dst + 1, src + 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_chunk(0);
+    issue_chunk(1);
+    issue_chunk(2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
-    int64_t cur = 0, end = 0, used = 0;  // arena chunk of this contig (warp-uniform)
+    // ---- the working spine: level `lane` of the right spine of heap `cur_ord` (complete: L levels) ----
+    int64_t ksum = 0;
+    int32_t kanom = 0, knz = 0, ktot = 0, left = -1, lrank = 0, rank = 0, id = -1, eid = 0;
+    int32_t L = 0;
+    int32_t cur_ord = -1;  // chain ordinal of the vertex whose heap the working spine is (-1: the empty heap)
+    int32_t cv = 0;        // chain vertices finished
+    int32_t cur = 0, end = 0;
+    int64_t used = 0;
     bool overflow = false;
     int32_t save_at = 0;
-    // ---- insert stream: chunk [kbase, kbase+32) in kreg, the following chunk in knext ----
-    const int64_t kend = w.ins_off[v0 + nt];  // vertices behind the tree have no inserts, so this is the contig's end
-    int64_t kbase = w.ins_off[v0];
-    InsKey kreg, knext;
-    kreg.sum = knext.sum = 0;
-    kreg.anom = kreg.nz = kreg.tot = kreg.eid = 0;
-    knext.anom = knext.nz = knext.tot = knext.eid = 0;
-    if (kbase + lane < kend) kreg = ins_ld(ins + kbase + lane);
-    if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
-    Spine sp;
-    sp.nd.sum = sp.nx.sum = 0;
-    sp.nd.anom = sp.nd.nz = sp.nd.tot = sp.nx.anom = sp.nx.nz = sp.nx.tot = 0;
-    sp.nd.left = sp.nd.right = sp.nx.left = sp.nx.right = -1;
-    sp.nd.rank = sp.nd.lrank = sp.nx.rank = sp.nx.lrank = 0;
-    sp.nd_id = -1;
-    sp.nd_eid = sp.nx_eid = 0;
-    sp.L = 0;
-    sp.next = -1;
-    int32_t cur_root = -1;  // the working spine is the spine of heap cur_root (-1: empty heap)
-    // ---- vertex stream ----
-    VInfo vnext;
-    vnext.x = -1;
-    vnext.ins_beg = 0;
-    vnext.nins = 0;
-    vnext.ppos = -1;
-    if (lane < nt) vnext = vinfo_ld(vinfo + lane);
-    for (int32_t base = 0; base < nt && !overflow; base += 32) {
-        const VInfo vi = vnext;
-        if (base + 32 + lane < nt) vnext = vinfo_ld(vinfo + base + 32 + lane);
-        // roots of parents that were finished in earlier batches (parents inside this batch come by shuffle)
-        int32_t proot = -1;
-        if (base + lane < nt && vi.ppos >= 0 && vi.ppos < base) proot = root_at[vi.ppos];
-        int32_t myroot = -1, mycnt = 0, mybase = -1;
-        const int32_t cnt = nt - base < 32 ? nt - base : 32;
-        for (int32_t j = 0; j < cnt && !overflow; j++) {
-            const int32_t nins_f = __shfl_sync(FULL, vi.nins, j);
-            const int32_t ppos = __shfl_sync(FULL, vi.ppos, j);
-            const int32_t pr = __shfl_sync(FULL, proot, j);
-            const int32_t inb = __shfl_sync(FULL, myroot, ppos >= base ? ppos - base : 0);
-            int32_t root = ppos >= base ? inb : pr;
-            const int32_t nins = nins_f & (VI_KIDS - 1);
-            int32_t vseq = 0;  // nodes this vertex has allocated
-            // a leaf of the tree feeds no other heap: its inserts are done by f_heaps_level, off this serial chain.  It gets
-            // its node ids here, in sequence (32 per insert is the most a spine can copy), so that ids stay in allocation order
-            if (nins > 0 && nins <= LEAF_MAX_INS && !(nins_f & VI_KIDS)) {
-                const int32_t need = nins * 32;
+    // a fresh arena chunk (warp-uniform result; -1: arena exhausted)
+    auto new_chunk = [&]() -> int32_t {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+        at = __shfl_sync(FULL, at, 0);
+        if ((int64_t)at + HEAP_CHUNK > w.Hcap) return -1;
+        return (int32_t)__reduce_max_sync(FULL, (uint32_t)at);
+    };
+    // spine of the heap rooted at `from` appended below level L0 (complete right spine, read through the cache)
+    auto extend = [&](int32_t L0, int32_t from) -> int32_t {
+        int32_t nx = from, l = L0;
+        while (nx >= 0) {
+            if (l >= SPMAX - 1) return -1;
+            int32_t nright;
+            bool hit = false;
+            if (cmask >= 0) {
+                const int32_t s = nx & cmask;
+                const IdEid t = ctag[s];
+                nright = cnode[s].right;
+                hit = t.id == nx;
+                if (hit && lane == l) {  // only the lane of this level takes the record
+                    const HNode n = hn_load(&cnode[s]);
+                    ksum = n.sum;
+                    kanom = n.anom;
+                    knz = n.nz;
+                    ktot = n.tot;
+                    left = n.left;
+                    lrank = n.lrank;
+                    rank = n.rank;
+                    id = nx;
+                    eid = t.eid;
+                }
+            }
+            if (!hit) {
+                const HNode n = hn_load(hn + nx);
+                const int32_t ne = hn_eid[nx];
+                nright = n.right;
+                if (lane == l) {
+                    ksum = n.sum;
+                    kanom = n.anom;
+                    knz = n.nz;
+                    ktot = n.tot;
+                    left = n.left;
+                    lrank = n.lrank;
+                    rank = n.rank;
+                    id = nx;
+                    eid = ne;
+                }
+            }
+            l++;
+            nx = nright;
+            HT_COUNT(7);
+        }
+        return l;
+    };
+    const uint32_t oring_s = (uint32_t)__cvta_generic_to_shared(&sm.oring[0]);
+    auto op_read = [&](int32_t i) -> HOp {
+        union {
+            HOp o;
+            unsigned long long v[4];
+        } u;
+        const uint32_t a = oring_s + (uint32_t)((i & (OPRING - 1)) * (int32_t)sizeof(HOp));
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(u.v[0]), "=l"(u.v[1]) : "r"(a) : "memory");
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(u.v[2]), "=l"(u.v[3]) : "r"(a + 16) : "memory");
+        return u.o;
+    };
+    HOp op = op_read(0);
+    int32_t oi = 0;
+    while (oi < nops) {
+        HT(0);
+        // ---- descent: first level whose key is not < k (leftist_heap.hpp:30).  The sum decides unless a level ties on
+        // it; ties and the control flags of the operation take the slow path below ----
+        bool known = lane < L;
+        uint32_t stop = __ballot_sync(FULL, known && ksum >= op.sum);
+        const uint32_t slow = __ballot_sync(FULL, (known && ksum == op.sum) || (op.ctl & HOP_RESERVE) != 0 ||
+                                                      ((op.ctl & HOP_FIRST) != 0 && op.aux != cur_ord));
+        if (slow) {
+            if (op.ctl & HOP_RESERVE) {  // a leaf takes its node ids here, in sequence; f_heaps_level fills them in later
+                const int32_t need = op.anom;
                 if (cur + need > end) {
-                    unsigned long long at = 0;
-                    if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
-                    at = __shfl_sync(FULL, at, 0);
-                    if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
+                    cur = new_chunk();
+                    if (cur < 0) {
                         overflow = true;
                         break;
                     }
-                    cur = (int64_t)at;
                     end = cur + HEAP_CHUNK;
                 }
-                if (lane == j) mybase = (int32_t)cur;
+                if (lane == 0) w.leaf_base[v0 + op.aux] = cur;
                 cur += need;
-            } else if (nins > 0) {
-                int64_t ki = (int64_t)__shfl_sync(FULL, vi.ins_beg, j);  // global index of this vertex's first insert
-                // ---- working spine := spine of `root` ----
-                if (root != cur_root) {
-                    // the spine being left is remembered first: its heap may be the parent of a vertex that comes later
-                    // (the main chain comes back to it after a side branch); a heap that is not in the ring is
-                    // rebuilt from its nodes
-                    if (cur_root >= 0) {
-                        const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == cur_root);
-                        if (!have) {
-                            const int32_t sl = save_at;
-                            save_at = (save_at + 1) % NSAVE;
-                            if (lane < sp.L) {
-                                hn_store(&sm.snode[sl][lane], sp.nd);
-                                IdEid ie;
-                                ie.id = sp.nd_id;
-                                ie.eid = sp.nd_eid;
-                                sm.sid[sl][lane] = ie;
-                            }
-                            if (lane == 0) {
-                                sm.sroot[sl] = cur_root;
-                                sm.sL[sl] = sp.L;
-                                sm.snext[sl] = sp.next;
-                            }
-                            __syncwarp();
+                oi++;
+                if ((oi & 31) == 0) {
+                    issue_chunk((oi >> 5) + 2);
+                    asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    __syncwarp();
+                }
+                op = op_read(oi);
+                HT(1);
+                continue;
+            }
+            if ((op.ctl & HOP_FIRST) && op.aux != cur_ord) {  // this vertex does not continue the heap just built: switch spines
+                if (cur_ord >= 0) {
+                    const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sord[lane] == cur_ord);
+                    if (!have) {
+                        const int32_t sl = save_at;
+                        save_at = (save_at + 1) % NSAVE;
+                        if (lane < L) {
+                            HNode n;
+                            n.sum = ksum;
+                            n.anom = kanom;
+                            n.nz = knz;
+                            n.tot = ktot;
+                            n.left = left;
+                            n.right = 0;
+                            n.rank = (int16_t)rank;
+                            n.lrank = (int16_t)lrank;
+                            hn_store(&sm.snode[sl][lane], n);
+                            IdEid ie;
+                            ie.id = id;
+                            ie.eid = eid;
+                            sm.sid[sl][lane] = ie;
                         }
-                    }
-                    const uint32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sroot[lane] == root);
-                    if (root >= 0 && hit) {
-                        const int32_t sl = __ffs(hit) - 1;
-                        sp.L = sm.sL[sl];
-                        sp.next = sm.snext[sl];
-                        if (lane < sp.L) {
-                            sp.nd = hn_load(&sm.snode[sl][lane]);
-                            const IdEid ie = sm.sid[sl][lane];
-                            sp.nd_id = ie.id;
-                            sp.nd_eid = ie.eid;
+                        if (lane == 0) {
+                            sm.sord[sl] = cur_ord;
+                            sm.sL[sl] = L;
                         }
-                        if (sp.next >= 0) {
-                            sp.nx = hn_load(hn + sp.next);
-                            sp.nx_eid = hn_eid[sp.next];
-                        }
-                    } else {
-                        spine_reset(sp, hn, hn_eid, root);
+                        __syncwarp();
                     }
                 }
-                for (int32_t t = 0; t < nins && !overflow; t++, ki++) {
-                    if (ki - kbase >= 32) {  // inserts are consumed in stream order; skipped leaves may jump over chunks
-                        if (ki - kbase < 64) {
-                            kreg = knext;
-                            kbase += 32;
-                        } else {
-                            kbase += ((ki - kbase) >> 5) << 5;
-                            if (kbase + lane < kend) kreg = ins_ld(ins + kbase + lane);
-                        }
-                        if (kbase + 32 + lane < kend) knext = ins_ld(ins + kbase + 32 + lane);
+                const uint32_t hit = __ballot_sync(FULL, lane < NSAVE && sm.sord[lane] == op.aux);
+                if (op.aux >= 0 && hit) {
+                    const int32_t sl = __ffs(hit) - 1;
+                    L = sm.sL[sl];
+                    if (lane < L) {
+                        const HNode n = hn_load(&sm.snode[sl][lane]);
+                        const IdEid ie = sm.sid[sl][lane];
+                        ksum = n.sum;
+                        kanom = n.anom;
+                        knz = n.nz;
+                        ktot = n.tot;
+                        left = n.left;
+                        rank = n.rank;
+                        lrank = n.lrank;
+                        id = ie.id;
+                        eid = ie.eid;
                     }
-                    const InsKey k = ins_bcast(kreg, (int32_t)(ki - kbase));
-                    const int32_t p = spine_descend(sp, hn, hn_eid, k);
-                    if (p < 0) {
+                } else {
+                    L = extend(0, op.aux >= 0 ? __ldcg(chain_root + op.aux) : -1);
+                    if (L < 0) {
                         overflow = true;
                         break;
                     }
-                    const int32_t need = p + 1;
-                    if (cur + need > end) {
-                        unsigned long long at = 0;
-                        if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
-                        at = __shfl_sync(FULL, at, 0);
-                        if ((int64_t)at + HEAP_CHUNK > w.Hcap) {
-                            overflow = true;
-                            break;
-                        }
-                        cur = (int64_t)at;
-                        end = cur + HEAP_CHUNK;
-                    }
-                    const int32_t nbase = (int32_t)cur;
-                    cur += need;
-                    used += need;
-                    root = spine_apply<false>(sp, hn, hn_eid, hn_key, k, p, nbase, 0);  // ids are in order here: no key
-                    vseq += need;
                 }
-                if (overflow) break;
-                cur_root = root;
+                cur_ord = op.aux;
+                known = lane < L;
             }
-            if (lane == j) {
-                myroot = root;
-                mycnt = vseq;
+            bool lt;  // a->key < k (paf_data.hpp:142-159)
+            if (ksum != op.sum) lt = ksum < op.sum;
+            else if (kanom != op.anom) lt = kanom < op.anom;
+            else lt = (int64_t)knz * den(op.tot) > (int64_t)op.nz * den(ktot);
+            stop = __ballot_sync(FULL, known && !lt);
+            HT(2);
+        }
+        const int32_t p = stop ? __ffs(stop) - 1 : L;
+        HT(3);
+        const int32_t need = p + 1;
+        if (p >= SPMAX - 1 || cur + need > end) {
+            if (p >= SPMAX - 1) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
+                overflow = true;
+                break;
+            }
+            cur = new_chunk();
+            if (cur < 0) {
+                overflow = true;
+                break;
+            }
+            end = cur + HEAP_CHUNK;
+        }
+        const int32_t nbase = cur;
+        cur += need;
+        used += need;
+        // ---- ranks: the levels that swap are the strict suffix minima of a over [0, p]; the topmost one, m, is the last
+        // position of the minimum ----
+        const int32_t BIG = 1 << 20;
+        const int32_t a = lane < p ? (left < 0 ? lane : lrank + lane + 1) : (lane == p ? p + 1 : BIG);
+        const uint32_t enc = ((uint32_t)a << 5) | (uint32_t)(31 - lane);
+        const uint32_t mn = __reduce_min_sync(FULL, enc);
+        const int32_t amin = (int32_t)(mn >> 5);
+        const int32_t m = 31 - (int32_t)(mn & 31u);
+        int32_t smin = amin;   // min of a over [lane, p] (lanes <= m; set below for the others)
+        int32_t snext = amin;  // min of a over (lane, p]
+        for (int32_t mi = m; mi < p;) {  // suffix minima below the topmost swap: one redux each (usually one or two)
+            const uint32_t r = __reduce_min_sync(FULL, lane > mi ? enc : 0xffffffffu);
+            const int32_t am = (int32_t)(r >> 5);
+            const int32_t mj = 31 - (int32_t)(r & 31u);
+            smin = (lane > mi && lane <= mj) ? am : smin;
+            snext = (lane >= mi && lane < mj) ? am : snext;
+            mi = mj;
+        }
+        int32_t spill = -1;  // old left child of level m: its spine follows level m
+        if (m < p) spill = __shfl_sync(FULL, left, m);
+        HT(4);
+        // ---- records: N on lane p, the copy of level q on lane q, ids nbase + (p - q) (allocation order) ----
+        const bool is_copy = lane < p, is_new = lane == p, has = p < L;
+        const bool swp = is_copy && a < snext;  // swap: the new subtree goes left
+        const int32_t ch = nbase + (p - 1 - lane);
+        const int32_t right = is_copy ? (swp ? left : ch) : -1;
+        const int32_t old_id = id, old_rank = rank;
+        left = is_copy ? (swp ? ch : left) : (has ? old_id : -1);
+        lrank = is_copy ? (swp ? snext - (lane + 1) : lrank) : (has ? old_rank : 0);
+        rank = is_copy ? smin - lane : 1;
+        id = nbase + (p - lane);
+        ksum = is_new ? op.sum : ksum;
+        kanom = is_new ? op.anom : kanom;
+        knz = is_new ? op.nz : knz;
+        ktot = is_new ? op.tot : ktot;
+        eid = is_new ? op.eid : eid;
+        const bool last = (op.ctl & HOP_LAST) != 0;
+        if (lane <= p) {
+            HNode n;
+            n.sum = ksum;
+            n.anom = kanom;
+            n.nz = knz;
+            n.tot = ktot;
+            n.left = left;
+            n.right = right;
+            n.rank = (int16_t)rank;
+            n.lrank = (int16_t)lrank;
+            hn_store(hn + id, n);
+            hn_eid[id] = eid;
+            if (cmask >= 0) {
+                const int32_t s = id & cmask;
+                hn_store(&cnode[s], n);
+                IdEid ie;
+                ie.id = id;
+                ie.eid = eid;
+                ctag[s] = ie;
             }
         }
-        if (overflow) break;
-        if (base + lane < nt) {
-            root_at[base + lane] = myroot;
-            hroot[vi.x] = myroot;  // (an active leaf: the inherited root for now, its own after f_heaps_level)
-            w.vcnt[v0 + base + lane] = mycnt;
-            w.leaf_base[v0 + base + lane] = mybase;
+        // the next operation is read now (its chunk was issued three chunks ahead)
+        oi++;
+        if ((oi & 31) == 0) {
+            issue_chunk((oi >> 5) + 2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
         }
         __syncwarp();
+        op = op_read(oi);
+        HT(5);
+        if (m < p) {
+            L = extend(m + 1, spill);
+            if (L < 0) {
+                overflow = true;
+                break;
+            }
+        } else {
+            L = p + 1;
+        }
+        if (last) {
+            if (lane == 0) chain_root[cv] = nbase + p;
+            cur_ord = cv;
+            cv++;
+        }
+        HT(6);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef AA_HEAP_TIMERS
+    if (lane == 0 && w.vbase)
+        for (int i = 0; i < 8; i++) {
+            w.vbase[2 * i] = ht_acc[i];
+            w.vbase[2 * i + 1] = ht_n[i];
+        }
+#endif
     if (lane == 0) {
         w.heap_used[c] = used;
         w.status[c] = overflow ? 3 : 0;
@@ -2509,6 +2828,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
     int32_t root = vi.ppos < 0 ? -1 : w.root_at[v0 + vi.ppos];
     const int32_t nins = vi.nins & (VI_KIDS - 1);
     int32_t used = 0;
+    if (w.hmode[c] == 0 && w.status[c] != 0) return;  // a leaf of a contig the serial builder gave up on (arena overflow: rebuilt)
     bool overflow = *w.lvl_overflow != 0;
     if (nins > 0 && !overflow) {
         const InsKey *__restrict__ ins = w.ins + vi.ins_beg;
@@ -2590,15 +2910,24 @@ AA_HDN void f_node_rank(const Ws &w, int64_t id) {
     const unsigned long long key = w.hn_key[id];
     if (key != ~0ull) w.hn_key[id] = (unsigned long long)(w.vbase[key >> 32] + (int64_t)(uint32_t)key);
 }
-AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {
+AA_HDN void f_heaps_any(const Ws &w, int64_t c, void *scratch) {  // the serial builder of one streaming-mode contig
 #if defined(__CUDA_ARCH__)
-    f_heaps_warp(w, c, scratch);
+    f_heaps_chain(w, c, scratch);
 #else
     (void)scratch;
-    f_heaps(w, c);
+    f_heaps_ops(w, c);
 #endif
 }
-constexpr size_t HEAP_SMEM_BYTES = 12 * 1024;  // >= sizeof(HeapSmem) (device only)
+AA_HDN void f_heaps_leaf_any(const Ws &w, int64_t slot) {
+#if defined(__CUDA_ARCH__)
+    f_heaps_level(w, slot);
+#else
+    f_heaps_leaf_host(w, slot);
+#endif
+}
+AA_HD size_t heaps_chain_smem_bytes(int bits) {  // f_heaps_chain: fixed part + node cache of 1 << bits entries (tag 8 B + node 32 B)
+    return HEAP2_FIXED_BYTES + (bits > 0 ? ((size_t)1 << bits) * 40 : 0);
+}
 
 // ---- enumeration priority queue: binary min-heap under the total order (distance, node id, entry index)
 AA_HD bool pq_less(const PQEnt &a, const PQEnt &b) {

@@ -89,6 +89,10 @@ struct FnCtgEdges {
     int64_t *out;
     AA_HD void operator()(int64_t i, void *) const { f_ctg_edges(w, i, out); }
 };
+AA_FUNCTOR(FnOpsClass, f_ops_class(w, i))
+AA_FUNCTOR(FnOwnerJump, (f_owner_jump(w, i), f_owner_jump(w, i)))
+AA_FUNCTOR(FnOpsFill, f_ops_fill(w, i))
+AA_FUNCTOR(FnRootFill, f_root_fill(w, i))
 AA_FUNCTOR(FnLeafFlag, f_leaf_flag(w, i))
 AA_FUNCTOR(FnLeafList, f_leaf_list(w, i))
 AA_FUNCTOR(FnNodeRank, f_node_rank(w, i))
@@ -105,11 +109,11 @@ struct FnHeapsLevel {  // one warp per tree vertex of one depth (device only)
     int64_t first;
     __device__ void operator()(int64_t i, void *) const { f_heaps_level(w, first + i); }
 };
-struct FnHeapsLeaf {  // one warp per tree leaf with inserts (device only)
-    Ws w;
-    __device__ void operator()(int64_t i, void *) const { f_heaps_level(w, (int64_t)w.leaf_list[i]); }
-};
 #endif
+struct FnHeapsLeaf {  // one warp per tree leaf with inserts
+    Ws w;
+    AA_HD void operator()(int64_t i, void *) const { f_heaps_leaf_any(w, (int64_t)w.leaf_list[i]); }
+};
 AA_FUNCTOR(FnBfsPos, f_bfs_pos(w, i))
 AA_FUNCTOR(FnVInfo, f_vinfo(w, i))
 AA_FUNCTOR(FnInsFill, f_ins_fill(w, i))
@@ -792,6 +796,7 @@ struct Pipeline {
             return AA_ERR_NOMEM;
         }
         bk.for_each("heap_prep", Vtot, FnHeapPrep{w});
+        int64_t n_ins = 0;
         // BFS order of every contig's shortest-path tree, in parallel: Euler tour -> list ranking by pointer
         // jumping -> sort by (contig, depth, preorder); then the flat stream of inserts in that order
         {
@@ -822,7 +827,7 @@ struct Pipeline {
             bk.zero(w.ins_cnt + Vtot, 4);
             bk.for_each("vinfo", Vtot, FnVInfo{w});
             bk.scan_i32(w.ins_cnt, w.ins_off, Vtot + 1);
-            const int64_t n_ins = bk.read_i64(w.ins_off + Vtot);
+            n_ins = bk.read_i64(w.ins_off + Vtot);
             w.ins = A<InsKey>(n_ins);
             if (!w.ins) {
                 err = "device allocation failed (insert stream)";
@@ -830,6 +835,29 @@ struct Pipeline {
             }
             bk.for_each("ins_fill", Vtot, FnInsFill{w});
             bk.fill_ff(w.hroot, (size_t)Vtot * 4);  // vertices outside the tree have no heap
+#ifdef AA_HEAP_DUMP  // tools/heap_lab only: the insert stream of the largest contig, for the stand-alone kernel harness
+            if (const char *dp = std::getenv("AA_HEAP_DUMP_PATH")) {
+                const int64_t c = ctg_order[0];
+                const int64_t v0 = h_voff[(size_t)c], Vc = h_voff[(size_t)c + 1] - v0;
+                int32_t nt = 0;
+                bk.d2h(&nt, w.ntree + c, 4);
+                std::vector<VInfo> hv((size_t)nt);
+                bk.d2h(hv.data(), w.vinfo + v0, (size_t)nt * sizeof(VInfo));
+                int64_t io[2];
+                bk.d2h(&io[0], w.ins_off + v0, 8);
+                bk.d2h(&io[1], w.ins_off + v0 + nt, 8);
+                std::vector<InsKey> hk((size_t)(io[1] - io[0]));
+                bk.d2h(hk.data(), w.ins + io[0], hk.size() * sizeof(InsKey));
+                for (auto &v : hv) v.ins_beg -= (uint32_t)io[0];
+                if (FILE *f = std::fopen(dp, "wb")) {
+                    const int64_t hdr[4] = {nt, (int64_t)hk.size(), Vc, c};
+                    std::fwrite(hdr, 8, 4, f);
+                    std::fwrite(hv.data(), sizeof(VInfo), hv.size(), f);
+                    std::fwrite(hk.data(), sizeof(InsKey), hk.size(), f);
+                    std::fclose(f);
+                }
+            }
+#endif
         }
         // shallow, wide trees (dense contigs) are built level by level with one warp per vertex; everything else by the
         // streaming builder (one warp per contig)
@@ -863,19 +891,48 @@ struct Pipeline {
         w.lvl_overflow = A<int32_t>(1);
         // tree leaves with inserts leave the serial builder (they feed no other heap): one warp each, after it
         int64_t n_leaf = 0;
+        w.leaf_flag = A<int32_t>(Vtot + 1);
+        w.leaf_off = A<int64_t>(Vtot + 2);
+        w.leaf_base = A<int32_t>(Vtot);
         if (bk.device_kahn()) {
             w.vcnt = A<int32_t>(Vtot + 1);
             w.vbase = A<int64_t>(Vtot + 2);
-            w.leaf_flag = A<int32_t>(Vtot + 1);
-            w.leaf_off = A<int64_t>(Vtot + 2);
-            bk.zero(w.leaf_flag + Vtot, 4);
-            bk.for_each("leaf_flag", Vtot, FnLeafFlag{w});
-            bk.scan_i32(w.leaf_flag, w.leaf_off, Vtot + 1);
-            n_leaf = bk.read_i64(w.leaf_off + Vtot);
-            w.leaf_list = A<uint32_t>(n_leaf);
-            w.leaf_base = A<int32_t>(Vtot);
-            bk.for_each("leaf_list", Vtot, FnLeafList{w});
         }
+        bk.zero(w.leaf_flag + Vtot, 4);
+        bk.for_each("leaf_flag", Vtot, FnLeafFlag{w});
+        bk.scan_i32(w.leaf_flag, w.leaf_off, Vtot + 1);
+        n_leaf = bk.read_i64(w.leaf_off + Vtot);
+        w.leaf_list = A<uint32_t>(n_leaf);
+        bk.for_each("leaf_list", Vtot, FnLeafList{w});
+        // the operation stream of the serial builder (f_heaps_chain): inserts of the chain vertices + one id reservation per
+        // leaf, in BFS order; every vertex is pointed at the nearest chain vertex among itself and its tree ancestors
+        w.op_cnt = A<int32_t>(Vtot + 1);
+        w.op_off = A<int64_t>(Vtot + 2);
+        w.chain_flag = A<int32_t>(Vtot + 1);
+        w.chain_ord = A<int64_t>(Vtot + 2);
+        w.owner = A<int32_t>(Vtot);
+        w.chain_root = A<int32_t>(Vtot);
+        w.ops = A<HOp>(n_ins + n_leaf);
+        if (!w.leaf_flag || !w.leaf_off || !w.leaf_base || !w.leaf_list || !w.op_cnt || !w.op_off || !w.chain_flag || !w.chain_ord ||
+            !w.owner || !w.chain_root || !w.ops) {
+            err = "device allocation failed (heap operation stream)";
+            return AA_ERR_NOMEM;
+        }
+        bk.zero(w.op_cnt + Vtot, 4);
+        bk.zero(w.chain_flag + Vtot, 4);
+        bk.for_each("ops_class", Vtot, FnOpsClass{w});
+        bk.scan_i32(w.op_cnt, w.op_off, Vtot + 1);
+        bk.scan_i32(w.chain_flag, w.chain_ord, Vtot + 1);
+        {
+            int64_t maxV = 3;
+            for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
+            int jumps = 1;
+            while (((int64_t)1 << jumps) < maxV) jumps++;
+            for (int r = 0; r < (jumps + 1) / 2; r++) bk.for_each("owner_jump", Vtot, FnOwnerJump{w});  // two hops per launch
+        }
+        bk.for_each("ops_fill", Vtot, FnOpsFill{w});
+        // node cache of the serial builder: as large as still lets every contig of the batch be resident at once
+        w.heap_cache_bits = C <= 2 * 148 ? 11 : (C <= 4 * 148 ? 10 : (C <= 6 * 148 ? 9 : 8));
         // (a leaf of a streaming-mode contig reserves 32 ids per insert, at most a chunk; level mode wastes < 64 per vertex)
         int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 256 * n_leaf + 64 * (any_m1 ? Vtot : 0) + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
@@ -901,10 +958,11 @@ struct Pipeline {
             bk.zero(w.heap_top, 8);
             bk.zero(w.heap_used, (size_t)C * 8);
             bk.zero(w.lvl_overflow, 4);
-            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, HEAP_SMEM_BYTES);
+            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, heaps_chain_smem_bytes(w.heap_cache_bits));
+            bk.for_each("root_fill", Vtot, FnRootFill{w});
             bool overflow = false;
-#if defined(__CUDACC__)
             if (n_leaf > 0) bk.for_each_contig("heaps_leaf", n_leaf, FnHeapsLeaf{w});
+#if defined(__CUDACC__)
             if (any_m1)
                 for (int32_t d = 1; d < lvl_per; d++)
                     for (size_t k = 0; k < m1.size(); k++) {

@@ -20,6 +20,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #if defined(__CUDACC__)
 #define AA_HD __host__ __device__ __forceinline__
@@ -177,6 +178,19 @@ struct __attribute__((aligned(16))) ENext {
     int32_t hrank;  // its rank in the sequential allocation order (device path)
     int32_t pad;
 };
+// per heap node: everything a pop of this node needs (children, next heap root, their key deltas and order keys), gathered
+// by a parallel pass once the heaps are built, so that the enumeration's dependent chain is ONE load per pop instead of
+// node -> (children, edge) -> (keys)
+struct __attribute__((aligned(16))) XRec {
+    int32_t left, right, hv, hkey;  // successor nodes (-1: none); hkey/lkey/rkey: their order keys (id, or allocation rank)
+    int64_t lsum, rsum;             // key of the child minus key of the node
+    int64_t hsum;                   // key of the next heap's root
+    int32_t lanom, ranom;
+    int32_t hanom, lnz, ltot, rnz;
+    int32_t rtot, hnz, htot, lkey;
+    int32_t rkey, pad0, pad1, pad2;
+};
+static_assert(sizeof(XRec) == 96, "XRec is six 16-byte words");
 // ---- BFS order of the shortest-path tree, computed in parallel (Euler tour + list ranking), and the
 // flat stream of sidetrack inserts in that order (k_shortest_walks.hpp:196-215) -------------------------------
 constexpr uint32_t TOUR_END = 0xffffffffu;
@@ -328,6 +342,8 @@ struct Ws {
     uint32_t *leaf_list; // [n_leaf] their BFS slots
     int32_t *leaf_base;  // [Vtot] first of the 32 * nins node ids the streaming builder reserved for a leaf (keeps ids in order)
     ENext *enext;        // [E] (device enumeration only)
+    XRec *xrec;          // [heap_top] expansion records (device enumeration; nullptr when they would not fit)
+    int32_t *chunk_ctg;  // [Hcap / 64 + 1] contig that owns each run of 64 node ids (written by the heap builders)
     int64_t *heap_used;  // [C]
     // streaming builder, flat form (f_heaps_chain): the serial warp reads one stream of operations per contig
     HOp *ops;            // [n_ops] inserts of the chain vertices (tree vertices whose heap others inherit) + one id reservation per leaf
@@ -2542,6 +2558,10 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
         if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
         at = __shfl_sync(FULL, at, 0);
         if ((int64_t)at + HEAP_CHUNK > w.Hcap) return -1;
+        if (w.chunk_ctg) {
+            w.chunk_ctg[(at >> 6) + lane] = (int32_t)c;
+            w.chunk_ctg[(at >> 6) + 32 + lane] = (int32_t)c;
+        }
         return (int32_t)__reduce_max_sync(FULL, (uint32_t)at);
     };
     // spine of the heap rooted at `from` appended below level L0 (complete right spine, read through the cache)
@@ -2871,6 +2891,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
                     overflow = true;
                     break;
                 }
+                if (lane == 0 && w.chunk_ctg) w.chunk_ctg[at >> 6] = (int32_t)c;
                 cur = (int64_t)at;
                 end = cur + LCHUNK;
             }
@@ -3099,6 +3120,53 @@ AA_HDN void f_enext(const Ws &w, int64_t gv) {
         w.enext[k] = n;
     }
 }
+// parallel pass over the arena: the expansion record of every heap node (hn_eid < 0: the id was never allocated)
+AA_HDN void f_xrec(const Ws &w, int64_t id) {
+    const int32_t eid = w.hn_eid[id];
+    if (eid < 0) return;
+    const int64_t c = w.chunk_ctg[id >> 6];
+    if (w.status[c] != 0) return;
+    const bool keyed = w.hmode[c] != 0;
+    const HNode ch = hn_load(w.hn + id);
+    const ENext x = w.enext[w.eoff[w.vtx_off[c]] + eid];
+    XRec r;
+    r.left = ch.left;
+    r.right = ch.right;
+    r.hv = x.hv;
+    r.hkey = keyed ? x.hrank : x.hv;
+    r.hsum = x.sum;
+    r.hanom = x.anom;
+    r.hnz = x.nz;
+    r.htot = x.tot;
+    r.lsum = r.rsum = 0;
+    r.lanom = r.ranom = r.lnz = r.ltot = r.rnz = r.rtot = 0;
+    r.lkey = r.rkey = -1;
+    r.pad0 = r.pad1 = r.pad2 = 0;
+    if (ch.left >= 0) {
+        const HNode xl = hn_load(w.hn + ch.left);
+        r.lsum = xl.sum - ch.sum;
+        r.lanom = xl.anom - ch.anom;
+        r.lnz = xl.nz - ch.nz;
+        r.ltot = xl.tot - ch.tot;
+        r.lkey = keyed ? (int32_t)(uint32_t)w.hn_key[ch.left] : ch.left;
+    }
+    if (ch.right >= 0) {
+        const HNode xr = hn_load(w.hn + ch.right);
+        r.rsum = xr.sum - ch.sum;
+        r.ranom = xr.anom - ch.anom;
+        r.rnz = xr.nz - ch.nz;
+        r.rtot = xr.tot - ch.tot;
+        r.rkey = keyed ? (int32_t)(uint32_t)w.hn_key[ch.right] : ch.right;
+    }
+    union {
+        XRec r;
+        V16 v[6];
+    } u;
+    u.r = r;
+    V16 *q = reinterpret_cast<V16 *>(w.xrec + id);
+#pragma unroll
+    for (int i = 0; i < 6; i++) q[i] = u.v[i];
+}
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative K-walk enumeration (device only; the host emulation runs f_enum) ------------------------
 // Same pop sequence as the reference's std::priority_queue<tuple<Distance, heap_t*, int64_t>> (total order:
@@ -3136,7 +3204,18 @@ struct __attribute__((aligned(16))) QE {
 static_assert(sizeof(QE) == sizeof(PQEnt), "the backlog reuses the PQEnt array");
 struct EnumSmem {
     QE f[FCAP];
+    QE stage[4];  // successors of a serial step, written by lanes 0..2 and read back by all lanes
 };
+__device__ __forceinline__ XRec xrec_ld(const XRec *p) {
+    union {
+        XRec r;
+        V16 v[6];
+    } u;
+    const V16 *q = reinterpret_cast<const V16 *>(p);
+#pragma unroll
+    for (int i = 0; i < 6; i++) u.v[i] = q[i];
+    return u.r;
+}
 __device__ __forceinline__ QE qe_ld(const QE *p) {
     union {
         QE e;
@@ -3207,7 +3286,19 @@ __device__ __forceinline__ bool qe_dn_less(const QE &a, const QE &b, bool wide) 
     const int32_t k = (a.k1 < b.k1) | ((a.k1 == b.k1) & t);
     return ((a.sum < b.sum) | ((a.sum == b.sum) & k)) != 0;
 }
+#ifdef AA_ENUM_TIMERS
+#define ET_DECL long long et_t = clock64(), et_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long et_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define ET(i) do { const long long et_now = clock64(); et_acc[i] += et_now - et_t; et_n[i]++; et_t = et_now; } while (0)
+#else
+#define ET_DECL
+#define ET(i)
+#endif
 __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
+    ET_DECL
+#ifdef AA_ENUM_TIMERS
+    int32_t plat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long front_sz = 0, front_n = 0;
+#endif
     EnumSmem &sm = *reinterpret_cast<EnumSmem *>(scratch);
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
@@ -3227,6 +3318,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     QE *__restrict__ back = reinterpret_cast<QE *>(w.pq + 3 * wo);  // the backlog
     const HNode *__restrict__ hn = w.hn;
     const ENext *__restrict__ enext = w.enext + e0;
+    const XRec *__restrict__ xrec = w.xrec;  // nullptr: the arena was too large for expansion records
     const int32_t K = w.K;
     // key packing for this contig
     int32_t vb = 1;
@@ -3512,12 +3604,227 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     // following round as candidate 0 (already popped; only its successors are still to come)
     bool carry = false;
     QE cy = INF;
+    // Serial steps.  Queues full of exact distance ties pop in the order of the heap nodes, and a node's children were
+    // allocated before it: the next pop is almost always a successor of the last one (a descent through equal keys), so a
+    // 32-wide speculative round confirms one or two candidates.  In that regime one pop is handled at a time: lanes 0..2
+    // work out the three successors, the smallest one that precedes the front is popped at once (and carried, as in
+    // the rounds), the others enter the queue.  Same order, same entry indices.
+    bool serial = false;
+    int32_t pops16 = 16 * 16, ser_steps = 0;
+    // (a lone warp per SM is latency-bound: a round of ~5 k cycles loses against ~2.2 k per serial step below ~2.3 pops per
+    // round; with several contigs per SM the instruction count decides and the break-even is lower)
+    const int32_t ser_thr16 = w.C > 2 * 148 ? 22 : 36;
+    XRec xn;
+    int32_t p12n = -1;
+    bool have_xn = false;
+    auto record = [&](const QE &e) {
+        if (lane == 0) {
+            D4 cd;
+            cd.sum = e.sum;
+            cd.anom = (int32_t)(e.k1 >> (S + 1));
+            cd.nz = e.nz;
+            cd.tot = e.tot;
+            cd.aux = 0;
+            dist[nd] = cd;
+            last[nd] = (int32_t)(uint32_t)e.k2;
+        }
+        nd++;
+    };
     while (nd < K) {
         if (n0 == 0 && np == 0 && !carry) {
             if (nR == 0) break;
+            ET(7);
             refill();
+            ET(0);
             continue;
         }
+        if (serial) {
+            ET(7);
+            QE t;
+            if (carry) {
+                t = cy;
+                carry = false;
+            } else {  // pop the front minimum
+                const QE p0 = qe_shfl(P, ShIdx{0});
+                bool from_p = np > 0;
+                QE rh = INF;
+                if (n0 > 0) {
+                    rh = qe_ld(fslot(0));
+                    if (np == 0 || qe_less(rh, p0, wide)) from_p = false;
+                }
+                t = from_p ? p0 : rh;
+                if (from_p) {
+                    const QE dn = qe_shfl(P, ShDown{1});
+                    P = lane + 1 < np ? dn : INF;
+                    np--;
+                } else {
+                    head = (head + 1) & FMASK;
+                    n0--;
+                }
+                record(t);
+                if (nd >= K) break;
+            }
+            ET(1);
+            // ---- its successors: next-root on lane 0, left child on lane 1, right child on lane 2 ----
+            const int32_t idx = (int32_t)(uint32_t)t.k2;
+            const int32_t anom = (int32_t)(t.k1 >> (S + 1));
+            QE a = INF;
+            bool valid = false;
+            int32_t snode = -1;
+            int32_t p12;
+            if (xrec) {
+                XRec x;
+                if (have_xn) {  // the carried entry's record was requested when it was chosen
+                    x = xn;
+                    p12 = p12n;
+                    have_xn = false;
+                } else {
+                    const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
+                    x = xrec_ld(xrec + node);
+                    p12 = ep[idx];
+                }
+                snode = lane == 0 ? x.hv : (lane == 1 ? x.left : x.right);
+                valid = lane < 3 && snode >= 0;
+                if (valid) {
+                    const int64_t dsum = lane == 0 ? x.hsum : (lane == 1 ? x.lsum : x.rsum);
+                    const int32_t danom = lane == 0 ? x.hanom : (lane == 1 ? x.lanom : x.ranom);
+                    const int32_t dnz = lane == 0 ? x.hnz : (lane == 1 ? x.lnz : x.rnz);
+                    const int32_t dtot = lane == 0 ? x.htot : (lane == 1 ? x.ltot : x.rtot);
+                    const int32_t okv = lane == 0 ? x.hkey : (lane == 1 ? x.lkey : x.rkey);
+                    a.sum = t.sum + dsum;
+                    a.nz = t.nz + dnz;
+                    a.tot = t.tot + dtot;
+                    a.k1 = make_k1(anom + danom, a.nz, a.tot);
+                    a.k2 = (uint64_t)(uint32_t)okv << 32;
+                }
+            } else {
+                const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
+                const HNode ch = hn_load(hn + node);
+                const int32_t ceid = w.hn_eid[node];
+                p12 = ep[idx];
+                if (lane == 0) {
+                    const ENext x = enext[ceid];
+                    if (x.hv >= 0) {
+                        a.sum = t.sum + x.sum;
+                        a.nz = t.nz + x.nz;
+                        a.tot = t.tot + x.tot;
+                        a.k1 = make_k1(anom + x.anom, a.nz, a.tot);
+                        a.k2 = (uint64_t)(uint32_t)(keyed ? x.hrank : x.hv) << 32;
+                        snode = x.hv;
+                        valid = true;
+                    }
+                } else if (lane < 3) {
+                    const int32_t cid = lane == 1 ? ch.left : ch.right;
+                    if (cid >= 0) {
+                        const HNode xc = hn_load(hn + cid);
+                        a.sum = t.sum + xc.sum - ch.sum;
+                        a.nz = t.nz + xc.nz - ch.nz;
+                        a.tot = t.tot + xc.tot - ch.tot;
+                        a.k1 = make_k1(anom + xc.anom - ch.anom, a.nz, a.tot);
+                        a.k2 = okey(cid);
+                        snode = cid;
+                        valid = true;
+                    }
+                }
+            }
+            ET(2);
+            const uint32_t vmask = __ballot_sync(FULL, valid);
+            if (valid) {
+                const int32_t id = ne + __popc(vmask & lt);
+                a.k2 |= (uint32_t)id;
+                en[id] = snode;
+                ep[id] = lane == 0 ? idx : p12;
+            }
+            ne += __popc(vmask);
+            if (valid && hasB && !qe_less(a, B, wide)) valid = false;  // beyond the K walks: dropped
+            // ---- the smallest successor that precedes the front is the next pop ----
+            QE fm = qe_shfl(P, ShIdx{0});
+            if (n0 > 0) {
+                const QE rh = qe_ld(fslot(0));
+                if (np == 0 || qe_less(rh, fm, wide)) fm = rh;
+            }
+            const bool front_empty = n0 == 0 && np == 0;
+            if (lane < 3) qe_st(&sm.stage[lane], a);
+            uint32_t live = __ballot_sync(FULL, valid) & 7u;
+            __syncwarp();
+            const QE b0 = qe_ld(&sm.stage[0]), b1 = qe_ld(&sm.stage[1]), b2 = qe_ld(&sm.stage[2]);
+            __syncwarp();
+            int32_t best = -1;
+            {
+                QE bm = INF;
+                if ((live & 1u)) {
+                    bm = b0;
+                    best = 0;
+                }
+                if ((live & 2u) && (best < 0 || qe_less(b1, bm, wide))) {
+                    bm = b1;
+                    best = 1;
+                }
+                if ((live & 4u) && (best < 0 || qe_less(b2, bm, wide))) {
+                    bm = b2;
+                    best = 2;
+                }
+                const bool ok = best >= 0 && (front_empty ? (!hasT || qe_less(bm, T, wide)) : qe_less(bm, fm, wide));
+                if (ok) {
+                    record(bm);
+                    cy = bm;
+                    carry = true;
+                    live &= ~(1u << best);
+                    if (xrec && nd < K) {  // its expansion record is requested now and arrives while the others are queued
+                        const int32_t nnode = __shfl_sync(FULL, snode, best);
+                        xn = xrec_ld(xrec + nnode);
+                        p12n = best == 0 ? idx : p12;
+                        have_xn = true;
+                    }
+                }
+            }
+            ET(3);
+            if (nd >= K) break;
+            // ---- the other successors enter the queue ----
+#pragma unroll
+            for (int32_t j = 0; j < 3; j++) {
+                if (!(live & (1u << j))) continue;
+                const QE &e = j == 0 ? b0 : (j == 1 ? b1 : b2);
+                if (hasT && !qe_less(e, T, wide)) {
+                    if (lane == 0) qe_st(back + nR, e);
+                    nR++;
+                } else {
+                    pend_insert(e);
+                }
+            }
+            ET(5);
+            if (++ser_steps >= 24) {  // one speculative round as a probe: has the queue left the tie regime?
+                serial = false;
+                have_xn = false;  // (a carried entry is expanded by the round itself)
+                width = 8;
+                ser_steps = 0;
+            }
+            continue;
+        }
+        ET(7);
+        const int32_t nd_round = nd;
+#ifdef AA_ENUM_TIMERS
+        {   // plateau statistics: entries of the front that tie with its minimum on the distance
+            QE fm = qe_shfl(P, ShIdx{0});
+            if (n0 > 0) {
+                const QE rh = qe_ld(fslot(0));
+                if (np == 0 || qe_less(rh, fm, wide)) fm = rh;
+            }
+            int32_t cnt = __popc(__ballot_sync(FULL, lane < np && P.sum == fm.sum && P.k1 == fm.k1));
+            for (int32_t i0 = 0; i0 < n0; i0 += 32) {
+                const bool in = i0 + lane < n0;
+                QE x = INF;
+                if (in) x = qe_ld(fslot(i0 + lane));
+                const int32_t c1 = __popc(__ballot_sync(FULL, in && x.sum == fm.sum && x.k1 == fm.k1));
+                cnt += c1;
+                if (c1 < 32) break;
+            }
+            int32_t bkt = 0;
+            while ((1 << bkt) < cnt && bkt < 11) bkt++;
+            plat[bkt]++;
+            if (!carry) { front_sz += n0 + np; front_n++; }
+        }
+#endif
         // ---- candidates: the smallest entries of pending + run head, sorted over the lanes ----
         QE t = INF;
         int32_t from_pend = 0;
@@ -3562,12 +3869,47 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         int32_t ncand = n0 + np + cr < width ? n0 + np + cr : width;
         if (ncand > K - nd + cr) ncand = K - nd + cr;
         const bool have = lane < ncand;
+        ET(1);
         // ---- their successors (speculative beyond the first candidate) ----
         QE a0 = INF, a1 = INF, a2 = INF;
         int32_t p0 = -1, p12 = -1;  // prev of the successors
         bool v0s = false, v1s = false, v2s = false;
         int32_t sn0 = -1, sn1 = -1, sn2 = -1;  // node ids of the successors
-        if (have) {
+        if (have && xrec) {
+            const int32_t idx = (int32_t)(uint32_t)t.k2;
+            const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
+            const int32_t anom = (int32_t)(t.k1 >> (S + 1));
+            const XRec x = xrec_ld(xrec + node);
+            p12 = ep[idx];
+            p0 = idx;
+            if (x.hv >= 0) {
+                a0.sum = t.sum + x.hsum;
+                a0.nz = t.nz + x.hnz;
+                a0.tot = t.tot + x.htot;
+                a0.k1 = make_k1(anom + x.hanom, a0.nz, a0.tot);
+                a0.k2 = (uint64_t)(uint32_t)x.hkey << 32;
+                sn0 = x.hv;
+                v0s = true;
+            }
+            if (x.left >= 0) {
+                a1.sum = t.sum + x.lsum;
+                a1.nz = t.nz + x.lnz;
+                a1.tot = t.tot + x.ltot;
+                a1.k1 = make_k1(anom + x.lanom, a1.nz, a1.tot);
+                a1.k2 = (uint64_t)(uint32_t)x.lkey << 32;
+                sn1 = x.left;
+                v1s = true;
+            }
+            if (x.right >= 0) {
+                a2.sum = t.sum + x.rsum;
+                a2.nz = t.nz + x.rnz;
+                a2.tot = t.tot + x.rtot;
+                a2.k1 = make_k1(anom + x.ranom, a2.nz, a2.tot);
+                a2.k2 = (uint64_t)(uint32_t)x.rkey << 32;
+                sn2 = x.right;
+                v2s = true;
+            }
+        } else if (have) {
             const int32_t idx = (int32_t)(uint32_t)t.k2;
             const int32_t node = keyed ? en[idx] : (int32_t)(t.k2 >> 32);
             const int32_t anom = (int32_t)(t.k1 >> (S + 1));
@@ -3607,6 +3949,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 v2s = true;
             }
         }
+        ET(2);
         // ---- how many candidates does the sequential order confirm? ----
         int32_t m = ncand;
         bool violated = false;
@@ -3629,6 +3972,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             }
         }
         width = m >= ncand ? (2 * width < 32 ? 2 * width : 32) : (2 * m + 2 < 32 ? 2 * m + 2 : 32);
+        ET(3);
         // ---- commit candidates 0..m-1 ----
         const bool com = lane < m;
         if (com && !(carry && lane == 0)) {
@@ -3699,6 +4043,9 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             nd++;
             carry = true;
         }
+        // pops this round (running mean, 1/16 units): below ~2 a round costs more than serial steps
+        pops16 = (pops16 + 16 * (nd - nd_round)) >> 1;
+        if (!wide && pops16 < ser_thr16 && !(w.heaps_variant & 1)) serial = true;
         {  // the committed entries leave the front: a prefix of the pending lanes and a prefix of the run
             const int32_t na = __popc(__ballot_sync(FULL, com && from_pend));
             if (na > 0) {
@@ -3710,6 +4057,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             n0 -= m - cr - na;
         }
         if (nd >= K) break;
+        ET(4);
         // ---- the successors enter the queue: backlog appends in parallel, pending inserts one by one ----
 #pragma unroll
         for (int32_t sidx = 0; sidx < 3; sidx++) {
@@ -3734,7 +4082,17 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 }
             }
         }
+        ET(5);
     }
+#ifdef AA_ENUM_TIMERS
+    if (lane == 0 && g.V > 4000)
+        printf("enum ctg %ld V %d walks %d entries %d | refill %lld/%lld cand %lld/%lld expand %lld/%lld scan %lld/%lld commit %lld/%lld succ %lld/%lld other %lld/%lld\n",
+               (long)c, g.V, nd, ne, et_acc[0], et_n[0], et_acc[1], et_n[1], et_acc[2], et_n[2], et_acc[3], et_n[3], et_acc[4], et_n[4], et_acc[5], et_n[5],
+               et_acc[7], et_n[7]);
+    if (lane == 0 && g.V > 4000)
+        printf("  plateau size (log2 buckets 1,2,4,..): %d %d %d %d %d %d %d %d %d %d %d %d | avg front %lld backlog %d\n", plat[0], plat[1], plat[2], plat[3], plat[4],
+               plat[5], plat[6], plat[7], plat[8], plat[9], plat[10], plat[11], front_n ? front_sz / front_n : 0, nR);
+#endif
     if (lane == 0) w.n_walk[c] = nd;
 }
 #endif
@@ -3746,7 +4104,7 @@ AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {
     f_enum(w, c);
 #endif
 }
-constexpr size_t ENUM_SMEM_BYTES = 1024 * 32;  // >= sizeof(EnumSmem) (device only)
+constexpr size_t ENUM_SMEM_BYTES = 1024 * 32 + 128;  // >= sizeof(EnumSmem) (device only)
 
 // phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.

@@ -129,6 +129,7 @@ struct FnBfsKey {
 };
 AA_FUNCTOR(FnRevPack, f_rev_pack(w, i))
 AA_FUNCTOR(FnENext, f_enext(w, i))
+AA_FUNCTOR(FnXRec, f_xrec(w, i))
 AA_FUNCTOR(FnRelaxInit, f_relax_init(w, i))
 AA_FUNCTOR(FnRelaxUnpack, f_relax_unpack(w, i))
 AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
@@ -936,13 +937,15 @@ struct Pipeline {
         // (a leaf of a streaming-mode contig reserves 32 ids per insert, at most a chunk; level mode wastes < 64 per vertex)
         int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 256 * n_leaf + 64 * (any_m1 ? Vtot : 0) + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
+        int64_t heap_top_h = 0;  // node ids handed out (device path)
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
             w.Hcap = hcap;
             const size_t arena_mark = bk.alloc_mark();
             w.hn = A<HNode>(hcap);
             w.hn_eid = A<int32_t>(hcap);
-            if (!w.hn || !w.hn_eid) {
+            w.chunk_ctg = bk.device_kahn() ? A<int32_t>(hcap / 64 + 66) : nullptr;
+            if (!w.hn || !w.hn_eid || (bk.device_kahn() && !w.chunk_ctg)) {
                 err = "device allocation failed (sidetrack heap arena)";
                 return AA_ERR_NOMEM;
             }
@@ -953,6 +956,7 @@ struct Pipeline {
                     return AA_ERR_NOMEM;
                 }
                 bk.fill_ff(w.hn_key, (size_t)hcap * 8);
+                bk.fill_ff(w.hn_eid, (size_t)hcap * 4);  // ids that are never allocated stay -1 (f_xrec skips them)
                 bk.zero(w.vcnt, (size_t)(Vtot + 1) * 4);
             }
             bk.zero(w.heap_top, 8);
@@ -981,6 +985,7 @@ struct Pipeline {
             if (!overflow && bk.device_kahn()) {
                 // (owner slot, number) of every node -> its rank in the sequential allocation order
                 const int64_t top = bk.read_i64((const int64_t *)w.heap_top);
+                heap_top_h = top;
                 bk.scan_i32(w.vcnt, w.vbase, Vtot + 1);
                 bk.for_each("node_rank", top, FnNodeRank{w});
             }
@@ -1015,6 +1020,17 @@ struct Pipeline {
                 return AA_ERR_NOMEM;
             }
             bk.for_each("enext", Vtot, FnENext{w});
+            // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
+            w.xrec = nullptr;
+            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records
+            if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget() / 2) {
+                w.xrec = A<XRec>(heap_top_h);
+                if (!w.xrec) {
+                    err = "device allocation failed (expansion records)";
+                    return AA_ERR_NOMEM;
+                }
+                bk.for_each("xrec", heap_top_h, FnXRec{w});
+            }
         }
         bk.for_each_contig("enum", C, FnEnum{w, d_ord}, ENUM_SMEM_BYTES);
         bk.phase_end(PH_ENUM);

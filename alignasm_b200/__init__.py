@@ -282,15 +282,18 @@ class Solver:
         self._h = h
         self.device = device
 
-    def _check(self, st):
+    def _check(self, st, res=None):
         if st != 0:
-            raise AlignasmError(st, self._lib.aa_last_error(self._h).decode())
+            msg = self._lib.aa_last_error(self._h).decode()
+            if res is not None:  # AA_ERR_UNSOLVABLE leaves a filled result behind: it is the library's memory, give it back
+                self._lib.aa_result_free(C.byref(res))
+            raise AlignasmError(st, msg)
 
     def solve(self, batch, copy=True, **kw):
         """Host buffers in, host result out (the e2e path: H2D + kernels + D2H).  copy=False: see Result."""
         res = aa_result()
         o = _opts(**kw)
-        self._check(self._lib.aa_solve(self._h, C.byref(batch.c_struct()), C.byref(o), C.byref(res)))
+        self._check(self._lib.aa_solve(self._h, C.byref(batch.c_struct()), C.byref(o), C.byref(res)), res)
         return Result(res, batch.n_blk, self._lib.aa_result_free, copy=copy)
 
     def upload(self, batch):
@@ -305,7 +308,7 @@ class Solver:
             self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), None))
             return None
         res = aa_result()
-        self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), C.byref(res)))
+        self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), C.byref(res)), res)
         return Result(res, dev.n_blk, self._lib.aa_result_free)
 
     def stats(self):
@@ -360,7 +363,9 @@ def solve_multi(batch, devices, **kw):
     o = _opts(**kw)
     st = lib.aa_solve_multi(dev, len(devices), C.byref(batch.c_struct()), C.byref(o), C.byref(res))
     if st != 0:
-        raise AlignasmError(st, (lib.aa_multi_last_error() or b"").decode())
+        msg = (lib.aa_multi_last_error() or b"").decode()
+        lib.aa_result_free(C.byref(res))  # (a no-op on an empty result; AA_ERR_UNSOLVABLE leaves a filled one)
+        raise AlignasmError(st, msg)
     return Result(res, batch.n_blk, lib.aa_result_free)
 
 

@@ -217,10 +217,18 @@ struct CudaBackend {
         cudaError_t e = cudaMalloc(&p, n ? n : 256);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            oom = true;  // recoverable: the next solve / upload starts from an empty pool
             fail("cudaMalloc(batch)", e);
             return nullptr;
         }
         return p;
+    }
+    // after a solve that stopped half-way: nothing may still be running on either stream when the pool is reused
+    void quiesce() {
+        cudaStreamSynchronize(main_stream);
+        cudaStreamSynchronize(side_stream);
+        side_pending = false;
+        stream = main_stream;
     }
     void free_persistent(void *p) { cudaFree(p); }
 

@@ -7,7 +7,7 @@
 #include "../../include/alignasm_b200.h"
 
 #include <algorithm>
-#include <map>
+#include <condition_variable>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -19,27 +19,47 @@
 namespace {
 thread_local std::string g_multi_err;
 
-// contexts are kept between calls (a context owns its pooled workspace: a warm one makes no cudaMalloc); the key
-// is (device, how many times the device was named before in the list), so naming a device twice gives two contexts
+// Contexts are kept between calls (a context owns its pooled workspace: a warm one makes no cudaMalloc).  This is the one
+// piece of process-wide state of the library, and it is guarded: a call CHECKS OUT one context per shard for the whole
+// shard solve (a context is one bump pool, one pinned staging buffer and one pair of streams: never shared), a device whose
+// cached contexts are all busy gets a fresh one, and aa_multi_release waits for running solves.
+struct CtxSlot {
+    int32_t device;
+    aa_ctx *ctx;
+    bool busy;
+};
 std::mutex g_ctx_mutex;
-std::map<std::pair<int32_t, int32_t>, aa_ctx *> g_ctx_cache;
+std::condition_variable g_ctx_cv;
+std::vector<CtxSlot> g_ctx_cache;
 
-aa_status cached_ctx(int32_t device, int32_t nth, aa_ctx **out, std::string &err) {
-    std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    auto it = g_ctx_cache.find({device, nth});
-    if (it != g_ctx_cache.end()) {
-        *out = it->second;
-        return AA_OK;
+aa_status checkout_ctx(int32_t device, aa_ctx **out, std::string &err) {
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        for (auto &s : g_ctx_cache)
+            if (s.device == device && !s.busy) {
+                s.busy = true;
+                *out = s.ctx;
+                return AA_OK;
+            }
     }
-    aa_ctx *ctx = nullptr;
+    aa_ctx *ctx = nullptr;  // created outside the lock: cudaMalloc / stream creation take milliseconds
     aa_status st = aa_create(&ctx, device);
     if (st != AA_OK) {
         err = aa_last_error(nullptr);
         return st;
     }
-    g_ctx_cache[{device, nth}] = ctx;
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    g_ctx_cache.push_back({device, ctx, true});
     *out = ctx;
     return AA_OK;
+}
+void checkin_ctx(aa_ctx *ctx) {
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        for (auto &s : g_ctx_cache)
+            if (s.ctx == ctx) s.busy = false;
+    }
+    g_ctx_cv.notify_all();
 }
 
 struct Shard {
@@ -82,14 +102,22 @@ extern "C" {
 
 const char *aa_multi_last_error(void) { return g_multi_err.c_str(); }
 
-/* release the contexts aa_solve_multi keeps between calls */
+/* release the contexts aa_solve_multi keeps between calls (waits for solves that are still running on them) */
 void aa_multi_release(void) {
-    std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    for (auto &kv : g_ctx_cache) aa_destroy(kv.second);
+    std::unique_lock<std::mutex> lock(g_ctx_mutex);
+    g_ctx_cv.wait(lock, [] {
+        for (auto &s : g_ctx_cache)
+            if (s.busy) return false;
+        return true;
+    });
+    for (auto &s : g_ctx_cache) aa_destroy(s.ctx);
     g_ctx_cache.clear();
 }
 
-/* cost model of one contig: the fixed K-walk enumeration plus the serial per-block chain (relax / heaps / walk 0) */
+/* cost model of one contig = the SM time it takes (one warp per contig in the serial phases): the K-walk enumeration is
+   ~1.3 us per walk whatever the contig's size, the heap / relax / walk-0 chains ~0.6 us per block (C2 on one B200, round 2:
+   13 ms of enumeration for every contig above a few thousand blocks, 22 ms of heap inserts for the 43 099-block contig).
+   Largest first also puts the longest serial chains, which bound a shard from below, on different devices. */
 void aa_shard_contigs(const aa_batch *b, int32_t max_walks, int32_t n_shards, int32_t *shard_of) {
     const int64_t C = b->n_ctg;
     const double K = max_walks > 0 ? std::min<double>(max_walks, 10000) : 10000.0;
@@ -97,7 +125,7 @@ void aa_shard_contigs(const aa_batch *b, int32_t max_walks, int32_t n_shards, in
     std::vector<int64_t> order((size_t)C);
     for (int64_t c = 0; c < C; c++) {
         const double n = (double)(b->ctg_off[c + 1] - b->ctg_off[c]);
-        cost[(size_t)c] = (n > 1 ? 0.4 * K : 0.0) + 14.0 * n;
+        cost[(size_t)c] = (n > 1 ? 1.3 * K : 0.0) + 0.6 * n;
         order[(size_t)c] = c;
     }
     std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
@@ -132,13 +160,12 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
             if (s.ctgs.empty()) return;
             s.ctg_off.assign(1, 0);
             for (int64_t c : s.ctgs) s.ctg_off.push_back(s.ctg_off.back() + (b->ctg_off[c + 1] - b->ctg_off[c]));
-            int32_t nth = 0;
-            for (int32_t q = 0; q < k; q++) nth += devices[q] == devices[k];
             aa_ctx *ctx = nullptr;
-            s.st = cached_ctx(devices[k], nth, &ctx, s.err);
+            s.st = checkout_ctx(devices[k], &ctx, s.err);  // exclusively ours until the shard is solved
             if (s.st != AA_OK) return;
             s.st = aa_solve_subset(ctx, b, s.ctgs.data(), (int64_t)s.ctgs.size(), &o, &s.res);  // staged from the caller's arrays
             if (s.st != AA_OK) s.err = aa_last_error(ctx);
+            checkin_ctx(ctx);
         });
     for (auto &t : pool) t.join();
     aa_status st = AA_OK;

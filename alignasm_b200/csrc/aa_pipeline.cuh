@@ -212,6 +212,10 @@ struct DevBatch {
     const int64_t *h_ctg_off = nullptr, *h_qs = nullptr, *h_qe = nullptr;  // the caller's arrays for a one-shot solve
     std::vector<void *> owned;
     bool pooled = false;  // arrays live in the solve workspace (one-shot aa_solve): nothing to free
+    // a resident batch is sorted once, when it is uploaded (the order depends on the batch alone); a one-shot solve sorts inside
+    bool sorted = false;
+    std::vector<int32_t> perm, sorted_index, ctg_order;
+    int32_t *d_perm = nullptr, *d_ord = nullptr;
 };
 
 inline void rows_alloc_host(aa_rows &r, int64_t n) {
@@ -379,6 +383,23 @@ struct Pipeline {
             d->h_qs = d->own_qs.data();
             d->h_qe = d->own_qe.data();
         }
+        if (!pooled) {  // resident: the host sort (OC1) and the contig order are part of the upload
+            host_sort_perm(*d, d->perm, d->sorted_index, d->ctg_order, bk.host_threads());
+            d->d_perm = (int32_t *)bk.alloc_persistent((size_t)std::max<int64_t>(d->B, 1) * 4);
+            d->d_ord = (int32_t *)bk.alloc_persistent((size_t)std::max<int64_t>(d->C, 1) * 4);
+            if (!d->d_perm || !d->d_ord) {
+                if (d->d_perm) d->owned.push_back(d->d_perm);
+                if (d->d_ord) d->owned.push_back(d->d_ord);
+                free_batch(d);
+                err = "device allocation failed while staging the batch";
+                return AA_ERR_NOMEM;
+            }
+            d->owned.push_back(d->d_perm);
+            d->owned.push_back(d->d_ord);
+            bk.h2d(d->d_perm, d->perm.data(), (size_t)d->B * 4);
+            bk.h2d(d->d_ord, d->ctg_order.data(), (size_t)d->C * 4);
+            d->sorted = true;
+        }
         if (!pooled) bk.sync();  // (the staged copies of a one-shot solve are ordered before its kernels on the stream)
         out = d;
         return AA_OK;
@@ -465,13 +486,19 @@ struct Pipeline {
         delete d;
     }
 
-#define AA_BK_CHECK()            \
-    do {                         \
-        if (!bk.ok()) {          \
-            err = bk.error();    \
-            return AA_ERR_CUDA;  \
-        }                        \
+#define AA_BK_CHECK()                                             \
+    do {                                                          \
+        if (!bk.ok()) {                                           \
+            err = bk.error();                                     \
+            return bk_out_of_memory() ? AA_ERR_NOMEM : AA_ERR_CUDA; \
+        }                                                         \
     } while (0)
+    // (a failed workspace allocation is reported as AA_ERR_NOMEM, as the header documents; backends without the notion say no)
+    template <class B = BK>
+    auto bk_oom_impl(int) -> decltype(std::declval<B &>().oom, bool()) { return bk.oom; }
+    template <class B = BK>
+    bool bk_oom_impl(long) { return false; }
+    bool bk_out_of_memory() { return bk_oom_impl<BK>(0); }
     // ---- the whole hot path over a staged batch ------------------------------------------------------
     aa_status solve(DevBatch &d, const aa_opts &opt, aa_result *res, bool keep_pool = false) {
         bk.begin_solve(keep_pool);
@@ -506,12 +533,17 @@ struct Pipeline {
 
         // ---- phase 0: host sort (OC1) + device gather ----
         bk.phase_begin(PH_SORT);
-        std::vector<int32_t> perm, sorted_index, ctg_order;
-        host_sort_perm(d, perm, sorted_index, ctg_order, bk.host_threads());
-        int32_t *d_perm = A<int32_t>(B);
-        int32_t *d_ord = A<int32_t>(C);
-        bk.h2d(d_perm, perm.data(), (size_t)B * 4);
-        bk.h2d(d_ord, ctg_order.data(), (size_t)C * 4);
+        std::vector<int32_t> perm_l, sorted_index_l, ctg_order_l;
+        int32_t *d_perm = d.d_perm, *d_ord = d.d_ord;
+        if (!d.sorted) {
+            host_sort_perm(d, perm_l, sorted_index_l, ctg_order_l, bk.host_threads());
+            d_perm = A<int32_t>(B);
+            d_ord = A<int32_t>(C);
+            bk.h2d(d_perm, perm_l.data(), (size_t)B * 4);
+            bk.h2d(d_ord, ctg_order_l.data(), (size_t)C * 4);
+        }
+        const std::vector<int32_t> &sorted_index = d.sorted ? d.sorted_index : sorted_index_l;
+        const std::vector<int32_t> &ctg_order = d.sorted ? d.ctg_order : ctg_order_l;
         w.perm = d_perm;
         w.blk_ctg = A<int32_t>(B);
         w.qs = A<int64_t>(B);
@@ -563,6 +595,11 @@ struct Pipeline {
         const int64_t Vtot = B + P + 2 * C;
         std::vector<int64_t> h_voff((size_t)C + 1);  // the one download of the vertex offsets (sizes the walk scratch, stats)
         bk.d2h(h_voff.data(), w.vtx_off, (size_t)(C + 1) * 8);
+        for (int64_t c = 0; c < C; c++)
+            if (h_voff[(size_t)c + 1] - h_voff[(size_t)c] >= ((int64_t)1 << 27)) {  // Edge.dst_fl keeps the head in 27 bits
+                err = "contig " + std::to_string(c) + " has 2^27 or more graph vertices (not supported: the edge record packs the head in 27 bits)";
+                return AA_ERR_NOMEM;
+            }
         bk.phase_end(PH_PAIRS);
         AA_BK_CHECK();
         if (Vtot >= ((int64_t)1 << 32) - 1) {

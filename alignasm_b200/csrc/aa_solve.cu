@@ -46,6 +46,7 @@ const char *aa_last_error(const aa_ctx *ctx) { return ctx ? ctx->err.c_str() : g
 aa_status aa_upload(aa_ctx *ctx, const aa_batch *batch, aa_dev_batch **dev) {
     if (!ctx || !dev) return AA_ERR_INVALID;
     *dev = nullptr;
+    if (!ctx->bk.ok() && ctx->bk.oom) ctx->bk.reset_pool();  // an allocation failure is recoverable: start from an empty pool
     if (!ctx->bk.ok()) {
         ctx->err = ctx->bk.error();
         return AA_ERR_CUDA;
@@ -83,7 +84,7 @@ aa_status aa_solve_device(aa_ctx *ctx, aa_dev_batch *dev, const aa_opts *opts, a
         ctx->err = ctx->pipe.err;
         if (st != AA_ERR_UNSOLVABLE) {
             if (res) aa::result_free_host(res);
-            cudaStreamSynchronize(ctx->bk.stream);
+            ctx->bk.quiesce();  // side-stream kernels (topo, walk-0 trace) may still be running
         }
     }
     return st;
@@ -114,7 +115,7 @@ aa_status aa_solve(aa_ctx *ctx, const aa_batch *batch, const aa_opts *opts, aa_r
         ctx->err = ctx->pipe.err;
         if (st != AA_ERR_UNSOLVABLE) {
             aa::result_free_host(res);
-            cudaStreamSynchronize(ctx->bk.stream);
+            ctx->bk.quiesce();  // side-stream kernels (topo, walk-0 trace) may still be running
         }
     }
     ctx->pipe.free_batch(d);
@@ -148,7 +149,7 @@ aa_status aa_solve_subset(aa_ctx *ctx, const aa_batch *batch, const int64_t *ctg
         ctx->err = ctx->pipe.err;
         if (st != AA_ERR_UNSOLVABLE) {
             aa::result_free_host(res);
-            cudaStreamSynchronize(ctx->bk.stream);
+            ctx->bk.quiesce();  // side-stream kernels (topo, walk-0 trace) may still be running
         }
     }
     ctx->pipe.free_batch(d);

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <charconv>
 #include <chrono>
 #include <memory>
@@ -747,15 +749,36 @@ extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const
         set_err(err, err_cap, "cannot open output files for " + pre);
         return AA_ERR_IO;
     }
-    // Contigs are formatted by all host threads (dynamic, one contig at a time) into per-contig text, which is then
-    // written in input-contig order (alignasm.cpp:417-441, 456-482).
+    // Contigs are formatted by all host threads (dynamic, one contig at a time) and written in input-contig order
+    // (alignasm.cpp:417-441, 456-482) AS SOON AS their turn comes: a worker that finishes contig c hands its text over, and
+    // whoever completes the contig the files are waiting for writes it and everything behind it that is ready, then frees
+    // the text.  Workers run at most WINDOW contigs ahead of the files, so the text in memory is bounded; a contig whose
+    // .aln.all.paf list is large (every tied max-coverage walk: gigabytes for a big contig) is not buffered at all: its
+    // worker waits for the contig's turn and streams the list to the file path by path, like the reference does.
     const int64_t C = res->n_ctg;
-    std::vector<std::string> text[3];
-    for (auto &t : text) t.resize((size_t)C);
-    std::vector<uint8_t> bad((size_t)C, 0);
-    std::vector<std::string> bad_why((size_t)C);
-    std::atomic<int64_t> next{0};
     const int T = host_threads((size_t)(res->out_off[C] + res->alt_off[C]) * 64);
+    const int64_t WINDOW = std::max<int64_t>(4 * (int64_t)T, 16);
+    int64_t ALL_STREAM_ROWS = 1 << 16;  // ~8 MB of text
+    if (const char *e = std::getenv("AA_WRITE_STREAM_ROWS")) ALL_STREAM_ROWS = std::atoll(e);  // (tests force the streamed form)
+    struct Slot {
+        std::string text[3];
+        bool done = false, bad = false;
+        std::string why;
+    };
+    std::vector<Slot> slot((size_t)WINDOW);
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t written = 0;  // next contig the files are waiting for
+    aa_status st = AA_OK;
+    bool stop = false;     // a bad row or a short write: rows up to there are on disk, like the reference's throw mid-write
+    std::atomic<int64_t> next{0};
+    auto write_text = [&](int k, const std::string &t) {  // under mu
+        if (!t.empty() && !stop && std::fwrite(t.data(), 1, t.size(), fo[k]) != t.size()) {
+            st = AA_ERR_IO;
+            stop = true;
+            set_err(err, err_cap, "short write to the output files of " + pre);
+        }
+    };
     run_parallel(T, [&](int) {
         std::vector<CsOp> ops, kept;
         std::string cs_out, why;
@@ -793,42 +816,81 @@ extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const
             dst.push_back('\n');
             return true;
         };
+        std::string t0, t1, t2;
         for (;;) {
             const int64_t c = next.fetch_add(1);
             if (c >= C) break;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return stop || c < written + WINDOW; });
+                if (stop) break;
+            }
             const std::string &name = p.ctg_name[(size_t)c];
+            t0.clear();
+            t1.clear();
+            t2.clear();
             bool ok = true;
-            for (int64_t k = res->out_off[c]; k < res->out_off[c + 1] && ok; k++) ok = put(text[0][(size_t)c], c, name, res->out, k);
-            for (int64_t k = res->alt_off[c]; k < res->alt_off[c + 1] && ok; k++) ok = put(text[1][(size_t)c], c, name, res->alt, k);
-            if (res->all_path_off && res->all_row_off) {
+            for (int64_t k = res->out_off[c]; k < res->out_off[c + 1] && ok; k++) ok = put(t0, c, name, res->out, k);
+            for (int64_t k = res->alt_off[c]; k < res->alt_off[c + 1] && ok; k++) ok = put(t1, c, name, res->alt, k);
+            const bool has_all = res->all_path_off && res->all_row_off;
+            int64_t all_rows = 0;
+            if (has_all) all_rows = res->all_row_off[res->all_path_off[c + 1]] - res->all_row_off[res->all_path_off[c]];
+            const bool stream_all = has_all && all_rows > ALL_STREAM_ROWS;
+            if (has_all && !stream_all) {
                 int32_t cnt = 0;
                 for (int64_t m = res->all_path_off[c]; m < res->all_path_off[c + 1] && ok; m++) {
                     const std::string qn = name + "." + std::to_string(++cnt);
-                    for (int64_t k = res->all_row_off[m]; k < res->all_row_off[m + 1] && ok; k++)
-                        ok = put(text[2][(size_t)c], c, qn, res->all, k);
+                    for (int64_t k = res->all_row_off[m]; k < res->all_row_off[m + 1] && ok; k++) ok = put(t2, c, qn, res->all, k);
                 }
             }
-            if (!ok) {
-                bad[(size_t)c] = 1;
-                bad_why[(size_t)c] = why;
+            std::unique_lock<std::mutex> lock(mu);
+            if (stream_all) {  // wait for this contig's turn, then write straight to the files, one path at a time
+                cv.wait(lock, [&] { return stop || written == c; });
+                if (stop) break;
+                write_text(0, t0);
+                write_text(1, t1);
+                int32_t cnt = 0;
+                for (int64_t m = res->all_path_off[c]; m < res->all_path_off[c + 1] && ok && !stop; m++) {
+                    const std::string qn = name + "." + std::to_string(++cnt);
+                    t2.clear();
+                    for (int64_t k = res->all_row_off[m]; k < res->all_row_off[m + 1] && ok; k++) ok = put(t2, c, qn, res->all, k);
+                    write_text(2, t2);
+                }
+                if (!ok && st == AA_OK) {
+                    st = AA_ERR_FORMAT;
+                    stop = true;
+                    set_err(err, err_cap, why);
+                }
+                written++;
+            } else {
+                Slot &s = slot[(size_t)(c % WINDOW)];
+                s.text[0].swap(t0);
+                s.text[1].swap(t1);
+                s.text[2].swap(t2);
+                s.bad = !ok;
+                s.why = ok ? std::string() : why;
+                s.done = true;
             }
+            // write whatever is ready, in order
+            while (!stop && written < C && slot[(size_t)(written % WINDOW)].done) {
+                Slot &s = slot[(size_t)(written % WINDOW)];
+                for (int k = 0; k < 3; k++) {
+                    write_text(k, s.text[k]);
+                    std::string().swap(s.text[k]);
+                }
+                if (s.bad && st == AA_OK) {
+                    st = AA_ERR_FORMAT;
+                    stop = true;
+                    set_err(err, err_cap, s.why);
+                }
+                s.done = false;
+                written++;
+            }
+            lock.unlock();
+            cv.notify_all();
         }
+        cv.notify_all();
     });
-    aa_status st = AA_OK;
-    for (int64_t c = 0; c < C; c++) {
-        for (int k = 0; k < 3; k++) {
-            const std::string &t = text[k][(size_t)c];
-            if (!t.empty() && std::fwrite(t.data(), 1, t.size(), fo[k]) != t.size() && st == AA_OK) {
-                st = AA_ERR_IO;
-                set_err(err, err_cap, "short write to the output files of " + pre);
-            }
-        }
-        if (bad[(size_t)c] && st == AA_OK) {  // rows up to the first bad one are on disk, like the reference's throw mid-write
-            st = AA_ERR_FORMAT;
-            set_err(err, err_cap, bad_why[(size_t)c]);
-            break;
-        }
-    }
     for (FILE *f : fo)
         if (std::fclose(f) != 0 && st == AA_OK) {
             st = AA_ERR_IO;

@@ -9,11 +9,12 @@ import numpy as np
 
 
 def contig_costs(batch, walks=10000):
-    """Estimated device cost per contig: the fixed K-walk enumeration plus the sequential per-block chain
-    (relax / heaps / walk 0 grow linearly with the contig; its overlap degree scales the edge count)."""
+    """Estimated SM time per contig (one warp per contig in the serial phases), same model as aa_shard_contigs in
+    csrc/aa_multi.cpp: ~1.3 us per enumerated walk whatever the contig's size, ~0.6 us per block for the heap / relax /
+    walk-0 chains.  Largest first also spreads the longest serial chains, which bound a shard from below."""
     n = np.diff(batch.ctg_off).astype(np.float64)
-    enum_cost = np.where(n > 1, 0.4 * min(walks, 10000), 0.0)
-    return enum_cost + 14.0 * n
+    enum_cost = np.where(n > 1, 1.3 * min(walks, 10000), 0.0)
+    return enum_cost + 0.6 * n
 
 
 def lpt_shards(costs, n_shards):

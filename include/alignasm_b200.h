@@ -22,7 +22,11 @@
  * non-zero aa_status and a message from aa_last_error().  There is NO CPU fallback: every aa_solve*
  * entry point fails with AA_ERR_NO_DEVICE when no CUDA device is usable.
  *
- * All functions are re-entrant per aa_ctx; there is no global mutable state.
+ * Threading: every function that takes an aa_ctx is re-entrant per context (one host thread per context at a time; two
+ * contexts never share state).  The library holds ONE piece of process-wide state: the cache of warm contexts behind
+ * aa_solve_multi (csrc/aa_multi.cpp).  It is mutex-guarded and contexts are checked out exclusively for the length of a
+ * shard solve, so concurrent aa_solve_multi calls are safe (a device whose cached contexts are all in use gets a new
+ * one); aa_multi_release() waits for running solves before it frees them.  aa_multi_last_error() is per thread.
  */
 #ifndef ALIGNASM_B200_H
 #define ALIGNASM_B200_H
@@ -157,7 +161,7 @@ aa_status aa_solve_subset(aa_ctx *ctx, const aa_batch *batch, const int64_t *ctg
 aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *batch, const aa_opts *opts, aa_result *res);
 void aa_shard_contigs(const aa_batch *batch, int32_t max_walks, int32_t n_shards, int32_t *shard_of /* [n_ctg] */);
 const char *aa_multi_last_error(void);
-void aa_multi_release(void); /* aa_solve_multi keeps one warm context per (device, repetition) between calls: free them */
+void aa_multi_release(void); /* aa_solve_multi keeps warm contexts between calls (as many per device as were ever in use at once): free them */
 /* statistics (sizes, per-phase CUDA-event times, algorithmic bytes) of the last solve on this context */
 aa_status aa_get_stats(const aa_ctx *ctx, aa_stats *stats);
 const char *aa_phase_name(int phase); /* NULL past the last phase */

@@ -14,5 +14,8 @@ SMALL = {
     # contigs of several buckets of 256 blocks: the segment-parallel relax (articulation blocks, tie-break conditions, sweep)
     "segments": (["--contigs", 6, "--blocks", 1500, "--sd", 300, "--p_dup", 0.1, "--p_trans", 0.1, "--p_inv", 0.1, "--seed", 31], [False, True]),
     "segments_long": (["--contigs", 3, "--blocks", 5000, "--sd", 1500, "--p_trans", 0.01, "--p_inv", 0.01, "--seed", 32], [False, True]),
+    # one chain-like contig of the bench workloads' shape, still small enough for the reference's 56 n^2 B tables (0.5 GB)
+    "chain3000": (["--contigs", 1, "--blocks", 3000, "--sd", 0, "--p_trans", 0.01, "--p_inv", 0.01, "--gap_max", 3000, "--lmin", 1000,
+                   "--lmax", 12000, "--seed", 33], [False]),
     "cancer_small": (["--preset", "c3", "--scale", 0.004], [False]),
 }

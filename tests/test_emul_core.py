@@ -47,3 +47,13 @@ def test_small_walk_budget(product_lib, workdir):
         want = oracle_py.oracle_solve(pf.batch, max_walks=k, want_all=True, keep_debug=True)
         assert pu.debug_equal(got.dbg, want.dbg) is None
         assert pu.result_rows_equal(got, want) is None
+
+
+def test_writer_streams_large_all_lists(product_lib, workdir, monkeypatch):
+    """aa_paf_write buffers at most a window of contigs and streams a large .aln.all.paf list path by path when the contig's turn
+    comes (the reference streams its rows too, alignasm.cpp:456-482): forced here for every contig, files must not change."""
+    import emul_py
+    monkeypatch.setenv("AA_WRITE_STREAM_ROWS", "0")
+    for case in ("ties", "tiny"):
+        pf = open_case(case)
+        check_against_golden(case, False, emul_py.emul_solve, pf, workdir)

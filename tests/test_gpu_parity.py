@@ -281,3 +281,25 @@ def test_big_contig_in_shuffled_row_order(p_dup, solver, workdir):
     got = solver.solve(pf.batch, want_all=False)
     want = oracle_py.oracle_solve(pf.batch, threads=8, want_all=False)
     assert pu.result_rows_equal(got, want, check_all=False) is None
+
+
+@pytest.mark.parametrize("tag", ["c2", "c3"])
+def test_fullsize_pins(tag, solver, workdir):
+    """The BENCH workloads themselves, at full size (C2: 260 contigs / 499 997 blocks incl. the 43 099-block contig that is the
+    critical path of every step; C3: 549 724 blocks), against the CPU restatement: tests/golden/fullsize_<tag>.json holds the
+    sha256 of every result array, of the ordered edge lists, of d / best and of the 2.6 M walk distances the port produced for the
+    same seed (tests/golden/make_fullsize.py, minutes of CPU, run in the CPU container)."""
+    import json
+    import alignasm_b200 as aa
+    from fullsize_util import STAT_KEYS, digest
+    want = json.load(open(os.path.join(pu.GOLDEN, f"fullsize_{tag}.json")))
+    paf = pu.synth(os.path.join(workdir, f"fullsize_{tag}.paf"), "--preset", tag, "--seed", want["seed"])
+    pf = aa.read_paf(paf)
+    got = solver.solve(pf.batch, want_all=False, keep_debug=True)
+    for k in STAT_KEYS:
+        assert int(got.stats[k]) == want["stats"][k], k
+    d, per = digest(got)
+    big = int(np.argmax(per[0]))
+    assert {"index": big, "V": int(per[0][big]), "E": int(per[1][big]), "K": int(per[2][big])} == want["largest_contig"]
+    bad = [k for k in want["sha256"] if d[k] != want["sha256"][k]]
+    assert not bad, f"{tag}: differs from the CPU restatement in {bad}"

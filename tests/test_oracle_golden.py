@@ -24,3 +24,14 @@ def test_oracle_threads_agree(product_lib):
     a = oracle_py.oracle_solve(pf.batch, threads=1, want_all=True)
     b = oracle_py.oracle_solve(pf.batch, threads=4, want_all=True)
     assert pu.result_rows_equal(a, b) is None
+
+
+def test_fullsize_pin_files_present():
+    """The full-size pins of the bench workloads (made by tests/golden/make_fullsize.py) are committed and carry every digest the
+    GPU test compares."""
+    import json
+    for tag, blocks in (("c2", 499997), ("c3", 549724)):
+        want = json.load(open(os.path.join(pu.GOLDEN, f"fullsize_{tag}.json")))
+        assert want["stats"]["n_blk"] == blocks and want["stats"]["n_walk"] == 2600000
+        assert {"out.qry_str", "alt.ref_end", "sorted_index", "dbg.w_sum", "dbg.edges", "dbg.d"} <= set(want["sha256"])
+        assert all(len(v) == 64 for v in want["sha256"].values())

@@ -17,7 +17,9 @@ def _ref():
 pytestmark = pytest.mark.skipif(_ref() is None, reason="oracle/_ref not built (no /root/reference on this box)")
 
 
-@pytest.mark.parametrize("name", ["c1_small", "ties", "overlappy", "tiny", "dense200"])
+# `segments` (1 500-block contigs: several parts, several relax segments, ~126 MB of reference tables per contig) and `chain3000`
+# (one 3 000-block chain-like contig, the shape of the bench's big contigs) pin the port to the real reference beyond small shapes
+@pytest.mark.parametrize("name", ["c1_small", "ties", "overlappy", "tiny", "dense200", "segments", "chain3000"])
 def test_port_equals_reference(name, product_lib, workdir):
     import alignasm_b200 as aa
     op = _ref()

@@ -125,11 +125,19 @@ class Batch:
     def select(self, contigs):
         """Sub-batch holding the given contigs (used for sharding across GPUs / ranks)."""
         contigs = np.asarray(contigs, dtype=np.int64)
+
+        def ranges(lo, cnt):  # concatenation of arange(lo[i], lo[i] + cnt[i]) without a Python loop
+            total = int(cnt.sum())
+            if total == 0:
+                return np.zeros(0, np.int64)
+            start = np.cumsum(cnt) - cnt
+            return np.repeat(lo - start, cnt) + np.arange(total, dtype=np.int64)
+
         lo, hi = self.ctg_off[contigs], self.ctg_off[contigs + 1]
-        blk = np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)]) if len(contigs) else np.zeros(0, np.int64)
-        rlo, rhi = self.run_off[blk], self.run_off[blk + 1]
-        rcnt = rhi - rlo
-        run = np.concatenate([np.arange(a, b) for a, b in zip(rlo, rhi)]) if len(blk) else np.zeros(0, np.int64)
+        blk = ranges(lo, hi - lo)
+        rlo = self.run_off[blk]
+        rcnt = self.run_off[blk + 1] - rlo
+        run = ranges(rlo, rcnt)
         arrays = {name: getattr(self, name)[blk] for name, _ in self.FIELDS
                   if name not in ("ctg_off", "run_off", "run_ql", "run_qr", "run_rl")}
         arrays["ctg_off"] = np.concatenate([[0], np.cumsum(hi - lo)])
@@ -301,15 +309,15 @@ class Solver:
         self._check(self._lib.aa_upload(self._h, C.byref(batch.c_struct()), C.byref(d)))
         return _DevBatch(self, d, batch.n_blk)
 
-    def solve_device(self, dev, fetch=True, **kw):
-        """Solve a batch that is already resident in HBM.  fetch=False leaves the result on the device."""
+    def solve_device(self, dev, fetch=True, copy=True, **kw):
+        """Solve a batch that is already resident in HBM.  fetch=False leaves the result on the device; copy=False: see Result."""
         o = _opts(**kw)
         if not fetch:
             self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), None))
             return None
         res = aa_result()
         self._check(self._lib.aa_solve_device(self._h, dev._h, C.byref(o), C.byref(res)), res)
-        return Result(res, dev.n_blk, self._lib.aa_result_free)
+        return Result(res, dev.n_blk, self._lib.aa_result_free, copy=copy)
 
     def stats(self):
         """Sizes, per-phase device times and algorithmic bytes of the last solve on this context."""

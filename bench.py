@@ -1,25 +1,38 @@
 #!/usr/bin/env python
 """bench.py — PAF alignment blocks/sec through the alignasm hot path (graph build + k-walks + selection).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload auto|c1|c2|c3|c4|c5] [--n BLOCKS] [--nsl] [--no-cpu-baseline]
 
-One step = one pass of solve_ctg_read over every contig of one synthetic PAF batch (BASELINE.json configs[1]:
-human-scale diploid assembly, ~500k alignment blocks, tools/synth_paf.cpp --preset c2).  One process per GPU;
-N>1 is launched by torchrun, every rank solves its own replica of the workload (seed 2+rank: contigs are
-independent, there is no data-path collective => weak scaling) and the job value is N*blocks / max-rank time.
+One step = one pass of solve_ctg_read over every contig of one synthetic PAF (tools/synth_paf.cpp, seeded).
+
+Workloads (BASELINE.json configs): c1 1k small contigs, c2 human-scale diploid assembly (~500k blocks, 260 contigs),
+c3 cancer karyotype, c4 one dense contig of --n blocks (--nsl: --non_skip_linkable), c5 the box-scaling input:
+8 concatenated cancer PAFs, ~4.4 M blocks, 2 080 contigs.
+
+--workload auto (the default, what the driver runs): the job is ONE c5 input, contig-sharded over the N ranks
+(alignasm_b200/sharding.py: cost-balanced LPT, no data-path collective; every rank keeps its shard resident, solves it, and
+publishes its row lists in a shared-memory segment that rank 0 maps, inside the timed region) => strong scaling, N = 1 is the whole input on one
+GPU.  At N = 1 the line also carries the single-GPU figures of c2 (BASELINE.json configs[1], the workload the metric is
+quoted on) as the sub-object "c2": value, e2e, roofline, phases, sizes, cli, same-work comparison and cpu_baseline.
 
 Prints ONE JSON line (rank 0):
-  value     blocks/s with the batch already resident in HBM (aa_solve_device), max over ranks
-  e2e       blocks/s through the public host-buffer call aa_solve (H2D of the batch + D2H of the rows inside)
-  roofline  the dominant kernel (phase) of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
-  cli       the stages of the drop-in command line: host reader (all host threads), solve, host writers
-  cpu_baseline  the reference's own solve_ctg_read (oracle/_ref, built from the reference sources) on this
-            box's host cores, on a bounded sample of the same workload
---impl reference times that CPU arm alone (no GPU code on its path).
+  value        blocks/s of the whole job with the shards resident in HBM (aa_solve_device + gather), max over ranks
+  e2e          blocks/s through the public host-buffer call aa_solve (H2D of the shard + D2H of the rows inside) + gather
+  roofline     the dominant kernel (phase) of the step: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  per_rank     device ms and shard sizes of every rank (the imbalance is the largest contig's serial chain)
+  cpu_baseline the reference's own solve_ctg_read (oracle/_ref, compiled from the reference sources) on this box's host
+               cores, on a bounded sample of the same workload; plus one host thread on a smaller sample, with peak RSS
+  same_work    the GPU timed on exactly the contigs of the CPU sample (resident and through aa_solve)
+--impl reference times the CPU arm alone (no GPU code on its path) on the sample the same --steps/--warmup give our arm.
+want_all is false throughout: the path's outputs are the .aln.paf / .aln.alt.paf rows (the .aln.all.paf list of c2, every tied
+max-coverage walk of every contig, is 25.7 GB); the reference builds that list too (paf_data.cpp:1595-1611).
 """
 import argparse
 import json
+import math
 import os
+import resource
 import subprocess
 import sys
 import tempfile
@@ -33,10 +46,10 @@ if ROOT not in sys.path:
 WORKLOADS = {
     "c1": (["--preset", "c1"], 1, "synthetic small PAF: 1k contigs x ~50 blocks (configs[0])"),
     "c2": (["--preset", "c2"], 2, "synthetic human-scale diploid assembly PAF, ~500k blocks, 260 contigs (configs[1])"),
-    "c3": (["--preset", "c3"], 3, "synthetic cancer-karyotype PAF, ~500k blocks (configs[2])"),
+    "c3": (["--preset", "c3"], 3, "synthetic cancer-karyotype PAF, ~550k blocks, 260 contigs (configs[2])"),
+    "c4": (["--preset", "c4"], 4, "pathological dense contig: one contig, every block overlaps the next 10-50 (configs[3])"),
+    "c5": (["--preset", "c5", "--replicas", "8"], 30, "whole-box scaling input: 8 concatenated cancer PAFs, ~4.4 M blocks, 2 080 contigs (configs[4])"),
 }
-SAMPLE_MAX_BLOCKS_PER_CONTIG = 4000   # the reference allocates 56*n^2 B per contig (paf_data.cpp:268-282)
-SAMPLE_TARGET_BLOCKS = 60000
 
 
 def synth_bin():
@@ -47,70 +60,121 @@ def synth_bin():
     return p
 
 
-def make_paf(workload, seed_shift, tmp):
+def make_paf(workload, tmp, n=None):
     args, seed, _ = WORKLOADS[workload]
-    path = os.path.join(tmp, f"{workload}_s{seed + seed_shift}.paf")
-    subprocess.run([synth_bin(), *[str(a) for a in args], "--seed", str(seed + seed_shift), "-o", path], check=True,
-                   capture_output=True)
+    extra = ["--n", str(n)] if (workload == "c4" and n) else []
+    path = os.path.join(tmp, f"{workload}{'_' + str(n) if extra else ''}_s{seed}.paf")
+    if not os.path.exists(path):
+        subprocess.run([synth_bin(), *[str(a) for a in args], *extra, "--seed", str(seed), "-o", path], check=True, capture_output=True)
     return path
 
 
-def make_sample(paf_path, out_path):
-    """Bounded sample of the workload for the CPU arm: whole contigs in file order, skipping contigs the reference
-    cannot hold (56*n^2 B tables), until ~SAMPLE_TARGET_BLOCKS blocks."""
-    groups, cur, name = [], [], None
+# ------------------------------------------------------------------------------------------------ CPU arm
+def mem_available():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 32 << 30
+
+
+def read_groups(paf_path, limit_rows=None):
+    """Contigs of a PAF in file order: list of lists of lines."""
+    groups, cur, name, rows = [], [], None, 0
     with open(paf_path) as f:
         for line in f:
             q = line.split("\t", 1)[0]
             if q != name:
                 if cur:
                     groups.append(cur)
+                    if limit_rows and rows >= limit_rows:
+                        cur = []
+                        break
                 cur, name = [], q
             cur.append(line)
+            rows += 1
     if cur:
         groups.append(cur)
+    return groups
+
+
+def pick_sample(paf_path, out_path, threads, passes):
+    """Bounded sample of the workload for the CPU arm: whole contigs in file order.
+      * a contig is admitted up to the size the reference's four n x n tables (56 n^2 B, paf_data.cpp:268-282) allow on this box
+        with every host thread holding one: n <= sqrt(MemAvailable / 2 / (56 threads)), capped at 6 000 (a 6 000-block contig alone is
+        2 GB of tables and several seconds of one core);
+      * contigs are taken until every host thread has at least 4 of them AND ~2 M / passes blocks (50 k .. 160 k) are reached, so that
+        `passes` passes stay within a few minutes."""
+    groups = read_groups(paf_path, limit_rows=1200000)  # (c5: the sample comes from the first replicas)
     total_ctg, total_blk = len(groups), sum(len(g) for g in groups)
+    n_mem = int(math.sqrt(mem_available() / 2 / (56.0 * max(1, threads))))
+    target = int(min(160000, max(50000, 2.0e6 / max(1, passes))))
+    n_max = max(500, min(n_mem, 6000 if target >= 120000 else 4000))
     picked, nblk = [], 0
     for g in groups:
-        if len(g) > SAMPLE_MAX_BLOCKS_PER_CONTIG:
+        if len(g) > n_max or len(g) < 2:
             continue
         picked.append(g)
         nblk += len(g)
-        if nblk >= SAMPLE_TARGET_BLOCKS:
+        if nblk >= target and len(picked) >= 4 * threads:
             break
     with open(out_path, "w") as f:
         for g in picked:
             f.writelines(g)
-    desc = (f"{len(picked)} of {total_ctg} contigs ({nblk} of {total_blk} blocks), file order, contigs with >"
-            f"{SAMPLE_MAX_BLOCKS_PER_CONTIG} blocks skipped (the reference allocates 56*n^2 B per contig)")
-    return nblk, desc
+    desc = (f"{len(picked)} whole contigs, {nblk} blocks, in file order out of the first {total_ctg} contigs / {total_blk} blocks; contigs above "
+            f"{n_max} blocks skipped (the reference allocates 56 n^2 B per contig: MemAvailable allows {n_mem} with {threads} threads; cap "
+            f"{6000 if target >= 120000 else 4000}); sized for {passes} pass(es): target {target} blocks and >= 4 contigs per host thread")
+    return picked, nblk, desc
 
 
-def cpu_reference(paf_path, tmp, steps=1, warmup=0):
-    """Time the reference's own CPU implementation of the path on a bounded sample, all host threads."""
+def run_cpu(sample_path, tmp, threads, steps=1, warmup=0):
+    """The reference's own CPU implementation of the path (oracle/_ref/alignasm_ref: paf_data.cpp + headers compiled unmodified, a
+    std::thread pool over contigs standing in for tbb::parallel_for, alignasm.cpp:351-359); falls back to the CPU restatement when
+    oracle/_ref was not built on a box with the reference sources.  Returns seconds per pass (mean of `steps`), kind, peak RSS."""
     from oracle import oracle_py
-    sample = os.path.join(tmp, "sample.paf")
-    nblk, desc = make_sample(paf_path, sample)
-    cores = os.cpu_count() or 1
     times = []
     if oracle_py.ref_binary("glibc"):
         kind = "reference"
         for i in range(warmup + steps):
-            js = oracle_py.run_ref(sample, os.path.join(tmp, "sample_ref"), variant="glibc", threads=cores, no_write=True)
+            js = oracle_py.run_ref(sample_path, os.path.join(tmp, "sample_ref"), variant="glibc", threads=threads, no_write=True)
             if i >= warmup:
                 times.append(js["solve_s"])
-    else:  # oracle/_ref was not built on a box with the reference sources: time the CPU restatement instead
+        rss = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1024.0  # MB, the largest child so far
+    else:
         kind = "port"
         import alignasm_b200 as aa
-        pf = aa.read_paf(sample)
+        pf = aa.read_paf(sample_path)
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            oracle_py.oracle_solve(pf.batch, threads=cores)
+            oracle_py.oracle_solve(pf.batch, threads=threads)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return {"value": nblk / sec, "unit": "blocks/s", "cores": cores, "kind": kind, "sample": desc,
-            "seconds_per_pass": sec, "sample_blocks": nblk}
+        rss = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
+    return sum(times) / len(times), kind, rss
+
+
+def cpu_arm(paf_path, tmp, passes, steps=1, warmup=0, one_thread=True):
+    """cpu_baseline object: all host threads on the sample, and one thread on its first ~12 k blocks."""
+    cores = os.cpu_count() or 1
+    sample = os.path.join(tmp, "sample.paf")
+    picked, nblk, desc = pick_sample(paf_path, sample, cores, passes)
+    out = {"unit": "blocks/s", "cores": cores, "sample": desc, "sample_blocks": nblk, "sample_path": sample}
+    if one_thread:
+        small = os.path.join(tmp, "sample_1t.paf")
+        nb1 = 0
+        with open(small, "w") as f:
+            for g in picked:
+                f.writelines(g)
+                nb1 += len(g)
+                if nb1 >= 12000:
+                    break
+        sec1, kind1, rss1 = run_cpu(small, tmp, 1)
+        out["one_thread"] = {"value": nb1 / sec1, "unit": "blocks/s", "cores": 1, "sample": f"the first {nb1} blocks of the sample", "peak_rss_mb": round(rss1, 1)}
+    sec, kind, rss = run_cpu(sample, tmp, cores, steps=steps, warmup=warmup)
+    out.update({"value": nblk / sec, "kind": kind, "seconds_per_pass": sec, "peak_rss_mb": round(rss, 1)})
+    return out
 
 
 class ClockSampler:
@@ -161,162 +225,282 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def roofline_of(names, ph, st, traffic_ok):
+    """The dominant phase of a step against the HBM roofline (algorithmic bytes per phase from the run's own sizes)."""
+    peak, peak_src = hbm_peak()
+    dom = max(range(len(names)), key=lambda i: ph[i])
+    algo = st["algo_bytes_phase"][dom]
+    achieved = algo / (ph[dom] * 1e-3) / 1e9 if ph[dom] > 0 else 0.0
+    traffic, tsrc = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if traffic_ok and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(names[dom])
+            tsrc = "static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this workload (profiles/traffic.json), not measured in this run"
+        except ValueError:
+            traffic = None
+    return {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+            "ms_per_launch": ph[dom], "note": "latency-bound integer graph work: see DESIGN.md for the per-phase byte model"}
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun notices) write to stdout: the one JSON line must be alone there
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=845, help="c4: blocks of the dense contig")
+    ap.add_argument("--nsl", action="store_true", help="--non_skip_linkable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    K, W = a.steps, a.warmup
-    wl_desc = WORKLOADS[a.workload][2]
-    config = {"workload": f"{a.workload}: {wl_desc}", "generator": "tools/synth_paf.cpp", "walks_per_contig": 10000,
-              "per_rank": "one replica of the workload per GPU (seed + rank), no collective on the data path",
-              "l2": "inputs + workspace (>1 GB) are larger than the 126 MB L2; nothing is cached between steps"}
+    K, W = max(1, a.steps), max(0, a.warmup)
+    auto = a.workload == "auto"
+    wl = "c5" if auto else a.workload
+    wl_desc = WORKLOADS[wl][2] + (f", n = {a.n}" if wl == "c4" else "") + (", --non_skip_linkable" if a.nsl else "")
+    config = {"workload": f"{wl}: {wl_desc}", "generator": "tools/synth_paf.cpp", "walks_per_contig": 10000, "want_all": False,
+              "non_skip_linkable": bool(a.nsl),
+              "sharding": ("one input, contigs LPT-sharded over the ranks by estimated cost (alignasm_b200/sharding.py), shards resident in HBM, "
+                           "no collective on the data path: every rank publishes the primary/alt rows of its shard in a POSIX shared-memory segment that "
+                           "rank 0 maps (host-side merge, inside the timed region); NCCL carries only the barriers and the timing reductions" if wl != "c4" else "a single contig does not shard: replicas only (every rank solves the same contig)"),
+              "cpu_sample_rule": "see cpu_baseline.sample",
+              "l2": "inputs + workspace (> 1 GB) are larger than the 126 MB L2; nothing is cached between steps"}
 
     with tempfile.TemporaryDirectory(prefix="aa_bench_") as tmp:
-        # ------------------------------------------------------------------ reference arm (CPU only)
+        # ------------------------------------------------------------------ reference arm (CPU only, rank 0 only)
         if a.impl == "reference":
             if rank != 0:
                 return 0
-            paf = make_paf(a.workload, 0, tmp)
-            cb = cpu_reference(paf, tmp, steps=max(1, K), warmup=min(W, 1))
+            paf = make_paf(wl, tmp, a.n)
+            cb = cpu_arm(paf, tmp, passes=K + W, steps=K, warmup=W, one_thread=False)
             line = {"impl": "reference", "metric": "paf_alignment_blocks_per_sec", "value": cb["value"], "unit": "blocks/s",
-                    "n_gpus": a.gpus, "steps": max(1, K), "warmup": min(W, 1), "ms_per_step": cb["seconds_per_pass"] * 1e3,
-                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-                    "config": config, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": cb["seconds_per_pass"] * 1e3,
+                    "higher_is_better": True, "scaling": "strong" if wl != "c4" else "weak", "vs_baseline": None, "dtype": "int64",
+                    "data": "synthetic", "config": config,
+                    "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "peak_rss_mb")},
                     "e2e": {"value": cb["value"], "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0}
-            print(json.dumps(line))
+            emit(line)
             return 0
 
         # ------------------------------------------------------------------ our arm (one process per GPU)
+        import numpy as np
         import torch
         import alignasm_b200 as aa
+        from alignasm_b200 import sharding
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device — alignasm_b200 has no CPU path")
         torch.cuda.set_device(local)
+        cuda = torch.device("cuda", local)
         dist = None
         if world > 1:
             # NCCL prints its version banner on stdout at the VERSION level: keep stdout to the one JSON line
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.init_process_group("nccl", device_id=cuda)
 
         def barrier():
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        paf = make_paf(a.workload, rank, tmp)
-        pf = aa.read_paf(paf)
-        batch = pf.batch
         solver = aa.Solver(local)
         names = solver.phase_names()
-        dev = solver.upload(batch)
+        opts = {"non_skip_linkable": bool(a.nsl)}
 
-        # ---- value: batch resident in HBM ----
-        for _ in range(W):
-            solver.solve_device(dev, fetch=False)
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        barrier()
-        t0 = time.perf_counter()
-        ev_ms, ph_ms, launches = 0.0, [0.0] * 16, 0
-        for _ in range(K):
-            solver.solve_device(dev, fetch=False)
-            st = solver.stats()
-            ev_ms += st["ms_total"]
-            ph_ms = [x + y for x, y in zip(ph_ms, st["ms_phase"])]
-            launches += st["n_launch"]
-        barrier()
-        wall = time.perf_counter() - t0
-        clocks = sampler.stop() if rank == 0 else None
-        st = solver.stats()
+        def timed(batch_full, shard_ids, sampler=None):
+            """value / e2e of one job: `batch_full` sharded as `shard_ids` (None: this rank solves all of it and nothing is gathered)."""
+            sub = batch_full.select(shard_ids[rank]) if shard_ids is not None else batch_full
+            have = sub.n_ctg > 0
+            dev = solver.upload(sub) if have else None
+            gather = shard_ids is not None and world > 1
+            shm = None
+            if gather:  # one solve tells how many rows the shard has; the shared segment gets 25 % head room
+                need = 64
+                if have:
+                    r = solver.solve_device(dev, copy=False, **opts)
+                    need = sharding.packed_size(r)
+                    r.close()
+                shm = sharding.ShmRows(f"aa_bench_{os.environ.get('MASTER_PORT', '0')}", rank, world, need + need // 4 + 4096)
+                barrier()
+                if rank == 0:
+                    shm.attach_all()
 
-        # ---- e2e: host buffers in, rows out, through the public call ----
-        for _ in range(min(W, 2)):
-            solver.solve(batch, copy=False).close()
-        barrier()
-        t1 = time.perf_counter()
-        for _ in range(K):
-            r = solver.solve(batch, copy=False)  # the rows as aa_solve hands them to a C caller (no second copy in Python)
-            d2h = sum(v.nbytes for v in r.out.values()) + sum(v.nbytes for v in r.alt.values()) + r.out_off.nbytes + r.alt_off.nbytes
-            r.close()
-        barrier()
-        wall_e2e = time.perf_counter() - t1
-        h2d = sum(getattr(batch, n).nbytes for n, _ in aa.Batch.FIELDS) + 4 * batch.n_blk
+            def step(resident):
+                nbytes = 0
+                if have:
+                    r = solver.solve_device(dev, copy=False, **opts) if resident else solver.solve(sub, copy=False, **opts)
+                    nbytes = sum(v.nbytes for v in r.out.values()) + sum(v.nbytes for v in r.alt.values()) + r.out_off.nbytes + r.alt_off.nbytes
+                    if gather:
+                        shm.publish(r)
+                    r.close()
+                elif gather:
+                    shm.publish_empty()
+                if gather:
+                    barrier()  # every rank's rows are in its segment
+                    if rank == 0:  # the writer's view: input contig -> (shard, position); the rows stay where their rank put them
+                        sharding.contig_index(batch_full.n_ctg, shard_ids)
+                        assert sum(int(v[0].shape[0]) - 1 for v in shm.views()) == batch_full.n_ctg
+                    barrier()  # (the segments are free to be overwritten by the next step)
+                return nbytes
 
-        # ---- drop-in CLI stages (parse + write reported separately): host reader, solve, host writers ----
-        cli = None
-        if rank == 0:
-            t2 = time.perf_counter()
-            pf2 = aa.read_paf(paf)
-            t3 = time.perf_counter()
-            r = solver.solve(pf2.batch)
-            t4 = time.perf_counter()
-            pf2.write(r, os.path.join(tmp, "cli_out"))
-            t5 = time.perf_counter()
-            out_bytes = sum(os.path.getsize(os.path.join(tmp, "cli_out" + e)) for e in (".aln.paf", ".aln.alt.paf", ".aln.all.paf"))
-            r.close()
-            pf2.close()
-            cli = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": batch.n_blk / (t5 - t2),
-                   "paf_bytes": os.path.getsize(paf), "out_bytes": out_bytes, "host_threads": os.cpu_count(),
-                   "note": "aa_paf_read + aa_solve + aa_paf_write as `alignasm --no_all` chains them (the .aln.all.paf of this workload, every tied "
-                           "max-coverage walk of every contig, is 25.7 GB and is left out); process and CUDA start-up excluded"}
+            for _ in range(W):
+                step(True)
+            if sampler is not None:
+                sampler.start()
+            barrier()
+            t0 = time.perf_counter()
+            ev_ms, ph_ms, launches = 0.0, [0.0] * 16, 0
+            for _ in range(K):
+                step(True)
+                if have:
+                    st = solver.stats()
+                    ev_ms += st["ms_total"]
+                    ph_ms = [x + y for x, y in zip(ph_ms, st["ms_phase"])]
+                    launches += st["n_launch"]
+            barrier()
+            wall = time.perf_counter() - t0
+            clocks = sampler.stop() if sampler is not None else None
+            st = solver.stats() if have else None
+            for _ in range(min(W, 2)):
+                step(False)
+            barrier()
+            t1 = time.perf_counter()
+            d2h = 0
+            for _ in range(K):
+                d2h = step(False)
+            barrier()
+            wall_e2e = time.perf_counter() - t1
+            h2d = sum(getattr(sub, n).nbytes for n, _ in aa.Batch.FIELDS) + 4 * sub.n_blk if have else 0
+            if dev is not None:
+                dev.free()
+            if shm is not None:
+                barrier()
+                shm.close()
+            return {"wall": wall, "wall_e2e": wall_e2e, "ev_ms": ev_ms / K, "ph": [m / K for m in ph_ms], "launches": launches,
+                    "st": st, "clocks": clocks, "h2d": int(h2d), "d2h": int(d2h), "blocks": sub.n_blk, "contigs": sub.n_ctg,
+                    "largest": int(np.diff(sub.ctg_off).max()) if have else 0}
 
-        # max over ranks
-        tv = torch.tensor([wall, wall_e2e, ev_ms / 1e3], dtype=torch.float64, device="cuda")
-        nb = torch.tensor([batch.n_blk], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-            dist.all_reduce(nb, op=dist.ReduceOp.SUM)
-        wall_max, e2e_max, ev_max = tv.tolist()
-        blocks = nb.item()
+        def allmax(vals):
+            t = torch.tensor(vals, dtype=torch.float64, device=cuda)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.tolist()
+
+        def allsum(vals):
+            t = torch.tensor(vals, dtype=torch.float64, device=cuda)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t.tolist()
+
+        # ---- the job ----
+        paf = make_paf(wl, tmp, a.n)
+        pf = aa.read_paf(paf)
+        batch = pf.batch
+        if wl == "c4":
+            shard_ids, job_blocks = None, batch.n_blk * world  # replicas only
+        else:
+            shard_ids = sharding.lpt_shards(sharding.contig_costs(batch), world)
+            job_blocks = batch.n_blk
+        sampler = ClockSampler(local) if rank == 0 else None
+        m = timed(batch, shard_ids, sampler)
+        wall_max, e2e_max, ev_max = allmax([m["wall"], m["wall_e2e"], m["ev_ms"]])
+        launches, h2d, d2h = allsum([m["launches"], m["h2d"], m["d2h"]])
+        per_rank = None
+        if world > 1:
+            t = torch.zeros(world, 4, dtype=torch.float64, device=cuda)
+            t[rank] = torch.tensor([m["ev_ms"], m["blocks"], m["contigs"], m["largest"]], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank = [{"rank": r, "device_ms": round(v[0], 3), "blocks": int(v[1]), "contigs": int(v[2]), "largest_contig": int(v[3])}
+                        for r, v in enumerate(t.tolist())]
         if rank != 0:
             if dist is not None:
                 dist.destroy_process_group()
             return 0
-
-        peak, peak_src = hbm_peak()
-        ph = [m / K for m in ph_ms]
-        dom = max(range(len(names)), key=lambda i: ph[i])
-        algo = st["algo_bytes_phase"][dom]
-        achieved = algo / (ph[dom] * 1e-3) / 1e9 if ph[dom] > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and a.workload == "c2":  # the ncu capture is of this workload
-            try:
-                traffic = json.load(open(tpath)).get(names[dom])
-            except ValueError:
-                traffic = None
+        st = m["st"]
         line = {
-            "metric": "paf_alignment_blocks_per_sec", "value": blocks * K / wall_max, "unit": "blocks/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": wall_max / K * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
-            "device_ms_per_step": ev_max / K * 1e3,
-            "e2e": {"value": blocks * K / e2e_max, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "metric": "paf_alignment_blocks_per_sec", "value": job_blocks * K / wall_max, "unit": "blocks/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": wall_max / K * 1e3, "higher_is_better": True,
+            "scaling": "strong" if wl != "c4" else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+            "device_ms_per_step": ev_max,
+            "e2e": {"value": job_blocks * K / e2e_max, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo, "ms_per_launch": ph[dom],
-                         "note": "latency-bound integer graph work: see DESIGN.md for the per-phase byte model"},
-            "phases_ms": {n: round(m, 3) for n, m in zip(names, ph)},
+            "clocks": m["clocks"],
+            "roofline": roofline_of(names, m["ph"], st, traffic_ok=False),
+            "phases_ms": {n: round(x, 3) for n, x in zip(names, m["ph"])},
             "sizes": {k: st[k] for k in ("n_ctg", "n_blk", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task")},
-            "cli": cli,
+            "per_rank": per_rank,
         }
-        if not a.no_cpu_baseline and world == 1:
-            cb = cpu_reference(paf, tmp)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        if world == 1:
+            line["sizes_note"] = "rank 0 = the whole input"
+        else:
+            line["sizes_note"] = "sizes and phases_ms are rank 0's shard; per_rank has every rank's device time"
+
+        # ---- N = 1: the CPU arm on a bounded sample, the GPU on the same contigs, and the c2 figures ----
+        def same_work(cb):
+            sb = aa.read_paf(cb["sample_path"]).batch
+            sm = timed(sb, None)
+            return {"sample": cb["sample"], "blocks": sb.n_blk, "contigs": sb.n_ctg,
+                    "gpu_resident_blocks_per_s": sb.n_blk * K / sm["wall"], "gpu_e2e_blocks_per_s": sb.n_blk * K / sm["wall_e2e"],
+                    "gpu_ms_per_pass": sm["wall"] / K * 1e3, "cpu_blocks_per_s": cb["value"], "cpu_cores": cb["cores"], "cpu_kind": cb["kind"],
+                    "ratio_e2e": (sb.n_blk * K / sm["wall_e2e"]) / cb["value"]}
+
+        def cpu_fields(cb):
+            out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "peak_rss_mb")}
+            if "one_thread" in cb:
+                out["one_thread"] = cb["one_thread"]
+            return out
+
+        if world == 1 and not a.no_cpu_baseline and wl != "c4":
+            cb = cpu_arm(paf, tmp, passes=K + W)
+            line["cpu_baseline"] = cpu_fields(cb)
+            line["same_work"] = same_work(cb)
+        if world == 1 and auto:
+            paf2 = make_paf("c2", tmp)
+            pf2 = aa.read_paf(paf2)
+            m2 = timed(pf2.batch, None)
+            st2 = m2["st"]
+            c2 = {"workload": "c2: " + WORKLOADS["c2"][2], "value": pf2.batch.n_blk * K / m2["wall"], "unit": "blocks/s",
+                  "ms_per_step": m2["wall"] / K * 1e3, "device_ms_per_step": m2["ev_ms"],
+                  "e2e": {"value": pf2.batch.n_blk * K / m2["wall_e2e"], "unit": "blocks/s", "h2d_bytes_per_step": m2["h2d"], "d2h_bytes_per_step": m2["d2h"]},
+                  "roofline": roofline_of(names, m2["ph"], st2, traffic_ok=True),
+                  "phases_ms": {n: round(x, 3) for n, x in zip(names, m2["ph"])},
+                  "sizes": {k: st2[k] for k in ("n_ctg", "n_blk", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task")}}
+            # the stages of the drop-in command line (SURVEY 8(d): parse + write reported separately)
+            t2 = time.perf_counter()
+            pf3 = aa.read_paf(paf2)
+            t3 = time.perf_counter()
+            r = solver.solve(pf3.batch)
+            t4 = time.perf_counter()
+            pf3.write(r, os.path.join(tmp, "cli_out"))
+            t5 = time.perf_counter()
+            out_bytes = sum(os.path.getsize(os.path.join(tmp, "cli_out" + e)) for e in (".aln.paf", ".aln.alt.paf", ".aln.all.paf"))
+            r.close()
+            pf3.close()
+            c2["cli"] = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": pf2.batch.n_blk / (t5 - t2),
+                         "paf_bytes": os.path.getsize(paf2), "out_bytes": out_bytes, "host_threads": os.cpu_count(),
+                         "note": "aa_paf_read + aa_solve + aa_paf_write as `alignasm --no_all` chains them; process and CUDA start-up excluded"}
+            if not a.no_cpu_baseline:
+                cb2 = cpu_arm(paf2, tmp, passes=K + W)
+                c2["cpu_baseline"] = cpu_fields(cb2)
+                c2["same_work"] = same_work(cb2)
+            line["c2"] = c2
+        emit(line)
         if dist is not None:
             dist.destroy_process_group()
     return 0

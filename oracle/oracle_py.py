@@ -65,7 +65,7 @@ def oracle_solve(batch, threads=1, **kw):
 
 def ref_binary(variant="canon"):
     name = {"canon": "alignasm_ref_canon", "glibc": "alignasm_ref", "dump": "alignasm_ref_dump",
-            "dbg": "alignasm_ref_dbg"}[variant]
+            "dbg": "alignasm_ref_dbg", "b200": "alignasm_ref_b200"}[variant]
     p = os.path.join(REF_DIR, name)
     return p if os.path.exists(p) else None
 

@@ -35,6 +35,13 @@
 
 bool NON_SKIP_LINKABLE;  // alignasm.cpp:26
 
+#ifdef REF_USE_B200
+// the binding of INTEGRATION.md §2 (oracle/solve_batch_b200.cpp): replaces the solve loop below
+void solve_all_contigs_b200(std::vector<std::vector<PafReadData>> &paf_data, std::vector<std::vector<PafOutputData>> &out,
+                            std::vector<std::vector<PafOutputData>> &alt_out,
+                            std::vector<std::vector<std::vector<PafOutputData>>> &max_out, int device);
+#endif
+
 #ifdef REF_DUMP
 FILE *g_ref_dump_file = nullptr;  // consumed by ref_dump_tu.cpp
 #endif
@@ -351,6 +358,21 @@ int main(int argc, char **argv) {
 #endif
       }
     };
+#ifdef REF_USE_B200
+    {   // alignasm.cpp:346-397 replaced by ONE call into libalignasm_b200.so; containers pre-sized as alignasm.cpp:343-344 does
+        (void)worker;
+        std::vector<std::vector<PafOutputData>> o((size_t)n_ctg), a((size_t)n_ctg);
+        std::vector<std::vector<std::vector<PafOutputData>>> m((size_t)n_ctg);
+        solve_all_contigs_b200(paf_data, o, a, m, 0);
+        for (int64_t i = 0; i < n_ctg; i++) {
+            out[(size_t)i].assign(o[(size_t)i]);
+            alt[(size_t)i].assign(a[(size_t)i]);
+            all[(size_t)i].n = m[(size_t)i].size();
+            all[(size_t)i].p = (RowList *)std::calloc(m[(size_t)i].size() ? m[(size_t)i].size() : 1, sizeof(RowList));
+            for (size_t k = 0; k < m[(size_t)i].size(); k++) all[(size_t)i].p[k].assign(m[(size_t)i][k]);
+        }
+    }
+#else
     if (threads == 1) {
         worker();
     } else {
@@ -358,6 +380,7 @@ int main(int argc, char **argv) {
         for (int t = 0; t < threads; t++) pool.emplace_back(worker);
         for (auto &t : pool) t.join();
     }
+#endif
     double t3 = now_s();
 
     // ---- writers: alignasm.cpp:398-490 ----

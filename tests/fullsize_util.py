@@ -28,3 +28,15 @@ def digest(res):
     return d, per
 
 
+
+# tag -> (tools/synth_paf.cpp arguments, solve options): the inputs pinned at full size by tests/golden/make_fullsize.py
+PINS = {
+    "c2": (["--preset", "c2", "--seed", 2], {}),
+    "c3": (["--preset", "c3", "--seed", 3], {}),
+    # BASELINE config 4 ladder (one dense contig): the sizes the CPU restatement still finishes
+    "dense845": (["--preset", "c4", "--n", 845], {}),
+    "dense845.nsl": (["--preset", "c4", "--n", 845], {"non_skip_linkable": True}),
+    "dense1645": (["--preset", "c4", "--n", 1645], {}),
+    "dense1645.nsl": (["--preset", "c4", "--n", 1645], {"non_skip_linkable": True}),
+    "dense3290.nsl": (["--preset", "c4", "--n", 3290], {"non_skip_linkable": True}),
+}

@@ -2,7 +2,7 @@
 """Pins the BENCH workloads themselves (C2 seed 2, C3 seed 3 at full size) against the CPU restatement (oracle/oracle_port.cpp).
 
 Run in the CPU container (minutes: the 43 099-block contig of C2 takes ~4 min of one core):
-    python tests/golden/make_fullsize.py [c2] [c3]
+    python tests/golden/make_fullsize.py [c2] [c3] [dense845] [dense845.nsl] [dense1645] [dense1645.nsl] [dense3290.nsl]
 Writes tests/golden/fullsize_<tag>.json: sha256 of every result array of the port (primary rows, alt rows, sorted index, per-contig
 offsets), sha256 of the walk-distance lists, per-contig (blocks, vertices, edges, walks) and the totals (n_pair, n_vtx, n_edge,
 n_heap, n_walk, n_task).  tests/test_gpu_parity.py::test_fullsize_pins solves the same synthetic input on the GPU and compares.
@@ -20,22 +20,22 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity_util as pu  # noqa: E402
 
-from fullsize_util import STAT_KEYS, digest  # noqa: E402
+from fullsize_util import PINS, STAT_KEYS, digest  # noqa: E402
 
 
 def main():
     import alignasm_b200 as aa
     from oracle import oracle_py
-    for tag in sys.argv[1:] or ["c2", "c3"]:
-        seed = {"c1": 1, "c2": 2, "c3": 3}[tag]
-        paf = pu.synth(os.path.join("/tmp", f"fullsize_{tag}.paf"), "--preset", tag, "--seed", seed)
+    for tag in sys.argv[1:] or list(PINS):
+        args, opts = PINS[tag]
+        paf = pu.synth(os.path.join("/tmp", f"fullsize_{tag}.paf"), *args)
         pf = aa.read_paf(paf)
         t0 = time.time()
-        res = oracle_py.oracle_solve(pf.batch, threads=os.cpu_count() or 1, want_all=False, keep_debug=True)
+        res = oracle_py.oracle_solve(pf.batch, threads=os.cpu_count() or 1, want_all=False, keep_debug=True, **opts)
         dt = time.time() - t0
         d, per = digest(res)
         big = int(np.argmax(per[0]))
-        out = {"workload": tag, "seed": seed, "generator": "tools/synth_paf.cpp --preset " + tag, "oracle": "oracle/oracle_port.cpp",
+        out = {"workload": tag, "generator": "tools/synth_paf.cpp " + " ".join(str(x) for x in args), "options": opts, "oracle": "oracle/oracle_port.cpp",
                "oracle_seconds": round(dt, 1), "stats": {k: int(res.stats[k]) for k in STAT_KEYS},
                "largest_contig": {"index": big, "V": int(per[0][big]), "E": int(per[1][big]), "K": int(per[2][big])}, "sha256": d}
         with open(os.path.join(HERE, f"fullsize_{tag}.json"), "w") as f:

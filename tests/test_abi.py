@@ -174,3 +174,20 @@ def test_parallel_reader_equals_sequential(product_lib, workdir, monkeypatch):
             aa.read_paf(bad)
         msgs.add(str(e.value))
     assert len(msgs) == 1 and "Unsupported operation" in msgs.pop()
+
+
+def test_integration_snippet_is_the_compiled_binding():
+    """INTEGRATION.md §2 is not prose: the snippet is oracle/solve_batch_b200.cpp, which oracle/Makefile compiles against the
+    reference's own headers and links into oracle/_ref/alignasm_ref_b200 (run on the GPU by tests/test_gpu_parity.py)."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"```cpp\n(// src/solve_batch_b200\.cpp.*?)```", md, re.S)
+    assert m, "INTEGRATION.md lost its binding snippet"
+    src = open(os.path.join(root, "oracle", "solve_batch_b200.cpp")).read()
+    assert src.endswith(m.group(1)), "oracle/solve_batch_b200.cpp and the INTEGRATION.md snippet differ"
+    exe = os.path.join(root, "oracle", "_ref", "alignasm_ref_b200")
+    if os.path.exists(exe):  # built where /root/reference exists: it must link the product library, nothing of the oracle
+        out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+        assert "libalignasm_b200.so" in out and "liboracle" not in out

@@ -283,19 +283,26 @@ def test_big_contig_in_shuffled_row_order(p_dup, solver, workdir):
     assert pu.result_rows_equal(got, want, check_all=False) is None
 
 
-@pytest.mark.parametrize("tag", ["c2", "c3"])
+def _pinned():
+    from fullsize_util import PINS
+    return [t for t in PINS if os.path.exists(os.path.join(pu.GOLDEN, f"fullsize_{t}.json"))]
+
+
+@pytest.mark.parametrize("tag", _pinned())
 def test_fullsize_pins(tag, solver, workdir):
     """The BENCH workloads themselves, at full size (C2: 260 contigs / 499 997 blocks incl. the 43 099-block contig that is the
-    critical path of every step; C3: 549 724 blocks), against the CPU restatement: tests/golden/fullsize_<tag>.json holds the
-    sha256 of every result array, of the ordered edge lists, of d / best and of the 2.6 M walk distances the port produced for the
-    same seed (tests/golden/make_fullsize.py, minutes of CPU, run in the CPU container)."""
+    critical path of every step; C3: 549 724 blocks), and the dense-contig ladder of BASELINE config 4 (n = 845, 1 645, and
+    3 290 with --non_skip_linkable), against the CPU restatement: tests/golden/fullsize_<tag>.json holds the sha256 of every
+    result array, of the ordered edge lists, of d / best and of the walk distances the port produced for the same seed
+    (tests/golden/make_fullsize.py, minutes of CPU, run in the CPU container)."""
     import json
     import alignasm_b200 as aa
-    from fullsize_util import STAT_KEYS, digest
+    from fullsize_util import PINS, STAT_KEYS, digest
     want = json.load(open(os.path.join(pu.GOLDEN, f"fullsize_{tag}.json")))
-    paf = pu.synth(os.path.join(workdir, f"fullsize_{tag}.paf"), "--preset", tag, "--seed", want["seed"])
+    args, opts = PINS[tag]
+    paf = pu.synth(os.path.join(workdir, f"fullsize_{tag}.paf"), *args)
     pf = aa.read_paf(paf)
-    got = solver.solve(pf.batch, want_all=False, keep_debug=True)
+    got = solver.solve(pf.batch, want_all=False, keep_debug=True, **opts)
     for k in STAT_KEYS:
         assert int(got.stats[k]) == want["stats"][k], k
     d, per = digest(got)
@@ -303,3 +310,22 @@ def test_fullsize_pins(tag, solver, workdir):
     assert {"index": big, "V": int(per[0][big]), "E": int(per[1][big]), "K": int(per[2][big])} == want["largest_contig"]
     bad = [k for k in want["sha256"] if d[k] != want["sha256"][k]]
     assert not bad, f"{tag}: differs from the CPU restatement in {bad}"
+
+
+@pytest.mark.parametrize("case,nsl", [("ties", False), ("ties", True), ("withalt", False), ("tiny", True)])
+def test_reference_with_binding_writes_golden_bytes(case, nsl, product_lib, workdir):
+    """The drop-in, compiled: oracle/_ref/alignasm_ref_b200 is the reference's own reader, get_edited_paf_data and writers
+    (paf_data.cpp unmodified) with its solve loop (alignasm.cpp:346-397) replaced by the binding of INTEGRATION.md §2
+    (oracle/solve_batch_b200.cpp) calling libalignasm_b200.so.  Its three output files equal the reference's goldens."""
+    from oracle import oracle_py
+    if oracle_py.ref_binary("b200") is None:
+        pytest.skip("oracle/_ref/alignasm_ref_b200 was not built (needs /root/reference at build time)")
+    tag = case + (".nsl" if nsl else "")
+    alt = os.path.join(pu.GOLDEN, case + ".altin.paf")
+    pre = os.path.join(workdir, "bind_" + tag)
+    js = oracle_py.run_ref(os.path.join(pu.GOLDEN, case + ".paf"), pre, variant="b200", non_skip_linkable=nsl,
+                           alt=alt if os.path.exists(alt) else None)
+    assert js["blocks"] > 0
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        want = os.path.join(pu.GOLDEN, tag + "." + ext)
+        assert pu.files_equal(pre + "." + ext, want), f"{tag}.{ext}:\n" + pu.first_diff(pre + "." + ext, want)

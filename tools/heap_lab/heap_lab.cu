@@ -17,8 +17,7 @@ using namespace aa;
 template <int VAR>
 __global__ void __launch_bounds__(32) k_build(Ws w) {
     extern __shared__ __align__(16) unsigned char smem[];
-    if (VAR == 0) f_heaps_warp(w, 0, smem);
-    else f_heaps_chain(w, 0, smem);
+    f_heaps_chain(w, 0, smem);
 }
 __global__ void k_root_fill(Ws w, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,16 +194,16 @@ int main(int argc, char **argv) {
     }
     std::vector<int> variants;
     for (int i = 2; i < argc; i++) variants.push_back(atoi(argv[i]));
-    if (variants.empty()) variants.push_back(0);
+    if (variants.empty()) variants.push_back(110);
     cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     std::vector<HNode> hn((size_t)Hcap); std::vector<int32_t> heid((size_t)Hcap), hroot_at((size_t)nt);
     std::vector<uint64_t> gh((size_t)Hcap);
     int rc = 0;
     for (int var : variants) {
         float best = 1e30f, bestl = 0;
-        // variant 0: f_heaps_warp; variant 100*flags + bits: f_heaps_chain with a node cache of 1 << bits entries (0: none)
+        // variant 100*flags + bits: f_heaps_chain with a node cache of 1 << bits entries (bits 0: none)
         const int bits = var % 100;
-        size_t smem = var == 0 ? HEAP_SMEM_BYTES : heaps_chain_smem_bytes(bits);
+        size_t smem = heaps_chain_smem_bytes(bits);
         w.heap_cache_bits = bits;
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaMemset(w.heap_top, 0, 8)); CK(cudaMemset(w.status, 0, 4)); CK(cudaMemset(w.heap_used, 0, 8));
@@ -212,13 +211,9 @@ int main(int argc, char **argv) {
             CK(cudaMemset(w.vcnt, 0, 4 * ((size_t)hdr[2] + 1)));
             w.heaps_variant = var / 100;
             CK(cudaEventRecord(e0));
-            if (var == 0) {
-                k_build<0><<<1, 32, smem>>>(w);
-            } else {
-                CK(cudaFuncSetAttribute(k_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build<1><<<1, 32, smem>>>(w);
-            }
-            if (var != 0) k_root_fill<<<(unsigned)((hdr[2] + 255) / 256), 256>>>(w, hdr[2]);
+            CK(cudaFuncSetAttribute(k_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_build<1><<<1, 32, smem>>>(w);
+            k_root_fill<<<(unsigned)((hdr[2] + 255) / 256), 256>>>(w, hdr[2]);
             CK(cudaEventRecord(e1));
             k_leaf<<<(unsigned)leaf_list.size(), 32>>>(w, (int64_t)leaf_list.size());
             CK(cudaEventRecord(e2));
@@ -249,7 +244,7 @@ int main(int argc, char **argv) {
         printf("variant %d: %.3f ms (+ leaves %.3f ms)  status %d  used %ld (cpu %zu)  top %llu  smem %zu  mismatching vertices %ld (first %ld)  %s\n", var, best, bestl, st,
                (long)used, cn.size(), top, smem, (long)bad, (long)firstbad, bad == 0 ? "OK" : "FAIL");
 #ifdef AA_HEAP_TIMERS
-        if (var != 0) {
+        {
             int64_t t[16]; CK(cudaMemcpy(t, w.vbase, 128, cudaMemcpyDeviceToHost));
             const char *nm[8] = {"op-read", "reserve", "switch", "descent", "ranks", "stores", "newspine", "extend(count)"};
             for (int i = 0; i < 8; i++) printf("   %-14s cycles %10ld  n %8ld  avg %7.1f\n", nm[i], (long)t[2 * i], (long)t[2 * i + 1], t[2 * i + 1] ? (double)t[2 * i] / t[2 * i + 1] : 0.0);

@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 
 #include <atomic>
 #include <chrono>
@@ -39,6 +40,15 @@ __global__ void __launch_bounds__(32) k_warp_items(int64_t n, F f) {
     if (i < n) f(i, (void *)aa_smem);  // all 32 lanes enter; sequential phases continue on lane 0 only
 }
 
+struct MaxI64 {
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; }
+};
+struct MaxI32 {
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+struct MinI32 {
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a < b ? a : b; }
+};
 struct CastI32 {
     __host__ __device__ __forceinline__ int64_t operator()(const int32_t &x) const { return (int64_t)x; }
 };
@@ -472,6 +482,40 @@ struct CudaBackend {
         AA_CUDA(cub::DeviceScan::ExclusiveSum(t, tmp, it, out, n, stream));
         n_launch++;
         mark("scan");
+    }
+    // segmented scans (segments = runs of equal keys): the parts phase
+    void seg_excl_max_i64(const int32_t *keys, const int64_t *in, int64_t *out, int64_t n) {
+        if (n <= 0 || failed) return;
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceScan::ExclusiveScanByKey(nullptr, tmp, keys, in, out, MaxI64(), (int64_t)-1, n, cub::Equality(), stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceScan::ExclusiveScanByKey(t, tmp, keys, in, out, MaxI64(), (int64_t)-1, n, cub::Equality(), stream));
+        n_launch++;
+        mark("seg_scan");
+    }
+    void seg_incl_max_i32(const int32_t *keys, const int32_t *in, int32_t *out, int64_t n) {
+        if (n <= 0 || failed) return;
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceScan::InclusiveScanByKey(nullptr, tmp, keys, in, out, MaxI32(), n, cub::Equality(), stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceScan::InclusiveScanByKey(t, tmp, keys, in, out, MaxI32(), n, cub::Equality(), stream));
+        n_launch++;
+        mark("seg_scan");
+    }
+    void seg_rexcl_min_i32(const int32_t *keys, const int32_t *in, int32_t *out, int64_t n) {  // from the right
+        if (n <= 0 || failed) return;
+        auto rk = thrust::make_reverse_iterator(keys + n);
+        auto ri = thrust::make_reverse_iterator(in + n);
+        auto ro = thrust::make_reverse_iterator(out + n);
+        size_t tmp = 0;
+        AA_CUDA(cub::DeviceScan::ExclusiveScanByKey(nullptr, tmp, rk, ri, ro, MinI32(), (int32_t)0x7fffffff, n, cub::Equality(), stream));
+        void *t = alloc_bytes(tmp);
+        if (!t) return;
+        AA_CUDA(cub::DeviceScan::ExclusiveScanByKey(t, tmp, rk, ri, ro, MinI32(), (int32_t)0x7fffffff, n, cub::Equality(), stream));
+        n_launch++;
+        mark("seg_scan");
     }
     void sort_pairs_u32(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit) {
         if (n <= 0 || failed) return;

@@ -49,6 +49,10 @@ constexpr int64_t SV_TRANS_PENALTY = 2000;
 constexpr int64_t SV_INV_PENALTY = 500;
 constexpr int64_t SV_FRONT_END = 2;
 constexpr int64_t REF_NEG_PENALTY = 2;
+// run capacity of the enumeration's sorted front (entries of 32 B in shared memory)
+#ifndef AA_FCAP
+#define AA_FCAP 512  // (1024 measured the same or slightly slower on C1 / C2 / C5; 16 KB lets more contigs be resident)
+#endif
 constexpr size_t HEAP2_FIXED_BYTES = 16 * 1024;  // f_heaps_chain: saved spines + op ring (>= sizeof(ChainSmem))
 constexpr int32_t HEAP_CHUNK = 4096;  // leftist-heap nodes handed to a contig per arena grab
 constexpr int64_t I64_MAX = 0x7fffffffffffffffLL;
@@ -486,6 +490,24 @@ AA_HDN void f_parts(const Ws &w, int64_t c) {
         if (e > part_end) part_end = e;
     }
     for (int32_t k = start; k < n; k++) w.part_r[b0 + k] = n;
+}
+
+// parts, device form: three segmented scans over all blocks of the batch (keys = contig of the block) instead of one warp per
+// contig.  pm = exclusive prefix max of the ends; a block is a boundary iff it starts beyond pm (paf_data.cpp:249-261);
+// part_l = inclusive prefix max of (boundary ? index : -1); part_r = exclusive suffix min of (boundary ? index : +inf).
+AA_HDN void f_parts_bnd(const Ws &w, int64_t i, const int64_t *pm, int32_t *bl, int32_t *br) {
+    const int64_t c = w.blk_ctg[i];
+    const int64_t b0 = w.ctg_off[c];
+    const int32_t li = (int32_t)(i - b0);
+    const bool bnd = pm[i] < w.qs[i];
+    bl[i] = bnd ? li : -1;
+    br[i] = bnd ? li : 0x7fffffff;
+    if (li == 0) w.status[c] = (w.ctg_off[c + 1] - b0 == 1) ? 1 : 0;
+}
+AA_HDN void f_parts_fin(const Ws &w, int64_t i, const int32_t *br) {
+    const int64_t c = w.blk_ctg[i];
+    const int32_t n = (int32_t)(w.ctg_off[c + 1] - w.ctg_off[c]);
+    w.part_r[i] = br[i] < n ? br[i] : n;
 }
 
 // qry_partial_overlap for sorted i < j (paf_data.hpp:78-86)
@@ -3189,12 +3211,12 @@ AA_HDN void f_xrec(const Ws &w, int64_t id) {
 // Keys are packed for cheap comparisons: the mapq ratio nz/tot (descending) becomes the exact fixed-point
 // number RMAX - floor(nz * 2^S / tot), S = 2 * bits(V): two different fractions with denominators < 2^(S/2)
 // differ by more than 2^-S.  Contigs too large for that (V >= 2^20) compare the ratio by cross-multiplying.
-constexpr int32_t FCAP = 1024;  // run capacity (entries of 32 B)
+constexpr int32_t FCAP = AA_FCAP;  // run capacity (entries of 32 B)
 constexpr int32_t FMASK = FCAP - 1;
-constexpr int32_t FKEEP = 512;         // entries that stay when a full run spills its upper part
-constexpr int32_t REFILL_ALL = 768;    // a backlog this small is moved as a whole
-constexpr int32_t REFILL_TARGET = 384;
-constexpr int32_t NSAMPLE = 512;
+constexpr int32_t FKEEP = FCAP / 2;            // entries that stay when a full run spills its upper part
+constexpr int32_t REFILL_ALL = 3 * FCAP / 4;   // a backlog this small is moved as a whole
+constexpr int32_t REFILL_TARGET = 3 * FCAP / 8;
+constexpr int32_t NSAMPLE = 512 < FCAP ? 512 : FCAP;
 struct __attribute__((aligned(16))) QE {
     int64_t sum;
     uint64_t k1;  // anom << (S + 1) | ratio key        (wide mode: anom << 32)
@@ -4104,7 +4126,7 @@ AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {
     f_enum(w, c);
 #endif
 }
-constexpr size_t ENUM_SMEM_BYTES = 1024 * 32 + 128;  // >= sizeof(EnumSmem) (device only)
+constexpr size_t ENUM_SMEM_BYTES = (size_t)AA_FCAP * 32 + 128;  // >= sizeof(EnumSmem) (device only)
 
 // phase: plan the edge_path_to_paf_path calls of a contig in the reference's order (paf_data.cpp:1585-1649):
 // walk 0, the walks tied with it on (score_sum, anom), then the alt candidates.
@@ -4154,67 +4176,6 @@ AA_HDN void f_plan(const Ws &w, int64_t c) {
     w.last_group[c] = group;
 }
 #if defined(__CUDA_ARCH__)
-// ---- warp-parallel parts (paf_data.cpp:249-261): a boundary is a block whose start lies beyond the running
-// maximum of the ends before it; part_l = last boundary at or before, part_r = next boundary after
-__device__ void f_parts_warp(const Ws &w, int64_t c) {
-    const uint32_t FULL = 0xffffffffu;
-    const int32_t lane = (int32_t)(threadIdx.x & 31);
-    const int64_t b0 = w.ctg_off[c];
-    const int32_t n = (int32_t)(w.ctg_off[c + 1] - b0);
-    if (lane == 0) w.status[c] = (n == 1) ? 1 : 0;
-    int64_t carry_max = -1;   // max qry_end over the blocks before this chunk
-    int32_t carry_l = 0;      // last boundary so far
-    for (int32_t base = 0; base < n; base += 32) {
-        const int32_t i = base + lane;
-        const bool in = i < n;
-        const int64_t s = in ? w.qs[b0 + i] : 0;
-        int64_t e = in ? w.qe[b0 + i] : -1;
-        // exclusive prefix max of the ends
-        int64_t inc = e;
-        for (int32_t d = 1; d < 32; d <<= 1) {
-            const int64_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d && o > inc) inc = o;
-        }
-        int64_t exc = __shfl_up_sync(FULL, inc, 1);
-        if (lane == 0) exc = -1;
-        if (carry_max > exc) exc = carry_max;
-        const bool bnd = in && exc < s;
-        // last boundary at or before i
-        int32_t pl = bnd ? i : -1;
-        for (int32_t d = 1; d < 32; d <<= 1) {
-            const int32_t o = __shfl_up_sync(FULL, pl, d);
-            if (lane >= d && o > pl) pl = o;
-        }
-        if (pl < 0) pl = carry_l;
-        if (in) w.part_l[b0 + i] = pl;
-        carry_l = __shfl_sync(FULL, pl, 31 < n - base - 1 ? 31 : n - base - 1);
-        const int64_t last_inc = __shfl_sync(FULL, inc, 31);
-        if (last_inc > carry_max) carry_max = last_inc;
-    }
-    __syncwarp();
-    // part_r: next boundary after i = part_l of the first later block whose part_l differs; scan from the right
-    int32_t carry_r = n;  // boundary following the current chunk
-    for (int32_t base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
-        const int32_t i = base + lane;
-        const bool in = i < n;
-        const int32_t pl = in ? w.part_l[b0 + i] : 0x7fffffff;
-        // a block is a boundary iff part_l == i; next boundary strictly after i
-        int32_t nb = (in && pl == i) ? i : 0x7fffffff;   // boundary index or +inf
-        // suffix min over lanes > me (exclusive)
-        int32_t suf = nb;
-        for (int32_t d = 1; d < 32; d <<= 1) {
-            const int32_t o = __shfl_down_sync(FULL, suf, d);
-            if (lane + d < 32 && o < suf) suf = o;
-        }
-        int32_t exc = __shfl_down_sync(FULL, suf, 1);
-        if (lane == 31) exc = 0x7fffffff;
-        if (exc > carry_r) exc = carry_r;   // nothing later in the chunk: the carried one
-        if (exc == 0x7fffffff) exc = carry_r;
-        if (in) w.part_r[b0 + i] = exc < carry_r ? exc : carry_r;
-        const int32_t first = __shfl_sync(FULL, suf, 0);
-        if (first < carry_r) carry_r = first;
-    }
-}
 // ---- warp-parallel plan (paf_data.cpp:1585-1649): lanes scan the distance list, the rare candidates
 // (anom below the minimum walk's) are handled in order
 __device__ void f_plan_warp(const Ws &w, int64_t c) {
@@ -4297,12 +4258,8 @@ __device__ void f_plan_warp(const Ws &w, int64_t c) {
     }
 }
 #endif
-AA_HDN void f_parts_any(const Ws &w, int64_t c) {
-#if defined(__CUDA_ARCH__)
-    f_parts_warp(w, c);
-#else
+AA_HDN void f_parts_any(const Ws &w, int64_t c) {  // (the device path runs three segmented scans instead: f_parts_bnd / f_parts_fin)
     f_parts(w, c);
-#endif
 }
 AA_HDN void f_plan_any(const Ws &w, int64_t c) {
 #if defined(__CUDA_ARCH__)

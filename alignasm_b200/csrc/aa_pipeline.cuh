@@ -168,6 +168,17 @@ struct FnTasksB {
         }                                                           \
     };
 AA_CTG_FUNCTOR(FnParts, f_parts_any(w, c))
+struct FnPartsBnd {
+    Ws w;
+    const int64_t *pm;
+    int32_t *bl, *br;
+    AA_HD void operator()(int64_t i, void *) const { f_parts_bnd(w, i, pm, bl, br); }
+};
+struct FnPartsFin {
+    Ws w;
+    const int32_t *br;
+    AA_HD void operator()(int64_t i, void *) const { f_parts_fin(w, i, br); }
+};
 AA_CTG_FUNCTOR(FnRelax, f_relax_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnRelaxRedo, f_relax_redo_any(w, c, scratch))
 AA_CTG_FUNCTOR(FnRelaxSweep, f_relax_sweep_any(w, c, scratch))
@@ -567,7 +578,24 @@ struct Pipeline {
 
         // ---- phase 1: parts ----
         bk.phase_begin(PH_PARTS);
-        bk.for_each_contig("parts", C, FnParts{w, d_ord});
+#if defined(__CUDACC__)
+        if (bk.device_kahn()) {  // three segmented scans over the blocks (a 43 k-block contig took one warp 0.9 ms)
+            const size_t mark = bk.alloc_mark();
+            int64_t *pm = A<int64_t>(B);
+            int32_t *bl = A<int32_t>(B), *br = A<int32_t>(B), *brs = A<int32_t>(B);
+            if (!pm || !bl || !br || !brs) {
+                err = "device allocation failed (parts)";
+                return AA_ERR_NOMEM;
+            }
+            bk.seg_excl_max_i64(w.blk_ctg, w.qe, pm, B);
+            bk.for_each("parts_bnd", B, FnPartsBnd{w, pm, bl, br});
+            bk.seg_incl_max_i32(w.blk_ctg, bl, w.part_l, B);
+            bk.seg_rexcl_min_i32(w.blk_ctg, br, brs, B);
+            bk.for_each("parts_fin", B, FnPartsFin{w, brs});
+            bk.release_to(mark);  // (stream-ordered: the next allocation's first use comes after these kernels)
+        } else
+#endif
+            bk.for_each_contig("parts", C, FnParts{w, d_ord});
         bk.phase_end(PH_PARTS);
         AA_BK_CHECK();
 
@@ -1060,7 +1088,7 @@ struct Pipeline {
             // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
             w.xrec = nullptr;
             if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records
-            if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget() / 2) {
+            if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget()) {
                 w.xrec = A<XRec>(heap_top_h);
                 if (!w.xrec) {
                     err = "device allocation failed (expansion records)";

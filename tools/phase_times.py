@@ -6,7 +6,8 @@ import alignasm_b200 as aa, parity_util as pu
 s = aa.Solver(0)
 names = s.phase_names()
 for tag in sys.argv[1:] or ["c1", "c2", "c3"]:
-    b = aa.read_paf(pu.synth(f"/tmp/pt_{tag}.paf", "--preset", tag)).batch
+    args = ["--preset", "c5", "--replicas", 8] if tag == "c5x8" else ["--preset", tag]
+    b = aa.read_paf(pu.synth(f"/tmp/pt_{tag}.paf", *args)).batch
     dev = s.upload(b)
     for it in range(3):
         s.solve_device(dev, fetch=False)

@@ -220,11 +220,11 @@ struct __attribute__((aligned(16))) HOp {  // one operation of the serial heap b
     int64_t sum;
     int32_t anom, nz, tot;  // insert: the sidetrack key (reservation: anom = number of node ids)
     int32_t eid;
-    int32_t ctl;            // HOP_FIRST: first insert of its vertex, HOP_LAST: last one, HOP_RESERVE: id reservation for a leaf
-    int32_t aux;            // FIRST: chain ordinal (within the contig) of the vertex whose heap is inherited, -1: empty heap;
-                            // RESERVE: contig-local BFS slot of the leaf
+    int32_t ctl;            // HOP_FIRST: first insert of its vertex, HOP_LAST: last one; FIRST also carries, from bit HOP_RESV_SHIFT
+                            // up, the node ids to reserve BEFORE this vertex for the tree leaves that precede it in BFS order
+    int32_t aux;            // FIRST: chain ordinal (within the contig) of the vertex whose heap is inherited, -1: empty heap
 };
-constexpr int32_t HOP_FIRST = 1, HOP_LAST = 2, HOP_RESERVE = 4;
+constexpr int32_t HOP_FIRST = 1, HOP_LAST = 2, HOP_RESV_SHIFT = 3;
 constexpr int32_t LEAF_MAX_INS = 32;  // a leaf's reserved ids (32 per insert) fit one arena chunk
 struct CandRec {  // one candidate pair (i partially overlaps j): cut point, 48 B
     int32_t i, j;        // contig-local sorted block indices
@@ -350,7 +350,12 @@ struct Ws {
     int32_t *chunk_ctg;  // [Hcap / 64 + 1] contig that owns each run of 64 node ids (written by the heap builders)
     int64_t *heap_used;  // [C]
     // streaming builder, flat form (f_heaps_chain): the serial warp reads one stream of operations per contig
-    HOp *ops;            // [n_ops] inserts of the chain vertices (tree vertices whose heap others inherit) + one id reservation per leaf
+    HOp *ops;            // [n_ops] inserts of the chain vertices (tree vertices whose heap others inherit)
+    int32_t *leaf_need;  // [Vtot+1] node ids a tree leaf reserves (32 per insert), 0 for every other vertex
+    int64_t *leaf_lp;    // [Vtot+2] exclusive prefix sum of leaf_need
+    int32_t *chain_slot; // [n_chain] BFS slot (global) of every chain vertex
+    int32_t *resv_base;  // [n_chain + C] first reserved id of the leaf run before every chain vertex (+ one per contig: the run
+                         // behind its last chain vertex), written by the serial warp
     int32_t *op_cnt;     // [Vtot+1] operations of the vertex at each BFS slot
     int64_t *op_off;     // [Vtot+2]
     int32_t *chain_flag; // [Vtot+1] 1: chain vertex
@@ -1361,7 +1366,8 @@ AA_HDN void f_ops_class(const Ws &w, int64_t i) {
         if (n > 0) cls = (n <= LEAF_MAX_INS && !(vi.nins & VI_KIDS)) ? 2 : 1;
         own = cls == 1 ? (int32_t)(i - v0) : vi.ppos;
     }
-    w.op_cnt[i] = cls == 1 ? n : (cls == 2 ? 1 : 0);
+    w.op_cnt[i] = cls == 1 ? n : 0;
+    w.leaf_need[i] = cls == 2 ? 32 * n : 0;  // (32 per insert is the most a spine can copy)
     w.chain_flag[i] = cls == 1;
     w.owner[i] = own;
 }
@@ -1373,40 +1379,36 @@ AA_HDN void f_owner_jump(const Ws &w, int64_t i) {  // one round; in place (a ra
     if (w.chain_flag[v0 + o]) return;
     w.owner[i] = w.owner[v0 + o];
 }
+AA_HDN void f_chain_slot(const Ws &w, int64_t i) {
+    if (w.chain_flag[i]) w.chain_slot[w.chain_ord[i]] = (int32_t)i;
+}
+// slot where the leaf run in front of chain ordinal j (global) of the contig starting at v0 begins
+AA_HD int64_t run_start_slot(const Ws &w, int64_t v0, int64_t gord) { return gord > w.chain_ord[v0] ? (int64_t)w.chain_slot[gord - 1] : v0; }
 AA_HDN void f_ops_fill(const Ws &w, int64_t i) {
-    const int32_t cnt = w.op_cnt[i];
-    if (cnt == 0) return;
+    if (!w.chain_flag[i]) return;
     const int64_t c = upper_idx(w.vtx_off, w.C, i);
     const int64_t v0 = w.vtx_off[c];
     const VInfo vi = w.vinfo[i];
     const int64_t o = w.op_off[i];
     const int32_t n = vi.nins & (VI_KIDS - 1);
-    if (w.chain_flag[i]) {
-        int32_t src = -1;
-        if (vi.ppos >= 0) {
-            const int32_t po = w.owner[v0 + vi.ppos];
-            if (po >= 0) src = (int32_t)(w.chain_ord[v0 + po] - w.chain_ord[v0]);
-        }
-        for (int32_t k = 0; k < n; k++) {
-            const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
-            HOp op;
-            op.sum = ik.sum;
-            op.anom = ik.anom;
-            op.nz = ik.nz;
-            op.tot = ik.tot;
-            op.eid = ik.eid;
-            op.ctl = (k == 0 ? HOP_FIRST : 0) | (k == n - 1 ? HOP_LAST : 0);
-            op.aux = k == 0 ? src : 0;
-            w.ops[o + k] = op;
-        }
-    } else {
+    int32_t src = -1;
+    if (vi.ppos >= 0) {
+        const int32_t po = w.owner[v0 + vi.ppos];
+        if (po >= 0) src = (int32_t)(w.chain_ord[v0 + po] - w.chain_ord[v0]);
+    }
+    // ids of the leaves between the previous chain vertex and this one (BFS order): reserved in front of this vertex's nodes
+    const int64_t resv = w.leaf_lp[i] - w.leaf_lp[run_start_slot(w, v0, w.chain_ord[i])];
+    for (int32_t k = 0; k < n; k++) {
+        const InsKey ik = w.ins[(int64_t)vi.ins_beg + k];
         HOp op;
-        op.sum = 0;
-        op.anom = 32 * n;
-        op.nz = op.tot = op.eid = 0;
-        op.ctl = HOP_RESERVE;
-        op.aux = (int32_t)(i - v0);
-        w.ops[o] = op;
+        op.sum = ik.sum;
+        op.anom = ik.anom;
+        op.nz = ik.nz;
+        op.tot = ik.tot;
+        op.eid = ik.eid;
+        op.ctl = (k == 0 ? (HOP_FIRST | (int32_t)(resv << HOP_RESV_SHIFT)) : 0) | (k == n - 1 ? HOP_LAST : 0);
+        op.aux = k == 0 ? src : 0;
+        w.ops[o + k] = op;
     }
 }
 AA_HDN void f_root_fill(const Ws &w, int64_t i) {  // after the serial warp: every tree vertex takes the heap of its owner
@@ -1417,6 +1419,10 @@ AA_HDN void f_root_fill(const Ws &w, int64_t i) {  // after the serial warp: eve
     const int32_t root = o < 0 ? -1 : w.chain_root[w.chain_ord[v0 + o]];
     w.root_at[i] = root;
     w.hroot[v0 + w.vinfo[i].x] = root;
+    if (w.leaf_need[i] > 0) {  // a leaf: its ids lie in the run reserved in front of the next chain vertex (or behind the last one)
+        const int64_t gord = w.chain_ord[i];
+        w.leaf_base[i] = w.resv_base[gord + c] + (int32_t)(w.leaf_lp[i] - w.leaf_lp[run_start_slot(w, v0, gord)]);
+    }
 }
 
 // insert (key, eid) into the persistent heap rooted at a; returns the new root (or -1 on arena overflow).
@@ -1487,6 +1493,22 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot);  // level-parallel bui
 // phase: sidetrack heaps (k_shortest_walks.hpp:191-215): the tree vertices in BFS order, each inserting its sidetracks into the
 // heap it inherits from its tree parent.
 // Sequential forms of the flat builder (host emulation): the operation stream of one contig, then one leaf.
+AA_HD bool heap_reserve_host(const Ws &w, HeapAlloc &ha, int64_t n, int32_t &base) {  // n contiguous ids, not counted as used
+    if (ha.cur + n > ha.end) {
+        const int64_t chunks = (n + HEAP_CHUNK - 1) / HEAP_CHUNK;
+        const unsigned long long at = *w.heap_top;
+        *w.heap_top = at + (unsigned long long)(chunks * HEAP_CHUNK);
+        if ((int64_t)at + chunks * HEAP_CHUNK > w.Hcap) {
+            ha.overflow = true;
+            return false;
+        }
+        ha.cur = (int64_t)at;
+        ha.end = ha.cur + chunks * HEAP_CHUNK;
+    }
+    base = (int32_t)ha.cur;
+    ha.cur += n;
+    return true;
+}
 AA_HDN void f_heaps_ops(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
     if (w.status[c] != 0 && w.status[c] != 3) return;
@@ -1495,7 +1517,9 @@ AA_HDN void f_heaps_ops(const Ws &w, int64_t c) {
     const int32_t nt = w.ntree[c];
     const HOp *ops = w.ops + w.op_off[v0];
     const int64_t nops = w.op_off[v0 + nt] - w.op_off[v0];
-    int32_t *chain_root = w.chain_root + w.chain_ord[v0];
+    const int64_t cbase = w.chain_ord[v0];
+    int32_t *chain_root = w.chain_root + cbase;
+    int32_t *resv_base = w.resv_base + cbase + c;
     HeapAlloc ha;
     ha.cur = ha.end = 0;
     ha.used = 0;
@@ -1503,19 +1527,11 @@ AA_HDN void f_heaps_ops(const Ws &w, int64_t c) {
     int32_t root = -1, cv = 0;
     for (int64_t i = 0; i < nops && !ha.overflow; i++) {
         const HOp op = ops[i];
-        if (op.ctl & HOP_RESERVE) {
-            if (ha.cur + op.anom > ha.end) {  // the reservation is one piece of one chunk
-                ha.cur = ha.end;
-                const int64_t keep = ha.used;
-                if (heap_new(w, ha) < 0) break;
-                ha.cur--;
-                ha.used = keep;
-            }
-            w.leaf_base[v0 + op.aux] = (int32_t)ha.cur;
-            ha.cur += op.anom;
-            continue;
+        if (op.ctl & HOP_FIRST) {
+            root = op.aux < 0 ? -1 : chain_root[op.aux];
+            const int64_t resv = op.ctl >> HOP_RESV_SHIFT;
+            if (resv > 0 && !heap_reserve_host(w, ha, resv, resv_base[cv])) break;
         }
-        if (op.ctl & HOP_FIRST) root = op.aux < 0 ? -1 : chain_root[op.aux];
         SKey sk;
         sk.sum = op.sum;
         sk.anom = op.anom;
@@ -1525,6 +1541,10 @@ AA_HDN void f_heaps_ops(const Ws &w, int64_t c) {
         root = heap_insert(w.hn, w.hn_eid, w, ha, root, sk, op.eid);
         if (root < 0) break;
         if (op.ctl & HOP_LAST) chain_root[cv++] = root;
+    }
+    if (!ha.overflow) {  // the leaves behind the last chain vertex
+        const int64_t tail = w.leaf_lp[v0 + nt] - w.leaf_lp[run_start_slot(w, v0, cbase + cv)];
+        if (tail > 0) heap_reserve_host(w, ha, tail, resv_base[cv]);
     }
     w.heap_used[c] = ha.used;
     w.status[c] = ha.overflow ? 3 : 0;
@@ -2549,6 +2569,7 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
     const HOp *__restrict__ ops = w.ops + w.op_off[v0];
     const int32_t nops = (int32_t)(w.op_off[v0 + nt] - w.op_off[v0]);
     int32_t *__restrict__ chain_root = w.chain_root + w.chain_ord[v0];
+    int32_t *__restrict__ resv_base = w.resv_base + w.chain_ord[v0] + c;
     auto issue_chunk = [&](int32_t ch) {  // ops [32 ch, 32 ch + 32) -> ring (one cp.async group, possibly empty)
         const int32_t i = ch * 32 + lane;
         if (i < nops) {
@@ -2575,16 +2596,16 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
     bool overflow = false;
     int32_t save_at = 0;
     // a fresh arena chunk (warp-uniform result; -1: arena exhausted)
-    auto new_chunk = [&]() -> int32_t {
+    auto new_chunk = [&](int32_t need_ids) -> int32_t {  // enough whole chunks for need_ids contiguous ids; sets `end`
+        const int32_t chunks = (need_ids + HEAP_CHUNK - 1) / HEAP_CHUNK;
         unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)HEAP_CHUNK);
+        if (lane == 0) at = atomicAdd(w.heap_top, (unsigned long long)chunks * HEAP_CHUNK);
         at = __shfl_sync(FULL, at, 0);
-        if ((int64_t)at + HEAP_CHUNK > w.Hcap) return -1;
-        if (w.chunk_ctg) {
-            w.chunk_ctg[(at >> 6) + lane] = (int32_t)c;
-            w.chunk_ctg[(at >> 6) + 32 + lane] = (int32_t)c;
-        }
-        return (int32_t)__reduce_max_sync(FULL, (uint32_t)at);
+        if ((int64_t)at + (int64_t)chunks * HEAP_CHUNK > w.Hcap) return -1;
+        if (w.chunk_ctg)
+            for (int32_t k = lane; k < chunks * (HEAP_CHUNK / 64); k += 32) w.chunk_ctg[(at >> 6) + k] = (int32_t)c;
+        end = (int32_t)__reduce_max_sync(FULL, (uint32_t)at) + chunks * HEAP_CHUNK;
+        return end - chunks * HEAP_CHUNK;
     };
     // spine of the heap rooted at `from` appended below level L0 (complete right spine, read through the cache)
     auto extend = [&](int32_t L0, int32_t from) -> int32_t {
@@ -2652,31 +2673,8 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
         // it; ties and the control flags of the operation take the slow path below ----
         bool known = lane < L;
         uint32_t stop = __ballot_sync(FULL, known && ksum >= op.sum);
-        const uint32_t slow = __ballot_sync(FULL, (known && ksum == op.sum) || (op.ctl & HOP_RESERVE) != 0 ||
-                                                      ((op.ctl & HOP_FIRST) != 0 && op.aux != cur_ord));
+        const uint32_t slow = __ballot_sync(FULL, (known && ksum == op.sum) || ((op.ctl & HOP_FIRST) != 0 && op.aux != cur_ord));
         if (slow) {
-            if (op.ctl & HOP_RESERVE) {  // a leaf takes its node ids here, in sequence; f_heaps_level fills them in later
-                const int32_t need = op.anom;
-                if (cur + need > end) {
-                    cur = new_chunk();
-                    if (cur < 0) {
-                        overflow = true;
-                        break;
-                    }
-                    end = cur + HEAP_CHUNK;
-                }
-                if (lane == 0) w.leaf_base[v0 + op.aux] = cur;
-                cur += need;
-                oi++;
-                if ((oi & 31) == 0) {
-                    issue_chunk((oi >> 5) + 2);
-                    asm volatile("cp.async.wait_group 2;" ::: "memory");
-                    __syncwarp();
-                }
-                op = op_read(oi);
-                HT(1);
-                continue;
-            }
             if ((op.ctl & HOP_FIRST) && op.aux != cur_ord) {  // this vertex does not continue the heap just built: switch spines
                 if (cur_ord >= 0) {
                     const uint32_t have = __ballot_sync(FULL, lane < NSAVE && sm.sord[lane] == cur_ord);
@@ -2742,19 +2740,22 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
         }
         const int32_t p = stop ? __ffs(stop) - 1 : L;
         HT(3);
+        // ids: the leaves in front of this vertex take theirs first (FIRST carries the count), then the p + 1 nodes of the insert
+        const int32_t resv = (op.ctl >> HOP_RESV_SHIFT);
         const int32_t need = p + 1;
-        if (p >= SPMAX - 1 || cur + need > end) {
+        if (p >= SPMAX - 1 || cur + resv + need > end) {
             if (p >= SPMAX - 1) {  // cannot happen below 2^31 nodes per heap; fail loudly rather than corrupt
                 overflow = true;
                 break;
             }
-            cur = new_chunk();
+            cur = new_chunk(resv + need);
             if (cur < 0) {
                 overflow = true;
                 break;
             }
-            end = cur + HEAP_CHUNK;
         }
+        if (lane == 0 && resv > 0) resv_base[cv] = cur;
+        cur += resv;
         const int32_t nbase = cur;
         cur += need;
         used += need;
@@ -2840,6 +2841,15 @@ __device__ void f_heaps_chain(const Ws &w, int64_t c, void *scratch) {
             cv++;
         }
         HT(6);
+    }
+    if (!overflow) {  // the leaves behind the last chain vertex
+        const int64_t gord = w.chain_ord[v0] + cv;
+        const int32_t tail = (int32_t)(w.leaf_lp[v0 + nt] - w.leaf_lp[run_start_slot(w, v0, gord)]);
+        if (tail > 0) {
+            if (cur + tail > end) cur = new_chunk(tail);
+            if (cur < 0) overflow = true;
+            else if (lane == 0) resv_base[cv] = cur;
+        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #ifdef AA_HEAP_TIMERS

@@ -92,6 +92,7 @@ struct FnCtgEdges {
 AA_FUNCTOR(FnOpsClass, f_ops_class(w, i))
 AA_FUNCTOR(FnOwnerJump, (f_owner_jump(w, i), f_owner_jump(w, i)))
 AA_FUNCTOR(FnOpsFill, f_ops_fill(w, i))
+AA_FUNCTOR(FnChainSlot, f_chain_slot(w, i))
 AA_FUNCTOR(FnRootFill, f_root_fill(w, i))
 AA_FUNCTOR(FnLeafFlag, f_leaf_flag(w, i))
 AA_FUNCTOR(FnLeafList, f_leaf_list(w, i))
@@ -978,17 +979,24 @@ struct Pipeline {
         w.chain_ord = A<int64_t>(Vtot + 2);
         w.owner = A<int32_t>(Vtot);
         w.chain_root = A<int32_t>(Vtot);
-        w.ops = A<HOp>(n_ins + n_leaf);
+        w.ops = A<HOp>(n_ins);
+        w.leaf_need = A<int32_t>(Vtot + 1);
+        w.leaf_lp = A<int64_t>(Vtot + 2);
+        w.chain_slot = A<int32_t>(Vtot);
+        w.resv_base = A<int32_t>(Vtot + C + 1);
         if (!w.leaf_flag || !w.leaf_off || !w.leaf_base || !w.leaf_list || !w.op_cnt || !w.op_off || !w.chain_flag || !w.chain_ord ||
-            !w.owner || !w.chain_root || !w.ops) {
+            !w.owner || !w.chain_root || !w.ops || !w.leaf_need || !w.leaf_lp || !w.chain_slot || !w.resv_base) {
             err = "device allocation failed (heap operation stream)";
             return AA_ERR_NOMEM;
         }
         bk.zero(w.op_cnt + Vtot, 4);
         bk.zero(w.chain_flag + Vtot, 4);
+        bk.zero(w.leaf_need + Vtot, 4);
         bk.for_each("ops_class", Vtot, FnOpsClass{w});
         bk.scan_i32(w.op_cnt, w.op_off, Vtot + 1);
         bk.scan_i32(w.chain_flag, w.chain_ord, Vtot + 1);
+        bk.scan_i32(w.leaf_need, w.leaf_lp, Vtot + 1);
+        bk.for_each("chain_slot", Vtot, FnChainSlot{w});
         {
             int64_t maxV = 3;
             for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);

@@ -166,13 +166,17 @@ int main(int argc, char **argv) {
     {
         Ws h; memset(&h, 0, sizeof(h));
         const int64_t V = hdr[2];
-        std::vector<int32_t> z1(1, 0), nt1(1, (int32_t)nt), opc((size_t)V + 1, 0), cf((size_t)V + 1, 0), own((size_t)V, -1);
-        std::vector<int64_t> opo((size_t)V + 2, 0), co((size_t)V + 2, 0);
+        std::vector<int32_t> z1(1, 0), nt1(1, (int32_t)nt), opc((size_t)V + 1, 0), cf((size_t)V + 1, 0), own((size_t)V, -1), ln((size_t)V + 1, 0),
+            cs((size_t)V, 0);
+        std::vector<int64_t> opo((size_t)V + 2, 0), co((size_t)V + 2, 0), lp((size_t)V + 2, 0);
         std::vector<VInfo> hv((size_t)V); memcpy(hv.data(), vi.data(), sizeof(VInfo) * (size_t)nt);
         h.C = 1; h.vtx_off = h_voff; h.hmode = z1.data(); h.status = z1.data(); h.ntree = nt1.data(); h.vinfo = hv.data(); h.ins = ins.data();
         h.op_cnt = opc.data(); h.op_off = opo.data(); h.chain_flag = cf.data(); h.chain_ord = co.data(); h.owner = own.data();
+        h.leaf_need = ln.data(); h.leaf_lp = lp.data(); h.chain_slot = cs.data();
         for (int64_t i = 0; i < V; i++) f_ops_class(h, i);
-        for (int64_t i = 0; i < V; i++) { opo[(size_t)i + 1] = opo[(size_t)i] + opc[(size_t)i]; co[(size_t)i + 1] = co[(size_t)i] + cf[(size_t)i]; }
+        for (int64_t i = 0; i < V; i++) { opo[(size_t)i + 1] = opo[(size_t)i] + opc[(size_t)i]; co[(size_t)i + 1] = co[(size_t)i] + cf[(size_t)i];
+                                           lp[(size_t)i + 1] = lp[(size_t)i] + ln[(size_t)i]; }
+        for (int64_t i = 0; i < V; i++) f_chain_slot(h, i);
         n_ops = opo[(size_t)V]; n_chain = co[(size_t)V];
         // pointer jumping, worst order for an in-place update (descending), until nothing changes
         for (int round = 0;; round++) {
@@ -190,6 +194,10 @@ int main(int argc, char **argv) {
         w.chain_ord = (int64_t *)D(8 * co.size()); CK(cudaMemcpy(w.chain_ord, co.data(), 8 * co.size(), cudaMemcpyHostToDevice));
         w.owner = (int32_t *)D(4 * own.size()); CK(cudaMemcpy(w.owner, own.data(), 4 * own.size(), cudaMemcpyHostToDevice));
         w.chain_root = (int32_t *)D(4 * (size_t)n_chain + 4);
+        w.leaf_need = (int32_t *)D(4 * ln.size()); CK(cudaMemcpy(w.leaf_need, ln.data(), 4 * ln.size(), cudaMemcpyHostToDevice));
+        w.leaf_lp = (int64_t *)D(8 * lp.size()); CK(cudaMemcpy(w.leaf_lp, lp.data(), 8 * lp.size(), cudaMemcpyHostToDevice));
+        w.chain_slot = (int32_t *)D(4 * cs.size()); CK(cudaMemcpy(w.chain_slot, cs.data(), 4 * cs.size(), cudaMemcpyHostToDevice));
+        w.resv_base = (int32_t *)D(4 * (size_t)n_chain + 64);
         printf("ops: %ld (chain vertices %ld)\n", (long)n_ops, (long)n_chain);
     }
     std::vector<int> variants;

@@ -3386,6 +3386,8 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t head = 0, n0 = 0, np = 0, nR = 0;  // run ring [head, head + n0), pending lanes [0, np), backlog [0, nR)
     bool hasT = false, hasB = false;           // threshold between front and backlog; bound of the useful keys
     QE T = INF, B = INF, P = INF;              // P: this lane's pending entry
+    QE p0u = INF;                              // warp-uniform copy of lane 0's pending entry, valid while p0_ok
+    bool p0_ok = false;
     const D4 ds = w.d[v0 + g.src];
     if (lane == 0) {
         dist[0] = ds;
@@ -3422,6 +3424,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     // merge the pending registers into the run (one pass over the part of the run that has to move)
     auto flush = [&]() {
         if (np == 0) return;
+        p0_ok = false;
         if (n0 + np > FCAP) {  // the run spills its upper part to the backlog; the threshold drops to the first spilled key
             const QE t0 = qe_ld(fslot(FKEEP));
             for (int32_t i = FKEEP + lane; i < n0; i += 32) qe_st(back + nR + (i - FKEEP), qe_ld(fslot(i)));
@@ -3497,6 +3500,10 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         if (lane > pos) P = up;
         if (lane == pos) P = e;
         np++;
+        if (pos == 0) {  // (the serial steps keep a warp-uniform copy of the smallest pending entry)
+            p0u = e;
+            p0_ok = true;
+        }
     };
     // bitonic sort of sm.f[0, n) padded to a power of two (run must be empty: head is reset by the caller)
     auto sort_run = [&](int32_t n) {
@@ -3677,7 +3684,11 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 t = cy;
                 carry = false;
             } else {  // pop the front minimum
-                const QE p0 = qe_shfl(P, ShIdx{0});
+                if (!p0_ok) {
+                    p0u = qe_shfl(P, ShIdx{0});
+                    p0_ok = true;
+                }
+                const QE p0 = p0u;
                 bool from_p = np > 0;
                 QE rh = INF;
                 if (n0 > 0) {
@@ -3689,6 +3700,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                     const QE dn = qe_shfl(P, ShDown{1});
                     P = lane + 1 < np ? dn : INF;
                     np--;
+                    p0_ok = false;
                 } else {
                     head = (head + 1) & FMASK;
                     n0--;
@@ -3770,7 +3782,11 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             ne += __popc(vmask);
             if (valid && hasB && !qe_less(a, B, wide)) valid = false;  // beyond the K walks: dropped
             // ---- the smallest successor that precedes the front is the next pop ----
-            QE fm = qe_shfl(P, ShIdx{0});
+            if (!p0_ok) {
+                p0u = qe_shfl(P, ShIdx{0});
+                p0_ok = true;
+            }
+            QE fm = p0u;
             if (n0 > 0) {
                 const QE rh = qe_ld(fslot(0));
                 if (np == 0 || qe_less(rh, fm, wide)) fm = rh;
@@ -3835,6 +3851,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         }
         ET(7);
         const int32_t nd_round = nd;
+        p0_ok = false;  // (the round moves the pending lanes)
 #ifdef AA_ENUM_TIMERS
         {   // plateau statistics: entries of the front that tie with its minimum on the distance
             QE fm = qe_shfl(P, ShIdx{0});

@@ -78,6 +78,10 @@ def load_library():
     lib.aa_paf_write.restype = C.c_int
     lib.aa_paf_free.argtypes = [vp]
     lib.aa_paf_free.restype = None
+    lib.aa_paf_read_device.argtypes = [C.c_char_p, vp, C.POINTER(vp), C.c_char_p, C.c_int64]
+    lib.aa_paf_read_device.restype = C.c_int
+    lib.aa_paf_write_device.argtypes = [vp, vp, C.POINTER(aa_result), C.c_char_p, C.c_char_p, C.c_int64]
+    lib.aa_paf_write_device.restype = C.c_int
     lib.aa_solve_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(aa_batch), C.POINTER(aa_opts), C.POINTER(aa_result)]
     lib.aa_solve_multi.restype = C.c_int
     lib.aa_shard_contigs.argtypes = [C.POINTER(aa_batch), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
@@ -224,13 +228,17 @@ class Result:
 class PafFile:
     """A parsed PAF (reader + bucketing + cs:Z: -> runs), owned by the C library."""
 
-    def __init__(self, path, alt=None, alt_baseline=0.5):
-        """`alt`: an alternative PAF (reference CLI `--alt`, `--alt_baseline`; alignasm.cpp:186-332)."""
+    def __init__(self, path, alt=None, alt_baseline=0.5, solver=None):
+        """`alt`: an alternative PAF (reference CLI `--alt`, `--alt_baseline`; alignasm.cpp:186-332).
+        `solver`: parse the cs:Z: tags on that Solver's device (aa_paf_read_device) instead of on the host."""
         lib = load_library()
         self._lib = lib
         h = C.c_void_p()
         err = C.create_string_buffer(512)
-        st = lib.aa_paf_read(os.fsencode(path), C.byref(h), err, 512)
+        if solver is not None:
+            st = lib.aa_paf_read_device(os.fsencode(path), solver._h, C.byref(h), err, 512)
+        else:
+            st = lib.aa_paf_read(os.fsencode(path), C.byref(h), err, 512)
         if st != 0:
             raise AlignasmError(st, err.value.decode())
         self._h = h
@@ -249,9 +257,13 @@ class PafFile:
             self._batch = Batch.from_c(self._lib.aa_paf_batch(self._h).contents)
         return self._batch
 
-    def write(self, result, out_prefix):
+    def write(self, result, out_prefix, solver=None):
+        """`solver`: re-cut the cs:Z: tags of the primary / alternative rows on that Solver's device (aa_paf_write_device)."""
         err = C.create_string_buffer(512)
-        st = self._lib.aa_paf_write(self._h, C.byref(result._c), os.fsencode(out_prefix), err, 512)
+        if solver is not None:
+            st = self._lib.aa_paf_write_device(self._h, solver._h, C.byref(result._c), os.fsencode(out_prefix), err, 512)
+        else:
+            st = self._lib.aa_paf_write(self._h, C.byref(result._c), os.fsencode(out_prefix), err, 512)
         if st != 0:
             raise AlignasmError(st, err.value.decode())
 
@@ -267,8 +279,8 @@ class PafFile:
             pass
 
 
-def read_paf(path, alt=None, alt_baseline=0.5):
-    return PafFile(path, alt=alt, alt_baseline=alt_baseline)
+def read_paf(path, alt=None, alt_baseline=0.5, solver=None):
+    return PafFile(path, alt=alt, alt_baseline=alt_baseline, solver=solver)
 
 
 def _opts(non_skip_linkable=False, want_all=False, max_walks=0, keep_debug=False):
@@ -375,6 +387,38 @@ def solve_multi(batch, devices, **kw):
         lib.aa_result_free(C.byref(res))  # (a no-op on an empty result; AA_ERR_UNSOLVABLE leaves a filled one)
         raise AlignasmError(st, msg)
     return Result(res, batch.n_blk, lib.aa_result_free)
+
+
+def cs_runs_device(solver, text, cs_off, cs_len, qry_str, qry_end, ref_str, ref_end, aln_fwd):
+    """parse_short_cs + get_overlap_range on the device (aa_cs_runs_device): `text` holds the cs:Z: fields of the rows at
+    cs_off / cs_len.  Returns (run_off, run_ql, run_qr, run_rl, err) as numpy arrays."""
+    lib = load_library()
+    lib.aa_cs_runs_device.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(_abi.aa_cs_rows), C.POINTER(_abi.aa_cs_runs)]
+    lib.aa_cs_runs_device.restype = C.c_int
+    lib.aa_cs_runs_free.argtypes = [C.POINTER(_abi.aa_cs_runs)]
+    lib.aa_cs_last_error.restype = C.c_char_p
+    arr = {"cs_off": np.ascontiguousarray(cs_off, dtype=np.int64), "cs_len": np.ascontiguousarray(cs_len, dtype=np.int32),
+           "qry_str": np.ascontiguousarray(qry_str, dtype=np.int64), "qry_end": np.ascontiguousarray(qry_end, dtype=np.int64),
+           "ref_str": np.ascontiguousarray(ref_str, dtype=np.int64), "ref_end": np.ascontiguousarray(ref_end, dtype=np.int64),
+           "aln_fwd": np.ascontiguousarray(aln_fwd, dtype=np.uint8)}
+    rows = _abi.aa_cs_rows(len(arr["cs_off"]), ptr_of(arr["cs_off"], C.c_int64), ptr_of(arr["cs_len"], C.c_int32), ptr_of(arr["qry_str"], C.c_int64),
+                           ptr_of(arr["qry_end"], C.c_int64), ptr_of(arr["ref_str"], C.c_int64), ptr_of(arr["ref_end"], C.c_int64),
+                           ptr_of(arr["aln_fwd"], C.c_uint8))
+    out = _abi.aa_cs_runs()
+    st = lib.aa_cs_runs_device(solver._h, text, len(text), C.byref(rows), C.byref(out))
+    if st != 0:
+        raise AlignasmError(st, (lib.aa_cs_last_error() or b"").decode())
+    n, r = out.n_rows, out.n_run
+    res = (np_from(out.run_off, n + 1), np_from(out.run_ql, r), np_from(out.run_qr, r), np_from(out.run_rl, r), np_from(out.err, n))
+    lib.aa_cs_runs_free(C.byref(out))
+    return res
+
+
+def cs_error_text(code):
+    lib = load_library()
+    lib.aa_cs_error_text.argtypes = [C.c_int32]
+    lib.aa_cs_error_text.restype = C.c_char_p
+    return lib.aa_cs_error_text(int(code)).decode()
 
 
 def shard_contigs(batch, n_shards, max_walks=0):

@@ -69,7 +69,26 @@ STATUS = {0: "AA_OK", 1: "AA_ERR_INVALID", 2: "AA_ERR_NO_DEVICE", 3: "AA_ERR_CUD
 EXPORTS = ["aa_create", "aa_destroy", "aa_last_error", "aa_solve", "aa_upload", "aa_solve_device",
            "aa_dev_batch_free", "aa_result_free", "aa_get_stats", "aa_phase_name", "aa_version",
            "aa_paf_read", "aa_paf_read_alt", "aa_paf_batch", "aa_paf_write", "aa_paf_free", "aa_solve_subset", "aa_solve_multi", "aa_shard_contigs",
-           "aa_multi_last_error", "aa_multi_release"]
+           "aa_multi_last_error", "aa_multi_release",
+           # cs:Z: codec on the device (csrc/cs_codec.cu)
+           "aa_cs_runs_device", "aa_cs_runs_free", "aa_cs_edit_device", "aa_cs_edits_free", "aa_cs_error_text", "aa_cs_last_error",
+           "aa_ctx_device", "aa_paf_read_device", "aa_paf_write_device"]
+
+
+class aa_cs_rows(C.Structure):
+    _fields_ = [("n", C.c_int64), ("cs_off", C.POINTER(C.c_int64)), ("cs_len", C.POINTER(C.c_int32)), ("qry_str", C.POINTER(C.c_int64)),
+                ("qry_end", C.POINTER(C.c_int64)), ("ref_str", C.POINTER(C.c_int64)), ("ref_end", C.POINTER(C.c_int64)),
+                ("aln_fwd", C.POINTER(C.c_uint8))]
+
+
+class aa_cs_runs(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_run", C.c_int64), ("run_off", C.POINTER(C.c_int64)), ("run_ql", C.POINTER(C.c_int64)),
+                ("run_qr", C.POINTER(C.c_int64)), ("run_rl", C.POINTER(C.c_int64)), ("err", C.POINTER(C.c_int32))]
+
+
+class aa_cs_edits(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_bytes", C.c_int64), ("off", C.POINTER(C.c_int64)), ("text", C.POINTER(C.c_char)),
+                ("mat_num", C.POINTER(C.c_int32)), ("aln_len", C.POINTER(C.c_int32)), ("err", C.POINTER(C.c_int32))]
 
 _NP = {C.c_int64: np.int64, C.c_int32: np.int32, C.c_uint8: np.uint8}
 

@@ -41,6 +41,7 @@ void aa_destroy(aa_ctx *ctx) {
     ctx->bk.shutdown();
     delete ctx;
 }
+int aa_ctx_device(const aa_ctx *ctx) { return ctx ? ctx->bk.device : -1; }
 const char *aa_last_error(const aa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 aa_status aa_upload(aa_ctx *ctx, const aa_batch *batch, aa_dev_batch **dev) {

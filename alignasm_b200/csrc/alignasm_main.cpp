@@ -23,7 +23,8 @@ static void usage(FILE *f) {
         "  --non_skip_linkable            no edge a -> b when a -> c -> b exists\n"
         "  --device N                     CUDA device ordinal [default: 0]\n"
         "  --devices A,B,...              shard the contigs over several CUDA devices (cost-balanced, merged in input order)\n"
-        "  --no_all                       do not materialise <input>.aln.all.paf (written empty)\n",
+        "  --no_all                       do not materialise <input>.aln.all.paf (written empty)\n"
+        "  --cs_device                    parse and re-cut the cs:Z: tags on the GPU as well (same bytes; single device)\n",
         f);
 }
 
@@ -32,7 +33,7 @@ int main(int argc, char **argv) {
     int threads = 1, device = 0;
     double alt_baseline = 0.5;
     std::vector<int32_t> devices;
-    bool nsl = false, want_all = true;
+    bool nsl = false, want_all = true, cs_device = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&](const char *) -> const char * { return i + 1 < argc ? argv[++i] : nullptr; };
@@ -71,6 +72,8 @@ int main(int argc, char **argv) {
             }
         } else if (a == "--no_all") {
             want_all = false;
+        } else if (a == "--cs_device") {
+            cs_device = true;
         } else if (!a.empty() && a[0] == '-') {
             usage(stderr);
             return 1;
@@ -97,9 +100,22 @@ int main(int argc, char **argv) {
     }
     char err[512] = {0};
     aa_paf *paf = nullptr;
-    aa_status st = aa_paf_read(paf_loc.c_str(), &paf, err, sizeof err);
+    aa_ctx *cs_ctx = nullptr;  // --cs_device: the context that parses / re-cuts the cs:Z: tags (and solves, on one device)
+    aa_status st;
+    if (cs_device) {
+        if (devices.size() == 1) device = devices[0];
+        st = aa_create(&cs_ctx, device);
+        if (st != AA_OK) {
+            std::fprintf(stderr, "alignasm: %s (this build has no CPU path)\n", aa_last_error(nullptr));
+            return 1;
+        }
+        st = aa_paf_read_device(paf_loc.c_str(), cs_ctx, &paf, err, sizeof err);
+    } else {
+        st = aa_paf_read(paf_loc.c_str(), &paf, err, sizeof err);
+    }
     if (st != AA_OK) {
         std::fprintf(stderr, "%s\n", err);
+        if (cs_ctx) aa_destroy(cs_ctx);
         return 1;
     }
     if (!alt_loc.empty()) {  // alignasm.cpp:186-332
@@ -127,8 +143,8 @@ int main(int argc, char **argv) {
         }
     } else {
         if (devices.size() == 1) device = devices[0];
-        aa_ctx *ctx = nullptr;
-        st = aa_create(&ctx, device);
+        aa_ctx *ctx = cs_ctx;
+        st = ctx ? AA_OK : aa_create(&ctx, device);
         if (st != AA_OK) {
             std::fprintf(stderr, "alignasm: %s (this build has no CPU path)\n", aa_last_error(nullptr));
             aa_paf_free(paf);
@@ -141,12 +157,13 @@ int main(int argc, char **argv) {
             aa_paf_free(paf);
             return 1;
         }
-        aa_destroy(ctx);
+        if (!cs_ctx) aa_destroy(ctx);
     }
     std::puts("Write output PAF file");
     std::string prefix = paf_loc.substr(0, paf_loc.size() - 4);
-    st = aa_paf_write(paf, &res, prefix.c_str(), err, sizeof err);
+    st = cs_ctx ? aa_paf_write_device(paf, cs_ctx, &res, prefix.c_str(), err, sizeof err) : aa_paf_write(paf, &res, prefix.c_str(), err, sizeof err);
     if (st != AA_OK) std::fprintf(stderr, "alignasm: %s\n", err);
+    if (cs_ctx) aa_destroy(cs_ctx);
     aa_result_free(&res);
     aa_paf_free(paf);
     return st == AA_OK ? 0 : 1;

@@ -231,7 +231,7 @@ namespace {
 // strand, exact-match runs from the cs tag (get_overlap_range, paf_data.cpp:90-123).  `q_off` shifts the query
 // coordinates (rows of the alternative PAF are relative to their `ctg:START-END` segment, alignasm.cpp:266-268).
 aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t q_off, const char *what, ChrTable &chrs, Rows &t,
-                    std::vector<CsOp> &ops, std::string &why) {
+                    std::vector<CsOp> &ops, std::string &why, bool defer_cs = false) {
     if (f.size() < 12) {
         why = std::string(what) + " row " + std::to_string(row) + " has fewer than 12 columns";
         return AA_ERR_FORMAT;
@@ -260,9 +260,10 @@ aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t
         return AA_ERR_FORMAT;
     }
     // get_overlap_range (paf_data.cpp:90-123): walk the ops in query orientation
-    if (!parse_cs(cs, ops, why)) return AA_ERR_FORMAT;
+    // (defer_cs: aa_paf_read_device leaves this to the device codec, csrc/cs_codec.cu, once all rows are known)
+    if (!defer_cs && !parse_cs(cs, ops, why)) return AA_ERR_FORMAT;
     int64_t step = fwd ? 1 : -1, ri = rs, qi = qs;
-    size_t nop = ops.size();
+    size_t nop = defer_cs ? 0 : ops.size();
     for (size_t k = 0; k < nop; k++) {
         const CsOp &o = fwd ? ops[k] : ops[nop - 1 - k];
         if (o.type == ':') {
@@ -280,7 +281,7 @@ aa_status parse_row(const std::vector<std::string_view> &f, int64_t row, int64_t
             qi += 1;
         }
     }
-    if (qi != qe + 1 || ri != re + step) {
+    if (!defer_cs && (qi != qe + 1 || ri != re + step)) {
         t.run_ql.resize((size_t)t.run_off.back());
         t.run_qr.resize((size_t)t.run_off.back());
         t.run_rl.resize((size_t)t.run_off.back());
@@ -392,9 +393,10 @@ void aa_paf::bind() {
 
 extern "C" {
 
-aa_status aa_paf_read(const char *path, aa_paf **out, char *err, int64_t err_cap) {
+static aa_status paf_read_impl(const char *path, aa_ctx *ctx, aa_paf **out, char *err, int64_t err_cap) {
     if (!path || !out) return AA_ERR_INVALID;
     *out = nullptr;
+    const bool defer_cs = ctx != nullptr;
     IoTrace tr;
     auto img = std::make_unique<Image>();
     if (!img->open(path)) {
@@ -438,7 +440,7 @@ aa_status aa_paf_read(const char *path, aa_paf **out, char *err, int64_t err_cap
         c.rows.qs.reserve((size_t)c.n_rows);
         while (next_line(base, pos, c.end, line)) {
             split_tabs(line, f);
-            c.st = parse_row(f, c.row_base + row, 0, "PAF", c.chrs, c.rows, ops, c.why);
+            c.st = parse_row(f, c.row_base + row, 0, "PAF", c.chrs, c.rows, ops, c.why, defer_cs);
             if (c.st != AA_OK) return;
             if (row == 0 || cur != f[0]) {
                 cur = f[0];
@@ -514,10 +516,46 @@ aa_status aa_paf_read(const char *path, aa_paf **out, char *err, int64_t err_cap
     });
     r.run_off[N] = (int64_t)R;
     tr.mark("join");
+    if (defer_cs) {  // parse_short_cs + get_overlap_range on the device, over the file image as it lies
+        std::vector<int64_t> cs_off(N);
+        std::vector<int32_t> cs_len(N);
+        for (size_t i = 0; i < N; i++) {
+            cs_off[i] = (int64_t)(r.cs[i].data() - base);
+            cs_len[i] = (int32_t)r.cs[i].size();
+        }
+        aa_cs_rows rows{(int64_t)N, cs_off.data(), cs_len.data(), r.qs.data(), r.qe.data(), r.rs.data(), r.re.data(), r.fwd.data()};
+        aa_cs_runs runs{};
+        aa_status st = aa_cs_runs_device(ctx, base, (int64_t)size, &rows, &runs);
+        if (st != AA_OK) {
+            set_err(err, err_cap, std::string("cs codec on the device: ") + aa_cs_last_error());
+            delete p;
+            return st;
+        }
+        for (size_t i = 0; i < N; i++)
+            if (runs.err[i]) {  // the first row in error, in file order, with the reference's text
+                std::string why = aa_cs_error_text(runs.err[i]);
+                if (runs.err[i] == AA_CS_ERR_CONSUME) why += " (PAF row " + std::to_string(i) + ")";
+                set_err(err, err_cap, why);
+                aa_cs_runs_free(&runs);
+                delete p;
+                return AA_ERR_FORMAT;
+            }
+        r.run_ql.assign(runs.run_ql, runs.run_ql + runs.n_run);
+        r.run_qr.assign(runs.run_qr, runs.run_qr + runs.n_run);
+        r.run_rl.assign(runs.run_rl, runs.run_rl + runs.n_run);
+        std::memcpy(r.run_off.data(), runs.run_off, (N + 1) * sizeof(int64_t));
+        aa_cs_runs_free(&runs);
+        tr.mark("cs runs (device)");
+    }
     p->images.push_back(std::move(img));
     p->bind();
     *out = p;
     return AA_OK;
+}
+aa_status aa_paf_read(const char *path, aa_paf **out, char *err, int64_t err_cap) { return paf_read_impl(path, nullptr, out, err, err_cap); }
+aa_status aa_paf_read_device(const char *path, aa_ctx *ctx, aa_paf **out, char *err, int64_t err_cap) {
+    if (!ctx) return AA_ERR_INVALID;
+    return paf_read_impl(path, ctx, out, err, err_cap);
 }
 
 // --alt ingestion (alignasm.cpp:186-332).  Rows of the alternative PAF are alignments of contig segments named
@@ -732,13 +770,71 @@ bool edit_row(const aa_paf &p, int64_t g, int64_t eqs, int64_t eqe, int64_t ers,
 
 }  // namespace
 
-extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const char *out_prefix, char *err,
-                                  int64_t err_cap) {
+static aa_status paf_write_impl(const aa_paf *paf, aa_ctx *ctx, const aa_result *res, const char *out_prefix, char *err,
+                                int64_t err_cap) {
     if (!paf || !res || !out_prefix) return AA_ERR_INVALID;
     const aa_paf &p = *paf;
     if (res->n_ctg != p.batch.n_ctg) {
         set_err(err, err_cap, "result does not belong to this PAF");
         return AA_ERR_INVALID;
+    }
+    // get_edited_paf_data of the primary and alternative rows on the device (the .aln.all.paf list, which can be gigabytes,
+    // stays with the host codec below)
+    aa_cs_edits ded{};
+    struct EditsGuard {
+        aa_cs_edits *e;
+        ~EditsGuard() { aa_cs_edits_free(e); }
+    } ded_guard{&ded};
+    const int64_t n_out_rows = res->out.n, n_alt_rows = res->alt.n;
+    if (ctx) {
+        const size_t N = p.r.size();
+        std::vector<int64_t> cs_off(N);
+        std::vector<int32_t> cs_len(N);
+        const char *base = nullptr;
+        int64_t text_len = 0;
+        std::string joined;  // more than one file image (--alt): the fields are laid out back to back
+        if (p.images.size() == 1) {
+            base = p.images[0]->data;
+            text_len = (int64_t)p.images[0]->size;
+            for (size_t i = 0; i < N; i++) cs_off[i] = (int64_t)(p.r.cs[i].data() - base);
+        } else {
+            size_t total = 0;
+            for (size_t i = 0; i < N; i++) total += p.r.cs[i].size();
+            joined.reserve(total);
+            for (size_t i = 0; i < N; i++) {
+                cs_off[i] = (int64_t)joined.size();
+                joined.append(p.r.cs[i]);
+            }
+            base = joined.data();
+            text_len = (int64_t)joined.size();
+        }
+        for (size_t i = 0; i < N; i++) cs_len[i] = (int32_t)p.r.cs[i].size();
+        const int64_t M = n_out_rows + n_alt_rows;
+        std::vector<int64_t> orow((size_t)M), eqs((size_t)M), eqe((size_t)M), ers((size_t)M), ere((size_t)M);
+        for (int64_t c = 0; c < res->n_ctg; c++) {
+            for (int64_t k = res->out_off[c]; k < res->out_off[c + 1]; k++) orow[(size_t)k] = p.ctg_off[(size_t)c] + res->out.ctg_index[k];
+            for (int64_t k = res->alt_off[c]; k < res->alt_off[c + 1]; k++)
+                orow[(size_t)(n_out_rows + k)] = p.ctg_off[(size_t)c] + res->alt.ctg_index[k];
+        }
+        for (int64_t k = 0; k < n_out_rows; k++) {
+            eqs[(size_t)k] = res->out.qry_str[k];
+            eqe[(size_t)k] = res->out.qry_end[k];
+            ers[(size_t)k] = res->out.ref_str[k];
+            ere[(size_t)k] = res->out.ref_end[k];
+        }
+        for (int64_t k = 0; k < n_alt_rows; k++) {
+            eqs[(size_t)(n_out_rows + k)] = res->alt.qry_str[k];
+            eqe[(size_t)(n_out_rows + k)] = res->alt.qry_end[k];
+            ers[(size_t)(n_out_rows + k)] = res->alt.ref_str[k];
+            ere[(size_t)(n_out_rows + k)] = res->alt.ref_end[k];
+        }
+        aa_cs_rows rows{(int64_t)N, cs_off.data(), cs_len.data(), p.r.qs.data(), p.r.qe.data(), p.r.rs.data(), p.r.re.data(), p.r.fwd.data()};
+        aa_status dst = aa_cs_edit_device(ctx, base, text_len, &rows, p.r.mat_num.data(), p.r.aln_len.data(), M, orow.data(), eqs.data(),
+                                          eqe.data(), ers.data(), ere.data(), &ded);
+        if (dst != AA_OK) {
+            set_err(err, err_cap, std::string("cs codec on the device: ") + aa_cs_last_error());
+            return dst;
+        }
     }
     std::string pre(out_prefix);
     FILE *fo[3] = {std::fopen((pre + ".aln.paf").c_str(), "wb"), std::fopen((pre + ".aln.alt.paf").c_str(), "wb"),
@@ -793,7 +889,18 @@ extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const
             const size_t g = (size_t)(p.ctg_off[(size_t)c] + rows.ctg_index[k]);
             int32_t mat, aln;
             const int64_t qs = rows.qry_str[k], qe = rows.qry_end[k], rs = rows.ref_str[k], re = rows.ref_end[k];
-            if (!edit_row(p, (int64_t)g, qs, qe, rs, re, cs_out, mat, aln, ops, kept, why)) return false;
+            if (ctx && &rows != &res->all) {  // edited on the device: row k of the primary list, n_out_rows + k of the alternative one
+                const int64_t e = (&rows == &res->out) ? k : n_out_rows + k;
+                if (ded.err[e]) {
+                    why = aa_cs_error_text(ded.err[e]);
+                    return false;
+                }
+                cs_out.assign(ded.text + ded.off[e], (size_t)(ded.off[e + 1] - ded.off[e]));
+                mat = ded.mat_num[e];
+                aln = ded.aln_len[e];
+            } else if (!edit_row(p, (int64_t)g, qs, qe, rs, re, cs_out, mat, aln, ops, kept, why)) {
+                return false;
+            }
             const bool fwd = p.r.fwd[g] != 0;
             dst.append(qname);
             dst.push_back('\t');
@@ -897,4 +1004,12 @@ extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const
             set_err(err, err_cap, "cannot finish the output files of " + pre);
         }
     return st;
+}
+extern "C" aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const char *out_prefix, char *err, int64_t err_cap) {
+    return paf_write_impl(paf, nullptr, res, out_prefix, err, err_cap);
+}
+extern "C" aa_status aa_paf_write_device(const aa_paf *paf, aa_ctx *ctx, const aa_result *res, const char *out_prefix, char *err,
+                                         int64_t err_cap) {
+    if (!ctx) return AA_ERR_INVALID;
+    return paf_write_impl(paf, ctx, res, out_prefix, err, err_cap);
 }

@@ -495,6 +495,22 @@ def main():
             c2["cli"] = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": pf2.batch.n_blk / (t5 - t2),
                          "paf_bytes": os.path.getsize(paf2), "out_bytes": out_bytes, "host_threads": os.cpu_count(),
                          "note": "aa_paf_read + aa_solve + aa_paf_write as `alignasm --no_all` chains them; process and CUDA start-up excluded"}
+            # the same with the cs:Z: codec on the device (aa_paf_read_device / aa_paf_write_device)
+            aa.read_paf(paf2, solver=solver).close()  # (warm-up: first-touch of the device buffers)
+            t2 = time.perf_counter()
+            pf4 = aa.read_paf(paf2, solver=solver)
+            t3 = time.perf_counter()
+            r = solver.solve(pf4.batch)
+            t4 = time.perf_counter()
+            pf4.write(r, os.path.join(tmp, "cli_out_dev"), solver=solver)
+            t5 = time.perf_counter()
+            same = all(open(os.path.join(tmp, "cli_out" + e), "rb").read() == open(os.path.join(tmp, "cli_out_dev" + e), "rb").read()
+                       for e in (".aln.paf", ".aln.alt.paf", ".aln.all.paf"))
+            r.close()
+            pf4.close()
+            c2["cli_cs_device"] = {"read_s": t3 - t2, "solve_s": t4 - t3, "write_s": t5 - t4, "blocks_per_s": pf2.batch.n_blk / (t5 - t2),
+                                   "files_identical_to_host_codec": bool(same),
+                                   "note": "`alignasm --cs_device --no_all`: parse_short_cs / get_overlap_range / get_edited_paf_data as CUDA kernels over the file image"}
             if not a.no_cpu_baseline:
                 cb2 = cpu_arm(paf2, tmp, passes=K + W)
                 c2["cpu_baseline"] = cpu_fields(cb2)

@@ -182,6 +182,57 @@ const aa_batch *aa_paf_batch(const aa_paf *paf);
 aa_status aa_paf_write(const aa_paf *paf, const aa_result *res, const char *out_prefix, char *err, int64_t err_cap);
 void aa_paf_free(aa_paf *paf);
 
+/* ---- the cs:Z: codec on the device (csrc/cs_codec.cu) -------------------------------------------------------------
+ * The same two functions of the reference as above, computed by CUDA kernels over the file image (one thread per row, one
+ * forward walk of the cs string whatever the strand), bit-identical to the host codec:
+ *   aa_cs_runs_device   parse_short_cs + get_overlap_range   (paf_data.cpp:29-72, 90-123)
+ *   aa_cs_edit_device   get_edited_paf_data                  (paf_data.cpp:125-220)
+ * aa_paf_read_device / aa_paf_write_device are the reader and the writers with those stages on the device of `ctx`
+ * (`alignasm --cs_device`); everything else (TSV fields, contig bucketing, row formatting) is the host code above.
+ * Per-row error codes stand for the reference's exception sites; aa_cs_error_text gives the text. */
+enum {
+    AA_CS_ERR_TAG = 1,      /* no short-form cs:Z: tag                      paf_data.cpp:31-33   */
+    AA_CS_ERR_LENGTH = 2,   /* invalid :length operation                    :44-47               */
+    AA_CS_ERR_SUBST = 3,    /* invalid substitution operation               :50-53               */
+    AA_CS_ERR_INDEL = 4,    /* empty indel operation                        :58-61               */
+    AA_CS_ERR_OP = 5,       /* unsupported operation                        :65-67               */
+    AA_CS_ERR_CONSUME = 6,  /* consumption does not match the coordinates   :119-122             */
+    AA_CS_ERR_CLIP_INS = 7, /* alignment clipped inside an insertion        :160-163             */
+    AA_CS_ERR_EDIT = 8      /* edited cs does not match edited coordinates  :214-217             */
+};
+typedef struct aa_cs_rows {  /* n alignment rows: where each cs:Z: field lies in `text`, and the row's (closed) coordinates */
+    int64_t n;
+    const int64_t *cs_off;   /* [n] byte offset of the field (it starts with "cs:Z:")            */
+    const int32_t *cs_len;   /* [n] its length                                                     */
+    const int64_t *qry_str, *qry_end, *ref_str, *ref_end; /* [n] like the aa_batch arrays: ref_str > ref_end on '-' */
+    const uint8_t *aln_fwd;  /* [n]                                                                */
+} aa_cs_rows;
+typedef struct aa_cs_runs {  /* library-owned; release with aa_cs_runs_free */
+    int64_t n_rows, n_run;
+    int64_t *run_off;        /* [n_rows+1] */
+    int64_t *run_ql, *run_qr, *run_rl; /* [n_run], query orientation, as aa_batch wants them */
+    int32_t *err;            /* [n_rows] 0 or AA_CS_ERR_* (a row in error has no runs) */
+} aa_cs_runs;
+typedef struct aa_cs_edits { /* library-owned; release with aa_cs_edits_free */
+    int64_t n, n_bytes;
+    int64_t *off;            /* [n+1] -> text */
+    char *text;              /* the edited cs:Z: fields, back to back (no terminators) */
+    int32_t *mat_num, *aln_len, *err; /* [n] */
+} aa_cs_edits;
+aa_status aa_cs_runs_device(aa_ctx *ctx, const char *text, int64_t text_len, const aa_cs_rows *rows, aa_cs_runs *out);
+void aa_cs_runs_free(aa_cs_runs *runs);
+/* one edited field per output row k: the row `out_row[k]` of `rows` cut to the query interval [eqs[k], eqe[k]]; ers / ere are the
+ * edited reference ends (for the consistency check); row_mat / row_aln are the columns 10 / 11 of the rows as read */
+aa_status aa_cs_edit_device(aa_ctx *ctx, const char *text, int64_t text_len, const aa_cs_rows *rows, const int32_t *row_mat,
+                            const int32_t *row_aln, int64_t n_out, const int64_t *out_row, const int64_t *eqs, const int64_t *eqe,
+                            const int64_t *ers, const int64_t *ere, aa_cs_edits *out);
+void aa_cs_edits_free(aa_cs_edits *edits);
+const char *aa_cs_error_text(int32_t code);
+const char *aa_cs_last_error(void); /* per thread: the CUDA / allocation failure behind a non-zero status of the two calls above */
+int aa_ctx_device(const aa_ctx *ctx);
+aa_status aa_paf_read_device(const char *path, aa_ctx *ctx, aa_paf **paf, char *err, int64_t err_cap);
+aa_status aa_paf_write_device(const aa_paf *paf, aa_ctx *ctx, const aa_result *res, const char *out_prefix, char *err, int64_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,12 +24,14 @@ def test_struct_layouts_match_header(workdir):
     src = os.path.join(workdir, "sizes.c")
     exe = os.path.join(workdir, "sizes")
     with open(src, "w") as f:
-        f.write('#include <stdio.h>\n#include "alignasm_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
-                "sizeof(aa_batch),sizeof(aa_opts),sizeof(aa_rows),sizeof(aa_debug),sizeof(aa_stats),sizeof(aa_result));return 0;}\n")
+        f.write('#include <stdio.h>\n#include "alignasm_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                "sizeof(aa_batch),sizeof(aa_opts),sizeof(aa_rows),sizeof(aa_debug),sizeof(aa_stats),sizeof(aa_result),"
+                "sizeof(aa_cs_rows),sizeof(aa_cs_runs),sizeof(aa_cs_edits));return 0;}\n")
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([cc, "-I", os.path.join(pu.ROOT, "include"), "-o", exe, src], check=True)
     got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    want = [C.sizeof(t) for t in (_abi.aa_batch, _abi.aa_opts, _abi.aa_rows, _abi.aa_debug, _abi.aa_stats, _abi.aa_result)]
+    want = [C.sizeof(t) for t in (_abi.aa_batch, _abi.aa_opts, _abi.aa_rows, _abi.aa_debug, _abi.aa_stats, _abi.aa_result,
+                                  _abi.aa_cs_rows, _abi.aa_cs_runs, _abi.aa_cs_edits)]
     assert got == want
 
 

@@ -329,3 +329,91 @@ def test_reference_with_binding_writes_golden_bytes(case, nsl, product_lib, work
     for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
         want = os.path.join(pu.GOLDEN, tag + "." + ext)
         assert pu.files_equal(pre + "." + ext, want), f"{tag}.{ext}:\n" + pu.first_diff(pre + "." + ext, want)
+
+
+def _cs_fields(paf_path):
+    """(text, cs_off, cs_len, qs, qe, rs, re, fwd) of a PAF file, parsed in Python the way the reader does (alignasm.cpp:141-159)."""
+    text = open(paf_path, "rb").read()
+    off, ln, qs, qe, rs, re_, fwd = [], [], [], [], [], [], []
+    pos = 0
+    for line in text.split(b"\n"):
+        if line:
+            f = line.split(b"\t")
+            k = line.index(b"\tcs:Z:") + 1
+            end = line.find(b"\t", k)
+            off.append(pos + k)
+            ln.append((len(line) if end < 0 else end) - k)
+            a, b = int(f[2]), int(f[3]) - 1
+            c, d = int(f[7]), int(f[8]) - 1
+            plus = f[4] == b"+"
+            qs.append(a), qe.append(b), rs.append(c if plus else d), re_.append(d if plus else c), fwd.append(1 if plus else 0)
+        pos += len(line) + 1
+    return text, off, ln, qs, qe, rs, re_, fwd
+
+
+@pytest.mark.parametrize("case", ["micro", "tiny", "ties", "c1"])
+def test_cs_runs_on_device_equal_host_parser(case, solver, workdir):
+    """parse_short_cs + get_overlap_range as CUDA kernels (csrc/cs_codec.cu) against the host codec that the
+    goldens pin: same run offsets and the same (q_l, q_r, r_l) of every exact-match run, '+' and '-' rows alike."""
+    import alignasm_b200 as aa
+    paf = (pu.synth(os.path.join(workdir, "cs_c1.paf"), "--preset", "c1", "--scale", 0.2) if case == "c1"
+           else os.path.join(pu.GOLDEN, case + ".paf"))
+    want = aa.read_paf(paf).batch
+    text, off, ln, qs, qe, rs, re_, fwd = _cs_fields(paf)
+    assert np.array_equal(qs, want.qry_str) and np.array_equal(rs, want.ref_str) and np.array_equal(re_, want.ref_end)
+    run_off, ql, qr, rl, err = aa.cs_runs_device(solver, text, off, ln, qs, qe, rs, re_, fwd)
+    assert not err.any()
+    assert np.array_equal(run_off, want.run_off)
+    assert np.array_equal(ql, want.run_ql) and np.array_equal(qr, want.run_qr) and np.array_equal(rl, want.run_rl)
+    # the reader with the device codec gives the same batch
+    dev = aa.read_paf(paf, solver=solver).batch
+    for name, _ in aa.Batch.FIELDS:
+        assert np.array_equal(getattr(dev, name), getattr(want, name)), name
+
+
+def test_cs_codec_error_sites(solver):
+    """The reference's exception sites of the cs codec (paf_data.cpp:31-122) come back as per-row codes."""
+    import alignasm_b200 as aa
+    from alignasm_b200 import _abi  # noqa: F401
+    rows = [(b"cs:Z::10", 0, 9, 100, 109, 1, 0), (b"xx:Z::10", 0, 9, 100, 109, 1, 1), (b"cs:Z::0", 0, 9, 100, 109, 1, 2),
+            (b"cs:Z:*a", 0, 0, 100, 100, 1, 3), (b"cs:Z:+", 0, 9, 100, 109, 1, 4), (b"cs:Z:=ACGT", 0, 3, 100, 103, 1, 5),
+            (b"cs:Z::9", 0, 9, 100, 109, 1, 6), (b"cs:Z::4*ag-tt+cc:3", 0, 9, 109, 100, 0, 0)]
+    text, off = b"", []
+    for r in rows:
+        off.append(len(text))
+        text += r[0] + b"\t"
+    run_off, ql, qr, rl, err = aa.cs_runs_device(solver, text, off, [len(r[0]) for r in rows], [r[1] for r in rows], [r[2] for r in rows],
+                                                  [r[3] for r in rows], [r[4] for r in rows], [r[5] for r in rows])
+    assert err.tolist() == [r[6] for r in rows]
+    assert "consumption" in aa.cs_error_text(6)
+    # the '-' row: operations applied from the last one back (paf_data.cpp:97-117): run ":3" first, then ":4"
+    a = int(run_off[7])
+    assert (ql[a:].tolist(), qr[a:].tolist(), rl[a:].tolist()) == ([0, 6], [2, 9], [109, 103])
+
+
+def test_cli_cs_device_writes_reference_bytes(product_lib, workdir):
+    """`alignasm --cs_device`: cs:Z: parsing and re-cutting (get_edited_paf_data, paf_data.cpp:125-220) on the GPU; the three files
+    are the reference's goldens byte for byte, with and without --alt."""
+    import shutil
+    import subprocess
+    exe = os.path.join(pu.ROOT, "alignasm_b200", "alignasm")
+    for case, extra in (("ties", []), ("tiny", []), ("withalt", ["--alt", os.path.join(pu.GOLDEN, "withalt.altin.paf")])):
+        paf = os.path.join(workdir, f"csdev_{case}.paf")
+        shutil.copy(os.path.join(pu.GOLDEN, case + ".paf"), paf)
+        out = subprocess.run([exe, "--cs_device", *extra, paf], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+            assert pu.files_equal(paf[:-4] + "." + ext, os.path.join(pu.GOLDEN, case + "." + ext)), (case, ext)
+
+
+def test_writer_with_device_codec_on_bench_workload(solver, workdir):
+    """The writers with the device cs codec against the host codec on a sizeable input (C2 at 1/5 scale: clipped rows of both
+    strands, every operation type)."""
+    import alignasm_b200 as aa
+    paf = pu.synth(os.path.join(workdir, "csw.paf"), "--preset", "c2", "--scale", 0.2)
+    pf = aa.read_paf(paf, solver=solver)
+    res = solver.solve(pf.batch)
+    pf.write(res, os.path.join(workdir, "csw_dev"), solver=solver)
+    pf.write(res, os.path.join(workdir, "csw_host"))
+    for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
+        assert pu.files_equal(os.path.join(workdir, "csw_dev." + ext), os.path.join(workdir, "csw_host." + ext)), ext

@@ -3652,7 +3652,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t pops16 = 16 * 16, ser_steps = 0;
     // (a lone warp per SM is latency-bound: a round of ~5 k cycles loses against ~2.2 k per serial step below ~2.3 pops per
     // round; with several contigs per SM the instruction count decides and the break-even is lower)
-    const int32_t ser_thr16 = w.C > 2 * 148 ? 22 : 36;
+    const int32_t ser_thr16 = (w.heaps_variant >> 4) ? (w.heaps_variant >> 4) : (w.C > 2 * 148 ? 22 : 36);
     XRec xn;
     int32_t p12n = -1;
     bool have_xn = false;

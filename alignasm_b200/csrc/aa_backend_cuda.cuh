@@ -56,8 +56,8 @@ struct CastI32 {
 struct CudaBackend {
     int device = 0;
     cudaStream_t stream = nullptr;   // the stream launches currently go to
-    cudaStream_t main_stream = nullptr, side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+    cudaStream_t main_stream = nullptr, side_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_side = nullptr, ev_aux0 = nullptr, ev_aux1 = nullptr;
     bool side_pending = false;
     bool failed = false;
     bool oom = false;  // the failure was an allocation: recoverable
@@ -139,6 +139,9 @@ struct CudaBackend {
         }
         AA_CUDA(cudaStreamCreateWithFlags(&main_stream, cudaStreamNonBlocking));
         AA_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+        AA_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+        AA_CUDA(cudaEventCreateWithFlags(&ev_aux0, cudaEventDisableTiming));
+        AA_CUDA(cudaEventCreateWithFlags(&ev_aux1, cudaEventDisableTiming));
         AA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         AA_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
         stream = main_stream;
@@ -170,6 +173,13 @@ struct CudaBackend {
             cudaEventDestroy(ev_fork);
             cudaEventDestroy(ev_side);
             cudaStreamDestroy(side_stream);
+            if (aux_stream) {
+                cudaStreamSynchronize(aux_stream);
+                cudaEventDestroy(ev_aux0);
+                cudaEventDestroy(ev_aux1);
+                cudaStreamDestroy(aux_stream);
+                aux_stream = nullptr;
+            }
             cudaStreamDestroy(main_stream);
             stream = main_stream = side_stream = nullptr;
         }
@@ -237,6 +247,7 @@ struct CudaBackend {
     void quiesce() {
         cudaStreamSynchronize(main_stream);
         cudaStreamSynchronize(side_stream);
+        if (aux_stream) cudaStreamSynchronize(aux_stream);
         side_pending = false;
         stream = main_stream;
     }
@@ -542,6 +553,18 @@ struct CudaBackend {
     }
     // ---- side stream: work that is off the critical path runs concurrently with the main stream ----
     bool device_kahn() const { return true; }
+    // a second, short-lived fork: the launches between aux_begin and aux_end run concurrently with what follows on the main
+    // stream until aux_end's matching join (used to build the heaps of the large and the small contigs side by side)
+    void aux_begin() {
+        AA_CUDA(cudaEventRecord(ev_aux0, main_stream));
+        AA_CUDA(cudaStreamWaitEvent(aux_stream, ev_aux0, 0));
+        stream = aux_stream;
+    }
+    void aux_end() {
+        AA_CUDA(cudaEventRecord(ev_aux1, aux_stream));
+        stream = main_stream;
+    }
+    void aux_join() { AA_CUDA(cudaStreamWaitEvent(main_stream, ev_aux1, 0)); }
     void side_begin() {
         AA_CUDA(cudaEventRecord(ev_fork, main_stream));
         AA_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));

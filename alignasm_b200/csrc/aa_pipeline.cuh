@@ -1010,6 +1010,7 @@ struct Pipeline {
         // (a leaf of a streaming-mode contig reserves 32 ids per insert, at most a chunk; level mode wastes < 64 per vertex)
         int64_t hcap = 6 * E + C * (int64_t)HEAP_CHUNK + 256 * n_leaf + 64 * (any_m1 ? Vtot : 0) + ((int64_t)1 << 20);
         std::vector<int32_t> h_status((size_t)C);
+        auto h_blk_of_order = [&](int64_t k) { return d.h_ctg_off[(size_t)ctg_order[(size_t)k] + 1] - d.h_ctg_off[(size_t)ctg_order[(size_t)k]]; };
         int64_t heap_top_h = 0;  // node ids handed out (device path)
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
@@ -1035,7 +1036,23 @@ struct Pipeline {
             bk.zero(w.heap_top, 8);
             bk.zero(w.heap_used, (size_t)C * 8);
             bk.zero(w.lvl_overflow, 4);
-            bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, heaps_chain_smem_bytes(w.heap_cache_bits));
+            // The contigs with long serial chains (>= 4096 blocks, at most one per SM) get a kernel of their own with the
+            // largest node cache: 180 KB of shared memory per CTA leaves room for one small contig beside them, so their
+            // warps are not slowed by seven neighbours (C5 on one GPU: 34 -> 27 ms for the largest contig).  The rest run
+            // concurrently on the aux stream.
+            int64_t n_big = 0;
+            while (n_big < C && n_big < 148 && h_blk_of_order(n_big) >= 4096) n_big++;
+            if (n_big > 0 && n_big < C) {
+                Ws wb = w;
+                wb.heap_cache_bits = 12;
+                bk.aux_begin();
+                bk.for_each_contig("heaps_small", C - n_big, FnHeaps{w, d_ord + n_big}, heaps_chain_smem_bytes(w.heap_cache_bits));
+                bk.aux_end();
+                bk.for_each_contig("heaps", n_big, FnHeaps{wb, d_ord}, heaps_chain_smem_bytes(wb.heap_cache_bits));
+                bk.aux_join();
+            } else {
+                bk.for_each_contig("heaps", C, FnHeaps{w, d_ord}, heaps_chain_smem_bytes(w.heap_cache_bits));
+            }
             bk.for_each("root_fill", Vtot, FnRootFill{w});
             bool overflow = false;
             if (n_leaf > 0) bk.for_each_contig("heaps_leaf", n_leaf, FnHeapsLeaf{w});

@@ -79,6 +79,9 @@ struct HostBackend {
     void fill_ff(void *p, size_t n) { std::memset(p, 0xff, n); }
     int64_t read_i64(const int64_t *p) { return *p; }
     bool device_kahn() const { return false; }
+    void aux_begin() {}
+    void aux_end() {}
+    void aux_join() {}
     void side_begin() {}
     void side_end() {}
     void side_join() {}

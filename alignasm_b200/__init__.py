@@ -374,7 +374,7 @@ class _DevBatch:
             pass
 
 
-def solve_multi(batch, devices, **kw):
+def solve_multi(batch, devices, copy=True, **kw):
     """The batch sharded by contig over several GPUs of this box (aa_solve_multi: LPT shards, one host thread and
     one context per device, rows merged in input order; no collective)."""
     lib = load_library()
@@ -386,7 +386,7 @@ def solve_multi(batch, devices, **kw):
         msg = (lib.aa_multi_last_error() or b"").decode()
         lib.aa_result_free(C.byref(res))  # (a no-op on an empty result; AA_ERR_UNSOLVABLE leaves a filled one)
         raise AlignasmError(st, msg)
-    return Result(res, batch.n_blk, lib.aa_result_free)
+    return Result(res, batch.n_blk, lib.aa_result_free, copy=copy)
 
 
 def cs_runs_device(solver, text, cs_off, cs_len, qry_str, qry_end, ref_str, ref_end, aln_fwd):

@@ -336,16 +336,22 @@ struct CudaBackend {
         size_t n, off;
     };
     std::vector<Piece> pieces;
-    size_t staged_bytes = 0;
+    size_t staged_bytes = 0, staged_tail = 0;  // padded total / end of the last piece
     void stage(void *d, const void *h, size_t n) {
         if (!n) return;
-        pieces.push_back({d, h, n, staged_bytes});
-        staged_bytes += (n + 255) & ~(size_t)255;
+        // a piece that continues the previous one on the device also continues it in the staging buffer, so that the two
+        // go up in ONE copy (a shard staged contig by contig is thousands of pieces per array)
+        const bool cont = !pieces.empty() && (char *)pieces.back().dst + pieces.back().n == (char *)d &&
+                          pieces.back().off + pieces.back().n == staged_tail;
+        const size_t off = cont ? staged_tail : ((staged_tail + 255) & ~(size_t)255);
+        pieces.push_back({d, h, n, off});
+        staged_tail = off + n;
+        staged_bytes = (staged_tail + 255) & ~(size_t)255;
     }
     void flush_staged() {
         if (failed || pieces.empty()) {
             pieces.clear();
-            staged_bytes = 0;
+            staged_bytes = staged_tail = 0;
             return;
         }
         if (staged_bytes > pinned_cap) {
@@ -381,10 +387,19 @@ struct CudaBackend {
             for (int t = 1; t < nt; t++) pool.emplace_back(work);
             work();
             for (auto &t : pool) t.join();
-            for (auto &p : pieces) AA_CUDA(cudaMemcpyAsync(p.dst, pinned + p.off, p.n, cudaMemcpyHostToDevice, stream));
+            for (size_t i = 0; i < pieces.size();) {  // one copy per run of contiguous pieces
+                size_t j = i + 1, n = pieces[i].n;
+                while (j < pieces.size() && (char *)pieces[j - 1].dst + pieces[j - 1].n == (char *)pieces[j].dst &&
+                       pieces[j - 1].off + pieces[j - 1].n == pieces[j].off) {
+                    n += pieces[j].n;
+                    j++;
+                }
+                AA_CUDA(cudaMemcpyAsync(pieces[i].dst, pinned + pieces[i].off, n, cudaMemcpyHostToDevice, stream));
+                i = j;
+            }
         }
         pieces.clear();
-        staged_bytes = 0;
+        staged_bytes = staged_tail = 0;
     }
     // ---- staged download (result rows): asynchronous copies into the pinned buffer, one synchronisation, then a parallel
     // memcpy into the caller's (fresh, pageable) arrays: their pages are first touched by all host threads

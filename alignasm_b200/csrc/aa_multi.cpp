@@ -7,6 +7,8 @@
 #include "../../include/alignasm_b200.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <mutex>
 #include <cstdlib>
@@ -149,6 +151,9 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
         g_multi_err = "aa_solve_multi: keep_debug is only available on a single device";
         return AA_ERR_INVALID;
     }
+    const bool trace = std::getenv("AA_MULTI_TRACE") != nullptr;  // stderr: where the wall time of the call goes
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     std::vector<int32_t> shard_of((size_t)C);
     aa_shard_contigs(b, o.max_walks, n_dev, shard_of.data());
     std::vector<Shard> sh((size_t)n_dev);
@@ -163,8 +168,12 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
             aa_ctx *ctx = nullptr;
             s.st = checkout_ctx(devices[k], &ctx, s.err);  // exclusively ours until the shard is solved
             if (s.st != AA_OK) return;
+            const double t0 = ms_since();
             s.st = aa_solve_subset(ctx, b, s.ctgs.data(), (int64_t)s.ctgs.size(), &o, &s.res);  // staged from the caller's arrays
             if (s.st != AA_OK) s.err = aa_last_error(ctx);
+            if (trace)
+                std::fprintf(stderr, "[aa_multi] shard %d on device %d: %zu contigs, solve call %.1f .. %.1f ms (device %.1f ms)\n", k, devices[k],
+                             s.ctgs.size(), t0, ms_since(), s.res.stats.ms_total);
             checkin_ctx(ctx);
         });
     for (auto &t : pool) t.join();
@@ -184,6 +193,7 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
         for (auto &s : sh) aa_result_free(&s.res);
         return st;
     }
+    if (trace) std::fprintf(stderr, "[aa_multi] shards done at %.1f ms\n", ms_since());
     // ---- merge in input contig order ----
     std::memset(res, 0, sizeof *res);
     res->n_ctg = C;
@@ -271,7 +281,9 @@ aa_status aa_solve_multi(const int32_t *devices, int32_t n_dev, const aa_batch *
         }
         for (int p = 0; p < 16; p++) t.algo_bytes_phase[p] += x.algo_bytes_phase[p];
     }
+    if (trace) std::fprintf(stderr, "[aa_multi] merged at %.1f ms\n", ms_since());
     for (auto &s : sh) aa_result_free(&s.res);
+    if (trace) std::fprintf(stderr, "[aa_multi] shard results freed at %.1f ms\n", ms_since());
     return st;
 }
 

@@ -459,26 +459,39 @@ struct Pipeline {
             err = "device allocation failed while staging the batch";
             return AA_ERR_NOMEM;
         }
-        int64_t at = 0, rat = 0;
+        // host side: the shard's sort keys and rebased run offsets; device side: one array after the other, so that the
+        // pieces of an array are contiguous in the staging buffer and go up in one copy (bk.stage coalesces them)
+        std::vector<int64_t> at_of((size_t)n_ctgs + 1, 0), rat_of((size_t)n_ctgs + 1, 0);
         for (int64_t k = 0; k < n_ctgs; k++) {
-            const int64_t b0 = b->ctg_off[ctgs[k]], b1 = b->ctg_off[ctgs[k] + 1], n = b1 - b0;
-            const int64_t r0 = b->run_off[b0], r1 = b->run_off[b1], nr = r1 - r0;
+            const int64_t b0 = b->ctg_off[ctgs[k]], b1 = b->ctg_off[ctgs[k] + 1];
+            at_of[(size_t)k + 1] = at_of[(size_t)k] + (b1 - b0);
+            rat_of[(size_t)k + 1] = rat_of[(size_t)k] + (b->run_off[b1] - b->run_off[b0]);
+        }
+        for (int64_t k = 0; k < n_ctgs; k++) {
+            const int64_t b0 = b->ctg_off[ctgs[k]], n = at_of[(size_t)k + 1] - at_of[(size_t)k], at = at_of[(size_t)k];
+            const int64_t r0 = b->run_off[b0], rat = rat_of[(size_t)k];
             std::memcpy(d->own_qs.data() + at, b->qry_str + b0, (size_t)n * 8);
             std::memcpy(d->own_qe.data() + at, b->qry_end + b0, (size_t)n * 8);
             for (int64_t i = 0; i < n; i++) roff[(size_t)(at + i)] = b->run_off[b0 + i] - r0 + rat;
-            bk.stage(d->rs + at, b->ref_str + b0, (size_t)n * 8);
-            bk.stage(d->re + at, b->ref_end + b0, (size_t)n * 8);
-            bk.stage(d->qtot + at, b->qry_total + b0, (size_t)n * 8);
-            bk.stage(d->chr + at, b->ref_chr + b0, (size_t)n * 4);
-            bk.stage(d->fwd + at, b->aln_fwd + b0, (size_t)n);
-            bk.stage(d->mapq + at, b->map_qul + b0, (size_t)n);
-            if (nr > 0) {
-                bk.stage(d->run_ql + rat, b->run_ql + r0, (size_t)nr * 8);
-                bk.stage(d->run_qr + rat, b->run_qr + r0, (size_t)nr * 8);
-                bk.stage(d->run_rl + rat, b->run_rl + r0, (size_t)nr * 8);
-            }
-            at += n;
-            rat += nr;
+        }
+        auto stage_blocks = [&](auto *dst, const auto *src) {
+            for (int64_t k = 0; k < n_ctgs; k++)
+                bk.stage(dst + at_of[(size_t)k], src + b->ctg_off[ctgs[k]], (size_t)(at_of[(size_t)k + 1] - at_of[(size_t)k]) * sizeof(*src));
+        };
+        auto stage_runs = [&](auto *dst, const auto *src) {
+            for (int64_t k = 0; k < n_ctgs; k++)
+                bk.stage(dst + rat_of[(size_t)k], src + b->run_off[b->ctg_off[ctgs[k]]], (size_t)(rat_of[(size_t)k + 1] - rat_of[(size_t)k]) * sizeof(*src));
+        };
+        stage_blocks(d->rs, b->ref_str);
+        stage_blocks(d->re, b->ref_end);
+        stage_blocks(d->qtot, b->qry_total);
+        stage_blocks(d->chr, b->ref_chr);
+        stage_blocks(d->fwd, b->aln_fwd);
+        stage_blocks(d->mapq, b->map_qul);
+        if (R > 0) {
+            stage_runs(d->run_ql, b->run_ql);
+            stage_runs(d->run_qr, b->run_qr);
+            stage_runs(d->run_rl, b->run_rl);
         }
         roff[(size_t)B] = R;
         bk.stage(d->ctg_off, d->own_ctg_off.data(), (size_t)(d->C + 1) * 8);

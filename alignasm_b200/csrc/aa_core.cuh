@@ -2520,18 +2520,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ HOp hop_lds(const HOp *p) {
-    union {
-        HOp o;
-        V16 v[2];
-    } u;
-    const volatile V16 *q = reinterpret_cast<const volatile V16 *>(p);
-    u.v[0].a = q[0].a;
-    u.v[0].b = q[0].b;
-    u.v[1].a = q[1].a;
-    u.v[1].b = q[1].b;
-    return u.o;
-}
 #ifdef AA_HEAP_TIMERS
 #define HT_DECL long long ht_t = clock64(), ht_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ht_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define HT(i) do { const long long ht_now = clock64(); ht_acc[i] += ht_now - ht_t; ht_n[i]++; ht_t = ht_now; } while (0)

@@ -3214,7 +3214,10 @@ constexpr int32_t FMASK = FCAP - 1;
 constexpr int32_t FKEEP = FCAP / 2;            // entries that stay when a full run spills its upper part
 constexpr int32_t REFILL_ALL = 3 * FCAP / 4;   // a backlog this small is moved as a whole
 constexpr int32_t REFILL_TARGET = 3 * FCAP / 8;
-constexpr int32_t NSAMPLE = 512 < FCAP ? 512 : FCAP;
+#ifndef AA_NSAMPLE
+#define AA_NSAMPLE 512
+#endif
+constexpr int32_t NSAMPLE = AA_NSAMPLE < FCAP ? AA_NSAMPLE : FCAP;
 struct __attribute__((aligned(16))) QE {
     int64_t sum;
     uint64_t k1;  // anom << (S + 1) | ratio key        (wide mode: anom << 32)

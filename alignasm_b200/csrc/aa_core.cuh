@@ -371,6 +371,7 @@ struct Ws {
     int32_t *wlast;      // [C*K] path_last_node
     int32_t *ent_node, *ent_prev;  // [C*3K]
     PQEnt *pq;           // [C*3K]
+    PQEnt *pq_far;       // [C*3K] second backlog region of the device enumeration (null: one region)
     // tasks
     Task *task;          // [C*2K]
     int32_t *n_task;     // [C]
@@ -3214,6 +3215,10 @@ constexpr int32_t FMASK = FCAP - 1;
 constexpr int32_t FKEEP = FCAP / 2;            // entries that stay when a full run spills its upper part
 constexpr int32_t REFILL_ALL = 3 * FCAP / 4;   // a backlog this small is moved as a whole
 constexpr int32_t REFILL_TARGET = 3 * FCAP / 8;
+#ifndef AA_NEAR
+#define AA_NEAR 3072
+#endif
+constexpr int32_t NEAR_TARGET = AA_NEAR;  // the near backlog after a split (the only part a refill scans)
 #ifndef AA_NSAMPLE
 #define AA_NSAMPLE 512
 #endif
@@ -3312,9 +3317,17 @@ __device__ __forceinline__ bool qe_dn_less(const QE &a, const QE &b, bool wide) 
 #ifdef AA_ENUM_TIMERS
 #define ET_DECL long long et_t = clock64(), et_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long et_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define ET(i) do { const long long et_now = clock64(); et_acc[i] += et_now - et_t; et_n[i]++; et_t = et_now; } while (0)
+#define RT_DECL long long rt_t = 0, rt_acc[6] = {0, 0, 0, 0, 0, 0};
+#define RT0 rt_t = clock64()
+#define RT(i) do { const long long rt_now = clock64(); rt_acc[i] += rt_now - rt_t; rt_t = rt_now; } while (0)
+#define RT_ADD(i, v) rt_acc[i] += (v)
 #else
 #define ET_DECL
 #define ET(i)
+#define RT_DECL
+#define RT0
+#define RT(i)
+#define RT_ADD(i, v)
 #endif
 __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     ET_DECL
@@ -3338,7 +3351,10 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     int32_t *__restrict__ last = w.wlast + wo;
     int32_t *__restrict__ en = w.ent_node + 3 * wo;
     int32_t *__restrict__ ep = w.ent_prev + 3 * wo;
-    QE *__restrict__ back = reinterpret_cast<QE *>(w.pq + 3 * wo);  // the backlog
+    // The backlog is kept in two regions: `back` (near: keys in [T, T2)) and `far` (keys >= T2).  A refill scans the near
+    // region only; when it runs empty the two arrays swap roles and the next refill splits the former far region again.
+    QE *back = reinterpret_cast<QE *>(w.pq + 3 * wo);
+    QE *far = w.pq_far ? reinterpret_cast<QE *>(w.pq_far + 3 * wo) : nullptr;
     const HNode *__restrict__ hn = w.hn;
     const ENext *__restrict__ enext = w.enext + e0;
     const XRec *__restrict__ xrec = w.xrec;  // nullptr: the arena was too large for expansion records
@@ -3375,8 +3391,20 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
 
     int32_t nd = 1, ne = 0;
     int32_t head = 0, n0 = 0, np = 0, nR = 0;  // run ring [head, head + n0), pending lanes [0, np), backlog [0, nR)
+    int32_t nF = 0;                            // far backlog [0, nF)
     bool hasT = false, hasB = false;           // threshold between front and backlog; bound of the useful keys
-    QE T = INF, B = INF, P = INF;              // P: this lane's pending entry
+    bool hasT2 = false;                        // threshold between the near and the far backlog (T <= T2)
+    QE T = INF, B = INF, P = INF, T2 = INF;    // P: this lane's pending entry
+    // a warp-uniform entry that is not below T joins the backlog
+    auto back_put = [&](const QE &e) {
+        if (hasT2 && !qe_less(e, T2, wide)) {
+            if (lane == 0) qe_st(far + nF, e);
+            nF++;
+        } else {
+            if (lane == 0) qe_st(back + nR, e);
+            nR++;
+        }
+    };
     QE p0u = INF;                              // warp-uniform copy of lane 0's pending entry, valid while p0_ok
     bool p0_ok = false;
     const D4 ds = w.d[v0 + g.src];
@@ -3517,14 +3545,25 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             }
     };
     // the front is empty: pick a threshold, move the backlog entries below it into the run, sort them
+    RT_DECL
     auto refill = [&]() {
         head = 0;
+        RT0;
         const int32_t remaining = K - nd;
+        if (nR == 0 && nF > 0) {  // the near region ran empty: the far region becomes the near one (split again below)
+            QE *const t = back;
+            back = far;
+            far = t;
+            nR = nF;
+            nF = 0;
+            hasT2 = false;
+        }
         if (nR <= REFILL_ALL) {
             for (int32_t i = lane; i < nR; i += 32) qe_st(&sm.f[i], qe_ld(back + i));
             n0 = nR;
             nR = 0;
-            hasT = false;
+            hasT = nF > 0;  // what is left of the backlog starts at T2
+            if (hasT) T = T2;
         } else {
             // sample stride ~ target / 4: the threshold is the 4th sample or so, the sample sort stays small
             int32_t stride = REFILL_TARGET / 4;
@@ -3532,6 +3571,10 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             const int32_t ns = nR / stride < NSAMPLE ? nR / stride : NSAMPLE;
             int32_t r = REFILL_TARGET / stride;
             if (r > ns - 1) r = ns - 1;
+            // a large near region is split in the same pass: keys from the r2-th sample up move to the far region
+            bool split = far != nullptr && nR > 2 * NEAR_TARGET;
+            int32_t r2 = NEAR_TARGET / stride;
+            if (r2 > ns - 1) r2 = ns - 1;
             for (;;) {
                 if (r < 1) {
                     // last resort (a sample could not split the backlog): move the single minimum
@@ -3571,8 +3614,16 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 for (int32_t i = lane; i < ns; i += 32) qe_st(&sm.f[i], qe_ld(back + (int64_t)i * stride));
                 __syncwarp();
                 sort_run(ns);
+                RT(0);
+                RT_ADD(3, ns);
+                RT_ADD(4, nR);
                 T = qe_ld(&sm.f[r]);
                 hasT = true;
+                QE T2n = INF;
+                if (split) {
+                    T2n = qe_ld(&sm.f[r2]);
+                    split = r2 > r && qe_less(T, T2n, wide);
+                }
                 // candidate bound of the useful keys: about 1.25 * remaining entries are below it
                 bool tryB = false;
                 QE Bc = INF;
@@ -3599,14 +3650,27 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                         const uint32_t mb = __ballot_sync(FULL, below);
                         const int32_t at = nb + __popc(mb & lt);
                         const bool stage = below && at < FCAP;
-                        const uint32_t mk = __ballot_sync(FULL, valid && !stage);
                         if (tryB) ncb += __popc(__ballot_sync(FULL, valid && qe_less(xs[u], Bc, wide)));
+                        if (split) {
+                            const bool hi = valid && !below && !qe_less(xs[u], T2n, wide);
+                            const uint32_t mh = __ballot_sync(FULL, hi);
+                            if (hi) qe_st(far + nF + __popc(mh & lt), xs[u]);
+                            nF += __popc(mh);
+                            if (hi) valid = false;  // it left the near region
+                        }
+                        const uint32_t mk = __ballot_sync(FULL, valid && !stage);
                         if (stage) qe_st(&sm.f[at], xs[u]);
                         if (valid && !stage) qe_st(back + wpos + __popc(mk & lt), xs[u]);
                         nb += __popc(mb);
                         wpos += __popc(mk);
                     }
                     __syncwarp();
+                }
+                RT(1);
+                if (split) {  // done once: a retry below works on the near region that is left
+                    T2 = T2n;
+                    hasT2 = true;
+                    split = false;
                 }
                 if (nb <= FCAP) {
                     n0 = nb;
@@ -3625,8 +3689,11 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             }
         }
         __syncwarp();
+        RT0;
         if (n0 > 1) sort_run(n0);
         __syncwarp();
+        RT(2);
+        RT_ADD(5, n0);
     };
 
     int32_t width = 32;  // candidates per round: follows the commit length (tie-heavy queues confirm few)
@@ -3662,7 +3729,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     };
     while (nd < K) {
         if (n0 == 0 && np == 0 && !carry) {
-            if (nR == 0) break;
+            if (nR == 0 && nF == 0) break;
             ET(7);
             refill();
             ET(0);
@@ -3825,8 +3892,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                 if (!(live & (1u << j))) continue;
                 const QE &e = j == 0 ? b0 : (j == 1 ? b1 : b2);
                 if (hasT && !qe_less(e, T, wide)) {
-                    if (lane == 0) qe_st(back + nR, e);
-                    nR++;
+                    back_put(e);
                 } else {
                     pend_insert(e);
                 }
@@ -4105,7 +4171,14 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
             bool valid = sidx == 0 ? s0 : (sidx == 1 ? s1 : s2);
             if (valid && hasB && !qe_less(a, B, wide)) valid = false;  // beyond the K walks: dropped
             const bool toF = valid && (!hasT || qe_less(a, T, wide));
-            const bool toR = valid && !toF;
+            bool toR = valid && !toF;
+            if (hasT2) {  // keys at or above T2 go to the far region
+                const bool toFar = toR && !qe_less(a, T2, wide);
+                const uint32_t mX = __ballot_sync(FULL, toFar);
+                if (toFar) qe_st(far + nF + __popc(mX & lt), a);
+                nF += __popc(mX);
+                toR = toR && !toFar;
+            }
             const uint32_t mR = __ballot_sync(FULL, toR);
             if (toR) qe_st(back + nR + __popc(mR & lt), a);
             nR += __popc(mR);
@@ -4125,11 +4198,13 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
         ET(5);
     }
 #ifdef AA_ENUM_TIMERS
-    if (lane == 0 && g.V > 4000)
+    if (lane == 0 && (g.V > 4000 || c % 250 == 7))
         printf("enum ctg %ld V %d walks %d entries %d | refill %lld/%lld cand %lld/%lld expand %lld/%lld scan %lld/%lld commit %lld/%lld succ %lld/%lld other %lld/%lld\n",
                (long)c, g.V, nd, ne, et_acc[0], et_n[0], et_acc[1], et_n[1], et_acc[2], et_n[2], et_acc[3], et_n[3], et_acc[4], et_n[4], et_acc[5], et_n[5],
                et_acc[7], et_n[7]);
-    if (lane == 0 && g.V > 4000)
+    if (lane == 0 && (g.V > 4000 || c % 250 == 7))
+        printf("  refill parts: sample sort %lld pass %lld run sort %lld | sum ns %lld sum scanned %lld sum n0 %lld\n", rt_acc[0], rt_acc[1], rt_acc[2], rt_acc[3], rt_acc[4], rt_acc[5]);
+    if (lane == 0 && (g.V > 4000 || c % 250 == 7))
         printf("  plateau size (log2 buckets 1,2,4,..): %d %d %d %d %d %d %d %d %d %d %d %d | avg front %lld backlog %d\n", plat[0], plat[1], plat[2], plat[3], plat[4],
                plat[5], plat[6], plat[7], plat[8], plat[9], plat[10], plat[11], front_n ? front_sz / front_n : 0, nR);
 #endif
@@ -4539,11 +4614,14 @@ AA_HDN int32_t auto_step(const Ws &w, const Ctg &g, const DPBuf &s, Auto &A, int
 }
 
 // ---- main chain = the automaton's states along walk 0 (no sidetracks: the tree walk from src) -----------------
+// The main-chain kernels run on the side stream beside the heaps and the enumeration.  Status 3 (heap arena overflow) is
+// raised and cleared by the heaps while they run: it says nothing about walk 0.
+AA_HD bool main_skip(const Ws &w, int64_t c) { return w.status[c] != 0 && w.status[c] != 3; }
 // S0 (per contig): trace walk 0, mark its blocks with call 0
 AA_HDN void f_main_trace(const Ws &w, int64_t c) {
     if (aa_lane() != 0) return;
     w.m_len[c] = 0;
-    if (w.status[c] != 0) return;
+    if (main_skip(w, c)) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     for (int32_t v = 0; v < g.V; v++) {
@@ -4570,7 +4648,7 @@ AA_HDN void f_main_trace(const Ws &w, int64_t c) {
 // S1 (per walk-0 position, parallel): the step at position i under the assumption cs == walk vertex
 AA_HDN void f_main_spec(const Ws &w, int64_t gv) {
     const int64_t c = upper_idx(w.vtx_off, w.C, gv);
-    if (w.status[c] != 0) return;
+    if (main_skip(w, c)) return;
     const int64_t v0 = w.vtx_off[c];
     const int32_t i = (int32_t)(gv - v0), m = w.m_len[c];
     if (i >= m) return;
@@ -4597,7 +4675,7 @@ AA_HDN void f_main_spec(const Ws &w, int64_t gv) {
 // S2 (per contig, sequential but cheap): resolve the true cs chain; take the speculated step whenever its
 // assumption holds, otherwise run the step with the real cs (and emit its rows right away)
 AA_HDN void f_main_resolve(const Ws &w, int64_t c, const Slot &s) {
-    if (w.status[c] != 0) return;
+    if (main_skip(w, c)) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     const int32_t m = w.m_len[c];
@@ -4630,9 +4708,13 @@ AA_HDN void f_main_resolve(const Ws &w, int64_t c, const Slot &s) {
     }
     w.m_tot_cov[c] = A.cov;
     w.m_tot_rows[c] = A.rows;
+}
+// task 0 of a contig is its walk 0: coverage and row count come from the main chain (once the task table exists)
+AA_HDN void f_main_totals(const Ws &w, int64_t c) {
+    if (w.status[c] != 0) return;
     const int64_t t0 = w.task_off[c];
-    w.task_cov[t0] = A.cov;
-    w.task_rows[t0] = A.rows;
+    w.task_cov[t0] = w.m_tot_cov[c];
+    w.task_rows[t0] = w.m_tot_rows[c];
 }
 #if defined(__CUDA_ARCH__)
 // S2 on the device: the same chain, but the per-position records are loaded 32 at a time (coalesced, one chunk
@@ -4640,7 +4722,7 @@ AA_HDN void f_main_resolve(const Ws &w, int64_t c, const Slot &s) {
 __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
-    if (w.status[c] != 0) return;
+    if (main_skip(w, c)) return;
     Ctg g = ctg_view(w, c);
     const int64_t v0 = g.v0;
     const int32_t m = w.m_len[c];
@@ -4764,16 +4846,13 @@ __device__ void f_main_resolve_warp(const Ws &w, int64_t c, const Slot &s) {
     if (lane == 0) {
         w.m_tot_cov[c] = A.cov;
         w.m_tot_rows[c] = A.rows;
-        const int64_t t0 = w.task_off[c];
-        w.task_cov[t0] = A.cov;
-        w.task_rows[t0] = A.rows;
     }
 }
 #endif
 // S3 (per walk-0 position, parallel): emit the rows of every state the resolve pass took from speculation
 AA_HDN void f_main_rows(const Ws &w, int64_t gv) {
     const int64_t c = upper_idx(w.vtx_off, w.C, gv);
-    if (w.status[c] != 0) return;
+    if (main_skip(w, c)) return;
     const int64_t v0 = w.vtx_off[c];
     const int32_t i = (int32_t)(gv - v0), m = w.m_len[c];
     if (i >= m || w.m_cs[gv] < 0 || w.m_done[gv]) return;

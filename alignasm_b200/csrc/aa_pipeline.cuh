@@ -137,6 +137,10 @@ AA_FUNCTOR(FnMainSpec, f_main_spec(w, i))
 AA_FUNCTOR(FnMainRows, f_main_rows(w, i))
 AA_FUNCTOR(FnTasksA1, f_tasks_a1(w, i))
 AA_FUNCTOR(FnTasksA1Solo, f_tasks_a1_solo(w, i))
+struct FnMainTotals {
+    Ws w;
+    AA_HD void operator()(int64_t i, void *) const { f_main_totals(w, i); }
+};
 struct FnTasksA0 {
     Ws w;
     const int32_t *ord;
@@ -846,8 +850,35 @@ struct Pipeline {
             err = "device allocation failed (main chain)";
             return AA_ERR_NOMEM;
         }
+        // ... and so is the rest of the main chain (speculate every step in parallel, resolve sequentially, emit rows in
+        // parallel): it needs walk 0 only, and the resolve of the largest contig is a serial chain of several ms.  It
+        // has a DP scratch of its own (a few slots: one per resolving warp) and its own work counter.
+        int64_t maxV = 3;
+        for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
+        w.slot_stride = maxV + 1;
+        Ws wm = w;
+        int64_t S0 = 0;
+        {
+            const int64_t sb = w.slot_stride * (int64_t)(4 + sizeof(D5) + 4 + 1);
+            S0 = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(C, 2 * bk.max_workers() / 32), bk.scratch_budget() / 4 / std::max<int64_t>(1, sb)));
+            wm.sc_walk = nullptr;
+            wm.sc_side = nullptr;
+            wm.sc_up = A<int32_t>(S0 * w.slot_stride);
+            wm.sc_dp = A<D5>(S0 * w.slot_stride);
+            wm.sc_pre = A<int32_t>(S0 * w.slot_stride);
+            wm.sc_seen = A<uint8_t>(S0 * w.slot_stride);
+            wm.task_next = (unsigned long long *)A<int64_t>(1);
+            if (!wm.sc_up || !wm.sc_dp || !wm.sc_pre || !wm.sc_seen || !wm.task_next) {
+                err = "device allocation failed (main chain scratch)";
+                return AA_ERR_NOMEM;
+            }
+        }
         bk.side_begin();
         bk.for_each_contig("main_trace", C, FnMainTrace{w, d_ord});
+        bk.for_each("main_spec", Vtot, FnMainSpec{w});
+        bk.zero(wm.task_next, 8);
+        bk.workers("main_resolve", S0, FnTasksA0{wm, d_ord});
+        bk.for_each("main_rows", Vtot, FnMainRows{w});
         bk.side_end();
 
         // ---- phase 7: sidetrack heaps (arena doubles on overflow) ----
@@ -1116,6 +1147,7 @@ struct Pipeline {
             err = "device allocation failed (walk enumeration)";
             return AA_ERR_NOMEM;
         }
+        w.pq_far = nullptr;
         if (bk.device_kahn()) {
             w.enext = A<ENext>(E);
             if (!w.enext) {
@@ -1125,7 +1157,7 @@ struct Pipeline {
             bk.for_each("enext", Vtot, FnENext{w});
             // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
             w.xrec = nullptr;
-            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records
+            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records, 4: one backlog region
             if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget()) {
                 w.xrec = A<XRec>(heap_top_h);
                 if (!w.xrec) {
@@ -1134,6 +1166,8 @@ struct Pipeline {
                 }
                 bk.for_each("xrec", heap_top_h, FnXRec{w});
             }
+            // the second backlog region is an optimisation: without the memory for it the queue keeps one region
+            if (!(w.heaps_variant & 4) && 3 * WK * (int64_t)sizeof(PQEnt) <= bk.scratch_budget()) w.pq_far = A<PQEnt>(3 * WK);
         }
         bk.for_each_contig("enum", C, FnEnum{w, d_ord}, ENUM_SMEM_BYTES);
         bk.phase_end(PH_ENUM);
@@ -1164,9 +1198,6 @@ struct Pipeline {
         // ---- phase 10: walks, pass A ----
         bk.side_join();
         bk.phase_begin(PH_WALKS_A);
-        int64_t maxV = 3;
-        for (int64_t c = 0; c < C; c++) maxV = std::max(maxV, h_voff[(size_t)c + 1] - h_voff[(size_t)c]);
-        w.slot_stride = maxV + 1;
         const int64_t slot_bytes = w.slot_stride * (int64_t)(4 + 4 + 4 + sizeof(D5) + 4 + 1);
         int64_t S = std::min<int64_t>(std::max<int64_t>(NT, 2 * C), bk.max_workers());
         S = std::max<int64_t>(1, std::min<int64_t>(S, bk.scratch_budget() / std::max<int64_t>(1, slot_bytes)));
@@ -1181,11 +1212,8 @@ struct Pipeline {
             err = "device allocation failed (walk scratch)";
             return AA_ERR_NOMEM;
         }
-        // walk 0 of every contig: trace, speculate every step in parallel, resolve sequentially, emit rows in parallel
-        bk.for_each("main_spec", Vtot, FnMainSpec{w});
-        bk.zero(w.task_next, 8);
-        bk.workers("main_resolve", std::min<int64_t>(S, C), FnTasksA0{w, d_ord});
-        bk.for_each("main_rows", Vtot, FnMainRows{w});
+        // walk 0 of every contig was resolved on the side stream: its totals become task 0
+        bk.for_each("main_totals", C, FnMainTotals{w});
         // every other planned walk
         if (NT > C) {
             w.fb_list = A<int32_t>(NT);

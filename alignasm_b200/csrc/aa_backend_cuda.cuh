@@ -17,6 +17,8 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -52,6 +54,72 @@ struct MinI32 {
 struct CastI32 {
     __host__ __device__ __forceinline__ int64_t operator()(const int32_t &x) const { return (int64_t)x; }
 };
+
+// Pinned host slabs for result arrays, shared by every context of the process (results outlive solves and contexts).
+// A released slab is kept for the next result of about the same size; at most KEEP_BYTES stay cached.
+class ResultSlabs {
+  public:
+    static ResultSlabs &get() {
+        static ResultSlabs *p = new ResultSlabs();  // never destroyed: results may be freed during process exit
+        return *p;
+    }
+    void *acquire(size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = SIZE_MAX;
+            for (size_t i = 0; i < idle.size(); i++)
+                if (idle[i].cap >= bytes && idle[i].cap <= 4 * bytes + (1u << 20) && (best == SIZE_MAX || idle[i].cap < idle[best].cap)) best = i;
+            if (best != SIZE_MAX) {
+                Slab sl = idle[best];
+                idle.erase(idle.begin() + (long)best);
+                idle_bytes -= sl.cap;
+                busy[sl.base] = sl.cap;
+                return sl.base;
+            }
+        }
+        void *base = nullptr;
+        const size_t cap = bytes + bytes / 8;
+        if (cudaHostAlloc(&base, cap, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;  // the caller falls back to pageable arrays
+        }
+        std::lock_guard<std::mutex> g(mu);
+        busy[base] = cap;
+        return base;
+    }
+    bool release(void *base) {
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = busy.find(base);
+            if (it == busy.end()) return false;
+            idle.push_back({base, it->second});
+            idle_bytes += it->second;
+            busy.erase(it);
+            while (idle_bytes > KEEP_BYTES && !idle.empty()) {  // oldest first
+                drop.push_back(idle.front().base);
+                idle_bytes -= idle.front().cap;
+                idle.erase(idle.begin());
+            }
+        }
+        for (void *q : drop)
+            if (cudaFreeHost(q) != cudaSuccess) cudaGetLastError();
+        return true;
+    }
+
+  private:
+    struct Slab {
+        void *base;
+        size_t cap;
+    };
+    static constexpr size_t KEEP_BYTES = (size_t)2 << 30;
+    std::mutex mu;
+    std::vector<Slab> idle;
+    size_t idle_bytes = 0;
+    std::unordered_map<void *, size_t> busy;
+};
+inline bool result_slab_release(void *base) { return ResultSlabs::get().release(base); }
 
 struct CudaBackend {
     int device = 0;
@@ -405,13 +473,21 @@ struct CudaBackend {
     // memcpy into the caller's (fresh, pageable) arrays: their pages are first touched by all host threads
     std::vector<Piece> dpieces;
     size_t dstaged_bytes = 0;
+    void *result_slab(size_t bytes) { return ResultSlabs::get().acquire(bytes); }
     void stage_d2h(void *h, const void *d, size_t n) {
         if (!n) return;
         dpieces.push_back({h, d, n, dstaged_bytes});
         dstaged_bytes += (n + 255) & ~(size_t)255;
     }
-    void flush_d2h() {
+    void flush_d2h(bool dst_pinned = false) {
         if (failed || dpieces.empty()) {
+            dpieces.clear();
+            dstaged_bytes = 0;
+            return;
+        }
+        if (dst_pinned) {  // the destinations are pinned (a result slab): straight copies, one synchronisation
+            for (auto &p : dpieces) AA_CUDA(cudaMemcpyAsync(p.dst, p.src, p.n, cudaMemcpyDeviceToHost, stream));
+            AA_CUDA(cudaStreamSynchronize(stream));
             dpieces.clear();
             dstaged_bytes = 0;
             return;

@@ -50,6 +50,9 @@ constexpr int64_t SV_INV_PENALTY = 500;
 constexpr int64_t SV_FRONT_END = 2;
 constexpr int64_t REF_NEG_PENALTY = 2;
 // run capacity of the enumeration's sorted front (entries of 32 B in shared memory)
+#ifndef AA_RC_SLOTS
+#define AA_RC_SLOTS 512
+#endif
 #ifndef AA_FCAP
 #define AA_FCAP 512  // (1024 measured the same or slightly slower on C1 / C2 / C5; 16 KB lets more contigs be resident)
 #endif
@@ -1744,7 +1747,7 @@ __device__ void f_relax_warp(const Ws &w, int64_t c, void *scratch) {
 // once, with its final state, and leaves the table.  Two open vertices that map to one slot make the warp give up:
 // the contig is flagged (status 4) and redone by the global-memory form above (f_relax_redo_warp).
 // The first 32 in-edge records of the next queue entry are loaded one pop ahead whenever the queue holds one.
-constexpr int32_t RC_SLOTS = 512;  // per table
+constexpr int32_t RC_SLOTS = AA_RC_SLOTS;  // per table
 struct __attribute__((aligned(16))) RCEnt {
     int64_t sum;
     int32_t anom, nz;
@@ -1758,7 +1761,7 @@ struct RelaxSmemC {
     RelaxSmem ring;
     RCEnt tab[2 * RC_SLOTS];
 };
-static_assert(sizeof(RelaxSmemC) <= 58 * 1024, "RelaxSmemC does not fit its shared-memory allotment");
+static_assert(sizeof(RelaxSmemC) <= 10 * 1024 + 2 * RC_SLOTS * 48, "RelaxSmemC does not fit its shared-memory allotment");
 __device__ __forceinline__ RevRec rrec_ld(const RevRec *p) {
     const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
     RevRec r;
@@ -2324,7 +2327,7 @@ AA_HDN void f_topo_any(const Ws &w, int64_t c, void *scratch) {
 }
 constexpr size_t KAHN_SMEM_BYTES = 4 * 1024;
 constexpr size_t RELAX_SMEM_BYTES = 10 * 1024;        // global-state form (redo launch)
-constexpr size_t RELAX_SMEM_C_BYTES = 10 * 1024 + 48 * 1024;  // ring + open-vertex tables
+constexpr size_t RELAX_SMEM_C_BYTES = 10 * 1024 + (size_t)2 * AA_RC_SLOTS * 48;  // ring + open-vertex tables
 
 #if defined(__CUDA_ARCH__)
 // ---- warp-cooperative sidetrack heaps (device only; the host emulation runs f_heaps above) --------------------

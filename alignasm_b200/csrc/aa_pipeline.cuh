@@ -257,16 +257,24 @@ template <class T>
 inline T *host_n(int64_t n) {
     return (T *)std::calloc((size_t)(n > 0 ? n : 1), sizeof(T));
 }
+// A device backend may hand out the arrays of a result as ONE slab of pinned host memory (the rows are then copied from the
+// device straight into the caller's arrays, no staging copy and no page faults); out_off is the slab's base.  The hook gives
+// the slab back and says whether `base` was one.
+inline bool (*g_result_slab_release)(void *base) = nullptr;
 inline void result_free_host(aa_result *res) {
     if (!res) return;
-    std::free(res->out_off);
-    std::free(res->alt_off);
-    std::free(res->all_path_off);
-    std::free(res->all_row_off);
-    std::free(res->sorted_index);
-    rows_free_host(res->out);
-    rows_free_host(res->alt);
-    rows_free_host(res->all);
+    if (res->out_off && g_result_slab_release && g_result_slab_release(res->out_off)) {
+        // every array below lived in the slab
+    } else {
+        std::free(res->out_off);
+        std::free(res->alt_off);
+        std::free(res->all_path_off);
+        std::free(res->all_row_off);
+        std::free(res->sorted_index);
+        rows_free_host(res->out);
+        rows_free_host(res->alt);
+        rows_free_host(res->all);
+    }
     if (aa_debug *g = res->dbg) {
         void *ptrs[] = {g->vtx_off, g->edge_off, g->walk_off, g->e_src, g->e_dst, g->e_qry, g->e_ref, g->e_anom, g->e_qnz,
                         g->e_qtot, g->d_reach, g->d_sum, g->d_anom, g->d_qnz, g->d_qtot, g->best, g->order, g->w_sum,
@@ -1307,11 +1315,33 @@ struct Pipeline {
         if (res) {
             std::memset(res, 0, sizeof *res);
             res->n_ctg = C;
-            res->out_off = host_n<int64_t>(C + 1);
-            res->alt_off = host_n<int64_t>(C + 1);
-            res->all_path_off = host_n<int64_t>(C + 1);
-            res->all_row_off = host_n<int64_t>(n_paths + 1);
-            res->sorted_index = host_n<int32_t>(B);
+            // one pinned slab for every array of the result when the backend has one to give
+            auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+            size_t slab_need = 3 * al((size_t)(C + 1) * 8) + al((size_t)(n_paths + 1) * 8) + al((size_t)B * 4);
+            for (int k = 0; k < 3; k++) {
+                const size_t m = (size_t)std::max<int64_t>(nrow[k], 1);
+                slab_need += al(m * 4) + 4 * al(m * 8) + al(m);
+            }
+            char *slab = (char *)bk.result_slab(slab_need);
+            size_t slab_off = 0;
+            auto carve = [&](size_t b) {
+                void *q = slab + slab_off;
+                slab_off += al(b);
+                return q;
+            };
+            if (slab) {
+                res->out_off = (int64_t *)carve((size_t)(C + 1) * 8);
+                res->alt_off = (int64_t *)carve((size_t)(C + 1) * 8);
+                res->all_path_off = (int64_t *)carve((size_t)(C + 1) * 8);
+                res->all_row_off = (int64_t *)carve((size_t)(n_paths + 1) * 8);
+                res->sorted_index = (int32_t *)carve((size_t)B * 4);
+            } else {
+                res->out_off = host_n<int64_t>(C + 1);
+                res->alt_off = host_n<int64_t>(C + 1);
+                res->all_path_off = host_n<int64_t>(C + 1);
+                res->all_row_off = host_n<int64_t>(n_paths + 1);
+                res->sorted_index = host_n<int32_t>(B);
+            }
             std::memcpy(res->sorted_index, sorted_index.data(), (size_t)B * 4);
             bk.d2h(res->out_off, w.out_off, (size_t)(C + 1) * 8);
             bk.d2h(res->alt_off, w.alt_off, (size_t)(C + 1) * 8);
@@ -1319,7 +1349,18 @@ struct Pipeline {
             bk.d2h(res->all_row_off, w.all_row_off, (size_t)(n_paths + 1) * 8);
             aa_rows *dst[3] = {&res->out, &res->alt, &res->all};
             for (int k = 0; k < 3; k++) {
-                rows_alloc_host(*dst[k], nrow[k]);
+                if (slab) {
+                    const size_t m = (size_t)std::max<int64_t>(nrow[k], 1);
+                    dst[k]->n = nrow[k];
+                    dst[k]->ctg_index = (int32_t *)carve(m * 4);
+                    dst[k]->qry_str = (int64_t *)carve(m * 8);
+                    dst[k]->qry_end = (int64_t *)carve(m * 8);
+                    dst[k]->ref_str = (int64_t *)carve(m * 8);
+                    dst[k]->ref_end = (int64_t *)carve(m * 8);
+                    dst[k]->is_alt = (uint8_t *)carve(m);
+                } else {
+                    rows_alloc_host(*dst[k], nrow[k]);
+                }
                 if (nrow[k] > 0) {
                     bk.stage_d2h(dst[k]->ctg_index, w.r_idx[k], (size_t)nrow[k] * 4);
                     bk.stage_d2h(dst[k]->qry_str, w.r_qs[k], (size_t)nrow[k] * 8);
@@ -1329,7 +1370,7 @@ struct Pipeline {
                     bk.stage_d2h(dst[k]->is_alt, w.r_alt[k], (size_t)nrow[k]);
                 }
             }
-            bk.flush_d2h();
+            bk.flush_d2h(slab != nullptr);
             if (opt.keep_debug) download_debug(w, res, h_status, h_voff, h_nwalk, E, Vtot);
         }
         bk.phase_end(PH_D2H);

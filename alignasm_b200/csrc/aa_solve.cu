@@ -23,6 +23,9 @@ extern "C" {
 const char *aa_version(void) { return "alignasm_b200 0.1.0 (sm_100a)"; }
 const char *aa_phase_name(int phase) { return aa::phase_name(phase); }
 
+// results of this library may live in pinned slabs (aa_backend_cuda.cuh): aa_result_free gives them back
+static const bool g_slab_hook = (aa::g_result_slab_release = aa::result_slab_release, true);
+
 aa_status aa_create(aa_ctx **ctx, int device) {
     if (!ctx) return AA_ERR_INVALID;
     *ctx = nullptr;

@@ -34,7 +34,8 @@ struct HostBackend {
     void flush_staged() {}
     void d2h(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
     void stage_d2h(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
-    void flush_d2h() {}
+    void flush_d2h(bool = false) {}
+    void *result_slab(size_t) { return nullptr; }  // pageable arrays
     void zero(void *p, size_t n) { std::memset(p, 0, n); }
     void sync() {}
     template <class F>

@@ -82,6 +82,10 @@ def load_library():
     lib.aa_paf_read_device.restype = C.c_int
     lib.aa_paf_write_device.argtypes = [vp, vp, C.POINTER(aa_result), C.c_char_p, C.c_char_p, C.c_int64]
     lib.aa_paf_write_device.restype = C.c_int
+    lib.aa_host_alloc.argtypes = [C.c_int64]
+    lib.aa_host_alloc.restype = vp
+    lib.aa_host_free.argtypes = [vp]
+    lib.aa_host_free.restype = None
     lib.aa_solve_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(aa_batch), C.POINTER(aa_opts), C.POINTER(aa_result)]
     lib.aa_solve_multi.restype = C.c_int
     lib.aa_shard_contigs.argtypes = [C.POINTER(aa_batch), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
@@ -90,6 +94,22 @@ def load_library():
     lib.aa_multi_last_error.restype = C.c_char_p
     _LIB = lib
     return lib
+
+
+class _Pins:
+    """Owner of aa_host_alloc blocks (freed with the batch that views them)."""
+
+    def __init__(self, ptrs):
+        self.ptrs = ptrs
+
+    def __del__(self):
+        try:
+            lib = load_library()
+            for p in self.ptrs:
+                lib.aa_host_free(p)
+        except Exception:
+            pass
+        self.ptrs = []
 
 
 class Batch:
@@ -125,6 +145,28 @@ class Batch:
                 setattr(b, name, ptr_of(getattr(self, name), ct[dt]))
             self._c = b
         return self._c
+
+    def pinned(self):
+        """A copy of the batch whose arrays live in page-locked host memory (aa_host_alloc): solve() then copies them to the
+        device directly instead of through the library's staging buffer."""
+        lib = load_library()
+        arrays, holds = {}, []
+        for name, dt in self.FIELDS:
+            src = getattr(self, name)
+            p = lib.aa_host_alloc(max(src.nbytes, 1))
+            if not p:
+                for q in holds:
+                    lib.aa_host_free(q)
+                raise MemoryError("aa_host_alloc: no page-locked memory")
+            holds.append(p)
+            dst = np.frombuffer((C.c_char * max(src.nbytes, 1)).from_address(p), dtype=dt, count=src.size)
+            dst[:] = src
+            arrays[name] = dst
+        out = Batch(**arrays)
+        for name, _ in self.FIELDS:  # np.ascontiguousarray keeps an already contiguous array of the right dtype as it is
+            assert getattr(out, name).ctypes.data == arrays[name].ctypes.data
+        out._pins = _Pins(holds)
+        return out
 
     def select(self, contigs):
         """Sub-batch holding the given contigs (used for sharding across GPUs / ranks)."""

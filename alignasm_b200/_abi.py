@@ -72,7 +72,7 @@ EXPORTS = ["aa_create", "aa_destroy", "aa_last_error", "aa_solve", "aa_upload", 
            "aa_multi_last_error", "aa_multi_release",
            # cs:Z: codec on the device (csrc/cs_codec.cu)
            "aa_cs_runs_device", "aa_cs_runs_free", "aa_cs_edit_device", "aa_cs_edits_free", "aa_cs_error_text", "aa_cs_last_error",
-           "aa_ctx_device", "aa_paf_read_device", "aa_paf_write_device"]
+           "aa_ctx_device", "aa_paf_read_device", "aa_paf_write_device", "aa_host_alloc", "aa_host_free"]
 
 
 class aa_cs_rows(C.Structure):

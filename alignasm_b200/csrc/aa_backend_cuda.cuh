@@ -405,8 +405,23 @@ struct CudaBackend {
     };
     std::vector<Piece> pieces;
     size_t staged_bytes = 0, staged_tail = 0;  // padded total / end of the last piece
+    // page-locked source (aa_host_alloc, cudaHostRegister, a pinned torch tensor ...): the DMA engine reads it as it is
+    static bool host_pinned(const void *h) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    }
     void stage(void *d, const void *h, size_t n) {
         if (!n) return;
+        if (n >= ((size_t)256 << 10) && host_pinned(h)) {  // (small pieces are not worth the query)
+            // (every entry point that stages synchronises the stream before it returns: aa_solve / aa_solve_subset when they
+            // fetch the rows or quiesce after a failure, aa_upload explicitly)
+            if (!failed) AA_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream));
+            return;
+        }
         // a piece that continues the previous one on the device also continues it in the staging buffer, so that the two
         // go up in ONE copy (a shard staged contig by contig is thousands of pieces per array)
         const bool cont = !pieces.empty() && (char *)pieces.back().dst + pieces.back().n == (char *)d &&

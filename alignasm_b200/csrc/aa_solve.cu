@@ -45,6 +45,19 @@ void aa_destroy(aa_ctx *ctx) {
     delete ctx;
 }
 int aa_ctx_device(const aa_ctx *ctx) { return ctx ? ctx->bk.device : -1; }
+
+void *aa_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) bytes = 1;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void aa_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
 const char *aa_last_error(const aa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 aa_status aa_upload(aa_ctx *ctx, const aa_batch *batch, aa_dev_batch **dev) {

@@ -278,7 +278,9 @@ def main():
                            "no collective on the data path: every rank publishes the primary/alt rows of its shard in a POSIX shared-memory segment that "
                            "rank 0 maps (host-side merge, inside the timed region); NCCL carries only the barriers and the timing reductions" if wl != "c4" else "a single contig does not shard: replicas only (every rank solves the same contig)"),
               "cpu_sample_rule": "see cpu_baseline.sample",
-              "l2": "inputs + workspace (> 1 GB) are larger than the 126 MB L2; nothing is cached between steps"}
+              "l2": "inputs + workspace (> 1 GB) are larger than the 126 MB L2; nothing is cached between steps",
+              "e2e_host_memory": "inputs in page-locked host arrays (aa_host_alloc), rows returned in the library's pinned result slab; "
+                                 "pageable inputs go through one more staging pass (see DESIGN.md section 6)"}
 
     with tempfile.TemporaryDirectory(prefix="aa_bench_") as tmp:
         # ------------------------------------------------------------------ reference arm (CPU only, rank 0 only)
@@ -328,6 +330,8 @@ def main():
             sub = batch_full.select(shard_ids[rank]) if shard_ids is not None else batch_full
             have = sub.n_ctg > 0
             dev = solver.upload(sub) if have else None
+            # the e2e leg reads its inputs from page-locked host memory (the bench contract; aa_host_alloc in the C ABI)
+            sub_host = sub.pinned() if have else sub
             gather = shard_ids is not None and world > 1
             shm = None
             if gather:  # one solve tells how many rows the shard has; the shared segment gets 25 % head room
@@ -344,7 +348,7 @@ def main():
             def step(resident):
                 nbytes = 0
                 if have:
-                    r = solver.solve_device(dev, copy=False, **opts) if resident else solver.solve(sub, copy=False, **opts)
+                    r = solver.solve_device(dev, copy=False, **opts) if resident else solver.solve(sub_host, copy=False, **opts)
                     nbytes = sum(v.nbytes for v in r.out.values()) + sum(v.nbytes for v in r.alt.values()) + r.out_off.nbytes + r.alt_off.nbytes
                     if gather:
                         shm.publish(r)

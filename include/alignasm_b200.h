@@ -233,6 +233,14 @@ int aa_ctx_device(const aa_ctx *ctx);
 aa_status aa_paf_read_device(const char *path, aa_ctx *ctx, aa_paf **paf, char *err, int64_t err_cap);
 aa_status aa_paf_write_device(const aa_paf *paf, aa_ctx *ctx, const aa_result *res, const char *out_prefix, char *err, int64_t err_cap);
 
+/* ---- page-locked host memory for the arrays of a batch (optional) ---------------------------
+ * aa_solve / aa_upload / aa_solve_subset copy arrays that live in page-locked memory to the device directly; pageable
+ * arrays go through the library's staging buffer first (one more pass over the input at host memcpy speed).  The
+ * reference keeps its blocks in std::vector (paf_data.hpp:96-107); a caller that fills the aa_batch arrays itself can
+ * place them here instead.  NULL when no page-locked memory can be had (use malloc then). */
+void *aa_host_alloc(int64_t bytes);
+void aa_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,3 +417,38 @@ def test_writer_with_device_codec_on_bench_workload(solver, workdir):
     pf.write(res, os.path.join(workdir, "csw_host"))
     for ext in ("aln.paf", "aln.alt.paf", "aln.all.paf"):
         assert pu.files_equal(os.path.join(workdir, "csw_dev." + ext), os.path.join(workdir, "csw_host." + ext)), ext
+
+
+def test_pinned_inputs_and_result_slabs(solver, workdir):
+    """A batch in page-locked memory (aa_host_alloc) goes up without the staging pass and gives the same rows; results live
+    in pooled pinned slabs: they stay valid after later solves and after their context is gone, and a released slab is reused."""
+    import alignasm_b200 as aa
+    args, _ = SMALL["c1_small"]
+    pf = aa.read_paf(pu.synth(os.path.join(workdir, "pinned.paf"), *args))
+    base = solver.solve(pf.batch, want_all=True)
+    hb = pf.batch.pinned()
+    for name, _ in aa.Batch.FIELDS:
+        assert np.array_equal(getattr(hb, name), getattr(pf.batch, name))
+    got = solver.solve(hb, want_all=True)
+    assert pu.result_rows_equal(base, got) is None
+    dev = solver.upload(hb)
+    assert pu.result_rows_equal(base, solver.solve_device(dev, want_all=True)) is None
+    dev.free()
+    # views (copy=False) of a result stay intact while other solves run and after the solver that made them is closed
+    other = aa.Solver(0)
+    keep = other.solve(pf.batch, copy=False)
+    snap = {k: np.array(v) for k, v in keep.out.items()}
+    seen = {keep.out["qry_str"].ctypes.data}
+    for _ in range(3):
+        r = other.solve(pf.batch, copy=False)
+        seen.add(r.out["qry_str"].ctypes.data)
+        r.close()
+    assert len(seen) == 2  # `keep` holds one slab, the three others took turns on a second one
+    other.close()
+    assert all(np.array_equal(snap[k], keep.out[k]) for k in snap)
+    assert pu.result_rows_equal(base, keep, check_all=False) is None
+    keep.close()
+    again = solver.solve(pf.batch, copy=False)  # a slab that was given back, not a new one
+    assert again.out["qry_str"].ctypes.data in seen
+    assert pu.result_rows_equal(base, again, check_all=False) is None
+    again.close()

@@ -65,6 +65,7 @@ class ResultSlabs {
     }
     void *acquire(size_t bytes) {
         if (bytes == 0) bytes = 256;
+        if (bytes > MAX_SLAB) return nullptr;  // (.aln.all rows of a large input: tens of GB are not worth pinning)
         {
             std::lock_guard<std::mutex> g(mu);
             size_t best = SIZE_MAX;
@@ -114,6 +115,7 @@ class ResultSlabs {
         size_t cap;
     };
     static constexpr size_t KEEP_BYTES = (size_t)2 << 30;
+    static constexpr size_t MAX_SLAB = (size_t)1 << 30;
     std::mutex mu;
     std::vector<Slab> idle;
     size_t idle_bytes = 0;

@@ -3332,7 +3332,11 @@ __device__ __forceinline__ bool qe_dn_less(const QE &a, const QE &b, bool wide) 
 #define RT(i)
 #define RT_ADD(i, v)
 #endif
-__device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
+// WIDE: contigs of more than 2^20 vertices, whose qul ratio does not fit the packed key (the comparisons then cross-multiply).
+// A template parameter because the compiler turns a run-time flag into straight-line code that does the two 64-bit products
+// in EVERY comparison (7 % of the kernel's instructions on inputs that never need them).
+template <bool WIDE>
+__device__ void f_enum_warp_t(const Ws &w, int64_t c, void *scratch) {
     ET_DECL
 #ifdef AA_ENUM_TIMERS
     int32_t plat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -3365,7 +3369,7 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
     // key packing for this contig
     int32_t vb = 1;
     while ((1 << vb) <= g.V) vb++;
-    const bool wide = vb > 20;
+    constexpr bool wide = WIDE;
     // the tie-break of the queue is the node's place in the sequential allocation order (what the reference's pointer
     // comparison sees).  Streaming-mode contigs have their node ids in that order (leaves get reserved id
     // ranges); heaps built level by level do not: there the rank recorded per node is compared and ent_node[] keeps the id
@@ -4212,6 +4216,13 @@ __device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
                plat[5], plat[6], plat[7], plat[8], plat[9], plat[10], plat[11], front_n ? front_sz / front_n : 0, nR);
 #endif
     if (lane == 0) w.n_walk[c] = nd;
+}
+__device__ void f_enum_warp(const Ws &w, int64_t c, void *scratch) {
+    bool wide = false;
+    if (w.status[c] == 0) wide = ctg_view(w, c).V >= (1 << 20);  // the packed key holds vertex numbers below 2^20 twice
+    if (w.heaps_variant & 8) wide = true;  // AA_TUNE bit 3 (tests): the wide comparisons are exact for every contig
+    if (wide) f_enum_warp_t<true>(w, c, scratch);
+    else f_enum_warp_t<false>(w, c, scratch);
 }
 #endif
 AA_HDN void f_enum_any(const Ws &w, int64_t c, void *scratch) {

@@ -1165,7 +1165,7 @@ struct Pipeline {
             bk.for_each("enext", Vtot, FnENext{w});
             // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
             w.xrec = nullptr;
-            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records, 4: one backlog region
+            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records, 4: one backlog region, 8: wide keys for every contig
             if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget()) {
                 w.xrec = A<XRec>(heap_top_h);
                 if (!w.xrec) {

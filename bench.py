@@ -18,7 +18,8 @@ quoted on) as the sub-object "c2": value, e2e, roofline, phases, sizes, cli, sam
 
 Prints ONE JSON line (rank 0):
   value        blocks/s of the whole job with the shards resident in HBM (aa_solve_device + gather), max over ranks
-  e2e          blocks/s through the public host-buffer call aa_solve (H2D of the shard + D2H of the rows inside) + gather
+  e2e          blocks/s through the public host-buffer call aa_solve (H2D of the shard from page-locked host arrays, aa_host_alloc,
+               + D2H of the rows inside) + gather
   roofline     the dominant kernel (phase) of the step: algorithmic bytes / CUDA-event time vs the measured HBM peak
   per_rank     device ms and shard sizes of every rank (the imbalance is the largest contig's serial chain)
   cpu_baseline the reference's own solve_ctg_read (oracle/_ref, compiled from the reference sources) on this box's host

@@ -452,3 +452,21 @@ def test_pinned_inputs_and_result_slabs(solver, workdir):
     assert again.out["qry_str"].ctypes.data in seen
     assert pu.result_rows_equal(base, again, check_all=False) is None
     again.close()
+
+
+@pytest.mark.parametrize("tune", ["8", "12", "1", "2"])
+def test_enumeration_variants(tune, solver, workdir, monkeypatch):
+    """The enumeration kernel exists in two instantiations (packed keys / wide keys for contigs of 2^20 vertices and more) and
+    has optional parts (serial steps, expansion records, the far backlog region).  AA_TUNE forces each variant on inputs every
+    variant must solve identically: 8 = wide keys, 12 = wide keys + one backlog region, 1 = no serial steps, 2 = no expansion records."""
+    import alignasm_b200 as aa
+    from oracle import oracle_py
+    monkeypatch.setenv("AA_TUNE", tune)
+    for name in ("ties", "segments"):
+        args, variants = SMALL[name]
+        pf = aa.read_paf(pu.synth(os.path.join(workdir, "tune_" + name + ".paf"), *args))
+        for nsl in variants:
+            got = solver.solve(pf.batch, non_skip_linkable=nsl, want_all=True, keep_debug=True)
+            want = oracle_py.oracle_solve(pf.batch, threads=8, non_skip_linkable=nsl, want_all=True, keep_debug=True)
+            assert pu.debug_equal(got.dbg, want.dbg) is None
+            assert pu.result_rows_equal(got, want) is None

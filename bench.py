@@ -490,7 +490,7 @@ def main():
             t2 = time.perf_counter()
             pf3 = aa.read_paf(paf2)
             t3 = time.perf_counter()
-            r = solver.solve(pf3.batch)
+            r = solver.solve(pf3.batch, copy=False)
             t4 = time.perf_counter()
             pf3.write(r, os.path.join(tmp, "cli_out"))
             t5 = time.perf_counter()
@@ -505,7 +505,7 @@ def main():
             t2 = time.perf_counter()
             pf4 = aa.read_paf(paf2, solver=solver)
             t3 = time.perf_counter()
-            r = solver.solve(pf4.batch)
+            r = solver.solve(pf4.batch, copy=False)
             t4 = time.perf_counter()
             pf4.write(r, os.path.join(tmp, "cli_out_dev"), solver=solver)
             t5 = time.perf_counter()

@@ -16,9 +16,9 @@ python tools/prof_run.py c2 2 > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python tools/prof_run.py c2 2 > gpurun_out/ncu_l.log 2>&1
 # full sections + source counters of the serial / per-contig kernels (both solves of prof_run; the summary keeps the second)
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+[ -n "$SKIP_FULL" ] || ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k 'regex:FnHeaps>|FnHeapsLeaf|FnEnum>|FnXRec|FnOpsFill|FnRootFill|FnMainTrace|FnTasksA0|FnParts|FnRelaxSeg' \
-    -c 20 -f -o gpurun_out/prof_r2 python tools/prof_run.py c2 2 > gpurun_out/ncu_f.log 2>&1
+    -c 24 -f -o gpurun_out/prof_r2 python tools/prof_run.py c2 2 > gpurun_out/ncu_f.log 2>&1
 AA_TRACE=1 python tools/prof_run.py c2 2 > gpurun_out/trace_c2.log 2>&1
 AA_TRACE=1 python tools/prof_run.py c3 2 > gpurun_out/trace_c3.log 2>&1
 tail -c 600 gpurun_out/bench.json

@@ -668,6 +668,7 @@ struct CudaBackend {
         AA_CUDA(cudaStreamWaitEvent(aux_stream, ev_aux0, 0));
         stream = aux_stream;
     }
+    void aux_enter() { stream = aux_stream; }  // back onto the aux stream after an aux_end (no new dependency on the main stream)
     void aux_end() {
         AA_CUDA(cudaEventRecord(ev_aux1, aux_stream));
         stream = main_stream;

@@ -367,6 +367,10 @@ struct Ws {
     int32_t *chain_root; // [n_chain] heap root of every chain vertex, written by the serial warp
     int32_t heap_cache_bits;  // log2 of the on-chip node cache of f_heaps_chain (entries of 40 B); 0: none
     int32_t heaps_variant;    // tuning switch (tools/heap_lab)
+    // Two-group pipelining of heaps -> enumeration (aa_pipeline.cuh): the passes between the two are launched once per group,
+    // each over all items, and skip the contigs of the other group.  grp == nullptr / grp_sel < 0: no filter.
+    const int8_t *grp;        // [C] group of the contig (1: long serial chains, 0: the rest)
+    int32_t grp_sel;          // the group this launch works on
     // enumeration
     int64_t *walk_off;   // [C+1] = c*K
     int32_t *n_walk;     // [C]
@@ -1415,8 +1419,10 @@ AA_HDN void f_ops_fill(const Ws &w, int64_t i) {
         w.ops[o + k] = op;
     }
 }
+AA_HD bool other_group(const Ws &w, int64_t c) { return w.grp_sel >= 0 && w.grp != nullptr && w.grp[c] != w.grp_sel; }
 AA_HDN void f_root_fill(const Ws &w, int64_t i) {  // after the serial warp: every tree vertex takes the heap of its owner
     const int64_t c = upper_idx(w.vtx_off, w.C, i);
+    if (other_group(w, c)) return;
     const int64_t v0 = w.vtx_off[c];
     if (w.hmode[c] != 0 || w.status[c] != 0 || i - v0 >= w.ntree[c]) return;
     const int32_t o = w.owner[i];
@@ -2865,6 +2871,7 @@ __device__ void f_heaps_level(const Ws &w, int64_t slot /* global BFS slot of th
     const uint32_t FULL = 0xffffffffu;
     const int32_t lane = (int32_t)(threadIdx.x & 31);
     const int64_t c = upper_idx(w.vtx_off, w.C, slot);
+    if (other_group(w, c)) return;
     const int64_t v0 = w.vtx_off[c];
     HNode *__restrict__ hn = w.hn;
     int32_t *__restrict__ hn_eid = w.hn_eid;
@@ -3122,6 +3129,7 @@ AA_HDN void f_enum(const Ws &w, int64_t c) {
 // parallel pre-pass over vertices for the warp enumeration: next-heap root + key of every out-edge
 AA_HDN void f_enext(const Ws &w, int64_t gv) {
     const int64_t c = upper_idx(w.vtx_off, w.C, gv);
+    if (other_group(w, c)) return;
     if (w.status[c] != 0) return;
     const int64_t v0 = w.vtx_off[c];
     const int64_t ea = w.eoff[gv], eb = w.eoff[gv + 1];
@@ -3149,6 +3157,7 @@ AA_HDN void f_xrec(const Ws &w, int64_t id) {
     const int32_t eid = w.hn_eid[id];
     if (eid < 0) return;
     const int64_t c = w.chunk_ctg[id >> 6];
+    if (c < 0 || other_group(w, c)) return;  // (c < 0: a chunk another group's builder has just taken; its own pass comes later)
     if (w.status[c] != 0) return;
     const bool keyed = w.hmode[c] != 0;
     const HNode ch = hn_load(w.hn + id);
@@ -3717,7 +3726,7 @@ __device__ void f_enum_warp_t(const Ws &w, int64_t c, void *scratch) {
     int32_t pops16 = 16 * 16, ser_steps = 0;
     // (a lone warp per SM is latency-bound: a round of ~5 k cycles loses against ~2.2 k per serial step below ~2.3 pops per
     // round; with several contigs per SM the instruction count decides and the break-even is lower)
-    const int32_t ser_thr16 = (w.heaps_variant >> 4) ? (w.heaps_variant >> 4) : (w.C > 2 * 148 ? 22 : 36);
+    const int32_t ser_thr16 = (w.heaps_variant >> 8) ? (w.heaps_variant >> 8) : (w.C > 2 * 148 ? 22 : 36);
     XRec xn;
     int32_t p12n = -1;
     bool have_xn = false;

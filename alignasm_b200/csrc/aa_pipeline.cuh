@@ -1064,6 +1064,54 @@ struct Pipeline {
         std::vector<int32_t> h_status((size_t)C);
         auto h_blk_of_order = [&](int64_t k) { return d.h_ctg_off[(size_t)ctg_order[(size_t)k] + 1] - d.h_ctg_off[(size_t)ctg_order[(size_t)k]]; };
         int64_t heap_top_h = 0;  // node ids handed out (device path)
+        if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records, 4: one backlog region, 8: wide keys for every contig, 16: no two-group pipelining, 32: pipelining for every batch (tests)
+        // large group: the contigs with long serial chains (>= 4096 blocks, at most one per SM)
+        int64_t n_big = 0;
+        while (n_big < C && n_big < 148 && h_blk_of_order(n_big) >= 4096) n_big++;
+        if ((w.heaps_variant & 32) && C >= 2 && n_big == 0) n_big = (C + 3) / 4;
+        // pipelining needs the streaming builder for every contig (no level mode) and pays when the large group is a small part of
+        // the batch: at least 8 contigs per SM-filling wave are left for the small group
+        const bool overlap = bk.device_kahn() && !any_m1 && !(w.heaps_variant & 16) && n_big > 0 && n_big < C &&
+                             (C - n_big >= 4 * n_big || (w.heaps_variant & 32));
+        std::vector<int8_t> h_grp;
+        if (overlap) {
+            h_grp.assign((size_t)C, 0);
+            for (int64_t k = 0; k < n_big; k++) h_grp[(size_t)ctg_order[(size_t)k]] = 1;
+            int8_t *d_grp = A<int8_t>(C);
+            if (!d_grp) {
+                err = "device allocation failed (contig groups)";
+                return AA_ERR_NOMEM;
+            }
+            bk.h2d(d_grp, h_grp.data(), (size_t)C);
+            w.grp = d_grp;
+        }
+        w.grp_sel = -1;
+        const int64_t WK = C * (int64_t)K;
+        // the arrays of the enumeration (inside an attempt when the two phases are pipelined: a retry releases them with the arena)
+        auto alloc_enum = [&]() -> bool {
+            w.n_walk = A<int32_t>(C + 1);
+            w.wdist = A<D4>(WK);
+            w.wlast = A<int32_t>(WK);
+            w.ent_node = A<int32_t>(3 * WK);
+            w.ent_prev = A<int32_t>(3 * WK);
+            w.pq = A<PQEnt>(3 * WK);
+            if (!w.wdist || !w.wlast || !w.ent_node || !w.ent_prev || !w.pq) {
+                err = "device allocation failed (walk enumeration)";
+                return false;
+            }
+            w.pq_far = nullptr;
+            if (bk.device_kahn()) {
+                w.enext = A<ENext>(E);
+                if (!w.enext) {
+                    err = "device allocation failed (enumeration)";
+                    return false;
+                }
+                // the second backlog region is an optimisation: without the memory for it the queue keeps one region
+                if (!(w.heaps_variant & 4) && 3 * WK * (int64_t)sizeof(PQEnt) <= bk.scratch_budget()) w.pq_far = A<PQEnt>(3 * WK);
+            }
+            return true;
+        };
+        bool enum_done = false;
         for (int attempt = 0;; attempt++) {
             if (hcap > 0x7ffffff0LL) hcap = 0x7ffffff0LL;
             w.Hcap = hcap;
@@ -1083,17 +1131,95 @@ struct Pipeline {
                 }
                 bk.fill_ff(w.hn_key, (size_t)hcap * 8);
                 bk.fill_ff(w.hn_eid, (size_t)hcap * 4);  // ids that are never allocated stay -1 (f_xrec skips them)
+                bk.fill_ff(w.chunk_ctg, (size_t)(hcap / 64 + 66) * 4);  // (-1: no owner yet)
                 bk.zero(w.vcnt, (size_t)(Vtot + 1) * 4);
             }
             bk.zero(w.heap_top, 8);
             bk.zero(w.heap_used, (size_t)C * 8);
             bk.zero(w.lvl_overflow, 4);
-            // The contigs with long serial chains (>= 4096 blocks, at most one per SM) get a kernel of their own with the
-            // largest node cache: 180 KB of shared memory per CTA leaves room for one small contig beside them, so their
-            // warps are not slowed by seven neighbours (C5 on one GPU: 34 -> 27 ms for the largest contig).  The rest run
+            // The contigs with long serial chains get a kernel of their own with the largest node cache (180 KB of shared memory per
+            // CTA leaves room for one small contig beside them, so their warps are not slowed by seven neighbours); the rest run
             // concurrently on the aux stream.
-            int64_t n_big = 0;
-            while (n_big < C && n_big < 148 && h_blk_of_order(n_big) >= 4096) n_big++;
+            if (overlap) {
+                // Two-group pipelining: the passes between the heaps and the enumeration, and the enumeration itself, are launched per
+                // group, so the small contigs enumerate on the aux stream WHILE the large contigs' heap chains are still being built
+                // (on the 2 080-contig input the largest chain takes 31 ms and everything else of that phase 12).
+                Ws wA = w, wB = w;
+                wA.grp_sel = 1;
+                wB.grp_sel = 0;
+                wA.heap_cache_bits = 12;
+                bk.aux_begin();
+                bk.for_each_contig("heaps_small", C - n_big, FnHeaps{wB, d_ord + n_big}, heaps_chain_smem_bytes(wB.heap_cache_bits));
+                bk.for_each("root_fill", Vtot, FnRootFill{wB});
+                if (n_leaf > 0) bk.for_each_contig("heaps_leaf", n_leaf, FnHeapsLeaf{wB});
+                bk.aux_end();
+                bk.for_each_contig("heaps", n_big, FnHeaps{wA, d_ord}, heaps_chain_smem_bytes(wA.heap_cache_bits));
+                bk.for_each("root_fill", Vtot, FnRootFill{wA});
+                if (n_leaf > 0) bk.for_each_contig("heaps_leaf", n_leaf, FnHeapsLeaf{wA});
+                // the small group is done long before the large one: read its outcome on the aux stream (the main stream runs on)
+                bk.aux_enter();
+                int32_t h_lo = 0;
+                bk.d2h(&h_lo, w.lvl_overflow, 4);
+                bk.d2h(h_status.data(), w.status, (size_t)C * 4);
+                AA_BK_CHECK();
+                bool overflow = h_lo != 0;
+                for (int32_t st3 : h_status) overflow = overflow || st3 == 3;
+                int64_t top_b = 0;
+                if (!overflow) {
+                    top_b = bk.read_i64((const int64_t *)w.heap_top);  // ids handed out so far: all of the small group's, some of the large one's
+                    if (!alloc_enum()) return AA_ERR_NOMEM;
+                    w.xrec = nullptr;
+                    if (!(w.heaps_variant & 2) && top_b > 0 && top_b * (int64_t)sizeof(XRec) <= bk.scratch_budget()) w.xrec = A<XRec>(top_b);
+                    wB = w;
+                    wB.grp_sel = 0;
+                    bk.for_each("enext", Vtot, FnENext{wB});
+                    if (w.xrec) bk.for_each("xrec", top_b, FnXRec{wB});
+                    bk.for_each_contig("enum_small", C - n_big, FnEnum{wB, d_ord + n_big}, ENUM_SMEM_BYTES);
+                }
+                bk.aux_end();
+                // ... and then the large group's, on the main stream
+                bk.d2h(&h_lo, w.lvl_overflow, 4);
+                bk.d2h(h_status.data(), w.status, (size_t)C * 4);
+                AA_BK_CHECK();
+                overflow = overflow || h_lo != 0;
+                for (int32_t st3 : h_status) overflow = overflow || st3 == 3;
+                if (!overflow) {
+                    const int64_t top = bk.read_i64((const int64_t *)w.heap_top);
+                    heap_top_h = top;
+                    bk.phase_end(PH_HEAPS);
+                    bk.phase_begin(PH_ENUM);
+                    wA = w;
+                    wA.grp_sel = 1;
+                    if (w.xrec) {
+                        // the records of the ids handed out since then go directly behind the first array when the allocator is in one
+                        // block (heap_top moves in whole chunks, so the first array ends on the allocator's alignment); else this group
+                        // gets an array of full length of its own
+                        if (top * (int64_t)sizeof(XRec) > bk.scratch_budget()) {
+                            wA.xrec = nullptr;
+                        } else if (top > top_b) {
+                            XRec *more = A<XRec>(top - top_b);
+                            if (more != w.xrec + top_b) wA.xrec = A<XRec>(top);  // (nullptr: this group expands without records)
+                        }
+                    }
+                    bk.for_each("enext", Vtot, FnENext{wA});
+                    if (wA.xrec) bk.for_each("xrec", top, FnXRec{wA});
+                    bk.for_each_contig("enum", n_big, FnEnum{wA, d_ord}, ENUM_SMEM_BYTES);
+                    bk.aux_join();
+                    bk.phase_end(PH_ENUM);
+                    AA_BK_CHECK();
+                    enum_done = true;
+                    break;
+                }
+                bk.aux_join();
+                bk.sync();  // (an enumeration of the small group may still be reading the arena)
+                if (hcap >= 0x7ffffff0LL || attempt > 8) {
+                    err = "sidetrack heap arena exhausted (contig too dense for one device)";
+                    return AA_ERR_NOMEM;
+                }
+                bk.release_to(arena_mark);
+                hcap *= 4;
+                continue;
+            }
             if (n_big > 0 && n_big < C) {
                 Ws wb = w;
                 wb.heap_cache_bits = 12;
@@ -1139,47 +1265,30 @@ struct Pipeline {
             bk.release_to(arena_mark);  // give the arena arrays (and the scan scratch) back before growing
             hcap *= 4;
         }
-        bk.phase_end(PH_HEAPS);
-        AA_BK_CHECK();
+        if (!enum_done) {
+            bk.phase_end(PH_HEAPS);
+            AA_BK_CHECK();
 
-        // ---- phase 8: enumeration ----
-        bk.phase_begin(PH_ENUM);
-        const int64_t WK = C * (int64_t)K;
-        w.n_walk = A<int32_t>(C + 1);
-        w.wdist = A<D4>(WK);
-        w.wlast = A<int32_t>(WK);
-        w.ent_node = A<int32_t>(3 * WK);
-        w.ent_prev = A<int32_t>(3 * WK);
-        w.pq = A<PQEnt>(3 * WK);
-        if (!w.wdist || !w.wlast || !w.ent_node || !w.ent_prev || !w.pq) {
-            err = "device allocation failed (walk enumeration)";
-            return AA_ERR_NOMEM;
-        }
-        w.pq_far = nullptr;
-        if (bk.device_kahn()) {
-            w.enext = A<ENext>(E);
-            if (!w.enext) {
-                err = "device allocation failed (enumeration)";
-                return AA_ERR_NOMEM;
-            }
-            bk.for_each("enext", Vtot, FnENext{w});
-            // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
-            w.xrec = nullptr;
-            if (const char *tn = std::getenv("AA_TUNE")) w.heaps_variant = std::atoi(tn);  // 1: no serial steps, 2: no expansion records, 4: one backlog region, 8: wide keys for every contig
-            if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget()) {
-                w.xrec = A<XRec>(heap_top_h);
-                if (!w.xrec) {
-                    err = "device allocation failed (expansion records)";
-                    return AA_ERR_NOMEM;
+            // ---- phase 8: enumeration ----
+            bk.phase_begin(PH_ENUM);
+            if (!alloc_enum()) return AA_ERR_NOMEM;
+            if (bk.device_kahn()) {
+                bk.for_each("enext", Vtot, FnENext{w});
+                // expansion records: one load per pop instead of a chain of three (skipped when the arena is too large for them)
+                w.xrec = nullptr;
+                if (!(w.heaps_variant & 2) && heap_top_h > 0 && heap_top_h * (int64_t)sizeof(XRec) <= bk.scratch_budget()) {
+                    w.xrec = A<XRec>(heap_top_h);
+                    if (!w.xrec) {
+                        err = "device allocation failed (expansion records)";
+                        return AA_ERR_NOMEM;
+                    }
+                    bk.for_each("xrec", heap_top_h, FnXRec{w});
                 }
-                bk.for_each("xrec", heap_top_h, FnXRec{w});
             }
-            // the second backlog region is an optimisation: without the memory for it the queue keeps one region
-            if (!(w.heaps_variant & 4) && 3 * WK * (int64_t)sizeof(PQEnt) <= bk.scratch_budget()) w.pq_far = A<PQEnt>(3 * WK);
+            bk.for_each_contig("enum", C, FnEnum{w, d_ord}, ENUM_SMEM_BYTES);
+            bk.phase_end(PH_ENUM);
+            AA_BK_CHECK();
         }
-        bk.for_each_contig("enum", C, FnEnum{w, d_ord}, ENUM_SMEM_BYTES);
-        bk.phase_end(PH_ENUM);
-        AA_BK_CHECK();
 
         // ---- phase 9: plan ----
         bk.phase_begin(PH_PLAN);

@@ -81,6 +81,7 @@ struct HostBackend {
     int64_t read_i64(const int64_t *p) { return *p; }
     bool device_kahn() const { return false; }
     void aux_begin() {}
+    void aux_enter() {}
     void aux_end() {}
     void aux_join() {}
     void side_begin() {}

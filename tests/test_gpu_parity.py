@@ -454,15 +454,17 @@ def test_pinned_inputs_and_result_slabs(solver, workdir):
     again.close()
 
 
-@pytest.mark.parametrize("tune", ["8", "12", "1", "2"])
+@pytest.mark.parametrize("tune", ["8", "12", "1", "2", "32", "42"])
 def test_enumeration_variants(tune, solver, workdir, monkeypatch):
     """The enumeration kernel exists in two instantiations (packed keys / wide keys for contigs of 2^20 vertices and more) and
     has optional parts (serial steps, expansion records, the far backlog region).  AA_TUNE forces each variant on inputs every
-    variant must solve identically: 8 = wide keys, 12 = wide keys + one backlog region, 1 = no serial steps, 2 = no expansion records."""
+    variant must solve identically: 8 = wide keys, 12 = wide keys + one backlog region, 1 = no serial steps, 2 = no expansion records,
+    32 = the two-group pipelining of heaps and enumeration forced on a small batch (a quarter of the contigs form the "large" group),
+    42 = that with wide keys and without expansion records."""
     import alignasm_b200 as aa
     from oracle import oracle_py
     monkeypatch.setenv("AA_TUNE", tune)
-    for name in ("ties", "segments"):
+    for name in ("ties", "segments", "c1_small"):
         args, variants = SMALL[name]
         pf = aa.read_paf(pu.synth(os.path.join(workdir, "tune_" + name + ".paf"), *args))
         for nsl in variants:

@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err || exit 1
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
+[ -n "$SKIP_REF" ] || python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
 python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2>> gpurun_out/bench.err
 python bench.py --workload c1 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c1.json 2>> gpurun_out/bench.err
 # launch list of bench.py itself (the default job: c5 on one GPU, then the c2 sub-object; warm-up, 2 timed steps, e2e solves)
@@ -19,6 +19,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 [ -n "$SKIP_FULL" ] || ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k 'regex:FnHeaps>|FnHeapsLeaf|FnEnum>|FnXRec|FnOpsFill|FnRootFill|FnMainTrace|FnTasksA0|FnParts|FnRelaxSeg' \
     -c 24 -f -o gpurun_out/prof_r2 python tools/prof_run.py c2 2 > gpurun_out/ncu_f.log 2>&1
-AA_TRACE=1 python tools/prof_run.py c2 2 > gpurun_out/trace_c2.log 2>&1
-AA_TRACE=1 python tools/prof_run.py c3 2 > gpurun_out/trace_c3.log 2>&1
+[ -n "$SKIP_TRACE" ] || AA_TRACE=1 python tools/prof_run.py c2 2 > gpurun_out/trace_c2.log 2>&1
+[ -n "$SKIP_TRACE" ] || AA_TRACE=1 python tools/prof_run.py c3 2 > gpurun_out/trace_c3.log 2>&1
 tail -c 600 gpurun_out/bench.json

@@ -47,6 +47,24 @@ def test_no_device_fails_loudly(product_lib):
     assert "CUDA" in str(e.value)
 
 
+def test_page_locked_batches_need_a_device(product_lib):
+    """aa_host_alloc hands out page-locked memory or NULL; Batch.pinned() raises instead of silently keeping pageable arrays."""
+    import numpy as np
+    import torch
+    import alignasm_b200 as aa
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = aa.load_library()
+    assert not lib.aa_host_alloc(1 << 20)
+    lib.aa_host_free(None)
+    z = np.zeros(1, np.int64)
+    b = aa.Batch(ctg_off=np.array([0, 1]), qry_str=z, qry_end=z + 5, ref_str=z, ref_end=z + 5, qry_total=z + 5, ref_chr=np.zeros(1, np.int32),
+                 aln_fwd=np.ones(1, np.uint8), map_qul=np.ones(1, np.uint8), run_off=np.array([0, 0]), run_ql=np.zeros(0, np.int64),
+                 run_qr=np.zeros(0, np.int64), run_rl=np.zeros(0, np.int64))
+    with pytest.raises(MemoryError):
+        b.pinned()
+
+
 def test_product_does_not_link_the_oracle(product_lib):
     import alignasm_b200 as aa
     out = subprocess.run(["ldd", aa.lib_path()], capture_output=True, text=True).stdout

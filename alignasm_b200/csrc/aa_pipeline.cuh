@@ -21,6 +21,13 @@
 //  11 select    primary / alt / .all winners
 //  12 walksB    rows of the winners
 //  13 d2h       result download
+//
+// Streams (device backend): the phases run on the main stream.  Three things run beside it: the forward order (topo)
+// and, after the relax, the main chain of walk 0 (trace, speculate, resolve, rows) on the side stream — joined before
+// walksA; the heaps of the small contigs on the aux stream; and, on batches of many contigs, the small contigs' whole
+// heaps -> enumeration pipeline on the aux stream while the large contigs' heap chains are still being built (two-group
+// pipelining).  The CUDA-event pair of a phase is recorded on the main stream: with pipelining the
+// small group's enumeration is inside the `heaps` phase time and `enum` is the large group's.
 #pragma once
 #include "../../include/alignasm_b200.h"
 #include "aa_core.cuh"

@@ -448,6 +448,8 @@ def main():
             "clocks": m["clocks"],
             "roofline": roofline_of(names, m["ph"], st, traffic_ok=False),
             "phases_ms": {n: round(x, 3) for n, x in zip(names, m["ph"])},
+            "phases_note": "CUDA-event pairs on the main stream; on batches of many contigs the small contigs' heaps + enumeration run on a second "
+                           "stream inside the `heaps` phase and `enum` is the large contigs' (DESIGN.md 3.5)",
             "sizes": {k: st[k] for k in ("n_ctg", "n_blk", "n_pair", "n_vtx", "n_edge", "n_heap", "n_walk", "n_task")},
             "per_rank": per_rank,
         }
